@@ -1,0 +1,213 @@
+// md_rule.h -- the per-column scalar rule of the modified LDL^T, FP64, host + device.
+//
+// Restates matrix/approximation/positive_semidefinite/Reimer.py:42-176 (_minimal_change),
+// :25-39 (_difference_frobenius_norm) and matrix/_util/roots.py:8-68 (solver_depressed_cubic, real
+// roots) in double precision.  The reference evaluates these in x87 long double; B200 has no such
+// type, so decisions can differ from the reference only when gamma - alpha is within rounding of a
+// bound (documented near-tie classes (ii)/(iii) in DESIGN.md).
+//
+// The same header is compiled by nvcc into the kernels and by g++ into the host test shim
+// (tests/host_rule_shim.cpp), so the rule is unit-tested on CPU against the reference's golden vectors.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define MD_HD __host__ __device__ __forceinline__
+#else
+#define MD_HD inline
+#endif
+
+#define MD_RULE_REIMER 0  // approximate: clamp d / shrink row by omega (Reimer.py)
+#define MD_RULE_EXACT 1   // decompose: d = gamma - alpha, omega = 1, fail when d <= 0 (dense/calculate.py:108-119)
+
+struct MdRuleParams {
+  int rule;                // MD_RULE_*
+  double min_diag_D;       // NaN = "None": per-index default of Reimer.py:488-491
+  double max_diag_D;       // +inf = none
+  double min_abs_value_D;  // Reimer.py:398-402 (default sqrt(eps(float128)) rounded to double)
+  double min_abs_value_L;  // Reimer.py:404-408
+  double min_diag_B;       // scalar bounds, used when the per-index vectors are null
+  double max_diag_B;
+};
+
+struct MdDecision {
+  double d;
+  double omega;
+  double f;
+  int clamped;  // 1 when the rule left the unclamped branch (Reimer.py:68)
+};
+
+MD_HD double md_pymax(double a, double b) { return (b > a) ? b : a; }  // Python max(a, b)
+MD_HD double md_pymin(double a, double b) { return (b < a) ? b : a; }  // Python min(a, b)
+
+// Real roots of x^3 + p x + q (roots.py:8-68).  Returns the count; order as in the reference.
+//
+// The reference evaluates D = (p/3)^3 + (q/2)^2 in long double, picks the branch by its sign, and then
+// pushes D through a DOUBLE (math.sqrt / cmath.sqrt, roots.py:15,36).  In the explosive regime
+// (alpha ~ 1e100+) that double underflows to a denormal or to zero and the reference's roots carry the
+// artifact (e.g. u = v = cbrt(-q/2) once sqrt(D) == 0).  The artifact decides how rows are shrunk, so
+// it is part of the behaviour to reproduce: magnitudes below use D as an FP64 value (same underflow),
+// the branch uses the true sign (recovered from rescaled coefficients when the FP64 D is exactly zero),
+// and the D < 0 roots are written as the reference forms them, 2 |u|^(1/3) cos(arg(u)/3 + 2 pi k/3)
+// with u = -q/2 + i sqrt(-D) and the exponent 1/3 rounded to double.
+MD_HD int md_cubic_real_roots(double p, double q, double* roots) {
+  const double P = p / 3.0, Q = q / 2.0;
+  const double D = P * P * P + Q * Q;  // roots.py:10, FP64 range
+  if (!isfinite(D)) {
+    // FP64 overflow (the reference's math.sqrt would see inf and produce NaN roots): solve the
+    // rescaled cubic x = s y instead, with the cancellation-free pairing.
+    const double scale = md_pymax(sqrt(fabs(p)), cbrt(fabs(q)));
+    const double ps = p / (scale * scale), qs = (q / scale) / (scale * scale);
+    const double Ps = ps / 3.0, Qs = qs / 2.0;
+    const double Ds = Ps * Ps * Ps + Qs * Qs;
+    if (Ds > 0) {
+      const double s = sqrt(Ds);
+      const double u = cbrt(-Qs - copysign(s, Qs));
+      const double v = (u != 0) ? -Ps / u : 0.0;
+      // u + v = (u^3 + v^3) / (u^2 - u v + v^2) = -2Q / (u^2 + P + v^2): no cancellation when P > 0
+      roots[0] = ((Ps > 0) ? -2.0 * Qs / (u * u + Ps + v * v) : (u + v)) * scale;
+      return 1;
+    } else if (Ds < 0) {
+      const double m = 2.0 * sqrt(-Ps), theta = atan2(sqrt(-Ds), -Qs);
+      const double two_pi_3 = 2.0943951023931954923;
+      roots[0] = m * cos(theta / 3.0) * scale;
+      roots[1] = m * cos(theta / 3.0 + two_pi_3) * scale;
+      roots[2] = m * cos(theta / 3.0 - two_pi_3) * scale;
+      return 3;
+    }
+    roots[0] = 3 * qs / ps * scale;
+    roots[1] = -0.5 * roots[0];
+    return 2;
+  }
+  int sgn = (D > 0) - (D < 0);
+  if (sgn == 0 && (p != 0 || q != 0)) {
+    // P^3 and Q^2 both underflowed (or cancelled exactly): recover the sign of the true D
+    const double scale = md_pymax(sqrt(fabs(p)), cbrt(fabs(q)));
+    const double Ps = p / (scale * scale) / 3.0, Qs = (q / scale) / (scale * scale) / 2.0;
+    const double Ds = Ps * Ps * Ps + Qs * Qs;
+    sgn = (Ds > 0) - (Ds < 0);
+  }
+  if (sgn > 0) {  // roots.py:13-31
+    // the reference's own (cancellation-prone) form: mirroring it tracks the reference's roots to
+    // ~1e-12, the mathematically stable form only to ~1e-9 (the reference itself is that inexact)
+    const double s = sqrt(D);
+    const double u = cbrt(-Q + s);
+    const double v = cbrt(-Q - s);
+    roots[0] = u + v;
+    return 1;
+  } else if (sgn < 0) {  // roots.py:34-51
+    const double s = sqrt(-D);
+    const double third = 1.0 / 3.0;
+    const double m = 2.0 * pow(hypot(Q, s), third);
+    const double theta = atan2(s, -Q) * third;
+    const double two_pi_3 = 2.0943951023931954923;
+    roots[0] = m * cos(theta);
+    roots[1] = m * cos(theta + two_pi_3);
+    roots[2] = m * cos(theta - two_pi_3);
+    return 3;
+  } else {  // roots.py:54-64
+    if (p == 0) { roots[0] = 0; return 1; }
+    roots[0] = 3 * q / p;
+    roots[1] = -0.5 * roots[0];
+    return 2;
+  }
+}
+
+// Reimer.py:25-39
+MD_HD double md_difference_frobenius_norm(double d, double omega, double alpha, double beta, double gamma) {
+  if (omega == 0) return (d - gamma) * (d - gamma) + beta;
+  if (omega == 1) return (d + alpha - gamma) * (d + alpha - gamma);
+  double t = d + omega * omega * alpha - gamma;
+  return t * t + (omega - 1) * (omega - 1) * beta;
+}
+
+// Reimer.py:42-176
+MD_HD MdDecision md_minimal_change(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
+                                   double min_diag_B, double max_diag_B, double min_abs_value_D) {
+  MdDecision r;
+  const double lo = md_pymax(min_diag_D, min_abs_value_D);  // :64
+  const double a = md_pymax(lo, min_diag_B - alpha);        // :65
+  const double b = md_pymin(max_diag_D, max_diag_B - alpha);  // :66
+  const double dstar = gamma - alpha;                       // :67
+  if (a <= dstar && dstar <= b) {                           // :68-72
+    r.d = dstar; r.omega = 1; r.f = 0; r.clamped = 0;
+    return r;
+  }
+  double best_d = 0, best_w = 0, best_f = 0;
+  int have = 0;
+#define MD_CONSIDER(dd_, ww_)                                                        \
+  do {                                                                               \
+    const double cd_ = (dd_), cw_ = (ww_);                                           \
+    const double cf_ = md_difference_frobenius_norm(cd_, cw_, alpha, beta, gamma);   \
+    int better_;                                                                     \
+    if (!have) better_ = 1;                                                          \
+    else if (cf_ != best_f) better_ = cf_ < best_f;                                  \
+    else if (cd_ != best_d) better_ = cd_ > best_d;                                  \
+    else better_ = cw_ < best_w;                                                     \
+    if (better_) { best_d = cd_; best_w = cw_; best_f = cf_; have = 1; }             \
+  } while (0)
+
+  int add_best_d_omega_zero = 0;
+  if (isfinite(alpha)) {
+    if (a <= b) {  // :82-88
+      if (dstar < a) MD_CONSIDER(a, 1.0);
+      else if (dstar > b) MD_CONSIDER(b, 1.0);
+    }
+    if (isfinite(beta)) {
+      if (alpha != 0) {
+        double dv[2];
+        int nd = 0;
+        if (min_diag_B - alpha <= lo) dv[nd++] = lo;                                  // :95-96
+        if (isfinite(max_diag_D) && max_diag_D <= max_diag_B) dv[nd++] = max_diag_D;  // :97-98
+        for (int t = 0; t < nd; ++t) {
+          const double dd = dv[t];
+          const double q = (-0.5 * beta / alpha) / alpha;  // :103
+          const double p = (dd - gamma) / alpha - q;       // :104
+          if (!isfinite(q) || !isfinite(p)) { add_best_d_omega_zero = 1; continue; }  // :105-110
+          double roots[3];
+          const int nr = md_cubic_real_roots(p, q, roots);
+          const double omega_lower = sqrt(md_pymax(min_diag_B - dd, 0.0) / alpha);        // :118
+          const double omega_upper = md_pymin(sqrt((max_diag_B - dd) / alpha), 1.0);      // :120
+          int add_lower = 0, add_upper = 0;
+          for (int k = 0; k < nr; ++k) {  // :125-131
+            const double w = roots[k];
+            if (w <= omega_lower) add_lower = 1;
+            else if (w >= omega_upper) add_upper = 1;
+            else MD_CONSIDER(dd, w);
+          }
+          if (add_lower) MD_CONSIDER(dd, omega_lower);
+          if (add_upper) MD_CONSIDER(dd, omega_upper);
+        }
+      }
+    } else {
+      add_best_d_omega_zero = 1;  // :136-139
+    }
+  } else {
+    add_best_d_omega_zero = 1;  // :140-143
+  }
+  if (add_best_d_omega_zero) {  // :146-148
+    const double dd = md_pymax(md_pymax(lo, min_diag_B), md_pymin(md_pymin(gamma, max_diag_D), max_diag_B));
+    MD_CONSIDER(dd, 0.0);
+  }
+  if (min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D) MD_CONSIDER(0.0, 0.0);  // :151-152
+#undef MD_CONSIDER
+  if (!have) { best_d = NAN; best_w = NAN; best_f = NAN; }
+  r.d = best_d; r.omega = best_w; r.f = best_f; r.clamped = 1;
+  return r;
+}
+
+// Decision for one column given its accumulated (alpha, beta, gamma) and per-index B bounds.
+// For MD_RULE_EXACT, clamped = 1 flags "not positive definite at this pivot" (d <= 0 or NaN).
+MD_HD MdDecision md_decide(const MdRuleParams& prm, double alpha, double beta, double gamma, double min_diag_B_i,
+                           double max_diag_B_i) {
+  if (prm.rule == MD_RULE_EXACT) {
+    MdDecision r;
+    r.d = gamma - alpha; r.omega = 1; r.f = 0;
+    r.clamped = !(r.d > 0);
+    return r;
+  }
+  double mD = prm.min_diag_D;
+  if (isnan(mD))  // Reimer.py:488-491
+    mD = md_pymin(0.5 * md_pymin(md_pymax(gamma, min_diag_B_i), max_diag_B_i), prm.max_diag_D);
+  return md_minimal_change(alpha, beta, gamma, mD, prm.max_diag_D, min_diag_B_i, max_diag_B_i, prm.min_abs_value_D);
+}

@@ -1,0 +1,23 @@
+// Test-only host build of csrc/md_rule.h (g++), so the FP64 scalar rule that the kernels use can be
+// checked on CPU against the reference's golden vectors and driven by the numpy model of the blocked
+// algorithm (oracle/blocked_model.py).  Not part of the product library.
+#include "../matrix_decomposition_b200/csrc/md_rule.h"
+
+extern "C" {
+int mdh_cubic(double p, double q, double* roots) { return md_cubic_real_roots(p, q, roots); }
+int mdh_minimal_change(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D, double min_diag_B,
+                       double max_diag_B, double mav, double* out3) {
+  MdDecision r = md_minimal_change(alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav);
+  out3[0] = r.d; out3[1] = r.omega; out3[2] = r.f;
+  return r.clamped;
+}
+int mdh_decide(int rule, double min_diag_D, double max_diag_D, double mavD, double alpha, double beta, double gamma,
+               double mB, double MB, double* out3) {
+  MdRuleParams prm;
+  prm.rule = rule; prm.min_diag_D = min_diag_D; prm.max_diag_D = max_diag_D; prm.min_abs_value_D = mavD;
+  prm.min_abs_value_L = 0; prm.min_diag_B = mB; prm.max_diag_B = MB;
+  MdDecision r = md_decide(prm, alpha, beta, gamma, mB, MB);
+  out3[0] = r.d; out3[1] = r.omega; out3[2] = r.f;
+  return r.clamped;
+}
+}

@@ -1,0 +1,112 @@
+"""The blocked right-looking restatement (oracle/blocked_model.py, the numpy twin of the CUDA
+kernels) and the FP64 scalar rule header (csrc/md_rule.h) against the oracle and the goldens."""
+import json
+import math
+
+import numpy as np
+import pytest
+
+import workloads
+from oracle import blocked_model as bm
+from oracle import cpu_oracle as orc
+from conftest import load_golden, ld_join
+
+
+def test_fp64_rule_against_reference_vectors():
+    """csrc/md_rule.h (the header the kernels compile) on the reference's own _minimal_change outputs."""
+    z = load_golden('scalar_rule.npz')
+    want = ld_join(z, 'mc_out').astype(np.float64)
+    shim = bm.rule_shim()
+    out = np.zeros(3)
+    import ctypes
+    n_far = 0
+    for row, w in zip(z['mc_in'], want):
+        cl = shim.mdh_minimal_change(*[float(v) for v in row], out.ctypes.data_as(ctypes.c_void_p))
+        assert bool(cl) == (not (w[1] == 1 and w[2] == 0))
+        assert abs(out[2] - w[2]) <= 1e-12 * max(1.0, abs(w[2]))       # same minimum
+        if abs(out[0] - w[0]) > 1e-12 * abs(w[0]) or abs(out[1] - w[1]) > 1e-9:
+            n_far += 1                                                   # degenerate ties only
+    assert n_far <= 4
+
+
+def test_fp64_cubic_against_reference_vectors():
+    z = load_golden('scalar_rule.npz')
+    want = ld_join(z, 'cubic_out').astype(np.float64)
+    import ctypes
+    r = np.zeros(3)
+    for (p, q), w in zip(z['cubic_in'], want):
+        k = bm.rule_shim().mdh_cubic(p, q, r.ctypes.data_as(ctypes.c_void_p))
+        w = w[~np.isnan(w)]
+        assert k == len(w)
+        np.testing.assert_allclose(np.sort(r[:k]), np.sort(w), rtol=2e-11, atol=1e-13)  # u + v cancels: last-bit differences in D are amplified
+
+
+def test_cubic_overflow_rescaling():
+    import ctypes
+    r = np.zeros(3)
+    p, q = 3e150, -2.9e150     # D overflows in FP64; root ~ -q/p
+    k = bm.rule_shim().mdh_cubic(p, q, r.ctypes.data_as(ctypes.c_void_p))
+    assert k == 1
+    assert abs(r[0] ** 3 + p * r[0] + q) <= 1e-10 * abs(q)
+
+
+CASES = [
+    # (family, n, seed, s/lo-hi, kwargs, benign, nb)
+    ('shifted_goe', 300, 1, 1.05, None, True, 64),
+    ('shifted_goe', 300, 1, 1.05, None, True, 128),
+    ('shifted_goe', 500, 2, 1.05, None, True, 128),
+    ('shifted_goe', 300, 3, 0.9, None, False, 64),
+    ('goe', 200, 4, None, dict(min_diag_D=1e-6, permutation='decreasing_diagonal_values'), False, 64),
+    ('goe', 200, 5, None, dict(min_diag_D=0.5, max_diag_D=3.0, permutation='increasing_absolute_diagonal_values'),
+     False, 32),
+    ('fixture', 96, 0, None, dict(min_diag_D=None, min_diag_B=1.0, max_diag_B=30.0, permutation='none'), False, 32),
+    ('fixture', 96, 0, None, dict(min_diag_D=0.0, max_diag_D=50.0, permutation='decreasing_diagonal_values'), False, 32),
+    ('lowrank', 200, 6, (-0.02, 1.0), dict(min_diag_D=1e-3, permutation='decreasing_diagonal_values'), True, 64),
+]
+
+
+def _make(family, n, seed, par, kw):
+    if family == 'shifted_goe':
+        A, kw2 = workloads.shifted_goe(n, seed, par)
+        return A, (kw or kw2)
+    if family == 'goe':
+        return workloads.goe(n, seed), kw
+    if family == 'fixture':
+        return workloads.reference_fixture(n), kw
+    if family == 'lowrank':
+        return workloads.lowrank_plus_diag(n, seed, *par), kw
+    raise ValueError(family)
+
+
+@pytest.mark.parametrize('family,n,seed,par,kw,benign,nb', CASES)
+def test_blocked_model_matches_oracle(family, n, seed, par, kw, benign, nb):
+    A, kw = _make(family, n, seed, par, kw)
+    ref = orc.approximate(A, **kw)
+    kw2 = {k: v for k, v in kw.items() if k != 'permutation'}
+    got = bm.blocked_factor(A, ref['p'], nb=nb, **kw2)
+    np.testing.assert_array_equal(got['clamped'], ref['clamped'])
+    d_ref = ref['d'].astype(np.float64)
+    L_ref = ref['L']
+    B_ref = L_ref @ (d_ref[:, None] * L_ref.T)
+    B = got['L'] @ (got['d'][:, None] * got['L'].T)
+    assert np.linalg.norm(B - B_ref) <= 1e-12 * np.linalg.norm(B_ref)
+    if benign:
+        np.testing.assert_allclose(got['d'], d_ref, rtol=1e-10)
+        assert np.all(np.abs(got['L'] - L_ref) <= 1e-10 * np.maximum(1.0, np.abs(L_ref)))
+        np.testing.assert_allclose(got['omega'], ref['omega'].astype(np.float64), rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(got['delta'], ref['delta'].astype(np.float64), rtol=1e-9,
+                                   atol=1e-11 * np.abs(A).max())
+
+
+def test_blocked_model_decompose_matches_potrf():
+    A = workloads.lowrank_plus_diag(300, 5)
+    ref = orc.decompose(A, 'decreasing_diagonal_values', 'LDL')
+    got = bm.blocked_factor(A, ref['p'], rule=bm.RULE_EXACT, nb=64)
+    assert got['info'] == 0 and not got['clamped'].any()
+    np.testing.assert_allclose(got['d'], ref['d'], rtol=1e-11)
+    np.testing.assert_allclose(got['L'], ref['L'], rtol=1e-10, atol=1e-13)
+    # failing pivot index like LAPACK's info
+    B = workloads.reference_fixture(40)
+    _, info = orc.potrf_lower(B)
+    got = bm.blocked_factor(B, np.arange(40), rule=bm.RULE_EXACT, nb=16)
+    assert got['info'] == info > 0
