@@ -1,0 +1,185 @@
+/*
+ * mdb200.h -- C ABI of libmdb200.so: the B200-native (sm_100a) dense factorization hot path of
+ * jor-/matrix-decomposition.  Plain pointers and sizes only; every call returns an int status
+ * (MDB_OK = 0) and leaves a message retrievable with mdb_last_error().
+ *
+ * The reference is pure Python and has no FFI seam; the boundary below is what its hot-path
+ * functions would bind if they were native.  Each entry point cites the reference interface it
+ * replaces (paths relative to /root/reference/matrix).  The ctypes binding a maintainer would add is
+ * shown in INTEGRATION.md; the in-tree binding is matrix_decomposition_b200/_native.py.
+ *
+ * Layout conventions: matrices are row-major (numpy C order) float64 with a leading dimension in
+ * elements; permutation vectors are int64; "position" means index in the permuted order
+ * (A[p][:, p]), "original" means index into the caller's A.  Unless a call says otherwise it is
+ * synchronous: results are complete when it returns.
+ */
+#ifndef MDB200_H
+#define MDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---- */
+#define MDB_OK 0
+#define MDB_ERR_INVALID 1        /* bad argument */
+#define MDB_ERR_CUDA 2           /* CUDA runtime failure (message holds cudaGetErrorString) */
+#define MDB_ERR_NO_DEVICE 3      /* no usable CUDA device: the library never falls back to the CPU */
+#define MDB_ERR_NOT_POSITIVE_DEFINITE 4 /* mdb_potrf: info holds the failing pivot (LAPACK convention) */
+#define MDB_ERR_STATE 5          /* call order violated (e.g. solve before factor) */
+
+/* ---- rules / types ---- */
+#define MDB_RULE_REIMER 0 /* approximation.positive_semidefinite.decomposition (Reimer.py:179-709) */
+#define MDB_RULE_EXACT 1  /* matrix.decompose (dense/calculate.py:15-126): plain LDL^T / LL^T, fails on d <= 0 */
+
+#define MDB_TYPE_LDL 0            /* constants.py:5  'LDL'            */
+#define MDB_TYPE_LDL_COMPRESSED 1 /* constants.py:6  'LDL_compressed' */
+#define MDB_TYPE_LL 2             /* constants.py:7  'LL'             */
+
+#define MDB_HOST 0   /* pointer refers to host memory   */
+#define MDB_DEVICE 1 /* pointer refers to device memory */
+
+typedef struct mdb_ctx mdb_ctx;       /* one per (device, stream); not shared between threads */
+typedef struct mdb_factor mdb_factor; /* device-resident factorization (W, d, omega, delta, p) */
+
+/* Bounds of the modified LDL^T, Reimer.py:180-182 keyword arguments after validation. */
+typedef struct mdb_bounds {
+    int32_t rule;            /* MDB_RULE_* */
+    double min_diag_D;       /* NaN = None: per-index default, Reimer.py:488-491 */
+    double max_diag_D;       /* +inf = None */
+    double min_abs_value_D;  /* Reimer.py:398-402 (the Python host resolves the default) */
+    double min_abs_value_L;  /* Reimer.py:404-408 */
+    const double *min_diag_B; /* host, indexed by ORIGINAL index with stride_B (0 = scalar), Reimer.py:480-487 */
+    const double *max_diag_B;
+    int64_t stride_B;
+} mdb_bounds;
+
+/* ---- context ---- */
+int mdb_version(void);
+/* Creates a context on `device`.  MDB_ERR_NO_DEVICE when CUDA is unavailable (no CPU fallback). */
+int mdb_ctx_create(int device, mdb_ctx **out);
+int mdb_ctx_destroy(mdb_ctx *ctx);
+/* Use an existing stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the own stream. */
+int mdb_ctx_set_stream(mdb_ctx *ctx, void *cuda_stream);
+int mdb_ctx_synchronize(mdb_ctx *ctx);
+const char *mdb_last_error(const mdb_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
+int64_t mdb_launch_count(const mdb_ctx *ctx);
+/* Per-phase device time of the last mdb_factor_run with profiling on: ms[0..3] = diag, panel, trailing, other */
+int mdb_ctx_set_profiling(mdb_ctx *ctx, int on);
+int mdb_ctx_get_phase_ms(const mdb_ctx *ctx, double ms[4]);
+
+/* ---- device memory (so that a host language without CUDA bindings can stage buffers) ---- */
+int mdb_malloc(mdb_ctx *ctx, size_t bytes, void **dptr);
+int mdb_free(mdb_ctx *ctx, void *dptr);
+int mdb_malloc_host(mdb_ctx *ctx, size_t bytes, void **hptr); /* pinned */
+int mdb_free_host(mdb_ctx *ctx, void *hptr);
+int mdb_memcpy(mdb_ctx *ctx, void *dst, const void *src, size_t bytes, int dst_loc, int src_loc);
+/* strided 2-D copy: rows x (cols * 8 bytes) */
+int mdb_memcpy2d(mdb_ctx *ctx, void *dst, int64_t ld_dst, const void *src, int64_t ld_src, int64_t rows,
+                 int64_t cols, int dst_loc, int src_loc);
+
+/* ---- symmetric permutation: B[i, j] = A[p[i], p[j]]  (permute.py:105-129, dense/permute.py:4-27) ----
+ * A, B: n x n with lda / ldb; p: n int64 on the host.  loc says where A and B live (both the same). */
+int mdb_permute_sym_f64(mdb_ctx *ctx, int64_t n, const double *A, int64_t lda, const int64_t *p, double *B,
+                        int64_t ldb, int loc);
+
+/* ---- one-shot factorizations with host numpy buffers (the drop-in path) ----
+ * Replaces Reimer._decomposition (Reimer.py:179-709) for a static permutation:
+ *   in : A (n x n, lda), p (n, host), bounds
+ *   out: L (n x n, ldl, unit lower, zero upper), d (n, by position), omega / delta (n, by ORIGINAL index,
+ *        Reimer.py:533-545), clamped (n, by position, 1 = the column left the branch at Reimer.py:68).
+ * out_type selects what L holds (MDB_TYPE_*; LL = L sqrt(D), LDL_compressed = d on the diagonal,
+ * decompositions.py:875-921).  loc = MDB_HOST or MDB_DEVICE for A and L (vectors are always host).
+ * If factor_out != NULL the device-resident factor is kept and returned (for solve), else freed. */
+int mdb_approximate_f64(mdb_ctx *ctx, int64_t n, const double *A, int64_t lda, const int64_t *p,
+                        const mdb_bounds *bounds, int out_type, double *L, int64_t ldl, double *d, double *omega,
+                        double *delta, uint8_t *clamped, int loc, mdb_factor **factor_out);
+
+/* Replaces dense.calculate._decompose (dense/calculate.py:15-126): permute + potrf + as_type.
+ * info: 0 or failing leading minor (LAPACK convention, dense/calculate.py:115-119); the status is
+ * MDB_ERR_NOT_POSITIVE_DEFINITE when info > 0 (L then holds the partial factor). */
+int mdb_decompose_f64(mdb_ctx *ctx, int64_t n, const double *A, int64_t lda, const int64_t *p, int out_type,
+                      double *L, int64_t ldl, double *d, int64_t *info, int loc, mdb_factor **factor_out);
+
+/* Batched many-small-matrix mode (BASELINE config 5): `batch` independent n x n matrices, A and L
+ * strided by n*lda / n*ldl, vectors strided by n, one permutation per matrix (p: batch x n). */
+int mdb_approximate_batched_f64(mdb_ctx *ctx, int64_t batch, int64_t n, const double *A, int64_t lda,
+                                const int64_t *p, const mdb_bounds *bounds, double *L, int64_t ldl, double *d,
+                                double *omega, double *delta, uint8_t *clamped, int loc);
+
+/* ---- device-resident factor objects (bench.py's HBM-resident leg, solve with a resident factor) ---- */
+int mdb_factor_create(mdb_ctx *ctx, int64_t n, int64_t batch, mdb_factor **out);
+int mdb_factor_destroy(mdb_factor *f);
+/* W = A[p][:, p], gamma = diag.  p may be NULL (identity).  a_loc: where A lives. */
+int mdb_factor_set_matrix(mdb_factor *f, const double *A, int64_t lda, const int64_t *p, int a_loc);
+/* Synthetic family F2 generated on the device: A = GOE(seed) + mu I, already permuted by p
+ * (host, may be NULL).  mdb_generate_diag_f2 returns the diagonal so the host can argsort it. */
+int mdb_generate_diag_f2(mdb_ctx *ctx, int64_t n, uint64_t seed, double mu, double *diag_host);
+int mdb_factor_generate_f2(mdb_factor *f, uint64_t seed, double mu, const int64_t *p);
+/* Same generator into a plain device matrix (unpermuted), for parity tests that feed the oracle. */
+int mdb_generate_f2(mdb_ctx *ctx, int64_t n, uint64_t seed, double mu, double *A_dev, int64_t lda);
+/* Runs the blocked factorization on the device (asynchronous on the context's stream). */
+int mdb_factor_run(mdb_factor *f, const mdb_bounds *bounds);
+/* Finalises (scale rows by omega, threshold, set diagonal) and copies results out.  Any pointer may be
+ * NULL.  l_loc: where L lives.  info: first failing pivot + 1 for MDB_RULE_EXACT. */
+int mdb_factor_get(mdb_factor *f, int out_type, double *L, int64_t ldl, int l_loc, double *d, double *omega,
+                   double *delta, uint8_t *clamped, int64_t *info);
+/* Uploads an existing factor (decompositions.py:800-868, :1180-1223) so solves can run on the device.
+ * type: MDB_TYPE_LDL (L unit lower + d) or MDB_TYPE_LL (L lower, d == NULL). */
+int mdb_factor_upload(mdb_ctx *ctx, int64_t n, int type, const double *L, int64_t ldl, const double *d,
+                      const int64_t *p, mdb_factor **out);
+/* x = A^-1 b for the composed matrix (decompositions.py:983-991 LDL, :1345-1352 LL, dense/util.py:24-29):
+ * b[p] -> forward substitution -> / d -> back substitution -> [p^-1].  B, X: n x nrhs row-major with
+ * ldb / ldx (a vector is nrhs = 1, ld = 1).  loc: where B and X live. */
+int mdb_factor_solve(mdb_factor *f, const double *B, int64_t ldb, int64_t nrhs, double *X, int64_t ldx, int loc);
+/* y = A x for the composed matrix (decompositions.py:961-968 LDL, :1324-1330 LL). */
+int mdb_factor_multiply(mdb_factor *f, const double *B, int64_t ldb, int64_t nrhs, double *X, int64_t ldx, int loc);
+/* Oracle-free identity check usable at any n (Reimer.py:947-957, tests/test_approximate.py:503-506):
+ * returns max over `nprobe` random vectors v of |P^T L D L^T P v - (A o Omega + diag(delta)) v|_inf /
+ * |A v|_inf, all evaluated on the device from the resident W (which still holds A in its upper triangle). */
+int mdb_factor_identity_residual(mdb_factor *f, int nprobe, uint64_t seed, double *residual);
+
+/* ---- introspection / unit-test hooks (used by tests/ and bench.py, not by the drop-in path) ----
+ * mdb_factor_device_ptr: which = 0 W, 1 gamma, 2 alpha, 3 beta, 4 rowmax, 5 d, 6 omega, 7 delta (device addresses
+ * of the resident state, position order); mdb_factor_ld: leading dimension of W. */
+void *mdb_factor_device_ptr(mdb_factor *f, int which);
+int64_t mdb_factor_ld(const mdb_factor *f);
+/* The DMMA tile kernel on host buffers: C (M x N, ldc) = beta C + sign A (M x K, lda) B^T (N x K, ldb);
+ * lower != 0 touches only elements with row_glob0 + i > col_glob0 + j.  K must be a multiple of 16.
+ * reps > 1 repeats the launch and returns the mean device time per launch in *ms (C is then garbage). */
+int mdb_debug_gemm_tn(mdb_ctx *ctx, int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B,
+                      int64_t ldb, double *C, int64_t ldc, int lower, int beta1, int neg, int64_t row_glob0,
+                      int64_t col_glob0, int reps, double *ms);
+
+/* ---- multi-GPU: 1-D block-cyclic column distribution, one process per GPU ----
+ * The Python driver (matrix_decomposition_b200/distributed.py) owns the loop and the NCCL broadcast
+ * (torch.distributed); these are the per-rank device steps.  Column block k (width 128) lives on rank
+ * k % world.  panel: (n_rows_below x 128) X then Y = -X D, plus a 3 x 128 header (d, omega, drop). */
+typedef struct mdb_dist mdb_dist;
+int mdb_dist_create(mdb_ctx *ctx, int64_t n, int rank, int world, mdb_dist **out);
+int mdb_dist_destroy(mdb_dist *s);
+/* local columns generated in place (family F2, permuted by p) -- both the S and the A copies */
+int mdb_dist_generate_f2(mdb_dist *s, uint64_t seed, double mu, const int64_t *p);
+/* local columns from a host matrix already permuted: Ap (n x n, ld) */
+int mdb_dist_set_matrix(mdb_dist *s, const double *Ap, int64_t ld);
+int mdb_dist_set_bounds(mdb_dist *s, const mdb_bounds *bounds, const int64_t *p);
+/* size in doubles of the broadcast buffer for panel k, and its device address on this rank */
+int64_t mdb_dist_panel_elems(const mdb_dist *s, int64_t k);
+void *mdb_dist_panel_buffer(mdb_dist *s, int slot);
+/* owner only: factor diagonal block + panel k into panel buffer `slot` (async on the ctx stream) */
+int mdb_dist_factor_panel(mdb_dist *s, int64_t k, int slot);
+/* every rank: apply panel k (already in buffer `slot`) to its local trailing columns.  If only_block >= 0
+ * only that global column block is updated (lookahead), if skip_block >= 0 that block is skipped. */
+int mdb_dist_apply_panel(mdb_dist *s, int64_t k, int slot, int64_t only_block, int64_t skip_block);
+/* gathers this rank's columns of the scaled L (position order) into a host/device n x ncols_local array */
+int mdb_dist_get_local(mdb_dist *s, double *Lloc, int64_t ld, int loc, double *d, double *omega, uint8_t *clamped);
+int64_t mdb_dist_local_cols(const mdb_dist *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDB200_H */

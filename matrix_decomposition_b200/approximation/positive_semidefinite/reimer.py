@@ -1,0 +1,256 @@
+"""Modified LDL^T approximation (Reimer's algorithm) behind the reference's API.
+
+Reference: matrix/approximation/positive_semidefinite/Reimer.py (`R.py` below).  This module is the
+host side only: argument validation and defaults exactly as R.py:273-457, the static permutation
+vector (numpy argsort of the diagonal, like the reference), and the call into libmdb200.so, where the
+column loop R.py:476-686 runs as a blocked right-looking factorization on the B200.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from ... import _native, constants, decompositions, errors, permute
+from ... import logger
+
+MINIMAL_DIFFERENCE_PERMUTATION_METHOD = 'minimal_difference'
+""" Permutation method supported by the decomposition and the positive_semidefinite_matrix algorithm. """
+MAXIMAL_STABILITY_PERMUTATION_METHOD = 'maximal_stability'
+""" Permutation method supported by the decomposition and the positive_semidefinite_matrix algorithm. """
+APPROXIMATION_ONLY_PERMUTATION_METHODS = (MINIMAL_DIFFERENCE_PERMUTATION_METHOD, MAXIMAL_STABILITY_PERMUTATION_METHOD)
+""" Permutation methods supported only by the decomposition and the positive_semidefinite_matrix algorithm. """
+
+# The reference keeps d / omega / delta in numpy float128 (R.py:396,460-464).  The device computes in
+# float64; results are returned as np.longdouble arrays so dtype-dependent behaviour downstream
+# (e.g. the singularity threshold finfo(d.dtype).resolution, decompositions.py:949-951) is unchanged.
+RESULT_DTYPE = np.longdouble
+
+
+def _check_float_scalar_or_vector(f, n, f_name, default_value, minus_inf_okay=False, plus_inf_okay=False):
+    """R.py:291-322"""
+    if f is not None:
+        try:
+            f = np.asarray(f)
+        except TypeError as original_error:
+            error = ValueError(f'{f_name} must a scalar value or a vector but it is {f}.')
+            logger.error(error)
+            raise error from original_error
+        if not (f.ndim == 0 or (f.ndim == 1 and f.shape[0] == n)):
+            error = ValueError(f'{f_name} must be a scalar or a vector with the same '
+                               f'dimension as A but its shape is {f.shape}.')
+            logger.error(error)
+            raise error
+        if not (np.all(np.isreal(f))):
+            error = ValueError(f'{f_name} must be real valued but it is {f}.')
+            logger.error(error)
+            raise error
+        ok = np.isfinite(f)
+        if plus_inf_okay:
+            ok = np.logical_or(ok, f == math.inf)
+        if minus_inf_okay:
+            ok = np.logical_or(ok, f == -math.inf)
+        if not np.all(ok):
+            error = ValueError(f'{f_name} must be finite'
+                               + (' or minus infinity' if minus_inf_okay else '')
+                               + (' or plus infinity' if plus_inf_okay else '')
+                               + f' but it is {f}.')
+            logger.error(error)
+            raise error
+    else:
+        f = np.asarray(default_value)
+    return f
+
+
+def _check_float_scalar(f, f_name, default_value=None, lower_bound=None, upper_bound=None,
+                        minus_inf_okay=False, plus_inf_okay=False):
+    """R.py:324-354"""
+    if f is not None:
+        try:
+            f = float(f)
+        except TypeError as original_error:
+            error = ValueError(f'{f_name} must a float value but it is {f}.')
+            logger.error(error)
+            raise error from original_error
+        if not (math.isfinite(f) or (minus_inf_okay and f == -math.inf) or (plus_inf_okay and f == math.inf)):
+            error = ValueError(f'{f_name} must be finite'
+                               + (' or minus infinity' if minus_inf_okay else '')
+                               + (' or plus infinity' if plus_inf_okay else '')
+                               + f' but it is {f}.')
+            logger.error(error)
+            raise error
+        if lower_bound is not None and f < lower_bound:
+            error = ValueError(f'{f_name} must be greater or equal to {lower_bound} but it is {f}.')
+            logger.error(error)
+            raise error
+        if upper_bound is not None and f > upper_bound:
+            error = ValueError(f'{f_name} must be less or equal to {upper_bound} but it is {f}.')
+            logger.error(error)
+            raise error
+    else:
+        f = default_value
+    return f
+
+
+def _prepare(A, min_diag_B, max_diag_B, min_diag_D, max_diag_D, min_abs_value_D, min_abs_value_L, permutation):
+    """Validation and defaults of R.py:273-457 for the dense real case."""
+    A = np.asarray(A)
+    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+        raise errors.MatrixNotSquareError(A)
+    n = A.shape[0]
+    if np.issubdtype(A.dtype, np.complexfloating):
+        gamma = A.diagonal()
+        if not np.all(np.isreal(gamma)):
+            raise errors.MatrixComplexDiagonalValueError(A, i=np.where(~np.isreal(gamma))[0][0])
+        raise ValueError('complex matrices are outside the dense real (float64) path of this package.')
+
+    min_diag_B = _check_float_scalar_or_vector(min_diag_B, n, 'min_diag_B', -math.inf, minus_inf_okay=True)
+    max_diag_B = _check_float_scalar_or_vector(max_diag_B, n, 'max_diag_B', math.inf, plus_inf_okay=True)
+    min_diag_D = _check_float_scalar(min_diag_D, 'min_diag_D', default_value=None, lower_bound=0)
+    max_diag_D = _check_float_scalar(max_diag_D, 'max_diag_D', default_value=math.inf, plus_inf_okay=True)
+    if not (max(np.max(min_diag_B), min_diag_D if min_diag_D is not None else 0)
+            <= min(np.min(max_diag_B), max_diag_D)):  # R.py:368-373
+        error = ValueError(('The values of min_diag_B and min_diag_D must be lower or equal '
+                            'to the values of max_diag_B and max_diag_D.'))
+        logger.error(error)
+        raise error
+
+    d_eps = np.finfo(np.longdouble).eps  # R.py:396-408
+    min_abs_value_D = _check_float_scalar(min_abs_value_D, 'min_abs_value_D', default_value=d_eps**0.5, lower_bound=0)
+    min_abs_value_D = max(min_abs_value_D, d_eps)
+    L_eps = np.finfo(np.float64).eps
+    min_abs_value_L = _check_float_scalar(min_abs_value_L, 'min_abs_value_L', default_value=L_eps,
+                                          lower_bound=0, upper_bound=1)
+    min_abs_value_L = max(min_abs_value_L, L_eps)
+
+    if permutation is None:  # R.py:415-416
+        permutation = MAXIMAL_STABILITY_PERMUTATION_METHOD
+    if isinstance(permutation, str):
+        permutation_method = permutation.lower()
+        supported = constants.UNIVERSAL_PERMUTATION_METHODS + APPROXIMATION_ONLY_PERMUTATION_METHODS
+        if permutation_method not in supported:
+            error = ValueError(f'Permutation method {permutation_method} is unknown. Only the '
+                               f'following methods are supported {supported}.')
+            logger.error(error)
+            raise error
+        if permutation_method in APPROXIMATION_ONLY_PERMUTATION_METHODS:
+            if (permutation_method == MINIMAL_DIFFERENCE_PERMUTATION_METHOD
+                    and min_diag_D is not None and min_diag_D <= 0):  # R.py:437-441
+                raise ValueError(f'The permutation method {MINIMAL_DIFFERENCE_PERMUTATION_METHOD} is '
+                                 f'only available if min_diag_D is greater zero.')
+            raise NotImplementedError(
+                f'The dynamic pivoting method "{permutation_method}" (R.py:497-523) is not built yet in '
+                f'matrix_decomposition_b200; pass one of {constants.UNIVERSAL_PERMUTATION_METHODS} or a '
+                f'permutation vector (see DESIGN.md, "next").')
+        p = permute.permutation_vector(A, permutation_method=permutation_method)
+    else:
+        p = np.asanyarray(permutation)
+        if p.ndim != 1 or p.shape[0] != n:
+            error = ValueError(f'Permutation vector must have same length as the dimensions of '
+                               f'A. Its shape is {p.shape} and the shape of A is {A.shape}.')
+            logger.error(error)
+            raise error
+    return A, n, p, min_diag_B, max_diag_B, min_diag_D, max_diag_D, float(min_abs_value_D), float(min_abs_value_L)
+
+
+def _run(A, out_type_str, keep_factor, **kw):
+    A, n, p, min_diag_B, max_diag_B, min_diag_D, max_diag_D, mavD, mavL = _prepare(A, **kw)
+    A64 = np.ascontiguousarray(A, dtype=np.float64)
+    p64 = np.ascontiguousarray(p, dtype=np.int64)
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, min_diag_D, max_diag_D, mavD, mavL, min_diag_B, max_diag_B)
+    Lout = np.empty((n, n), dtype=np.float64)
+    d = np.empty(n, dtype=np.float64)
+    omega = np.empty(n, dtype=np.float64)
+    delta = np.empty(n, dtype=np.float64)
+    clamped = np.zeros(n, dtype=np.uint8)
+    handle = ctypes.c_void_p()
+    ctx = _native.context()
+    rc = ctx.lib.mdb_approximate_f64(ctx.handle, n, _native.ptr(A64), n, _native.ptr(p64), ctypes.byref(bounds),
+                                     _native.TYPE_CODES[out_type_str], _native.ptr(Lout), n, _native.ptr(d),
+                                     _native.ptr(omega), _native.ptr(delta), _native.ptr(clamped), _native.HOST,
+                                     ctypes.byref(handle) if keep_factor else None)
+    ctx.check(rc, 'mdb_approximate_f64')
+    del keep
+    factor = _native.Factor(ctx, handle) if keep_factor else None
+    return Lout, d, p, omega, delta, clamped.astype(bool), factor
+
+
+def decomposition(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag_D=None,
+                  min_abs_value_D=None, min_abs_value_L=None, permutation=None, overwrite_A=False,
+                  return_type=None):
+    """
+    Computes an approximative decomposition of a matrix with the specified properties (R.py:712-816).
+
+    Same parameters, defaults, exceptions and return value as the reference: a decomposition object of
+    type `return_type` (default 'LDL') carrying the extra attributes `.omega` and `.delta`
+    (R.py:810-812; indexed by ORIGINAL index, float128 like the reference's).  Additionally `.clamped`
+    holds the boolean mask (by position) of the columns whose (d, omega) left the unclamped branch of
+    R.py:68.  `A` is never modified (`overwrite_A` only documents permission).
+
+    Deviation: the dynamic pivoting methods 'maximal_stability' (the reference's default for
+    permutation=None) and 'minimal_difference' are not built yet and raise NotImplementedError.
+    """
+    supported_return_types = constants.DECOMPOSITION_TYPES
+    if return_type is not None and return_type not in supported_return_types:
+        error = ValueError(f'Unkown return type {return_type}. Only values in '
+                           f'{supported_return_types} are supported.')
+        logger.error(error)
+        raise error
+    type_str = constants.LDL_DECOMPOSITION_TYPE if return_type is None else return_type
+    Lout, d, p, omega, delta, clamped, factor = _run(
+        A, type_str, True, min_diag_B=min_diag_B, max_diag_B=max_diag_B, min_diag_D=min_diag_D,
+        max_diag_D=max_diag_D, min_abs_value_D=min_abs_value_D, min_abs_value_L=min_abs_value_L,
+        permutation=permutation)
+    d = d.astype(RESULT_DTYPE)
+    if type_str == constants.LL_DECOMPOSITION_TYPE:
+        for i, d_i in enumerate(d):  # decompositions.py:903-908 (cannot happen: min_diag_D >= 0)
+            if d_i < 0:
+                raise errors.NoDecompositionPossibleWithProblematicSubdecompositionError(
+                    decompositions.LDL_Decomposition(np.eye(len(d)), d, p), constants.LL_DECOMPOSITION_TYPE, p[i])
+        dec = decompositions.LL_Decomposition(Lout, p=p)
+    elif type_str == constants.LDL_DECOMPOSITION_COMPRESSED_TYPE:
+        dec = decompositions.LDL_DecompositionCompressed(Lout, p=p)
+    else:
+        dec = decompositions.LDL_Decomposition(Lout, d, p=p)
+    dec._attach_device_factor(factor)
+    dec.omega = omega.astype(RESULT_DTYPE)
+    dec.delta = delta.astype(RESULT_DTYPE)
+    dec.clamped = clamped
+    return dec
+
+
+def positive_semidefinite_matrix(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag_D=None,
+                                 min_abs_value_D=None, min_abs_value_L=None, permutation=None, overwrite_A=False):
+    """
+    Computes an approximation `B` of `A` which has a LDL^H decomposition with the specified properties
+    (R.py:819-992): B[i, i] = A[i, i] + delta[i] clipped to [min_diag_B, max_diag_B] (R.py:924-945),
+    B[i, j] = A[i, j] * omega[later of (i, j) in elimination order] (R.py:947-957).
+
+    Status: the factorization runs on the device; the O(n^2) element-wise formation of B (an n^2 Python
+    double loop in the reference) is vectorised on the host here and is next in line for a device kernel
+    ("next").  The inner-product fallback for d == 0 (R.py:958-975) is included.
+    """
+    Lout, d, p, omega, delta, clamped, _ = _run(
+        A, constants.LDL_DECOMPOSITION_TYPE, False, min_diag_B=min_diag_B, max_diag_B=max_diag_B,
+        min_diag_D=min_diag_D, max_diag_D=max_diag_D, min_abs_value_D=min_abs_value_D,
+        min_abs_value_L=min_abs_value_L, permutation=permutation)
+    A = np.asarray(A)
+    n = A.shape[0]
+    q = permute.invert_permutation_vector(np.asarray(p, dtype=np.int64))
+    later = np.where(q[:, None] > q[None, :], np.arange(n)[:, None], np.arange(n)[None, :])   # b of R.py:949-955
+    earlier_pos = np.minimum(q[:, None], q[None, :])                                            # q[a]
+    B = A.astype(np.float64) * omega[later]
+    zero_d = d[earlier_pos] == 0
+    if np.any(zero_d):
+        LD = Lout * d[None, :]
+        for i, j in zip(*np.nonzero(np.triu(zero_d, 1))):
+            b = later[i, j]
+            m = earlier_pos[i, j]
+            val = 0.0 if omega[b] == 0 or m == 0 else float(LD[q[i], :m] @ Lout[q[j], :m])
+            B[i, j] = B[j, i] = val
+    diag = A.diagonal().astype(np.float64) + delta
+    if min_diag_B is not None:
+        diag = np.maximum(diag, np.asarray(min_diag_B, dtype=np.float64))
+    if max_diag_B is not None:
+        diag = np.minimum(diag, np.asarray(max_diag_B, dtype=np.float64))
+    B[np.diag_indices(n)] = diag
+    return B

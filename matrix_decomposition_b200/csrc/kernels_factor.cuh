@@ -1,0 +1,339 @@
+// kernels_factor.cuh -- gather, generator, diagonal-block, panel and finalize kernels of the blocked
+// right-looking modified LDL^T (the restatement validated by oracle/blocked_model.py).
+#pragma once
+#include "mdb_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Symmetric gather  W[i, j] = A[p[i], p[j]]   (dense/permute.py:26), gamma[i] = A[p[i], p[i]].
+// HBM bound: 8 n^2 written coalesced; reads are 8-byte gathers inside row p[i] (sector efficiency 1/4
+// for a random p, 1 for the identity).  grid = (n rows, column chunks of 1024, batch).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_sym(int64_t n, const double* __restrict__ A, int64_t lda,
+                                                    int64_t sA, const int64_t* __restrict__ p, int64_t sP,
+                                                    double* __restrict__ W, int64_t ldw, int64_t sW,
+                                                    double* __restrict__ gamma, int64_t sVec) {
+  const int64_t b = blockIdx.z;
+  const int64_t i = blockIdx.x;
+  A += b * sA;
+  W += b * sW;
+  const int64_t* pb = p ? p + b * sP : nullptr;
+  const int64_t pi = pb ? pb[i] : i;
+  const double* Arow = A + pi * lda;
+  double* Wrow = W + i * ldw;
+  const int64_t j0 = (int64_t)blockIdx.y * 1024 + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t j = j0 + 256 * e;
+    if (j < n) {
+      const int64_t pj = pb ? pb[j] : j;
+      const double v = Arow[pj];
+      Wrow[j] = v;
+      if (gamma && j == i) gamma[b * sVec + i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic family F2: A = (G + G^T)/2 + mu I, G ~ N(0,1) iid.  Counter-based: element
+// (i, j) depends only on (min, max, seed), so any rank can generate any column block, in any
+// permuted order.  Off-diagonal ~ N(0, 1/2), diagonal ~ N(0, 1) + mu.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mdb_splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ double mdb_f2_element(int64_t i, int64_t j, uint64_t seed, double mu) {
+  const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+  const uint64_t h1 = mdb_splitmix64(seed ^ mdb_splitmix64(((uint64_t)lo << 32) ^ (uint64_t)hi));
+  const uint64_t h2 = mdb_splitmix64(h1);
+  const double u1 = ((double)(h1 >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0, 1)
+  const double u2 = ((double)(h2 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+  return (i == j) ? z + mu : z * 0.70710678118654752440;
+}
+
+// out[r, c] = elem(prow[row0 + r], pcol[c]) for r < rows, c < cols (p null = identity)
+__global__ void __launch_bounds__(256) k_generate_f2(int64_t rows, int64_t cols, int64_t row0,
+                                                     const int64_t* __restrict__ prow,
+                                                     const int64_t* __restrict__ pcol, uint64_t seed, double mu,
+                                                     double* __restrict__ out, int64_t ld) {
+  const int64_t r = blockIdx.x;
+  const int64_t gi = prow ? prow[row0 + r] : row0 + r;
+  const int64_t c0 = (int64_t)blockIdx.y * 1024 + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t c = c0 + 256 * e;
+    if (c < cols) {
+      const int64_t gj = pcol ? pcol[c] : c;
+      out[r * ld + c] = mdb_f2_element(gi, gj, seed, mu);
+    }
+  }
+}
+
+__global__ void k_generate_f2_diag(int64_t n, uint64_t seed, double mu, double* __restrict__ diag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) diag[i] = mdb_f2_element(i, i, seed, mu);
+}
+
+__global__ void k_extract_diag(int64_t n, const double* __restrict__ W, int64_t ldw, double* __restrict__ gamma) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gamma[i] = W[i * ldw + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal block: columns K = k0 .. k0+kb-1, rows of the block only.  One CTA (NB threads, thread j
+// owns row j of the block), the whole block in shared memory.  Sequential over the columns because
+// the decision for column k needs alpha_k, which contains Lu[k, k0:k]^2 d from this very block:
+//   thread k : (d, omega) = rule(alpha_k, beta_k, gamma_k)                 Reimer.py:479-494 / :42-176
+//   threads m < k : u[m] = d_m * thresh(omega Lu[k, m])                    Reimer.py:553-560
+//   threads j > k : Lu[j, k] = (r_j - sum_m Lu[j, m] u[m]) / d,  alpha_j, beta_j, rowmax_j updates
+// with r_j = A[j, k] when the whole scaled row k is dropped, else (1 - omega) A[j, k] + omega S0[j, k].
+// Outputs: d, omega, delta, clamped; Ut (for the panel kernel); hdr = (d, omega, drop) of the panel.
+// ------------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int kb) {
+  extern __shared__ double smem_d[];
+  constexpr int LDT = NB + 1;
+  double* T = smem_d;           // T[r * LDT + c] = W[k0 + r, k0 + c]
+  double* s_u = T + NB * LDT;   // NB
+  double* s_d = s_u + NB;       // NB
+  __shared__ double s_dec[3];   // d, omega, drop of the current column
+
+  const int64_t b = blockIdx.z;
+  double* W = F.W + b * F.sW;
+  const int64_t vo = b * F.sVec;
+  double* Ut = F.Ut + b * F.sUt;
+  double* hdr = F.hdr + b * F.sHdr;
+  const int tid = threadIdx.x;
+  const double mavL = F.prm.min_abs_value_L;
+
+  for (int r = 0; r < kb; ++r)
+    for (int c = tid; c < kb; c += NB) T[r * LDT + c] = W[(k0 + r) * F.ldw + k0 + c];
+
+  double alpha_j = 0, beta_j = 0, rowmax_j = 0, gamma_j = 0, mB = F.prm.min_diag_B, MB = F.prm.max_diag_B;
+  if (tid < kb) {
+    alpha_j = F.alpha[vo + k0 + tid];
+    beta_j = F.beta[vo + k0 + tid];
+    rowmax_j = F.rowmax[vo + k0 + tid];
+    gamma_j = F.gamma[vo + k0 + tid];
+    if (F.minB) mB = F.minB[vo + k0 + tid];
+    if (F.maxB) MB = F.maxB[vo + k0 + tid];
+  }
+  __syncthreads();
+
+  for (int k = 0; k < kb; ++k) {
+    if (tid == k) {
+      const MdDecision dec = md_decide(F.prm, alpha_j, beta_j, gamma_j, mB, MB);
+      const int64_t K = k0 + k;
+      F.d[vo + K] = dec.d;
+      F.omega[vo + K] = dec.omega;
+      F.delta[vo + K] = (dec.d - gamma_j) + (dec.omega != 0 ? dec.omega * dec.omega * alpha_j : 0.0);  // :541-545
+      F.clamped[vo + K] = (uint8_t)dec.clamped;
+      if (F.prm.rule == MD_RULE_EXACT && dec.clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
+      const double drop = (dec.omega == 0 || dec.omega * rowmax_j < mavL) ? 1.0 : 0.0;
+      s_dec[0] = dec.d;
+      s_dec[1] = dec.omega;
+      s_dec[2] = drop;
+      s_d[k] = dec.d;
+      hdr[k] = dec.d;
+      hdr[NB + k] = dec.omega;
+      hdr[2 * NB + k] = drop;
+    }
+    __syncthreads();
+    const double dk = s_dec[0], wk = s_dec[1];
+    const bool drop = s_dec[2] != 0.0;
+    if (tid < k) {
+      double lt = wk * T[k * LDT + tid];
+      if (wk == 0 || fabs(lt) < mavL) lt = 0;
+      const double u = s_d[tid] * lt;
+      s_u[tid] = u;
+      Ut[tid * NB + k] = u;
+    }
+    __syncthreads();
+    if (tid > k && tid < kb) {
+      const double a = T[k * LDT + tid];
+      double r = a;
+      if (!drop) r = (1.0 - wk) * a + wk * T[tid * LDT + k];
+      double acc = 0;
+      const double* Trow = T + tid * LDT;
+#pragma unroll 4
+      for (int m = 0; m < k; ++m) acc += Trow[m] * s_u[m];
+      const double x = (dk != 0) ? (r - acc) / dk : 0.0;
+      T[tid * LDT + k] = x;
+      alpha_j += x * x * dk;
+      beta_j += 2.0 * a * a;
+      rowmax_j = fmax(rowmax_j, fabs(x));
+    }
+    // no barrier needed here: the next iteration's first barrier orders these writes before any read
+  }
+  __syncthreads();
+  if (tid < kb) {
+    F.alpha[vo + k0 + tid] = alpha_j;
+    F.beta[vo + k0 + tid] = beta_j;
+    F.rowmax[vo + k0 + tid] = rowmax_j;
+  }
+  // strict lower part of the block back to W (unscaled rows Lu)
+  for (int r = 1; r < kb; ++r)
+    for (int c = tid; c < r; c += NB) W[(k0 + r) * F.ldw + k0 + c] = T[r * LDT + c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Panel: rows j >= k1 = k0 + NB against the factored diagonal block.  Row-parallel forward
+// substitution X (D Ltilde^T) = R with the mix R = (1 - omega) A + omega S0 applied on load; one
+// thread per row, 8 columns at a time, U broadcast through L1, the row's X staged in shared memory.
+// Epilogue accumulates alpha / beta / rowmax in column order (like Reimer.py:604,684) and writes
+//   W[j, k0:k1] = X (unscaled Lu),  PX[j - k1, :] = X,  PY[j - k1, :] = -X d   (trailing-update operands).
+// A[j, k] for the mix comes from (Asrc, a_rs, a_cs): element (j, k) at Asrc[j * a_rs + k * a_cs]
+// (single GPU: the upper triangle of W, a_rs = 1, a_cs = ldw; multi GPU: the local copy of A).
+// ------------------------------------------------------------------------------------------------
+template <int NB, int R>
+__global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t row_begin, int64_t n_rows,
+                                             const double* __restrict__ Asrc, int64_t a_rs, int64_t a_cs,
+                                             double* __restrict__ Wcol, int64_t w_ld,
+                                             double* __restrict__ PX, double* __restrict__ PY, int64_t p_row0) {
+  // Wcol: pointer such that S0[j, k0 + c] lives at Wcol[j * w_ld + c]  (j = global row)
+  extern __shared__ double smem_d[];
+  constexpr int LDX = R + 1;
+  double* xs = smem_d;          // xs[c * LDX + r]
+  double* s_d = xs + NB * LDX;  // NB
+  double* s_w = s_d + NB;       // NB
+  double* s_drop = s_w + NB;    // NB
+
+  const int64_t b = blockIdx.z;
+  const int64_t vo = b * F.sVec;
+  const double* Ut = F.Ut + b * F.sUt;
+  const double* hdr = F.hdr + b * F.sHdr;
+  Asrc += b * F.sW;
+  Wcol += b * F.sW;
+  PX += b * F.sPanel;
+  PY += b * F.sPanel;
+  const int tid = threadIdx.x;
+  const int64_t jbase = row_begin + (int64_t)blockIdx.x * R;
+  const int64_t jend = row_begin + n_rows;
+  const int64_t j = jbase + tid;
+  const bool valid = j < jend;
+
+  for (int c = tid; c < NB; c += R) {
+    s_d[c] = hdr[c];
+    s_w[c] = hdr[NB + c];
+    s_drop[c] = hdr[2 * NB + c];
+  }
+  // S0 tile, transposed into shared memory (coalesced 1 KB row segments)
+  for (int rr = 0; rr < R; ++rr) {
+    const int64_t jj = jbase + rr;
+    if (jj < jend)
+      for (int c = tid; c < NB; c += R) xs[c * LDX + rr] = Wcol[jj * w_ld + c];
+  }
+  __syncthreads();
+
+  double alpha_j = 0, beta_j = 0, rowmax_j = 0;
+  if (valid) {
+    alpha_j = F.alpha[vo + j];
+    beta_j = F.beta[vo + j];
+    rowmax_j = F.rowmax[vo + j];
+    // mix with the original A column entries; beta in column order
+    const double* Aj = Asrc + j * a_rs + k0 * a_cs;
+#pragma unroll 8
+    for (int c = 0; c < NB; ++c) {
+      const double a = Aj[(int64_t)c * a_cs];
+      const double w = s_w[c];
+      double r = a;
+      if (s_drop[c] == 0.0) r = (1.0 - w) * a + w * xs[c * LDX + tid];
+      xs[c * LDX + tid] = r;
+      beta_j += 2.0 * a * a;
+    }
+    // forward substitution, 8 columns at a time
+    for (int c0 = 0; c0 < NB; c0 += 8) {
+      double acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = xs[(c0 + i) * LDX + tid];
+      for (int m = 0; m < c0; ++m) {
+        const double xm = xs[m * LDX + tid];
+        const double2* up = reinterpret_cast<const double2*>(Ut + m * NB + c0);
+        const double2 u0 = __ldg(up), u1 = __ldg(up + 1), u2 = __ldg(up + 2), u3 = __ldg(up + 3);
+        acc[0] -= xm * u0.x; acc[1] -= xm * u0.y; acc[2] -= xm * u1.x; acc[3] -= xm * u1.y;
+        acc[4] -= xm * u2.x; acc[5] -= xm * u2.y; acc[6] -= xm * u3.x; acc[7] -= xm * u3.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        const double dk = s_d[c];
+        const double x = (dk != 0) ? acc[i] / dk : 0.0;
+        xs[c * LDX + tid] = x;
+        alpha_j += x * x * dk;
+        rowmax_j = fmax(rowmax_j, fabs(x));
+#pragma unroll
+        for (int i2 = i + 1; i2 < 8; ++i2) acc[i2] -= x * __ldg(Ut + c * NB + c0 + i2);
+      }
+    }
+    F.alpha[vo + j] = alpha_j;
+    F.beta[vo + j] = beta_j;
+    F.rowmax[vo + j] = rowmax_j;
+  }
+  __syncthreads();
+  // write back (coalesced rows): Lu into W, X and Y = -X d into the compact panel buffers
+  for (int rr = 0; rr < R; ++rr) {
+    const int64_t jj = jbase + rr;
+    if (jj < jend) {
+      const int64_t pr = jj - p_row0;
+      for (int c = tid; c < NB; c += R) {
+        const double x = xs[c * LDX + rr];
+        Wcol[jj * w_ld + c] = x;
+        PX[pr * NB + c] = x;
+        PY[pr * NB + c] = -x * s_d[c];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Finalize in place: strict lower L[j, m] = thresh(omega_j Lu[j, m]) (Reimer.py:553-560), diagonal 1
+// (LDL, Reimer.py:689-692), d (LDL_compressed, decompositions.py:875-882) or sqrt(d) with columns
+// scaled by sqrt(d_m) (LL, decompositions.py:898-918); upper triangle zero (Reimer.py:698-701).
+// HBM bound: 16 n^2 bytes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(int64_t n, double* __restrict__ W, int64_t ldw, int64_t sW,
+                                                  const double* __restrict__ d, const double* __restrict__ omega,
+                                                  int64_t sVec, double mavL, int out_type, double* __restrict__ out,
+                                                  int64_t ldo, int64_t sOut) {
+  const int64_t b = blockIdx.z;
+  const int64_t i = blockIdx.x;
+  const double* Wrow = W + b * sW + i * ldw;
+  double* Orow = out + b * sOut + i * ldo;
+  const double w = omega[b * sVec + i];
+  const double* db = d + b * sVec;
+  const int64_t j0 = (int64_t)blockIdx.y * 1024 + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t j = j0 + 256 * e;
+    if (j < n) {
+      double v;
+      if (j < i) {
+        v = w * Wrow[j];
+        if (w == 0 || fabs(v) < mavL) v = 0;
+        if (out_type == MDB_TYPE_LL) v *= sqrt(db[j]);
+      } else if (j == i) {
+        v = (out_type == MDB_TYPE_LDL) ? 1.0 : (out_type == MDB_TYPE_LL ? sqrt(db[i]) : db[i]);
+      } else {
+        v = 0.0;
+      }
+      Orow[j] = v;
+    }
+  }
+}
+
+// position-indexed -> original-indexed scatter of omega / delta (Reimer.py:538,545): out[p[i]] = in[i]
+__global__ void k_scatter_by_p(int64_t n, const int64_t* __restrict__ p, const double* __restrict__ in,
+                               double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[p ? p[i] : i] = in[i];
+}
+
+__global__ void k_gather_by_p(int64_t n, const int64_t* __restrict__ p, const double* __restrict__ in, int64_t stride,
+                              double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[(p ? p[i] : i) * stride];
+}

@@ -1,0 +1,247 @@
+// kernels_solve.cuh -- device kernels behind LDL / LL solve and multiply with a resident factor
+// (decompositions.py:961-991, :1324-1352; dense/util.py:24-29).
+//
+// Storage: after finalisation W holds L (lower, with its diagonal); k_symmetrize mirrors it into the
+// upper triangle so that BOTH sweeps stream row-contiguous data: the forward sweep reads rows of L
+// (lower triangle), the backward sweep reads rows of U = L^T (upper triangle).  Each sweep therefore
+// reads n^2/2 doubles once: 8 n^2 bytes per solve in total, the algorithmic minimum.
+// Right-hand sides are kept transposed on the device (Bt: nrhs x n, one contiguous row per right-hand
+// side), which makes every block update a K-major "TN" product: Bt[:, I] -= Y[:, J] L[I, J]^T.
+// Diagonal blocks are applied through their explicit inverses (computed once per factor), so a block
+// step is two products and no sequential substitution.
+#pragma once
+#include "mdb_common.cuh"
+
+// W[i, j] = W[j, i] for i < j  (tile transpose through shared memory, coalesced both ways)
+__global__ void __launch_bounds__(256) k_symmetrize(int64_t n, double* __restrict__ W, int64_t ldw) {
+  __shared__ double tile[32][33];
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;  // tile (bi, bj) of the LOWER triangle, bj <= bi
+  if (bj > bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = bi * 32 + r, j = bj * 32 + tx;
+    tile[r][tx] = (i < n && j < n) ? W[i * ldw + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    // destination element (row = bj*32 + r, col = bi*32 + tx) = source (bi*32 + tx, bj*32 + r)
+    const int64_t i = bj * 32 + r, j = bi * 32 + tx;
+    if (i < n && j < n && i < j) W[i * ldw + j] = tile[tx][r];
+  }
+}
+
+// Per diagonal block J (NB x NB, lower triangular with diagonal; unit_diag forces a unit diagonal):
+//   Linv[J]  = inverse (lower),  LinvT[J] = its transpose (= inverse of the upper block U_JJ = L_JJ^T)
+//   Ltri[J]  = the lower triangle incl. diagonal, zeros above;  Utri[J] = its transpose
+// all row-major NB x NB.  Blocks past n are padded with the identity.  One CTA per block; thread c
+// owns column c of the inverse (forward substitution against e_c).  The block is kept packed
+// (r (r + 1) / 2 + c) so that block + inverse fit in shared memory.
+template <int NB>
+__global__ void __launch_bounds__(NB) k_prepare_blocks(int64_t n, const double* __restrict__ W, int64_t ldw,
+                                                       int unit_diag, double* __restrict__ Linv,
+                                                       double* __restrict__ LinvT, double* __restrict__ Ltri,
+                                                       double* __restrict__ Utri) {
+  extern __shared__ double smem_d[];
+  constexpr int LD = NB + 1;
+  double* Lp = smem_d;                      // packed lower triangle, NB (NB + 1) / 2
+  double* Xs = Lp + NB * (NB + 1) / 2;      // Xs[r * LD + c] = inverse
+  const int64_t J = blockIdx.x, j0 = J * NB;
+  const int tid = threadIdx.x;
+  for (int r = 0; r < NB; ++r) {
+    if (tid <= r) {
+      const int64_t i = j0 + r, j = j0 + tid;
+      double v = (r == tid) ? 1.0 : 0.0;
+      if (i < n && j < n && !(unit_diag && r == tid)) v = W[i * ldw + j];
+      Lp[r * (r + 1) / 2 + tid] = v;
+    }
+  }
+  __syncthreads();
+  {
+    const int c = tid;
+    for (int r = 0; r < NB; ++r) {
+      if (r < c) {
+        Xs[r * LD + c] = 0.0;
+        continue;
+      }
+      double s = (r == c) ? 1.0 : 0.0;
+      const double* Lr = Lp + r * (r + 1) / 2;
+      for (int m = c; m < r; ++m) s -= Lr[m] * Xs[m * LD + c];
+      Xs[r * LD + c] = s / Lr[r];
+    }
+  }
+  __syncthreads();
+  double* oLinv = Linv + J * NB * NB;
+  double* oLinvT = LinvT + J * NB * NB;
+  double* oLtri = Ltri + J * NB * NB;
+  double* oUtri = Utri + J * NB * NB;
+  for (int r = 0; r < NB; ++r) {
+    const double l_rt = (tid <= r) ? Lp[r * (r + 1) / 2 + tid] : 0.0;   // L[r][tid]
+    const double l_tr = (r <= tid) ? Lp[tid * (tid + 1) / 2 + r] : 0.0;  // L[tid][r]
+    oLinv[r * NB + tid] = Xs[r * LD + tid];
+    oLinvT[r * NB + tid] = Xs[tid * LD + r];
+    oLtri[r * NB + tid] = l_rt;
+    oUtri[r * NB + tid] = l_tr;
+  }
+}
+
+// Small-M "TN" product for up to 8 right-hand sides (bandwidth bound, one warp per B row):
+//   C[r, i] = beta C[r, i] + sign * sum_{k < K} A[r, k] B[i, k],  r < M <= 8, i < N, K multiple of 128.
+// A rows live in registers (each lane holds 4 consecutive doubles per 128-wide chunk), B rows are
+// streamed once with 32-byte per-lane loads: 8 N K bytes of traffic, the algorithmic minimum.
+template <int MMAX>
+__global__ void __launch_bounds__(256) k_gemv_tn(int M, int64_t N, int64_t K, const double* __restrict__ A, int64_t lda,
+                                                 const double* __restrict__ B, int64_t ldb, double* __restrict__ C,
+                                                 int64_t ldc, double beta, double sign) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= N) return;
+  double acc[MMAX];
+#pragma unroll
+  for (int r = 0; r < MMAX; ++r) acc[r] = 0.0;
+  const double* Brow = B + i * ldb;
+  for (int64_t k0 = 0; k0 < K; k0 += 128) {
+    const double2* bp = reinterpret_cast<const double2*>(Brow + k0 + lane * 4);
+    const double2 b0 = bp[0], b1 = bp[1];
+#pragma unroll
+    for (int r = 0; r < MMAX; ++r) {
+      if (r < M) {
+        const double2* ap = reinterpret_cast<const double2*>(A + r * lda + k0 + lane * 4);
+        const double2 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+        acc[r] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < MMAX; ++r) {
+    double v = acc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && r < M) {
+      double* c = C + r * ldc + i;
+      *c = (beta != 0.0 ? beta * (*c) : 0.0) + sign * v;
+    }
+  }
+}
+
+// Bt[r, i] = B[p[i] * ldb + r]   (gather + transpose of the right-hand sides: x = x[p], decompositions.py:986)
+__global__ void __launch_bounds__(256) k_rhs_gather_t(int64_t n, int64_t nrhs, const double* __restrict__ B,
+                                                      int64_t ldb, const int64_t* __restrict__ p,
+                                                      double* __restrict__ Bt, int64_t ldbt) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t i0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int a = ty; a < 32; a += 8) {  // rows i0 + a of B (after permutation), columns r0 + tx
+    const int64_t i = i0 + a, r = r0 + tx;
+    tile[a][tx] = (i < n && r < nrhs) ? B[(p ? p[i] : i) * ldb + r] : 0.0;
+  }
+  __syncthreads();
+  for (int a = ty; a < 32; a += 8) {
+    const int64_t r = r0 + a, i = i0 + tx;
+    if (r < nrhs && i < n) Bt[r * ldbt + i] = tile[tx][a];
+  }
+}
+
+// X[p[i] * ldx + r] = Xt[r, i]   (x = x[p_inverse], decompositions.py:990)
+__global__ void __launch_bounds__(256) k_rhs_scatter_t(int64_t n, int64_t nrhs, const double* __restrict__ Xt,
+                                                       int64_t ldxt, const int64_t* __restrict__ p,
+                                                       double* __restrict__ X, int64_t ldx) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t i0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int a = ty; a < 32; a += 8) {
+    const int64_t r = r0 + a, i = i0 + tx;
+    tile[a][tx] = (r < nrhs && i < n) ? Xt[r * ldxt + i] : 0.0;
+  }
+  __syncthreads();
+  for (int a = ty; a < 32; a += 8) {
+    const int64_t i = i0 + a, r = r0 + tx;
+    if (i < n && r < nrhs) X[(p ? p[i] : i) * ldx + r] = tile[tx][a];
+  }
+}
+
+// Yt[r, i] = Yt[r, i] / d[i]  (mode 0, decompositions.py:988)  or  * d[i]  (mode 1, :965)
+__global__ void __launch_bounds__(256) k_scale_by_d(int64_t n, int64_t nrhs, double* __restrict__ Yt, int64_t ld,
+                                                    const double* __restrict__ d, int mode) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t r = blockIdx.y;
+  if (i < n && r < nrhs) {
+    const double v = Yt[r * ld + i];
+    Yt[r * ld + i] = mode == 0 ? v / d[i] : v * d[i];
+  }
+}
+
+// y_i += (A o Omega + diag(gamma + delta)) v evaluated from the UPPER triangle of the un-finalised W
+// (which still holds the permuted A): position order, Omega[i, j] = omega[max(i, j)]  (Reimer.py:947-957).
+// One CTA per slab of 32 rows; the symmetric contribution of element (i, j), j > i, goes to y_i (row
+// dot, warp reduce) and to y_j (per-thread column accumulators, one atomic per column per slab).
+__global__ void __launch_bounds__(256) k_identity_rhs(int64_t n, const double* __restrict__ W, int64_t ldw,
+                                                      const double* __restrict__ gamma, const double* __restrict__ delta,
+                                                      const double* __restrict__ omega, const double* __restrict__ v,
+                                                      double* __restrict__ y_b, double* __restrict__ y_a) {
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int64_t jc0 = (int64_t)blockIdx.y * 1024;  // column chunk
+  const int tid = threadIdx.x;
+  if (jc0 + 1024 <= i0) return;  // every column of this chunk is left of the slab: nothing above the diagonal
+  double colacc_b[4] = {0, 0, 0, 0}, colacc_a[4] = {0, 0, 0, 0};
+  for (int r = 0; r < 32; ++r) {
+    const int64_t i = i0 + r;
+    if (i >= n) break;
+    const double vi = v[i];
+    double rowsum_b = 0, rowsum_a = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t j = jc0 + tid + 256 * e;
+      if (j < n && j > i) {
+        const double a = W[i * ldw + j];
+        const double wj = omega[j];
+        rowsum_b += a * wj * v[j];
+        rowsum_a += a * v[j];
+        colacc_b[e] += a * wj * vi;
+        colacc_a[e] += a * vi;
+      }
+    }
+    // block reduce of the two row sums
+    double s1 = rowsum_b, s2 = rowsum_a;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((tid & 31) == 0) {
+      atomicAdd(&y_b[i], s1);
+      atomicAdd(&y_a[i], s2);
+    }
+    if (tid == 0 && i >= jc0 && i < jc0 + 1024) {  // the chunk that holds the diagonal element (never skipped)
+      atomicAdd(&y_b[i], (gamma[i] + delta[i]) * vi);
+      atomicAdd(&y_a[i], gamma[i] * vi);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t j = jc0 + tid + 256 * e;
+    if (j < n && (colacc_b[e] != 0.0 || colacc_a[e] != 0.0)) {
+      atomicAdd(&y_b[j], colacc_b[e]);
+      atomicAdd(&y_a[j], colacc_a[e]);
+    }
+  }
+}
+
+__global__ void k_fill_random(int64_t n, uint64_t seed, double* __restrict__ v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint64_t h = mdb_splitmix64(seed ^ mdb_splitmix64((uint64_t)i));
+    v[i] = ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+  }
+}
+
+// out[0] = max_i |a_i - b_i|, out[1] = max_i |c_i|   (non-negative doubles compare like their bit patterns)
+__global__ void k_max_abs_diff(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                               const double* __restrict__ c, unsigned long long* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double e = fabs(a[i] - b[i]);
+    const double m = fabs(c[i]);
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(isnan(e) ? INFINITY : e));
+    atomicMax(&out[1], (unsigned long long)__double_as_longlong(m));
+  }
+}

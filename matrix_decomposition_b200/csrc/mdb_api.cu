@@ -1,0 +1,963 @@
+// mdb_api.cu -- the C ABI of libmdb200.so (see include/mdb200.h).  Host orchestration of the blocked
+// right-looking modified LDL^T, the permutation gather, and solve / multiply with a resident factor.
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <new>
+
+#include "kernels_factor.cuh"
+#include "kernels_gemm.cuh"
+#include "kernels_solve.cuh"
+
+#define NB MDB_NB
+#define PANEL_R 64
+
+enum { ST_EMPTY = 0, ST_MATRIX = 1, ST_FACTORED = 2, ST_FINAL = 3 };
+
+struct mdb_factor {
+  mdb_ctx* ctx;
+  int64_t n, ld, batch;
+  double* W;         // batch x n x ld
+  double* vec;       // 7 x batch x n: gamma, alpha, beta, rowmax, d, omega, delta
+  double *gamma, *alpha, *beta, *rowmax, *d, *omega, *delta;
+  uint8_t* clamped;  // batch x n
+  double *minB, *maxB;
+  int64_t* p_dev;    // batch x n (null = identity)
+  int* info;         // batch
+  double *Ut, *hdr;  // batch x NB*NB, batch x 3*NB
+  double *PX, *PY;   // batch x panel_rows x NB
+  int64_t panel_rows;
+  int state, out_type, rule;
+  double mavL;
+  bool prepared;
+  double *Linv, *LinvT, *Ltri, *Utri;
+  std::vector<int64_t> p_host;
+};
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int mdb_version(void) { return 100; }
+
+extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
+  if (!out) return MDB_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return MDB_ERR_NO_DEVICE;
+  mdb_ctx* ctx = new (std::nothrow) mdb_ctx();
+  if (!ctx) return MDB_ERR_INVALID;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  MDB_CUDA(ctx, cudaSetDevice(device));
+  MDB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  MDB_CUDA(ctx, cudaEventCreate(&ctx->ev[0]));
+  MDB_CUDA(ctx, cudaEventCreate(&ctx->ev[1]));
+  cudaDeviceProp prop;
+  MDB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+  ctx->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    snprintf(ctx->err, sizeof(ctx->err), "device %d is sm_%d%d; libmdb200 is built for sm_100a only", device,
+             prop.major, prop.minor);
+    // keep the context so the caller can read the message, but report the failure
+    *out = ctx;
+    return MDB_ERR_NO_DEVICE;
+  }
+  *out = ctx;
+  return MDB_OK;
+}
+
+extern "C" int mdb_ctx_destroy(mdb_ctx* ctx) {
+  if (!ctx) return MDB_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+  if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+  delete ctx;
+  return MDB_OK;
+}
+
+extern "C" int mdb_ctx_set_stream(mdb_ctx* ctx, void* s) {
+  if (!ctx) return MDB_ERR_INVALID;
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return MDB_OK;
+}
+
+extern "C" int mdb_ctx_synchronize(mdb_ctx* ctx) {
+  if (!ctx) return MDB_ERR_INVALID;
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDB_OK;
+}
+
+extern "C" const char* mdb_last_error(const mdb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" int64_t mdb_launch_count(const mdb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int mdb_ctx_set_profiling(mdb_ctx* ctx, int on) {
+  if (!ctx) return MDB_ERR_INVALID;
+  ctx->profiling = on;
+  return MDB_OK;
+}
+extern "C" int mdb_ctx_get_phase_ms(const mdb_ctx* ctx, double ms[4]) {
+  if (!ctx || !ms) return MDB_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) ms[i] = ctx->phase_ms[i];
+  return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// memory
+// ------------------------------------------------------------------------------------------------
+extern "C" int mdb_malloc(mdb_ctx* ctx, size_t bytes, void** dptr) {
+  if (!ctx || !dptr) return MDB_ERR_INVALID;
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MDB_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 8));
+  return MDB_OK;
+}
+extern "C" int mdb_free(mdb_ctx* ctx, void* dptr) {
+  if (!ctx) return MDB_ERR_INVALID;
+  if (dptr) MDB_CUDA(ctx, cudaFree(dptr));
+  return MDB_OK;
+}
+extern "C" int mdb_malloc_host(mdb_ctx* ctx, size_t bytes, void** hptr) {
+  if (!ctx || !hptr) return MDB_ERR_INVALID;
+  MDB_CUDA(ctx, cudaMallocHost(hptr, bytes ? bytes : 8));
+  return MDB_OK;
+}
+extern "C" int mdb_free_host(mdb_ctx* ctx, void* hptr) {
+  if (!ctx) return MDB_ERR_INVALID;
+  if (hptr) MDB_CUDA(ctx, cudaFreeHost(hptr));
+  return MDB_OK;
+}
+static cudaMemcpyKind copy_kind(int dst_loc, int src_loc) {
+  if (dst_loc == MDB_DEVICE && src_loc == MDB_HOST) return cudaMemcpyHostToDevice;
+  if (dst_loc == MDB_HOST && src_loc == MDB_DEVICE) return cudaMemcpyDeviceToHost;
+  if (dst_loc == MDB_DEVICE && src_loc == MDB_DEVICE) return cudaMemcpyDeviceToDevice;
+  return cudaMemcpyHostToHost;
+}
+extern "C" int mdb_memcpy(mdb_ctx* ctx, void* dst, const void* src, size_t bytes, int dst_loc, int src_loc) {
+  if (!ctx) return MDB_ERR_INVALID;
+  if (!bytes) return MDB_OK;
+  MDB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, copy_kind(dst_loc, src_loc), ctx->stream));
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDB_OK;
+}
+static int copy2d_async(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* src, int64_t ld_src, int64_t rows,
+                        int64_t cols, int dst_loc, int src_loc) {
+  if (rows <= 0 || cols <= 0) return MDB_OK;
+  MDB_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)ld_dst * 8, src, (size_t)ld_src * 8, (size_t)cols * 8, (size_t)rows,
+                                  copy_kind(dst_loc, src_loc), ctx->stream));
+  return MDB_OK;
+}
+extern "C" int mdb_memcpy2d(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* src, int64_t ld_src, int64_t rows,
+                            int64_t cols, int dst_loc, int src_loc) {
+  if (!ctx) return MDB_ERR_INVALID;
+  int rc = copy2d_async(ctx, dst, ld_dst, src, ld_src, rows, cols, dst_loc, src_loc);
+  if (rc) return rc;
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// factor object
+// ------------------------------------------------------------------------------------------------
+static void factor_release(mdb_factor* f) {
+  if (!f) return;
+  cudaSetDevice(f->ctx->device);
+  cudaFree(f->W); cudaFree(f->vec); cudaFree(f->clamped); cudaFree(f->minB); cudaFree(f->maxB);
+  cudaFree(f->p_dev); cudaFree(f->info); cudaFree(f->Ut); cudaFree(f->hdr); cudaFree(f->PX); cudaFree(f->PY);
+  cudaFree(f->Linv); cudaFree(f->LinvT); cudaFree(f->Ltri); cudaFree(f->Utri);
+  delete f;
+}
+
+extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_factor** out) {
+  if (!ctx || !out) return MDB_ERR_INVALID;
+  *out = nullptr;
+  MDB_CHECK(ctx, n >= 0 && batch >= 1, "mdb_factor_create: n >= 0 and batch >= 1 required");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  mdb_factor* f = new (std::nothrow) mdb_factor();
+  if (!f) return mdb_fail(ctx, MDB_ERR_INVALID, "%s", "out of host memory");
+  f->ctx = ctx; f->n = n; f->batch = batch;
+  f->ld = std::max<int64_t>(mdb_round_up(n, NB), NB);
+  f->W = nullptr; f->vec = nullptr; f->clamped = nullptr; f->minB = f->maxB = nullptr; f->p_dev = nullptr;
+  f->info = nullptr; f->Ut = f->hdr = f->PX = f->PY = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
+  f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
+  const int64_t nn = std::max<int64_t>(n, 1);
+  f->panel_rows = std::max<int64_t>(mdb_round_up(nn, NB), NB);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8); };
+  A((void**)&f->W, (size_t)batch * nn * f->ld * 8);
+  A((void**)&f->vec, (size_t)7 * batch * nn * 8);
+  A((void**)&f->clamped, (size_t)batch * nn);
+  A((void**)&f->info, (size_t)batch * sizeof(int));
+  A((void**)&f->Ut, (size_t)batch * NB * NB * 8);
+  A((void**)&f->hdr, (size_t)batch * 3 * NB * 8);
+  A((void**)&f->PX, (size_t)batch * f->panel_rows * NB * 8);
+  A((void**)&f->PY, (size_t)batch * f->panel_rows * NB * 8);
+  if (e != cudaSuccess) {
+    snprintf(ctx->err, sizeof(ctx->err), "mdb_factor_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    factor_release(f);
+    return MDB_ERR_CUDA;
+  }
+  const int64_t bn = batch * nn;
+  f->gamma = f->vec; f->alpha = f->vec + bn; f->beta = f->vec + 2 * bn; f->rowmax = f->vec + 3 * bn;
+  f->d = f->vec + 4 * bn; f->omega = f->vec + 5 * bn; f->delta = f->vec + 6 * bn;
+  // zero everything once: the padding columns of W (ld > n) must stay zero for the solve kernels
+  MDB_CUDA(ctx, cudaMemsetAsync(f->W, 0, (size_t)batch * nn * f->ld * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->vec, 0, (size_t)7 * bn * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->clamped, 0, (size_t)bn, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->Ut, 0, (size_t)batch * NB * NB * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->PX, 0, (size_t)batch * f->panel_rows * NB * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->PY, 0, (size_t)batch * f->panel_rows * NB * 8, ctx->stream));
+  *out = f;
+  return MDB_OK;
+}
+
+extern "C" int mdb_factor_destroy(mdb_factor* f) {
+  if (f) {
+    cudaStreamSynchronize(f->ctx->stream);
+    factor_release(f);
+  }
+  return MDB_OK;
+}
+
+static int factor_set_p(mdb_factor* f, const int64_t* p) {
+  mdb_ctx* ctx = f->ctx;
+  const int64_t bn = f->batch * f->n;
+  if (!p) {
+    f->p_host.clear();
+    if (f->p_dev) { cudaFree(f->p_dev); f->p_dev = nullptr; }
+    return MDB_OK;
+  }
+  for (int64_t b = 0; b < f->batch; ++b) {  // validate: a permutation of 0..n-1
+    std::vector<uint8_t> seen((size_t)f->n, 0);
+    for (int64_t i = 0; i < f->n; ++i) {
+      const int64_t v = p[b * f->n + i];
+      if (v < 0 || v >= f->n || seen[(size_t)v]) return mdb_fail(ctx, MDB_ERR_INVALID, "%s", "p is not a permutation");
+      seen[(size_t)v] = 1;
+    }
+  }
+  f->p_host.assign(p, p + bn);
+  if (!f->p_dev) MDB_CUDA(ctx, cudaMalloc((void**)&f->p_dev, (size_t)std::max<int64_t>(bn, 1) * 8));
+  MDB_CUDA(ctx, cudaMemcpyAsync(f->p_dev, p, (size_t)bn * 8, cudaMemcpyHostToDevice, ctx->stream));
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDB_OK;
+}
+
+static int gather_sym(mdb_ctx* ctx, int64_t n, int64_t batch, const double* A_dev, int64_t lda, int64_t sA,
+                      const int64_t* p_dev, double* W, int64_t ldw, int64_t sW, double* gamma) {
+  if (n == 0) return MDB_OK;
+  dim3 grid((unsigned)n, (unsigned)((n + 1023) / 1024), (unsigned)batch);
+  k_gather_sym<<<grid, 256, 0, ctx->stream>>>(n, A_dev, lda, sA, p_dev, n, W, ldw, sW, gamma, n);
+  MDB_LAUNCHED(ctx);
+  MDB_CUDA(ctx, cudaGetLastError());
+  return MDB_OK;
+}
+
+extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda, const int64_t* p, int a_loc) {
+  if (!f) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CHECK(ctx, A || f->n == 0, "mdb_factor_set_matrix: A is null");
+  MDB_CHECK(ctx, lda >= f->n, "mdb_factor_set_matrix: lda < n");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = factor_set_p(f, p);
+  if (rc) return rc;
+  const int64_t n = f->n;
+  if (n == 0) { f->state = ST_MATRIX; return MDB_OK; }
+  const double* A_dev = A;
+  double* staging = nullptr;
+  int64_t lds = lda;
+  if (a_loc == MDB_HOST) {
+    MDB_CUDA(ctx, cudaMalloc((void**)&staging, (size_t)f->batch * n * n * 8));
+    rc = copy2d_async(ctx, staging, n, A, lda, f->batch * n, n, MDB_DEVICE, MDB_HOST);  // batch stride = n*lda
+    if (rc) { cudaFree(staging); return rc; }
+    A_dev = staging;
+    lds = n;
+  }
+  rc = gather_sym(ctx, n, f->batch, A_dev, lds, n * lds, f->p_dev, f->W, f->ld, n * f->ld, f->gamma);
+  if (staging) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(staging);
+  }
+  if (rc) return rc;
+  f->state = ST_MATRIX;
+  f->prepared = false;
+  return MDB_OK;
+}
+
+extern "C" int mdb_generate_diag_f2(mdb_ctx* ctx, int64_t n, uint64_t seed, double mu, double* diag_host) {
+  if (!ctx || !diag_host) return MDB_ERR_INVALID;
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* dd = nullptr;
+  MDB_CUDA(ctx, cudaMalloc((void**)&dd, (size_t)std::max<int64_t>(n, 1) * 8));
+  if (n > 0) {
+    k_generate_f2_diag<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, seed, mu, dd);
+    MDB_LAUNCHED(ctx);
+  }
+  cudaError_t e = cudaMemcpyAsync(diag_host, dd, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dd);
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
+}
+
+static int generate_f2(mdb_ctx* ctx, int64_t rows, int64_t cols, int64_t row0, const int64_t* prow,
+                       const int64_t* pcol, uint64_t seed, double mu, double* out, int64_t ld) {
+  if (rows <= 0 || cols <= 0) return MDB_OK;
+  dim3 grid((unsigned)rows, (unsigned)((cols + 1023) / 1024), 1);
+  k_generate_f2<<<grid, 256, 0, ctx->stream>>>(rows, cols, row0, prow, pcol, seed, mu, out, ld);
+  MDB_LAUNCHED(ctx);
+  MDB_CUDA(ctx, cudaGetLastError());
+  return MDB_OK;
+}
+
+extern "C" int mdb_generate_f2(mdb_ctx* ctx, int64_t n, uint64_t seed, double mu, double* A_dev, int64_t lda) {
+  if (!ctx || !A_dev) return MDB_ERR_INVALID;
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = generate_f2(ctx, n, n, 0, nullptr, nullptr, seed, mu, A_dev, lda);
+  if (rc) return rc;
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDB_OK;
+}
+
+extern "C" int mdb_factor_generate_f2(mdb_factor* f, uint64_t seed, double mu, const int64_t* p) {
+  if (!f) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CHECK(ctx, f->batch == 1, "mdb_factor_generate_f2: batch must be 1");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = factor_set_p(f, p);
+  if (rc) return rc;
+  rc = generate_f2(ctx, f->n, f->n, 0, f->p_dev, f->p_dev, seed, mu, f->W, f->ld);
+  if (rc) return rc;
+  if (f->n > 0) {
+    k_extract_diag<<<(unsigned)((f->n + 255) / 256), 256, 0, ctx->stream>>>(f->n, f->W, f->ld, f->gamma);
+    MDB_LAUNCHED(ctx);
+    MDB_CUDA(ctx, cudaGetLastError());
+  }
+  f->state = ST_MATRIX;
+  f->prepared = false;
+  return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the blocked factorization
+// ------------------------------------------------------------------------------------------------
+static FactorDev make_dev(mdb_factor* f) {
+  FactorDev F;
+  memset(&F, 0, sizeof(F));
+  F.n = f->n; F.ldw = f->ld; F.W = f->W;
+  F.gamma = f->gamma; F.alpha = f->alpha; F.beta = f->beta; F.rowmax = f->rowmax;
+  F.d = f->d; F.omega = f->omega; F.delta = f->delta; F.clamped = f->clamped;
+  F.minB = f->minB; F.maxB = f->maxB; F.info = f->info; F.Ut = f->Ut; F.hdr = f->hdr;
+  F.sW = f->n * f->ld; F.sVec = f->n; F.sUt = NB * NB; F.sHdr = 3 * NB; F.sPanel = f->panel_rows * NB;
+  return F;
+}
+
+static int configure_kernels(mdb_ctx* ctx) {
+  static bool done = false;
+  if (done) return MDB_OK;
+  const int diag_smem = (NB * (NB + 1) + 2 * NB) * 8;
+  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB) * 8;
+  const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
+  MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+  MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel<NB, PANEL_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
+  MDB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_blocks<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
+  done = true;
+  return MDB_OK;
+}
+
+struct PhaseTimer {
+  mdb_ctx* ctx;
+  int phase;
+  PhaseTimer(mdb_ctx* c, int ph) : ctx(c), phase(ph) {
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
+  }
+  ~PhaseTimer() {
+    if (ctx->profiling) {
+      cudaEventRecord(ctx->ev[1], ctx->stream);
+      cudaEventSynchronize(ctx->ev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+      ctx->phase_ms[phase] += ms;
+    }
+  }
+};
+
+extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
+  if (!f || !bnd) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CHECK(ctx, f->state == ST_MATRIX, "mdb_factor_run: set a matrix first (state)");
+  MDB_CHECK(ctx, bnd->rule == MDB_RULE_REIMER || bnd->rule == MDB_RULE_EXACT, "mdb_factor_run: unknown rule");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = configure_kernels(ctx);
+  if (rc) return rc;
+  const int64_t n = f->n, batch = f->batch, bn = batch * n;
+  // per-index B bounds -> position order (Reimer.py:480-487 index them by p[j])
+  if (f->minB) { cudaFree(f->minB); f->minB = nullptr; }
+  if (f->maxB) { cudaFree(f->maxB); f->maxB = nullptr; }
+  double sc_minB = -INFINITY, sc_maxB = INFINITY;
+  if (bnd->rule == MDB_RULE_REIMER) {
+    if (bnd->min_diag_B) sc_minB = bnd->min_diag_B[0];
+    if (bnd->max_diag_B) sc_maxB = bnd->max_diag_B[0];
+    if (bnd->stride_B != 0 && n > 0) {
+      MDB_CHECK(ctx, bnd->min_diag_B && bnd->max_diag_B, "mdb_factor_run: vector bounds need both min_diag_B and max_diag_B");
+      std::vector<double> mb((size_t)bn), Mb((size_t)bn);
+      for (int64_t b = 0; b < batch; ++b)
+        for (int64_t i = 0; i < n; ++i) {
+          const int64_t pi = f->p_host.empty() ? i : f->p_host[(size_t)(b * n + i)];
+          mb[(size_t)(b * n + i)] = bnd->min_diag_B[pi * bnd->stride_B];
+          Mb[(size_t)(b * n + i)] = bnd->max_diag_B[pi * bnd->stride_B];
+        }
+      MDB_CUDA(ctx, cudaMalloc((void**)&f->minB, (size_t)bn * 8));
+      MDB_CUDA(ctx, cudaMalloc((void**)&f->maxB, (size_t)bn * 8));
+      MDB_CUDA(ctx, cudaMemcpyAsync(f->minB, mb.data(), (size_t)bn * 8, cudaMemcpyHostToDevice, ctx->stream));
+      MDB_CUDA(ctx, cudaMemcpyAsync(f->maxB, Mb.data(), (size_t)bn * 8, cudaMemcpyHostToDevice, ctx->stream));
+      MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  FactorDev F = make_dev(f);
+  F.prm.rule = bnd->rule;
+  F.prm.min_diag_D = bnd->min_diag_D;
+  F.prm.max_diag_D = bnd->max_diag_D;
+  F.prm.min_abs_value_D = bnd->min_abs_value_D;
+  // plain LDL^T / Cholesky (MDB_RULE_EXACT) must not drop tiny entries
+  F.prm.min_abs_value_L = (bnd->rule == MDB_RULE_EXACT) ? 0.0 : bnd->min_abs_value_L;
+  F.prm.min_diag_B = sc_minB;
+  F.prm.max_diag_B = sc_maxB;
+  f->rule = bnd->rule;
+  f->mavL = F.prm.min_abs_value_L;
+  for (int i = 0; i < 4; ++i) ctx->phase_ms[i] = 0;
+
+  if (bn > 0) {
+    MDB_CUDA(ctx, cudaMemsetAsync(f->alpha, 0, (size_t)3 * bn * 8, ctx->stream));  // alpha, beta, rowmax contiguous
+    MDB_CUDA(ctx, cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream));
+  }
+  const int diag_smem = (NB * (NB + 1) + 2 * NB) * 8;
+  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB) * 8;
+  for (int64_t k0 = 0; k0 < n; k0 += NB) {
+    const int kb = (int)std::min<int64_t>(NB, n - k0);
+    const int64_t k1 = k0 + kb;
+    {
+      PhaseTimer t(ctx, 0);
+      k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), NB, diag_smem, ctx->stream>>>(F, k0, kb);
+      MDB_LAUNCHED(ctx);
+    }
+    if (k1 < n) {
+      const int64_t rows = n - k1;
+      {
+        PhaseTimer t(ctx, 1);
+        dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, (unsigned)batch);
+        k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, ctx->stream>>>(F, k0, k1, rows, f->W, 1, f->ld, f->W + k0,
+                                                                         f->ld, f->PX, f->PY, k1);
+        MDB_LAUNCHED(ctx);
+      }
+      {
+        PhaseTimer t(ctx, 2);
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.A = f->PX; g.lda = NB; g.sA = F.sPanel;
+        g.B = f->PY; g.ldb = NB; g.sB = F.sPanel;
+        g.C = f->W + k1 * f->ld + k1; g.ldc = f->ld; g.sC = F.sW;
+        g.M = rows; g.N = rows; g.K = NB;
+        g.row_glob0 = k1; g.col_glob0 = k1;
+        rc = launch_gemm_tn<true, true, false>(ctx, g, batch);
+        if (rc) return rc;
+      }
+    }
+  }
+  MDB_CUDA(ctx, cudaGetLastError());
+  f->state = ST_FACTORED;
+  f->prepared = false;
+  return MDB_OK;
+}
+
+static int factor_finalize(mdb_factor* f, int out_type) {
+  mdb_ctx* ctx = f->ctx;
+  if (f->state == ST_FINAL) {
+    if (f->out_type != out_type) return mdb_fail(ctx, MDB_ERR_STATE, "%s", "factor already finalised with another type");
+    return MDB_OK;
+  }
+  if (f->state != ST_FACTORED) return mdb_fail(ctx, MDB_ERR_STATE, "%s", "factor not computed yet");
+  if (f->n > 0) {
+    dim3 grid((unsigned)f->n, (unsigned)((f->n + 1023) / 1024), (unsigned)f->batch);
+    k_finalize<<<grid, 256, 0, ctx->stream>>>(f->n, f->W, f->ld, f->n * f->ld, f->d, f->omega, f->n, f->mavL, out_type,
+                                              f->W, f->ld, f->n * f->ld);
+    MDB_LAUNCHED(ctx);
+    MDB_CUDA(ctx, cudaGetLastError());
+  }
+  f->state = ST_FINAL;
+  f->out_type = out_type;
+  return MDB_OK;
+}
+
+extern "C" int mdb_factor_get(mdb_factor* f, int out_type, double* L, int64_t ldl, int l_loc, double* d, double* omega,
+                              double* delta, uint8_t* clamped, int64_t* info) {
+  if (!f) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = factor_finalize(f, out_type);
+  if (rc) return rc;
+  const int64_t n = f->n, batch = f->batch, bn = batch * n;
+  if (L && n > 0) {
+    MDB_CHECK(ctx, ldl >= n, "mdb_factor_get: ldl < n");
+    // rows of consecutive batch members are contiguous in both layouts when viewed as (batch*n) x n
+    rc = copy2d_async(ctx, L, ldl, f->W, f->ld, bn, n, l_loc, MDB_DEVICE);
+    if (rc) return rc;
+  }
+  if (d && bn) MDB_CUDA(ctx, cudaMemcpyAsync(d, f->d, (size_t)bn * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (clamped && bn) MDB_CUDA(ctx, cudaMemcpyAsync(clamped, f->clamped, (size_t)bn, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((omega || delta) && bn) {
+    // position -> original index (Reimer.py:538,545); alpha / beta are free scratch after the run
+    for (int64_t b = 0; b < batch; ++b) {
+      const int64_t* pb = f->p_dev ? f->p_dev + b * n : nullptr;
+      k_scatter_by_p<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, pb, f->omega + b * n, f->alpha + b * n);
+      k_scatter_by_p<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, pb, f->delta + b * n, f->beta + b * n);
+      ctx->launches += 2;
+    }
+    if (omega) MDB_CUDA(ctx, cudaMemcpyAsync(omega, f->alpha, (size_t)bn * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (delta) MDB_CUDA(ctx, cudaMemcpyAsync(delta, f->beta, (size_t)bn * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  std::vector<int> inf((size_t)batch, 0);
+  if (info) MDB_CUDA(ctx, cudaMemcpyAsync(inf.data(), f->info, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (info)
+    for (int64_t b = 0; b < batch; ++b) info[b] = inf[(size_t)b];
+  return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-shot entry points
+// ------------------------------------------------------------------------------------------------
+static int one_shot(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int64_t lda, const int64_t* p,
+                    const mdb_bounds* bounds, int out_type, double* L, int64_t ldl, double* d, double* omega,
+                    double* delta, uint8_t* clamped, int64_t* info, int loc, mdb_factor** factor_out) {
+  if (!ctx) return MDB_ERR_INVALID;
+  MDB_CHECK(ctx, n >= 0, "n < 0");
+  MDB_CHECK(ctx, out_type == MDB_TYPE_LDL || out_type == MDB_TYPE_LDL_COMPRESSED || out_type == MDB_TYPE_LL,
+            "unknown decomposition type");
+  mdb_factor* f = nullptr;
+  int rc = mdb_factor_create(ctx, n, batch, &f);
+  if (rc) return rc;
+  rc = mdb_factor_set_matrix(f, A, lda, p, loc);
+  if (!rc) rc = mdb_factor_run(f, bounds);
+  if (!rc) rc = mdb_factor_get(f, out_type, L, ldl, loc, d, omega, delta, clamped, info);
+  if (rc || !factor_out) {
+    mdb_factor_destroy(f);
+    f = nullptr;
+  }
+  if (factor_out) *factor_out = f;
+  return rc;
+}
+
+extern "C" int mdb_approximate_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda, const int64_t* p,
+                                   const mdb_bounds* bounds, int out_type, double* L, int64_t ldl, double* d,
+                                   double* omega, double* delta, uint8_t* clamped, int loc, mdb_factor** factor_out) {
+  if (!ctx || !bounds) return MDB_ERR_INVALID;
+  MDB_CHECK(ctx, bounds->rule == MDB_RULE_REIMER, "mdb_approximate_f64: bounds->rule must be MDB_RULE_REIMER");
+  return one_shot(ctx, 1, n, A, lda, p, bounds, out_type, L, ldl, d, omega, delta, clamped, nullptr, loc, factor_out);
+}
+
+extern "C" int mdb_approximate_batched_f64(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int64_t lda,
+                                           const int64_t* p, const mdb_bounds* bounds, double* L, int64_t ldl,
+                                           double* d, double* omega, double* delta, uint8_t* clamped, int loc) {
+  if (!ctx || !bounds) return MDB_ERR_INVALID;
+  MDB_CHECK(ctx, batch >= 1, "batch < 1");
+  MDB_CHECK(ctx, lda == n && (ldl == n || !L), "batched mode expects densely packed matrices (lda == ldl == n)");
+  return one_shot(ctx, batch, n, A, lda, p, bounds, MDB_TYPE_LDL, L, ldl, d, omega, delta, clamped, nullptr, loc,
+                  nullptr);
+}
+
+extern "C" int mdb_decompose_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda, const int64_t* p, int out_type,
+                                 double* L, int64_t ldl, double* d, int64_t* info, int loc, mdb_factor** factor_out) {
+  if (!ctx) return MDB_ERR_INVALID;
+  mdb_bounds b;
+  memset(&b, 0, sizeof(b));
+  b.rule = MDB_RULE_EXACT;
+  b.min_diag_D = 0; b.max_diag_D = INFINITY; b.min_abs_value_D = 0; b.min_abs_value_L = 0;
+  int64_t inf = 0;
+  mdb_factor* f = nullptr;
+  int rc = one_shot(ctx, 1, n, A, lda, p, &b, out_type, L, ldl, d, nullptr, nullptr, nullptr, &inf, loc, &f);
+  if (info) *info = inf;
+  if (!rc && inf > 0) {
+    rc = MDB_ERR_NOT_POSITIVE_DEFINITE;
+    snprintf(ctx->err, sizeof(ctx->err), "leading minor of order %lld is not positive definite", (long long)inf);
+  }
+  if (rc || !factor_out) {
+    if (f) mdb_factor_destroy(f);
+    f = nullptr;
+  }
+  if (factor_out) *factor_out = f;
+  return rc;
+}
+
+extern "C" int mdb_permute_sym_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda, const int64_t* p, double* B,
+                                   int64_t ldb, int loc) {
+  if (!ctx) return MDB_ERR_INVALID;
+  MDB_CHECK(ctx, n >= 0 && lda >= n && ldb >= n, "mdb_permute_sym_f64: bad dimensions");
+  if (n == 0) return MDB_OK;
+  MDB_CHECK(ctx, A && B, "mdb_permute_sym_f64: null matrix");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int64_t* p_dev = nullptr;
+  double *A_dev = nullptr, *B_dev = nullptr;
+  int rc = MDB_OK;
+  cudaError_t e = cudaSuccess;
+  if (p) {
+    std::vector<uint8_t> seen((size_t)n, 0);
+    for (int64_t i = 0; i < n; ++i) {
+      if (p[i] < 0 || p[i] >= n || seen[(size_t)p[i]]) return mdb_fail(ctx, MDB_ERR_INVALID, "%s", "p is not a permutation");
+      seen[(size_t)p[i]] = 1;
+    }
+    e = cudaMalloc((void**)&p_dev, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p_dev, p, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  const double* src = A;
+  double* dst = B;
+  int64_t lsrc = lda, ldst = ldb;
+  if (e == cudaSuccess && loc == MDB_HOST) {
+    e = cudaMalloc((void**)&A_dev, (size_t)n * n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&B_dev, (size_t)n * n * 8);
+    if (e == cudaSuccess) rc = copy2d_async(ctx, A_dev, n, A, lda, n, n, MDB_DEVICE, MDB_HOST);
+    src = A_dev; dst = B_dev; lsrc = n; ldst = n;
+  }
+  if (e == cudaSuccess && !rc) rc = gather_sym(ctx, n, 1, src, lsrc, 0, p_dev, dst, ldst, 0, nullptr);
+  if (e == cudaSuccess && !rc && loc == MDB_HOST) rc = copy2d_async(ctx, B, ldb, B_dev, n, n, n, MDB_HOST, MDB_DEVICE);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(p_dev); cudaFree(A_dev); cudaFree(B_dev);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upload, solve, multiply
+// ------------------------------------------------------------------------------------------------
+extern "C" int mdb_factor_upload(mdb_ctx* ctx, int64_t n, int type, const double* L, int64_t ldl, const double* d,
+                                 const int64_t* p, mdb_factor** out) {
+  if (!ctx || !out) return MDB_ERR_INVALID;
+  *out = nullptr;
+  MDB_CHECK(ctx, type == MDB_TYPE_LDL || type == MDB_TYPE_LL, "mdb_factor_upload: type must be LDL or LL");
+  MDB_CHECK(ctx, (L || n == 0) && ldl >= n, "mdb_factor_upload: bad L");
+  MDB_CHECK(ctx, type == MDB_TYPE_LL || d || n == 0, "mdb_factor_upload: LDL needs d");
+  mdb_factor* f = nullptr;
+  int rc = mdb_factor_create(ctx, n, 1, &f);
+  if (rc) return rc;
+  rc = factor_set_p(f, p);
+  if (!rc && n > 0) rc = copy2d_async(ctx, f->W, f->ld, L, ldl, n, n, MDB_DEVICE, MDB_HOST);
+  if (!rc && n > 0 && d) {
+    cudaError_t e = cudaMemcpyAsync(f->d, d, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) rc = mdb_fail(ctx, MDB_ERR_CUDA, "%s", cudaGetErrorString(e));
+  }
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = mdb_fail(ctx, MDB_ERR_CUDA, "%s", cudaGetErrorString(e));
+  }
+  if (rc) { mdb_factor_destroy(f); return rc; }
+  f->state = ST_FINAL;
+  f->out_type = type;
+  *out = f;
+  return MDB_OK;
+}
+
+static int factor_prepare(mdb_factor* f) {
+  mdb_ctx* ctx = f->ctx;
+  if (f->prepared) return MDB_OK;
+  if (f->state != ST_FINAL) return mdb_fail(ctx, MDB_ERR_STATE, "%s", "solve/multiply need a finalised factor");
+  if (f->batch != 1) return mdb_fail(ctx, MDB_ERR_STATE, "%s", "solve/multiply are not available for batched factors");
+  int rc = configure_kernels(ctx);
+  if (rc) return rc;
+  const int64_t n = f->n;
+  if (n == 0) { f->prepared = true; return MDB_OK; }
+  const int64_t T = (n + NB - 1) / NB;
+  const size_t bytes = (size_t)T * NB * NB * 8;
+  if (!f->Linv) {
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->Linv, bytes));
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->LinvT, bytes));
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->Ltri, bytes));
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->Utri, bytes));
+  }
+  const int64_t t32 = (n + 31) / 32;
+  k_symmetrize<<<dim3((unsigned)t32, (unsigned)t32), 256, 0, ctx->stream>>>(n, f->W, f->ld);
+  MDB_LAUNCHED(ctx);
+  const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
+  k_prepare_blocks<NB><<<(unsigned)T, NB, prep_smem, ctx->stream>>>(n, f->W, f->ld, f->out_type != MDB_TYPE_LL ? 1 : 0,
+                                                                   f->Linv, f->LinvT, f->Ltri, f->Utri);
+  MDB_LAUNCHED(ctx);
+  MDB_CUDA(ctx, cudaGetLastError());
+  f->prepared = true;
+  return MDB_OK;
+}
+
+// C[0:M, 0:N] = beta C + sign * A (M x K) B^T (N x K)
+static int product_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B,
+                      int64_t ldb, double* C, int64_t ldc, bool beta1, bool neg) {
+  if (M <= 0 || N <= 0 || K <= 0) return MDB_OK;
+  if (M <= 8 && (K % 128) == 0) {
+    k_gemv_tn<8><<<(unsigned)((N + 7) / 8), 256, 0, ctx->stream>>>((int)M, N, K, A, lda, B, ldb, C, ldc, beta1 ? 1.0 : 0.0,
+                                                                  neg ? -1.0 : 1.0);
+    MDB_LAUNCHED(ctx);
+    MDB_CUDA(ctx, cudaGetLastError());
+    return MDB_OK;
+  }
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = (int)K;
+  if (beta1 && neg) return launch_gemm_tn<false, true, true>(ctx, g, 1);
+  if (beta1) return launch_gemm_tn<false, true, false>(ctx, g, 1);
+  return launch_gemm_tn<false, false, false>(ctx, g, 1);  // neg without beta is never needed
+}
+
+static int rhs_in(mdb_factor* f, const double* B, int64_t ldb, int64_t nrhs, int loc, double** Bt, double** Yt,
+                  int64_t* ldt_out, double** stage) {
+  mdb_ctx* ctx = f->ctx;
+  const int64_t n = f->n, ldt = mdb_round_up(n, NB);
+  *ldt_out = ldt;
+  MDB_CUDA(ctx, cudaMalloc((void**)Bt, (size_t)nrhs * ldt * 8));
+  MDB_CUDA(ctx, cudaMalloc((void**)Yt, (size_t)nrhs * ldt * 8));
+  MDB_CUDA(ctx, cudaMemsetAsync(*Bt, 0, (size_t)nrhs * ldt * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(*Yt, 0, (size_t)nrhs * ldt * 8, ctx->stream));
+  const double* src = B;
+  int64_t lsrc = ldb;
+  *stage = nullptr;
+  if (loc == MDB_HOST) {
+    MDB_CUDA(ctx, cudaMalloc((void**)stage, (size_t)n * nrhs * 8));
+    int rc = copy2d_async(ctx, *stage, nrhs, B, ldb, n, nrhs, MDB_DEVICE, MDB_HOST);
+    if (rc) return rc;
+    src = *stage;
+    lsrc = nrhs;
+  }
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((nrhs + 31) / 32));
+  k_rhs_gather_t<<<grid, 256, 0, ctx->stream>>>(n, nrhs, src, lsrc, f->p_dev, *Bt, ldt);
+  MDB_LAUNCHED(ctx);
+  MDB_CUDA(ctx, cudaGetLastError());
+  return MDB_OK;
+}
+
+static int rhs_out(mdb_factor* f, const double* Xt, int64_t ldt, int64_t nrhs, double* X, int64_t ldx, int loc,
+                   double* stage) {
+  mdb_ctx* ctx = f->ctx;
+  const int64_t n = f->n;
+  double* dst = X;
+  int64_t ldst = ldx;
+  if (loc == MDB_HOST) { dst = stage; ldst = nrhs; }
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((nrhs + 31) / 32));
+  k_rhs_scatter_t<<<grid, 256, 0, ctx->stream>>>(n, nrhs, Xt, ldt, f->p_dev, dst, ldst);
+  MDB_LAUNCHED(ctx);
+  MDB_CUDA(ctx, cudaGetLastError());
+  if (loc == MDB_HOST) {
+    int rc = copy2d_async(ctx, X, ldx, stage, nrhs, n, nrhs, MDB_HOST, MDB_DEVICE);
+    if (rc) return rc;
+  }
+  return MDB_OK;
+}
+
+extern "C" int mdb_factor_solve(mdb_factor* f, const double* B, int64_t ldb, int64_t nrhs, double* X, int64_t ldx,
+                                int loc) {
+  if (!f) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CHECK(ctx, nrhs >= 1 && ldb >= nrhs && ldx >= nrhs, "mdb_factor_solve: bad right-hand side shape");
+  MDB_CHECK(ctx, f->out_type == MDB_TYPE_LDL || f->out_type == MDB_TYPE_LL || f->out_type == MDB_TYPE_LDL_COMPRESSED,
+            "mdb_factor_solve: bad factor type");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = factor_prepare(f);
+  if (rc) return rc;
+  const int64_t n = f->n;
+  if (n == 0) return MDB_OK;
+  double *Bt = nullptr, *Yt = nullptr, *stage = nullptr;
+  int64_t ldt = 0;
+  rc = rhs_in(f, B, ldb, nrhs, loc, &Bt, &Yt, &ldt, &stage);
+  const int64_t T = (n + NB - 1) / NB;
+  // forward sweep  L z = b  (decompositions.py:987 / :1349)
+  for (int64_t J = 0; J < T && !rc; ++J) {
+    const int64_t j0 = J * NB, j1 = std::min<int64_t>(j0 + NB, n);
+    rc = product_tn(ctx, nrhs, NB, NB, Bt + j0, ldt, f->Linv + J * NB * NB, NB, Yt + j0, ldt, false, false);
+    if (!rc && j1 < n)
+      rc = product_tn(ctx, nrhs, n - j1, NB, Yt + j0, ldt, f->W + j1 * f->ld + j0, f->ld, Bt + j1, ldt, true, true);
+  }
+  if (!rc && f->out_type != MDB_TYPE_LL) {  // x / d  (decompositions.py:988)
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nrhs);
+    k_scale_by_d<<<grid, 256, 0, ctx->stream>>>(n, nrhs, Yt, ldt, f->d, 0);
+    MDB_LAUNCHED(ctx);
+  }
+  // backward sweep  L^T x = z  (decompositions.py:989 / :1350): rows of U = L^T from the mirrored upper triangle
+  for (int64_t J = T - 1; J >= 0 && !rc; --J) {
+    const int64_t j0 = J * NB;
+    rc = product_tn(ctx, nrhs, NB, NB, Yt + j0, ldt, f->LinvT + J * NB * NB, NB, Bt + j0, ldt, false, false);
+    if (!rc && j0 > 0) rc = product_tn(ctx, nrhs, j0, NB, Bt + j0, ldt, f->W + j0, f->ld, Yt, ldt, true, true);
+  }
+  if (!rc) rc = rhs_out(f, Bt, ldt, nrhs, X, ldx, loc, stage);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(Bt); cudaFree(Yt); cudaFree(stage);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
+}
+
+extern "C" int mdb_factor_multiply(mdb_factor* f, const double* B, int64_t ldb, int64_t nrhs, double* X, int64_t ldx,
+                                   int loc) {
+  if (!f) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CHECK(ctx, nrhs >= 1 && ldb >= nrhs && ldx >= nrhs, "mdb_factor_multiply: bad right-hand side shape");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = factor_prepare(f);
+  if (rc) return rc;
+  const int64_t n = f->n;
+  if (n == 0) return MDB_OK;
+  double *Xt = nullptr, *Zt = nullptr, *stage = nullptr;
+  int64_t ldt = 0;
+  rc = rhs_in(f, B, ldb, nrhs, loc, &Xt, &Zt, &ldt, &stage);
+  const int64_t T = (n + NB - 1) / NB;
+  // z = L^T x  (decompositions.py:964 / :1327): block row J of U = L^T
+  for (int64_t J = 0; J < T && !rc; ++J) {
+    const int64_t j0 = J * NB, j1 = j0 + NB, nb_rows = std::min<int64_t>(NB, n - j0);
+    rc = product_tn(ctx, nrhs, nb_rows, NB, Xt + j0, ldt, f->Utri + J * NB * NB, NB, Zt + j0, ldt, false, false);
+    if (!rc && j1 < ldt)
+      rc = product_tn(ctx, nrhs, nb_rows, ldt - j1, Xt + j1, ldt, f->W + j0 * f->ld + j1, f->ld, Zt + j0, ldt, true, false);
+  }
+  if (!rc && f->out_type != MDB_TYPE_LL) {  // d * z  (decompositions.py:965)
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nrhs);
+    k_scale_by_d<<<grid, 256, 0, ctx->stream>>>(n, nrhs, Zt, ldt, f->d, 1);
+    MDB_LAUNCHED(ctx);
+  }
+  // y = L z  (decompositions.py:966 / :1328), result back into Xt
+  for (int64_t J = 0; J < T && !rc; ++J) {
+    const int64_t j0 = J * NB, nb_rows = std::min<int64_t>(NB, n - j0);
+    rc = product_tn(ctx, nrhs, nb_rows, NB, Zt + j0, ldt, f->Ltri + J * NB * NB, NB, Xt + j0, ldt, false, false);
+    if (!rc && j0 > 0)
+      rc = product_tn(ctx, nrhs, nb_rows, j0, Zt, ldt, f->W + j0 * f->ld, f->ld, Xt + j0, ldt, true, false);
+  }
+  if (!rc) rc = rhs_out(f, Xt, ldt, nrhs, X, ldx, loc, stage);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(Xt); cudaFree(Zt); cudaFree(stage);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
+}
+
+extern "C" int mdb_factor_identity_residual(mdb_factor* f, int nprobe, uint64_t seed, double* residual) {
+  if (!f || !residual) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CHECK(ctx, f->state == ST_FACTORED && f->batch == 1, "identity check runs after mdb_factor_run and before mdb_factor_get");
+  MDB_CHECK(ctx, f->rule == MDB_RULE_REIMER || f->rule == MDB_RULE_EXACT, "bad rule");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = f->n;
+  *residual = 0;
+  if (n == 0) return MDB_OK;
+  // Right-hand side of the identity from the un-finalised W (upper triangle = A); then finalise a COPY-free
+  // way is not possible, so the left-hand side L D L^T v is evaluated here with two triangular sweeps over
+  // the unscaled rows: L[j, m] = thresh(omega_j Lu[j, m]).  To keep this check simple and independent of the
+  // solve path it finalises the factor (LDL) afterwards and uses mdb_factor_multiply.
+  double *v = nullptr, *yb = nullptr, *ya = nullptr, *lhs = nullptr;
+  unsigned long long* mx = nullptr;
+  MDB_CUDA(ctx, cudaMalloc((void**)&v, (size_t)nprobe * n * 8));
+  MDB_CUDA(ctx, cudaMalloc((void**)&yb, (size_t)nprobe * n * 8));
+  MDB_CUDA(ctx, cudaMalloc((void**)&ya, (size_t)nprobe * n * 8));
+  MDB_CUDA(ctx, cudaMalloc((void**)&lhs, (size_t)nprobe * n * 8));
+  MDB_CUDA(ctx, cudaMalloc((void**)&mx, 16));
+  MDB_CUDA(ctx, cudaMemsetAsync(yb, 0, (size_t)nprobe * n * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(ya, 0, (size_t)nprobe * n * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(mx, 0, 16, ctx->stream));
+  for (int q = 0; q < nprobe; ++q) {
+    k_fill_random<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, seed + 7919ull * q, v + (size_t)q * n);
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + 1023) / 1024));
+    k_identity_rhs<<<grid, 256, 0, ctx->stream>>>(n, f->W, f->ld, f->gamma, f->delta, f->omega, v + (size_t)q * n,
+                                                  yb + (size_t)q * n, ya + (size_t)q * n);
+    ctx->launches += 2;
+  }
+  MDB_CUDA(ctx, cudaGetLastError());
+  int rc = factor_finalize(f, MDB_TYPE_LDL);
+  // vectors here are in POSITION order already; multiply expects original order and applies p, so bypass p
+  int64_t* saved_p = f->p_dev;
+  f->p_dev = nullptr;
+  // probes as an n x nprobe row-major matrix: transpose the nprobe x n layout through the solve helpers
+  double* vcol = nullptr;
+  double* lcol = nullptr;
+  if (!rc) {
+    cudaError_t e = cudaMalloc((void**)&vcol, (size_t)nprobe * n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&lcol, (size_t)nprobe * n * 8);
+    if (e != cudaSuccess) rc = mdb_fail(ctx, MDB_ERR_CUDA, "%s", cudaGetErrorString(e));
+  }
+  if (!rc) {
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((nprobe + 31) / 32));
+    k_rhs_scatter_t<<<grid, 256, 0, ctx->stream>>>(n, nprobe, v, n, nullptr, vcol, nprobe);  // vcol[i, q] = v[q, i]
+    MDB_LAUNCHED(ctx);
+    rc = mdb_factor_multiply(f, vcol, nprobe, nprobe, lcol, nprobe, MDB_DEVICE);
+  }
+  if (!rc) {
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((nprobe + 31) / 32));
+    k_rhs_gather_t<<<grid, 256, 0, ctx->stream>>>(n, nprobe, lcol, nprobe, nullptr, lhs, n);  // lhs[q, i] = lcol[i, q]
+    MDB_LAUNCHED(ctx);
+    const int64_t tot = (int64_t)nprobe * n;
+    k_max_abs_diff<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(tot, lhs, yb, ya, mx);
+    MDB_LAUNCHED(ctx);
+  }
+  f->p_dev = saved_p;
+  unsigned long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, mx, 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(v); cudaFree(yb); cudaFree(ya); cudaFree(lhs); cudaFree(mx); cudaFree(vcol); cudaFree(lcol);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  double num, den;
+  memcpy(&num, &h[0], 8);
+  memcpy(&den, &h[1], 8);
+  *residual = den > 0 ? num / den : num;
+  return MDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection / unit-test hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" void* mdb_factor_device_ptr(mdb_factor* f, int which) {
+  if (!f) return nullptr;
+  switch (which) {
+    case 0: return f->W;
+    case 1: return f->gamma;
+    case 2: return f->alpha;
+    case 3: return f->beta;
+    case 4: return f->rowmax;
+    case 5: return f->d;
+    case 6: return f->omega;
+    case 7: return f->delta;
+    default: return nullptr;
+  }
+}
+extern "C" int64_t mdb_factor_ld(const mdb_factor* f) { return f ? f->ld : 0; }
+
+extern "C" int mdb_debug_gemm_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, const double* A, int64_t lda,
+                                 const double* B, int64_t ldb, double* C, int64_t ldc, int lower, int beta1, int neg,
+                                 int64_t row_glob0, int64_t col_glob0, int reps, double* ms) {
+  if (!ctx) return MDB_ERR_INVALID;
+  MDB_CHECK(ctx, M > 0 && N > 0 && K > 0 && K % 16 == 0, "mdb_debug_gemm_tn: bad shape");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  double *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  MDB_CUDA(ctx, cudaMalloc((void**)&dA, (size_t)M * K * 8));
+  MDB_CUDA(ctx, cudaMalloc((void**)&dB, (size_t)N * K * 8));
+  MDB_CUDA(ctx, cudaMalloc((void**)&dC, (size_t)M * N * 8));
+  int rc = copy2d_async(ctx, dA, K, A, lda, M, K, MDB_DEVICE, MDB_HOST);
+  if (!rc) rc = copy2d_async(ctx, dB, K, B, ldb, N, K, MDB_DEVICE, MDB_HOST);
+  if (!rc) rc = copy2d_async(ctx, dC, N, C, ldc, M, N, MDB_DEVICE, MDB_HOST);
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = dA; g.lda = K; g.B = dB; g.ldb = K; g.C = dC; g.ldc = N; g.M = M; g.N = N; g.K = (int)K;
+  g.row_glob0 = row_glob0; g.col_glob0 = col_glob0;
+  if (reps < 1) reps = 1;
+  cudaEventRecord(ctx->ev[0], ctx->stream);
+  for (int r = 0; r < reps && !rc; ++r) {
+    if (lower) rc = launch_gemm_tn<true, true, false>(ctx, g, 1);
+    else if (beta1 && neg) rc = launch_gemm_tn<false, true, true>(ctx, g, 1);
+    else if (beta1) rc = launch_gemm_tn<false, true, false>(ctx, g, 1);
+    else rc = launch_gemm_tn<false, false, false>(ctx, g, 1);
+  }
+  cudaEventRecord(ctx->ev[1], ctx->stream);
+  if (!rc) rc = copy2d_async(ctx, C, ldc, dC, N, M, N, MDB_HOST, MDB_DEVICE);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  float t = 0;
+  cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+  if (ms) *ms = (double)t / reps;
+  cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
+}
+
+#include "mdb_dist.cuh"

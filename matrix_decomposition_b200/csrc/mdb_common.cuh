@@ -1,0 +1,75 @@
+// mdb_common.cuh -- shared definitions of libmdb200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mdb200.h"
+#include "md_rule.h"
+
+#define MDB_NB 128  // panel width = distribution block = K of the trailing update
+
+struct mdb_ctx {
+  int device;
+  cudaStream_t stream;
+  cudaStream_t own_stream;
+  char err[512];
+  int64_t launches;
+  int profiling;
+  double phase_ms[4];
+  int num_sms;
+  cudaEvent_t ev[2];
+};
+
+static inline int mdb_fail(mdb_ctx* ctx, int code, const char* fmt, const char* a = "", const char* b = "") {
+  if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
+  return code;
+}
+
+#define MDB_CUDA(ctx, call)                                                                         \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), "%s failed: %s (%s:%d)", #call,             \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+      return MDB_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
+
+#define MDB_CHECK(ctx, cond, msg)                                        \
+  do {                                                                   \
+    if (!(cond)) return mdb_fail((ctx), MDB_ERR_INVALID, "%s", (msg));   \
+  } while (0)
+
+#define MDB_LAUNCHED(ctx) ((ctx)->launches++)
+
+static inline int64_t mdb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// device-side description of one factorization (passed by value to kernels)
+// ------------------------------------------------------------------------------------------------
+struct FactorDev {
+  int64_t n;      // matrix dimension
+  int64_t ldw;    // leading dimension of W
+  double* W;      // n x ldw: strict lower = S / Lu (unscaled rows), strict upper = permuted original A
+  double* gamma;  // n, diag of the permuted A (by position)
+  double* alpha;  // n, sum_k Lu[j,k]^2 d_k accumulated column by column (Reimer.py:679-684)
+  double* beta;   // n, sum_k 2 A[j,k]^2 (Reimer.py:602-604)
+  double* rowmax; // n, max_k |Lu[j,k]| (for the all-dropped shortcut)
+  double* d;      // n, by position
+  double* omega;  // n, by position
+  double* delta;  // n, by position
+  uint8_t* clamped;  // n, by position
+  const double* minB;  // n by position, or null (scalar bound in prm)
+  const double* maxB;
+  int* info;      // first failing pivot + 1 (MDB_RULE_EXACT), 0 = none
+  double* Ut;     // NB x NB scratch: Ut[m * NB + k] = d_m * Ltilde[k][m]  (m < k)
+  double* hdr;    // 3 x NB scratch: d, omega, drop flag of the current panel
+  // strides between consecutive matrices of a batch (elements)
+  int64_t sW, sVec, sUt, sHdr, sPanel;
+  MdRuleParams prm;
+};
