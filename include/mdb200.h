@@ -156,28 +156,38 @@ int mdb_debug_gemm_tn(mdb_ctx *ctx, int64_t M, int64_t N, int64_t K, const doubl
                       int64_t col_glob0, int reps, double *ms);
 
 /* ---- multi-GPU: 1-D block-cyclic column distribution, one process per GPU ----
- * The Python driver (matrix_decomposition_b200/distributed.py) owns the loop and the NCCL broadcast
- * (torch.distributed); these are the per-rank device steps.  Column block k (width 128) lives on rank
- * k % world.  panel: (n_rows_below x 128) X then Y = -X D, plus a 3 x 128 header (d, omega, drop). */
+ * The Python driver (matrix_decomposition_b200/distributed.py) owns the loop, the device buffers (torch
+ * tensors) and the NCCL panel broadcast (torch.distributed); these are the per-rank device steps.  Global
+ * column block J (width 128, position order) lives on rank J % world as local block J / world.
+ *   S_loc, A_loc : n x ld_loc device buffers (ld_loc = 128 * number of local blocks): the working copy
+ *                  (Schur complement / unscaled rows Lu below the diagonal) and the permuted original A.
+ *   panel0/1     : two broadcast buffers of mdb_dist_panel_elems(s, 0) doubles each.  Layout for panel k with
+ *                  rows = n - k1: [5 x 128 header: d, omega, drop, delta, clamped] [3 x rows: alpha, beta, rowmax
+ *                  of rows >= k1] [rows x 128: X] [rows x 128: Y = -X D]. */
 typedef struct mdb_dist mdb_dist;
-int mdb_dist_create(mdb_ctx *ctx, int64_t n, int rank, int world, mdb_dist **out);
+int mdb_dist_create(mdb_ctx *ctx, int64_t n, int rank, int world, double *S_loc, double *A_loc, int64_t ld_loc,
+                    double *panel0, double *panel1, mdb_dist **out);
 int mdb_dist_destroy(mdb_dist *s);
-/* local columns generated in place (family F2, permuted by p) -- both the S and the A copies */
+int64_t mdb_dist_local_cols(int64_t n, int rank, int world); /* 128 * number of local column blocks */
+int64_t mdb_dist_panel_elems(const mdb_dist *s, int64_t k);  /* doubles to broadcast for panel k */
+/* local columns of family F2, permuted by p (host, may be NULL), into A_loc and S_loc */
 int mdb_dist_generate_f2(mdb_dist *s, uint64_t seed, double mu, const int64_t *p);
-/* local columns from a host matrix already permuted: Ap (n x n, ld) */
+/* local columns from a host matrix that is already permuted: Ap (n x n, ld) */
 int mdb_dist_set_matrix(mdb_dist *s, const double *Ap, int64_t ld);
+/* bounds as in mdb_factor_run; p (host, may be NULL) maps position -> original index for vector B bounds.
+ * Resets alpha / beta / rowmax. */
 int mdb_dist_set_bounds(mdb_dist *s, const mdb_bounds *bounds, const int64_t *p);
-/* size in doubles of the broadcast buffer for panel k, and its device address on this rank */
-int64_t mdb_dist_panel_elems(const mdb_dist *s, int64_t k);
-void *mdb_dist_panel_buffer(mdb_dist *s, int slot);
-/* owner only: factor diagonal block + panel k into panel buffer `slot` (async on the ctx stream) */
+/* owner of panel k only: diagonal block + panel into panel buffer `slot` (asynchronous on the ctx stream) */
 int mdb_dist_factor_panel(mdb_dist *s, int64_t k, int slot);
-/* every rank: apply panel k (already in buffer `slot`) to its local trailing columns.  If only_block >= 0
- * only that global column block is updated (lookahead), if skip_block >= 0 that block is skipped. */
+/* every rank, once per panel, after the broadcast: take d / omega / delta / clamped and the alpha / beta /
+ * rowmax slices out of the panel buffer (asynchronous) */
+int mdb_dist_absorb_panel(mdb_dist *s, int64_t k, int slot);
+/* every rank: apply panel k (in buffer `slot`) to the local trailing columns.  only_block >= 0 restricts the
+ * update to that global column block (lookahead); skip_block >= 0 leaves that block out. */
 int mdb_dist_apply_panel(mdb_dist *s, int64_t k, int slot, int64_t only_block, int64_t skip_block);
-/* gathers this rank's columns of the scaled L (position order) into a host/device n x ncols_local array */
-int mdb_dist_get_local(mdb_dist *s, double *Lloc, int64_t ld, int loc, double *d, double *omega, uint8_t *clamped);
-int64_t mdb_dist_local_cols(const mdb_dist *s);
+/* finalises the local columns in place (S_loc then holds the local columns of L: scaled, thresholded, unit
+ * diagonal, zeros above) and copies the replicated vectors to the host (position order; any may be NULL) */
+int mdb_dist_finalize(mdb_dist *s, double *d, double *omega, double *delta, uint8_t *clamped);
 
 #ifdef __cplusplus
 }

@@ -89,17 +89,17 @@ SIGNATURES = {
     'mdb_factor_ld': (_i64, [_vp]),
     'mdb_debug_gemm_tn': (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _int, _int, _int, _i64, _i64,
                                  _int, _vp]),
-    'mdb_dist_create': (_int, [_vp, _i64, _int, _int, _pp]),
+    'mdb_dist_create': (_int, [_vp, _i64, _int, _int, _vp, _vp, _i64, _vp, _vp, _pp]),
     'mdb_dist_destroy': (_int, [_vp]),
+    'mdb_dist_local_cols': (_i64, [_i64, _int, _int]),
+    'mdb_dist_panel_elems': (_i64, [_vp, _i64]),
     'mdb_dist_generate_f2': (_int, [_vp, _u64, _dbl, _vp]),
     'mdb_dist_set_matrix': (_int, [_vp, _vp, _i64]),
     'mdb_dist_set_bounds': (_int, [_vp, ctypes.POINTER(Bounds), _vp]),
-    'mdb_dist_panel_elems': (_i64, [_vp, _i64]),
-    'mdb_dist_panel_buffer': (_vp, [_vp, _int]),
     'mdb_dist_factor_panel': (_int, [_vp, _i64, _int]),
+    'mdb_dist_absorb_panel': (_int, [_vp, _i64, _int]),
     'mdb_dist_apply_panel': (_int, [_vp, _i64, _int, _i64, _i64]),
-    'mdb_dist_get_local': (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp]),
-    'mdb_dist_local_cols': (_i64, [_vp]),
+    'mdb_dist_finalize': (_int, [_vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

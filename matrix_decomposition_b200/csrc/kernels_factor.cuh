@@ -83,6 +83,15 @@ __global__ void k_extract_diag(int64_t n, const double* __restrict__ W, int64_t 
   if (i < n) gamma[i] = W[i * ldw + i];
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): lets one thread keep a whole tile column in flight
+__device__ __forceinline__ void mdb_cp_async8(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void mdb_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // Diagonal block: columns K = k0 .. k0+kb-1, rows of the block only.  One CTA (NB threads, thread j
 // owns row j of the block), the whole block in shared memory.  Sequential over the columns because
@@ -93,8 +102,11 @@ __global__ void k_extract_diag(int64_t n, const double* __restrict__ W, int64_t 
 // with r_j = A[j, k] when the whole scaled row k is dropped, else (1 - omega) A[j, k] + omega S0[j, k].
 // Outputs: d, omega, delta, clamped; Ut (for the panel kernel); hdr = (d, omega, drop) of the panel.
 // ------------------------------------------------------------------------------------------------
+// Sblk / Ablk point at element (k0, k0) of the storage that holds S (lower part is read and written) and
+// the permuted original A (upper part is read): the same array W on one GPU, S_loc / A_loc when distributed.
 template <int NB>
-__global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int kb) {
+__global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
+                                                   int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
   extern __shared__ double smem_d[];
   constexpr int LDT = NB + 1;
   double* T = smem_d;           // T[r * LDT + c] = W[k0 + r, k0 + c]
@@ -103,15 +115,19 @@ __global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int 
   __shared__ double s_dec[3];   // d, omega, drop of the current column
 
   const int64_t b = blockIdx.z;
-  double* W = F.W + b * F.sW;
+  Sblk += b * F.sW;
+  Ablk += b * F.sW;
   const int64_t vo = b * F.sVec;
   double* Ut = F.Ut + b * F.sUt;
   double* hdr = F.hdr + b * F.sHdr;
   const int tid = threadIdx.x;
   const double mavL = F.prm.min_abs_value_L;
 
-  for (int r = 0; r < kb; ++r)
-    for (int c = tid; c < kb; c += NB) T[r * LDT + c] = W[(k0 + r) * F.ldw + k0 + c];
+  // whole block in flight at once (kb asynchronous 8-byte copies per thread, coalesced per row):
+  // strict lower part from S, diagonal and upper part from A
+  if (tid < kb)
+    for (int r = 0; r < kb; ++r)
+      mdb_cp_async8(&T[r * LDT + tid], (tid < r) ? &Sblk[r * ldS + tid] : &Ablk[r * ldA + tid]);
 
   double alpha_j = 0, beta_j = 0, rowmax_j = 0, gamma_j = 0, mB = F.prm.min_diag_B, MB = F.prm.max_diag_B;
   if (tid < kb) {
@@ -122,6 +138,7 @@ __global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int 
     if (F.minB) mB = F.minB[vo + k0 + tid];
     if (F.maxB) MB = F.maxB[vo + k0 + tid];
   }
+  mdb_cp_async_wait_all();
   __syncthreads();
 
   for (int k = 0; k < kb; ++k) {
@@ -141,6 +158,8 @@ __global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int 
       hdr[k] = dec.d;
       hdr[NB + k] = dec.omega;
       hdr[2 * NB + k] = drop;
+      hdr[3 * NB + k] = F.delta[vo + K];
+      hdr[4 * NB + k] = (double)dec.clamped;
     }
     __syncthreads();
     const double dk = s_dec[0], wk = s_dec[1];
@@ -157,10 +176,18 @@ __global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int 
       const double a = T[k * LDT + tid];
       double r = a;
       if (!drop) r = (1.0 - wk) * a + wk * T[tid * LDT + k];
-      double acc = 0;
+      // four interleaved partial sums: breaks the DFMA dependency chain (4x shorter critical path)
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
       const double* Trow = T + tid * LDT;
-#pragma unroll 4
-      for (int m = 0; m < k; ++m) acc += Trow[m] * s_u[m];
+      int m = 0;
+      for (; m + 4 <= k; m += 4) {
+        a0 += Trow[m] * s_u[m];
+        a1 += Trow[m + 1] * s_u[m + 1];
+        a2 += Trow[m + 2] * s_u[m + 2];
+        a3 += Trow[m + 3] * s_u[m + 3];
+      }
+      for (; m < k; ++m) a0 += Trow[m] * s_u[m];
+      const double acc = (a0 + a1) + (a2 + a3);
       const double x = (dk != 0) ? (r - acc) / dk : 0.0;
       T[tid * LDT + k] = x;
       alpha_j += x * x * dk;
@@ -177,7 +204,7 @@ __global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int 
   }
   // strict lower part of the block back to W (unscaled rows Lu)
   for (int r = 1; r < kb; ++r)
-    for (int c = tid; c < r; c += NB) W[(k0 + r) * F.ldw + k0 + c] = T[r * LDT + c];
+    for (int c = tid; c < r; c += NB) Sblk[r * ldS + c] = T[r * LDT + c];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -221,12 +248,13 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
     s_w[c] = hdr[NB + c];
     s_drop[c] = hdr[2 * NB + c];
   }
-  // S0 tile, transposed into shared memory (coalesced 1 KB row segments)
+  // S0 tile, transposed into shared memory: coalesced row segments, all rows in flight at once
   for (int rr = 0; rr < R; ++rr) {
     const int64_t jj = jbase + rr;
     if (jj < jend)
-      for (int c = tid; c < NB; c += R) xs[c * LDX + rr] = Wcol[jj * w_ld + c];
+      for (int c = tid; c < NB; c += R) mdb_cp_async8(&xs[c * LDX + rr], &Wcol[jj * w_ld + c]);
   }
+  mdb_cp_async_wait_all();
   __syncthreads();
 
   double alpha_j = 0, beta_j = 0, rowmax_j = 0;
@@ -236,14 +264,20 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
     rowmax_j = F.rowmax[vo + j];
     // mix with the original A column entries; beta in column order
     const double* Aj = Asrc + j * a_rs + k0 * a_cs;
-#pragma unroll 8
-    for (int c = 0; c < NB; ++c) {
-      const double a = Aj[(int64_t)c * a_cs];
-      const double w = s_w[c];
-      double r = a;
-      if (s_drop[c] == 0.0) r = (1.0 - w) * a + w * xs[c * LDX + tid];
-      xs[c * LDX + tid] = r;
-      beta_j += 2.0 * a * a;
+    for (int cb = 0; cb < NB; cb += 16) {
+      double av[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) av[i] = Aj[(int64_t)(cb + i) * a_cs];  // 16 independent loads in flight
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int c = cb + i;
+        const double a = av[i];
+        const double w = s_w[c];
+        double r = a;
+        if (s_drop[c] == 0.0) r = (1.0 - w) * a + w * xs[c * LDX + tid];
+        xs[c * LDX + tid] = r;
+        beta_j += 2.0 * a * a;
+      }
     }
     // forward substitution, 8 columns at a time
     for (int c0 = 0; c0 < NB; c0 += 8) {
@@ -336,4 +370,29 @@ __global__ void k_gather_by_p(int64_t n, const int64_t* __restrict__ p, const do
                               double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = in[(p ? p[i] : i) * stride];
+}
+
+// Distributed finalize: the local column slab S_loc (n x ld_loc) in place.  Local column lc belongs to global
+// column gc = ((lc / NB) * world + rank) * NB + lc % NB.
+__global__ void __launch_bounds__(256) k_finalize_cols(int64_t n, double* __restrict__ S, int64_t ld, int64_t ncols,
+                                                       int rank, int world, const double* __restrict__ omega,
+                                                       double mavL) {
+  const int64_t i = blockIdx.x;
+  const double w = omega[i];
+  const int64_t l0 = (int64_t)blockIdx.y * 1024 + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t lc = l0 + 256 * e;
+    if (lc < ncols) {
+      const int64_t gc = ((lc / MDB_NB) * world + rank) * MDB_NB + lc % MDB_NB;
+      double v;
+      if (gc < i) {
+        v = w * S[i * ld + lc];
+        if (w == 0 || fabs(v) < mavL) v = 0;
+      } else {
+        v = (gc == i) ? 1.0 : 0.0;
+      }
+      S[i * ld + lc] = v;
+    }
+  }
 }

@@ -29,6 +29,11 @@ struct GemmArgs {
   int64_t m_tile0;       // first M tile (units of 128) this launch covers (grid.y bands start here)
   int64_t n_tiles;       // number of N tiles (units of 64) this launch covers, starting at n_tile0
   int64_t n_tile0;
+  // 1-D block-cyclic columns (multi GPU): C holds the local column slab, local N tile nt belongs to global
+  // column ((nt / 2) * cyc_G + cyc_r) * 128 + (nt % 2) * 64 and its B rows start at that column - b_glob0.
+  // cyc_G <= 1: plain mapping (global column = col_glob0 + local column, B row = local column).
+  int cyc_G, cyc_r;
+  int64_t b_glob0;
 };
 
 namespace gemm {
@@ -68,7 +73,13 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) k_gemm_tn(GemmArgs g) {
   const int64_t nt = g.n_tile0 + (blockIdx.x >> 3);
   const int64_t i0 = mt * BM, j0 = nt * BN;
   if (i0 >= g.M || j0 >= g.N) return;
-  if (LOWER && (g.row_glob0 + i0 + BM - 1) <= (g.col_glob0 + j0)) return;  // tile entirely on/above the diagonal
+  // global column of the tile's first column, and the B row that belongs to it
+  const int64_t gj0 = (g.cyc_G > 1) ? ((nt / (MDB_NB / BN)) * g.cyc_G + g.cyc_r) * MDB_NB + (nt % (MDB_NB / BN)) * BN
+                                    : g.col_glob0 + j0;
+  const int64_t brow0 = (g.cyc_G > 1) ? gj0 - g.b_glob0 : j0;
+  const int64_t Nb = (g.cyc_G > 1) ? g.M : g.N;  // number of valid B rows (cyclic: the panel has M rows)
+  if (LOWER && (g.row_glob0 + i0 + BM - 1) <= gj0) return;  // tile entirely on/above the diagonal
+  if (brow0 < 0) return;                                     // column block already factored
 
   const int64_t bz = blockIdx.z;
   const double* A = g.A + bz * g.sA;
@@ -96,8 +107,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) k_gemm_tn(GemmArgs g) {
     }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      int64_t gr = j0 + ld_row + 32 * e;
-      gr = gr < g.N ? gr : g.N - 1;
+      int64_t gr = brow0 + ld_row + 32 * e;
+      gr = gr < Nb ? gr : Nb - 1;
       cp_async16(sb + A_BYTES + e * 32 * 128, B + gr * g.ldb + ko);
     }
   };
@@ -111,8 +122,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) k_gemm_tn(GemmArgs g) {
 
   // ---- accumulators, initialised from C (C tile traffic overlaps the pipeline fill) ----
   double acc[2][4][4];
-  const bool interior = (i0 + BM <= g.M) && (j0 + BN <= g.N) &&
-                        (!LOWER || (g.row_glob0 + i0) > (g.col_glob0 + j0 + BN - 1));
+  const bool interior = (i0 + BM <= g.M) && (j0 + BN <= g.N) && (!LOWER || (g.row_glob0 + i0) > (gj0 + BN - 1));
+  const int64_t cg_off = gj0 - j0;  // global column = local column + cg_off
   const int64_t crow0 = i0 + wm * 32 + rho;
   const int64_t ccol0 = j0 + wn * 32 + t;
   if (BETA1) {
@@ -125,7 +136,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) k_gemm_tn(GemmArgs g) {
           const int64_t r = crow0 + mb * 16 + (q >> 1) * 8;
           const int64_t c = ccol0 + nb * 8 + (q & 1) * 4;
           double v = 0.0;
-          if (interior || (r < g.M && c < g.N && (!LOWER || (g.row_glob0 + r) > (g.col_glob0 + c))))
+          if (interior || (r < g.M && c < g.N && (!LOWER || (g.row_glob0 + r) > (cg_off + c))))
             v = C[r * g.ldc + c];
           acc[mb][nb][q] = NEG ? -v : v;
         }
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) k_gemm_tn(GemmArgs g) {
       for (int q = 0; q < 4; ++q) {
         const int64_t r = crow0 + mb * 16 + (q >> 1) * 8;
         const int64_t c = ccol0 + nb * 8 + (q & 1) * 4;
-        if (interior || (r < g.M && c < g.N && (!LOWER || (g.row_glob0 + r) > (g.col_glob0 + c))))
+        if (interior || (r < g.M && c < g.N && (!LOWER || (g.row_glob0 + r) > (cg_off + c))))
           C[r * g.ldc + c] = NEG ? -acc[mb][nb][q] : acc[mb][nb][q];
       }
 }

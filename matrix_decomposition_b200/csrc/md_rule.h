@@ -100,10 +100,12 @@ MD_HD int md_cubic_real_roots(double p, double q, double* roots) {
     const double third = 1.0 / 3.0;
     const double m = 2.0 * pow(hypot(Q, s), third);
     const double theta = atan2(s, -Q) * third;
-    const double two_pi_3 = 2.0943951023931954923;
-    roots[0] = m * cos(theta);
-    roots[1] = m * cos(theta + two_pi_3);
-    roots[2] = m * cos(theta - two_pi_3);
+    // cos(theta +- 2 pi / 3) from one sin / cos pair
+    const double ct = cos(theta), st = sin(theta);
+    const double h3 = 0.86602540378443864676;  // sqrt(3) / 2
+    roots[0] = m * ct;
+    roots[1] = m * (-0.5 * ct - h3 * st);
+    roots[2] = m * (-0.5 * ct + h3 * st);
     return 3;
   } else {  // roots.py:54-64
     if (p == 0) { roots[0] = 0; return 1; }

@@ -27,6 +27,7 @@ struct mdb_factor {
   int* info;         // batch
   double *Ut, *hdr;  // batch x NB*NB, batch x 3*NB
   double *PX, *PY;   // batch x panel_rows x NB
+  double *PX2, *PY2; // second pair for lookahead
   int64_t panel_rows;
   int state, out_type, rule;
   double mavL;
@@ -51,7 +52,18 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
   memset(ctx, 0, sizeof(*ctx));
   ctx->device = device;
   MDB_CUDA(ctx, cudaSetDevice(device));
-  MDB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  {
+    int lo_pri = 0, hi_pri = 0;
+    MDB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    MDB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, hi_pri));
+    MDB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, lo_pri));
+    for (int i = 0; i < 2; ++i) {
+      MDB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_panel[i], cudaEventDisableTiming));
+      MDB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_upd[i], cudaEventDisableTiming));
+    }
+    const char* la = getenv("MDB200_LOOKAHEAD");
+    ctx->lookahead = !(la && la[0] == '0');
+  }
   ctx->stream = ctx->own_stream;
   MDB_CUDA(ctx, cudaEventCreate(&ctx->ev[0]));
   MDB_CUDA(ctx, cudaEventCreate(&ctx->ev[1]));
@@ -73,6 +85,11 @@ extern "C" int mdb_ctx_destroy(mdb_ctx* ctx) {
   if (!ctx) return MDB_OK;
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_panel[i]) cudaEventDestroy(ctx->ev_panel[i]);
+    if (ctx->ev_upd[i]) cudaEventDestroy(ctx->ev_upd[i]);
+  }
   if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
   if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
   delete ctx;
@@ -164,7 +181,7 @@ static void factor_release(mdb_factor* f) {
   if (!f) return;
   cudaSetDevice(f->ctx->device);
   cudaFree(f->W); cudaFree(f->vec); cudaFree(f->clamped); cudaFree(f->minB); cudaFree(f->maxB);
-  cudaFree(f->p_dev); cudaFree(f->info); cudaFree(f->Ut); cudaFree(f->hdr); cudaFree(f->PX); cudaFree(f->PY);
+  cudaFree(f->p_dev); cudaFree(f->info); cudaFree(f->Ut); cudaFree(f->hdr); cudaFree(f->PX); cudaFree(f->PY); cudaFree(f->PX2); cudaFree(f->PY2);
   cudaFree(f->Linv); cudaFree(f->LinvT); cudaFree(f->Ltri); cudaFree(f->Utri);
   delete f;
 }
@@ -179,7 +196,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   f->ctx = ctx; f->n = n; f->batch = batch;
   f->ld = std::max<int64_t>(mdb_round_up(n, NB), NB);
   f->W = nullptr; f->vec = nullptr; f->clamped = nullptr; f->minB = f->maxB = nullptr; f->p_dev = nullptr;
-  f->info = nullptr; f->Ut = f->hdr = f->PX = f->PY = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
+  f->info = nullptr; f->Ut = f->hdr = f->PX = f->PY = f->PX2 = f->PY2 = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
   f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
   const int64_t nn = std::max<int64_t>(n, 1);
   f->panel_rows = std::max<int64_t>(mdb_round_up(nn, NB), NB);
@@ -190,9 +207,11 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   A((void**)&f->clamped, (size_t)batch * nn);
   A((void**)&f->info, (size_t)batch * sizeof(int));
   A((void**)&f->Ut, (size_t)batch * NB * NB * 8);
-  A((void**)&f->hdr, (size_t)batch * 3 * NB * 8);
+  A((void**)&f->hdr, (size_t)batch * 5 * NB * 8);
   A((void**)&f->PX, (size_t)batch * f->panel_rows * NB * 8);
   A((void**)&f->PY, (size_t)batch * f->panel_rows * NB * 8);
+  A((void**)&f->PX2, (size_t)batch * f->panel_rows * NB * 8);
+  A((void**)&f->PY2, (size_t)batch * f->panel_rows * NB * 8);
   if (e != cudaSuccess) {
     snprintf(ctx->err, sizeof(ctx->err), "mdb_factor_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     factor_release(f);
@@ -349,7 +368,7 @@ static FactorDev make_dev(mdb_factor* f) {
   F.gamma = f->gamma; F.alpha = f->alpha; F.beta = f->beta; F.rowmax = f->rowmax;
   F.d = f->d; F.omega = f->omega; F.delta = f->delta; F.clamped = f->clamped;
   F.minB = f->minB; F.maxB = f->maxB; F.info = f->info; F.Ut = f->Ut; F.hdr = f->hdr;
-  F.sW = f->n * f->ld; F.sVec = f->n; F.sUt = NB * NB; F.sHdr = 3 * NB; F.sPanel = f->panel_rows * NB;
+  F.sW = f->n * f->ld; F.sVec = f->n; F.sUt = NB * NB; F.sHdr = 5 * NB; F.sPanel = f->panel_rows * NB;
   return F;
 }
 
@@ -434,12 +453,23 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
   }
   const int diag_smem = (NB * (NB + 1) + 2 * NB) * 8;
   const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB) * 8;
-  for (int64_t k0 = 0; k0 < n; k0 += NB) {
+  // Lookahead-1 (default): the trailing update of panel k is split into (a) the next column block, done on
+  // the main stream, and (b) the rest, done on the side stream while the main stream already factors
+  // diagonal block + panel k+1.  Panel operands are double buffered.  With profiling on, everything runs
+  // serialised on the main stream so that the per-phase timers mean something.
+  const bool lookahead = !ctx->profiling && ctx->lookahead && n > 2 * NB;
+  cudaStream_t main_s = ctx->stream, side_s = ctx->side_stream;
+  int64_t kidx = 0;
+  for (int64_t k0 = 0; k0 < n; k0 += NB, ++kidx) {
     const int kb = (int)std::min<int64_t>(NB, n - k0);
     const int64_t k1 = k0 + kb;
+    const int buf = lookahead ? (int)(kidx & 1) : 0;
+    double* PX = buf ? f->PX2 : f->PX;
+    double* PY = buf ? f->PY2 : f->PY;
     {
       PhaseTimer t(ctx, 0);
-      k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), NB, diag_smem, ctx->stream>>>(F, k0, kb);
+      k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), NB, diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
+                                                                                f->W + k0 * f->ld + k0, f->ld);
       MDB_LAUNCHED(ctx);
     }
     if (k1 < n) {
@@ -447,23 +477,47 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       {
         PhaseTimer t(ctx, 1);
         dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, (unsigned)batch);
-        k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, ctx->stream>>>(F, k0, k1, rows, f->W, 1, f->ld, f->W + k0,
-                                                                         f->ld, f->PX, f->PY, k1);
+        k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, main_s>>>(F, k0, k1, rows, f->W, 1, f->ld, f->W + k0, f->ld,
+                                                                    PX, PY, k1);
         MDB_LAUNCHED(ctx);
       }
-      {
+      GemmArgs g;
+      memset(&g, 0, sizeof(g));
+      g.A = PX; g.lda = NB; g.sA = F.sPanel;
+      g.B = PY; g.ldb = NB; g.sB = F.sPanel;
+      g.C = f->W + k1 * f->ld + k1; g.ldc = f->ld; g.sC = F.sW;
+      g.M = rows; g.N = rows; g.K = NB;
+      g.row_glob0 = k1; g.col_glob0 = k1;
+      if (!lookahead) {
         PhaseTimer t(ctx, 2);
-        GemmArgs g;
-        memset(&g, 0, sizeof(g));
-        g.A = f->PX; g.lda = NB; g.sA = F.sPanel;
-        g.B = f->PY; g.ldb = NB; g.sB = F.sPanel;
-        g.C = f->W + k1 * f->ld + k1; g.ldc = f->ld; g.sC = F.sW;
-        g.M = rows; g.N = rows; g.K = NB;
-        g.row_glob0 = k1; g.col_glob0 = k1;
         rc = launch_gemm_tn<true, true, false>(ctx, g, batch);
         if (rc) return rc;
+      } else {
+        const int64_t nt_block = NB / gemm::BN;  // N tiles of one column block
+        // all earlier (b) updates must have reached the next column block (and released this panel buffer's twin)
+        if (kidx >= 1) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(kidx - 1) & 1], 0));
+        GemmArgs ga = g;
+        ga.n_tile0 = 0; ga.n_tiles = nt_block;
+        rc = launch_gemm_tn<true, true, false>(ctx, ga, batch);  // (a) next column block, main stream
+        if (rc) return rc;
+        MDB_CUDA(ctx, cudaEventRecord(ctx->ev_panel[kidx & 1], main_s));
+        if (rows > NB) {
+          MDB_CUDA(ctx, cudaStreamWaitEvent(side_s, ctx->ev_panel[kidx & 1], 0));
+          GemmArgs gb = g;
+          gb.n_tile0 = nt_block; gb.n_tiles = 0; gb.m_tile0 = 1;
+          cudaStream_t saved = ctx->stream;
+          ctx->stream = side_s;
+          rc = launch_gemm_tn<true, true, false>(ctx, gb, batch);  // (b) the rest, side stream
+          ctx->stream = saved;
+          if (rc) return rc;
+        }
+        MDB_CUDA(ctx, cudaEventRecord(ctx->ev_upd[kidx & 1], side_s));
       }
     }
+  }
+  if (lookahead && kidx >= 1) {
+    MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(kidx - 1) & 1], 0));
+    if (kidx >= 2) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(kidx - 2) & 1], 0));
   }
   MDB_CUDA(ctx, cudaGetLastError());
   f->state = ST_FACTORED;

@@ -17,6 +17,9 @@ struct mdb_ctx {
   int device;
   cudaStream_t stream;
   cudaStream_t own_stream;
+  cudaStream_t side_stream;  // low priority: the bulk of the trailing update under lookahead
+  cudaEvent_t ev_panel[2], ev_upd[2];
+  int lookahead;
   char err[512];
   int64_t launches;
   int profiling;

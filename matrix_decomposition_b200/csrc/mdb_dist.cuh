@@ -1,22 +1,334 @@
 // mdb_dist.cuh -- per-rank device steps of the 1-D block-cyclic multi-GPU factorization.
-// Included at the end of mdb_api.cu.
+// Included at the end of mdb_api.cu.  The loop, the buffers and the NCCL broadcast live in
+// matrix_decomposition_b200/distributed.py; see include/mdb200.h for the contract.
 #pragma once
 
 struct mdb_dist {
   mdb_ctx* ctx;
+  int64_t n, ld;       // ld = number of local columns (multiple of NB)
+  int rank, world;
+  int64_t nblk_glob, nblk_loc;
+  double *S, *A;       // n x ld, owned by the caller (torch tensors)
+  double* panel[2];    // broadcast buffers, owned by the caller
+  double* vec;         // 7 x n: gamma, alpha, beta, rowmax, d, omega, delta (position order, full length)
+  double *gamma, *alpha, *beta, *rowmax, *d, *omega, *delta;
+  uint8_t* clamped;
+  double *minB, *maxB;
+  int* info;
+  double* Ut;
+  int64_t* pcol_dev;   // scratch for the generator
+  MdRuleParams prm;
+  bool have_bounds;
 };
 
-extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t, int, int, mdb_dist** out) {
-  if (out) *out = nullptr;
-  return mdb_fail(ctx, MDB_ERR_STATE, "%s", "mdb_dist: not built yet");
+static inline int64_t dist_local_blocks(int64_t n, int rank, int world) {
+  const int64_t nblk = (n + NB - 1) / NB;
+  return nblk > rank ? (nblk - rank + world - 1) / world : 0;
 }
-extern "C" int mdb_dist_destroy(mdb_dist*) { return MDB_OK; }
-extern "C" int mdb_dist_generate_f2(mdb_dist*, uint64_t, double, const int64_t*) { return MDB_ERR_STATE; }
-extern "C" int mdb_dist_set_matrix(mdb_dist*, const double*, int64_t) { return MDB_ERR_STATE; }
-extern "C" int mdb_dist_set_bounds(mdb_dist*, const mdb_bounds*, const int64_t*) { return MDB_ERR_STATE; }
-extern "C" int64_t mdb_dist_panel_elems(const mdb_dist*, int64_t) { return 0; }
-extern "C" void* mdb_dist_panel_buffer(mdb_dist*, int) { return nullptr; }
-extern "C" int mdb_dist_factor_panel(mdb_dist*, int64_t, int) { return MDB_ERR_STATE; }
-extern "C" int mdb_dist_apply_panel(mdb_dist*, int64_t, int, int64_t, int64_t) { return MDB_ERR_STATE; }
-extern "C" int mdb_dist_get_local(mdb_dist*, double*, int64_t, int, double*, double*, uint8_t*) { return MDB_ERR_STATE; }
-extern "C" int64_t mdb_dist_local_cols(const mdb_dist*) { return 0; }
+
+extern "C" int64_t mdb_dist_local_cols(int64_t n, int rank, int world) {
+  if (n < 0 || world < 1 || rank < 0 || rank >= world) return -1;
+  return std::max<int64_t>(dist_local_blocks(n, rank, world), 1) * NB;
+}
+
+// header 5 x NB | vectors 3 x rows | X rows x NB | Y rows x NB
+static inline int64_t dist_panel_elems(int64_t n, int64_t k) {
+  const int64_t k1 = std::min<int64_t>((k + 1) * NB, n);
+  const int64_t rows = n - k1;
+  return 5 * NB + 3 * rows + 2 * rows * NB;
+}
+extern "C" int64_t mdb_dist_panel_elems(const mdb_dist* s, int64_t k) { return s ? dist_panel_elems(s->n, k) : 0; }
+
+extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, double* S_loc, double* A_loc,
+                               int64_t ld_loc, double* panel0, double* panel1, mdb_dist** out) {
+  if (!ctx || !out) return MDB_ERR_INVALID;
+  *out = nullptr;
+  MDB_CHECK(ctx, n > 0 && world >= 1 && rank >= 0 && rank < world, "mdb_dist_create: bad n / rank / world");
+  MDB_CHECK(ctx, S_loc && A_loc && panel0 && panel1, "mdb_dist_create: null buffer");
+  MDB_CHECK(ctx, ld_loc == mdb_dist_local_cols(n, rank, world), "mdb_dist_create: ld_loc must be mdb_dist_local_cols()");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = configure_kernels(ctx);
+  if (rc) return rc;
+  mdb_dist* s = new (std::nothrow) mdb_dist();
+  if (!s) return MDB_ERR_INVALID;
+  s->ctx = ctx; s->n = n; s->ld = ld_loc; s->rank = rank; s->world = world;
+  s->nblk_glob = (n + NB - 1) / NB;
+  s->nblk_loc = dist_local_blocks(n, rank, world);
+  s->S = S_loc; s->A = A_loc; s->panel[0] = panel0; s->panel[1] = panel1;
+  s->vec = nullptr; s->clamped = nullptr; s->minB = s->maxB = nullptr; s->info = nullptr; s->Ut = nullptr;
+  s->pcol_dev = nullptr; s->have_bounds = false;
+  cudaError_t e = cudaMalloc((void**)&s->vec, (size_t)7 * n * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->clamped, (size_t)n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->info, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->Ut, (size_t)NB * NB * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->pcol_dev, (size_t)ld_loc * 8);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->vec, 0, (size_t)7 * n * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->clamped, 0, (size_t)n, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->info, 0, sizeof(int), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->Ut, 0, (size_t)NB * NB * 8, ctx->stream);
+  if (e != cudaSuccess) {
+    snprintf(ctx->err, sizeof(ctx->err), "mdb_dist_create: %s", cudaGetErrorString(e));
+    mdb_dist_destroy(s);
+    return MDB_ERR_CUDA;
+  }
+  s->gamma = s->vec; s->alpha = s->vec + n; s->beta = s->vec + 2 * n; s->rowmax = s->vec + 3 * n;
+  s->d = s->vec + 4 * n; s->omega = s->vec + 5 * n; s->delta = s->vec + 6 * n;
+  *out = s;
+  return MDB_OK;
+}
+
+extern "C" int mdb_dist_destroy(mdb_dist* s) {
+  if (!s) return MDB_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->vec); cudaFree(s->clamped); cudaFree(s->minB); cudaFree(s->maxB); cudaFree(s->info); cudaFree(s->Ut);
+  cudaFree(s->pcol_dev);
+  delete s;
+  return MDB_OK;
+}
+
+// gamma of the locally owned columns from A_loc: gamma[gc] = A_loc[gc, lc]
+__global__ void k_dist_extract_gamma(int64_t n, const double* __restrict__ A, int64_t ld, int64_t ncols, int rank,
+                                     int world, double* __restrict__ gamma) {
+  const int64_t lc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc < ncols) {
+    const int64_t gc = ((lc / MDB_NB) * world + rank) * MDB_NB + lc % MDB_NB;
+    if (gc < n) gamma[gc] = A[gc * ld + lc];
+  }
+}
+
+static int dist_after_matrix(mdb_dist* s) {
+  mdb_ctx* ctx = s->ctx;
+  MDB_CUDA(ctx, cudaMemcpyAsync(s->S, s->A, (size_t)s->n * s->ld * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  k_dist_extract_gamma<<<(unsigned)((s->ld + 255) / 256), 256, 0, ctx->stream>>>(s->n, s->A, s->ld, s->ld, s->rank,
+                                                                                s->world, s->gamma);
+  MDB_LAUNCHED(ctx);
+  MDB_CUDA(ctx, cudaGetLastError());
+  return MDB_OK;
+}
+
+extern "C" int mdb_dist_generate_f2(mdb_dist* s, uint64_t seed, double mu, const int64_t* p) {
+  if (!s) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = s->n;
+  // original index of every local column (columns past n map to themselves; they are never read)
+  std::vector<int64_t> pcol((size_t)s->ld);
+  for (int64_t lc = 0; lc < s->ld; ++lc) {
+    const int64_t gc = ((lc / NB) * s->world + s->rank) * NB + lc % NB;
+    pcol[(size_t)lc] = (gc < n) ? (p ? p[gc] : gc) : gc;
+  }
+  int64_t* prow = nullptr;
+  if (p) {
+    MDB_CUDA(ctx, cudaMalloc((void**)&prow, (size_t)n * 8));
+    MDB_CUDA(ctx, cudaMemcpyAsync(prow, p, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  MDB_CUDA(ctx, cudaMemcpyAsync(s->pcol_dev, pcol.data(), (size_t)s->ld * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = generate_f2(ctx, n, s->ld, 0, prow, s->pcol_dev, seed, mu, s->A, s->ld);
+  if (!rc) rc = dist_after_matrix(s);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(prow);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
+}
+
+extern "C" int mdb_dist_set_matrix(mdb_dist* s, const double* Ap, int64_t ld) {
+  if (!s || !Ap) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CHECK(ctx, ld >= s->n, "mdb_dist_set_matrix: ld < n");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MDB_CUDA(ctx, cudaMemsetAsync(s->A, 0, (size_t)s->n * s->ld * 8, ctx->stream));
+  for (int64_t lb = 0; lb < s->nblk_loc; ++lb) {
+    const int64_t gc0 = (lb * s->world + s->rank) * NB;
+    const int64_t w = std::min<int64_t>(NB, s->n - gc0);
+    int rc = copy2d_async(ctx, s->A + lb * NB, s->ld, Ap + gc0, ld, s->n, w, MDB_DEVICE, MDB_HOST);
+    if (rc) return rc;
+  }
+  int rc = dist_after_matrix(s);
+  if (rc) return rc;
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDB_OK;
+}
+
+extern "C" int mdb_dist_set_bounds(mdb_dist* s, const mdb_bounds* bnd, const int64_t* p) {
+  if (!s || !bnd) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CHECK(ctx, bnd->rule == MDB_RULE_REIMER || bnd->rule == MDB_RULE_EXACT, "mdb_dist_set_bounds: unknown rule");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = s->n;
+  if (s->minB) { cudaFree(s->minB); s->minB = nullptr; }
+  if (s->maxB) { cudaFree(s->maxB); s->maxB = nullptr; }
+  double sc_minB = -INFINITY, sc_maxB = INFINITY;
+  if (bnd->rule == MDB_RULE_REIMER) {
+    if (bnd->min_diag_B) sc_minB = bnd->min_diag_B[0];
+    if (bnd->max_diag_B) sc_maxB = bnd->max_diag_B[0];
+    if (bnd->stride_B != 0) {
+      MDB_CHECK(ctx, bnd->min_diag_B && bnd->max_diag_B, "vector bounds need both min_diag_B and max_diag_B");
+      std::vector<double> mb((size_t)n), Mb((size_t)n);
+      for (int64_t i = 0; i < n; ++i) {
+        const int64_t pi = p ? p[i] : i;
+        mb[(size_t)i] = bnd->min_diag_B[pi * bnd->stride_B];
+        Mb[(size_t)i] = bnd->max_diag_B[pi * bnd->stride_B];
+      }
+      MDB_CUDA(ctx, cudaMalloc((void**)&s->minB, (size_t)n * 8));
+      MDB_CUDA(ctx, cudaMalloc((void**)&s->maxB, (size_t)n * 8));
+      MDB_CUDA(ctx, cudaMemcpyAsync(s->minB, mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+      MDB_CUDA(ctx, cudaMemcpyAsync(s->maxB, Mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+      MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  s->prm.rule = bnd->rule;
+  s->prm.min_diag_D = bnd->min_diag_D;
+  s->prm.max_diag_D = bnd->max_diag_D;
+  s->prm.min_abs_value_D = bnd->min_abs_value_D;
+  s->prm.min_abs_value_L = (bnd->rule == MDB_RULE_EXACT) ? 0.0 : bnd->min_abs_value_L;
+  s->prm.min_diag_B = sc_minB;
+  s->prm.max_diag_B = sc_maxB;
+  MDB_CUDA(ctx, cudaMemsetAsync(s->alpha, 0, (size_t)3 * n * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(s->info, 0, sizeof(int), ctx->stream));
+  s->have_bounds = true;
+  return MDB_OK;
+}
+
+static FactorDev dist_make_dev(mdb_dist* s, double* hdr) {
+  FactorDev F;
+  memset(&F, 0, sizeof(F));
+  F.n = s->n; F.ldw = s->ld; F.W = s->S;
+  F.gamma = s->gamma; F.alpha = s->alpha; F.beta = s->beta; F.rowmax = s->rowmax;
+  F.d = s->d; F.omega = s->omega; F.delta = s->delta; F.clamped = s->clamped;
+  F.minB = s->minB; F.maxB = s->maxB; F.info = s->info; F.Ut = s->Ut; F.hdr = hdr;
+  F.prm = s->prm;
+  return F;
+}
+
+extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot) {
+  if (!s) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CHECK(ctx, s->have_bounds, "mdb_dist_factor_panel: call mdb_dist_set_bounds first");
+  MDB_CHECK(ctx, k >= 0 && k < s->nblk_glob && (k % s->world) == s->rank, "mdb_dist_factor_panel: not the owner of panel k");
+  MDB_CHECK(ctx, slot == 0 || slot == 1, "bad slot");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1;
+  const int kb = (int)(k1 - k0);
+  const int64_t lc0 = (k / s->world) * NB;
+  double* buf = s->panel[slot];
+  double* hdr = buf;
+  double* vecs = buf + 5 * NB;
+  double* PX = vecs + 3 * rows;
+  double* PY = PX + rows * NB;
+  FactorDev F = dist_make_dev(s, hdr);
+  const int diag_smem = (NB * (NB + 1) + 2 * NB) * 8;
+  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB) * 8;
+  k_diag_block<NB><<<1, NB, diag_smem, ctx->stream>>>(F, k0, kb, s->S + k0 * s->ld + lc0, s->ld, s->A + k0 * s->ld + lc0,
+                                                       s->ld);
+  MDB_LAUNCHED(ctx);
+  if (rows > 0) {
+    dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, 1);
+    // A[j, k0 + c] = A_loc[j * ld + lc0 + c]  ->  Asrc + j * a_rs + k0 * a_cs with a_rs = ld, a_cs = 1
+    k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
+                                                                     s->S + lc0, s->ld, PX, PY, k1);
+    MDB_LAUNCHED(ctx);
+    MDB_CUDA(ctx, cudaMemcpyAsync(vecs, s->alpha + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MDB_CUDA(ctx, cudaMemcpyAsync(vecs + rows, s->beta + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MDB_CUDA(ctx, cudaMemcpyAsync(vecs + 2 * rows, s->rowmax + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  MDB_CUDA(ctx, cudaGetLastError());
+  return MDB_OK;
+}
+
+// header -> replicated d / omega / delta / clamped
+__global__ void k_dist_absorb_hdr(int kb, int64_t k0, const double* __restrict__ hdr, double* __restrict__ d,
+                                  double* __restrict__ omega, double* __restrict__ delta, uint8_t* __restrict__ clamped) {
+  const int c = threadIdx.x;
+  if (c < kb) {
+    d[k0 + c] = hdr[c];
+    omega[k0 + c] = hdr[MDB_NB + c];
+    delta[k0 + c] = hdr[3 * MDB_NB + c];
+    clamped[k0 + c] = (uint8_t)(hdr[4 * MDB_NB + c] != 0.0);
+  }
+}
+
+extern "C" int mdb_dist_absorb_panel(mdb_dist* s, int64_t k, int slot) {
+  if (!s) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CHECK(ctx, k >= 0 && k < s->nblk_glob && (slot == 0 || slot == 1), "mdb_dist_absorb_panel: bad panel / slot");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((k % s->world) == s->rank) return MDB_OK;  // the owner's arrays are already up to date
+  const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1;
+  double* buf = s->panel[slot];
+  k_dist_absorb_hdr<<<1, NB, 0, ctx->stream>>>((int)(k1 - k0), k0, buf, s->d, s->omega, s->delta, s->clamped);
+  MDB_LAUNCHED(ctx);
+  if (rows > 0) {
+    double* vecs = buf + 5 * NB;
+    MDB_CUDA(ctx, cudaMemcpyAsync(s->alpha + k1, vecs, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MDB_CUDA(ctx, cudaMemcpyAsync(s->beta + k1, vecs + rows, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    MDB_CUDA(ctx, cudaMemcpyAsync(s->rowmax + k1, vecs + 2 * rows, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  MDB_CUDA(ctx, cudaGetLastError());
+  return MDB_OK;
+}
+
+extern "C" int mdb_dist_apply_panel(mdb_dist* s, int64_t k, int slot, int64_t only_block, int64_t skip_block) {
+  if (!s) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CHECK(ctx, k >= 0 && k < s->nblk_glob && (slot == 0 || slot == 1), "mdb_dist_apply_panel: bad panel / slot");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1;
+  if (rows <= 0) return MDB_OK;
+  double* buf = s->panel[slot];
+  double* PX = buf + 5 * NB + 3 * rows;
+  double* PY = PX + rows * NB;
+  const int64_t tpb = NB / gemm::BN;  // N tiles per column block
+  // local blocks with global index > k:  lb >= first
+  int64_t first = (k + 1 - s->rank + s->world - 1) / s->world;
+  if (first < 0) first = 0;
+  int64_t lb_begin = first, lb_end = s->nblk_loc;  // [begin, end)
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = PX; g.lda = NB; g.B = PY; g.ldb = NB;
+  g.C = s->S + k1 * s->ld; g.ldc = s->ld;
+  g.M = rows; g.N = s->nblk_loc * NB; g.K = NB;
+  g.row_glob0 = k1; g.col_glob0 = 0; g.b_glob0 = k1;
+  g.cyc_G = s->world; g.cyc_r = s->rank;
+  // one rank: the plain mapping (global column = local column); B is indexed by global column, so shift it
+  if (s->world == 1) { g.cyc_G = 1; g.b_glob0 = 0; g.B = PY - k1 * NB; }
+  auto launch = [&](int64_t b0, int64_t b1) -> int {  // local blocks [b0, b1)
+    if (b1 <= b0) return MDB_OK;
+    GemmArgs gg = g;
+    gg.n_tile0 = b0 * tpb;
+    gg.n_tiles = (b1 - b0) * tpb;
+    return launch_gemm_tn<true, true, false>(ctx, gg, 1);
+  };
+  int rc = MDB_OK;
+  if (only_block >= 0) {
+    if ((only_block % s->world) != s->rank || only_block <= k) return MDB_OK;
+    const int64_t lb = only_block / s->world;
+    rc = launch(lb, lb + 1);
+  } else if (skip_block >= 0 && (skip_block % s->world) == s->rank && skip_block > k) {
+    const int64_t lb = skip_block / s->world;
+    rc = launch(lb_begin, std::min(lb, lb_end));
+    if (!rc) rc = launch(std::max(lb + 1, lb_begin), lb_end);
+  } else {
+    rc = launch(lb_begin, lb_end);
+  }
+  return rc;
+}
+
+extern "C" int mdb_dist_finalize(mdb_dist* s, double* d, double* omega, double* delta, uint8_t* clamped) {
+  if (!s) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = s->n;
+  dim3 grid((unsigned)n, (unsigned)((s->ld + 1023) / 1024));
+  k_finalize_cols<<<grid, 256, 0, ctx->stream>>>(n, s->S, s->ld, s->ld, s->rank, s->world, s->omega,
+                                                 s->prm.min_abs_value_L);
+  MDB_LAUNCHED(ctx);
+  MDB_CUDA(ctx, cudaGetLastError());
+  if (d) MDB_CUDA(ctx, cudaMemcpyAsync(d, s->d, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (omega) MDB_CUDA(ctx, cudaMemcpyAsync(omega, s->omega, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (delta) MDB_CUDA(ctx, cudaMemcpyAsync(delta, s->delta, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (clamped) MDB_CUDA(ctx, cudaMemcpyAsync(clamped, s->clamped, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDB_OK;
+}

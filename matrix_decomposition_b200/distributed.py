@@ -1,0 +1,322 @@
+"""Multi-GPU factorization: 1-D block-cyclic column distribution, one process per GPU.
+
+Global column block J (width 128, in elimination order) lives on rank J % world.  Per panel k the owner
+factors the diagonal block and the panel on its GPU (mdb_dist_factor_panel), the result -- the unscaled
+rows X, Y = -X D, the (d, omega, ...) header and the alpha / beta / rowmax slices -- is broadcast with
+torch.distributed (NCCL over NVLink / NVSwitch), and every rank applies it to its own trailing column
+blocks with the FP64 DMMA tile kernel (mdb_dist_apply_panel).  Lookahead-1: the owner of panel k+1 updates
+that column block first and factors + broadcasts it while all ranks are still busy with the bulk of
+update k on a second stream, so the broadcast and the sequential panel work hide under the update.
+
+The orchestration below is backend-neutral: `Steps` is the per-rank device work, `Comm` the broadcast.
+The product backend is CudaSteps (libmdb200.so + torch.cuda streams) with NcclComm; the CPU tests in
+tests/test_distributed_cpu.py drive the same loop over gloo with a numpy stand-in for the device steps.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+
+NB = 128
+
+
+def owner_of(k, world):
+    return k % world
+
+
+def local_blocks(n, rank, world):
+    nblk = (n + NB - 1) // NB
+    return (nblk - rank + world - 1) // world if nblk > rank else 0
+
+
+def local_cols(n, rank, world):
+    return max(local_blocks(n, rank, world), 1) * NB
+
+
+def panel_elems(n, k):
+    k1 = min((k + 1) * NB, n)
+    rows = n - k1
+    return 5 * NB + 3 * rows + 2 * rows * NB
+
+
+class NullStream:
+    """Stream / event stand-in for CPU backends (everything is synchronous)."""
+
+    def record(self):
+        return None
+
+    def wait(self, event):
+        pass
+
+
+def factorize(n, rank, world, steps, comm, main=None, bulk=None, lookahead=True):
+    """The panel loop.  `steps` provides factor_panel / absorb_panel / apply_panel / panel_tensor,
+    `comm.broadcast(tensor, src, stream)` returns a handle whose wait(stream) makes `stream` wait for it.
+    `main` / `bulk` are stream objects with record() -> event and wait(event)."""
+    main = main or NullStream()
+    bulk = bulk or NullStream()
+    T = (n + NB - 1) // NB
+    if T == 0:
+        return
+    works = {}
+    bulk_done = {}
+
+    def issue_factor_and_broadcast(k):
+        slot = k % 2
+        if owner_of(k, world) == rank:
+            steps.factor_panel(k, slot, main)
+        works[k] = comm.broadcast(steps.panel_tensor(slot, k), owner_of(k, world), main)
+
+    issue_factor_and_broadcast(0)
+    for k in range(T):
+        slot = k % 2
+        works.pop(k).wait(main)                      # panel k has arrived
+        steps.absorb_panel(k, slot, main)
+        if k + 1 < T:
+            if k - 1 in bulk_done:
+                main.wait(bulk_done.pop(k - 1))      # bulk update k-1 reached block k+1 and released slot (k+1) % 2
+            if lookahead:
+                steps.apply_panel(k, slot, k + 1, -1, main)     # next column block first
+                ready = main.record()
+                issue_factor_and_broadcast(k + 1)                # overlaps with the bulk update below
+                bulk.wait(ready)
+                steps.apply_panel(k, slot, -1, k + 1, bulk)     # the rest
+                bulk_done[k] = bulk.record()
+            else:
+                steps.apply_panel(k, slot, -1, -1, main)
+                bulk_done[k] = main.record()
+                issue_factor_and_broadcast(k + 1)
+    for ev in bulk_done.values():
+        main.wait(ev)
+
+
+# ------------------------------------------------------------------------------------------------
+# product backend: libmdb200.so + torch.cuda + NCCL
+# ------------------------------------------------------------------------------------------------
+class TorchStream:
+    def __init__(self, stream):
+        self.stream = stream
+
+    def record(self):
+        import torch
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ev
+
+    def wait(self, event):
+        if event is not None:
+            self.stream.wait_event(event)
+
+
+class NcclComm:
+    def broadcast(self, tensor, src, stream):
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.stream(stream.stream):
+            work = dist.broadcast(tensor, src=src, async_op=True)
+
+        class Handle:
+            def wait(self, s):
+                with torch.cuda.stream(s.stream):
+                    work.wait()
+        return Handle()
+
+
+class CudaSteps:
+    """Per-rank device state: S_loc / A_loc / panel buffers are torch tensors, the steps are C-ABI calls."""
+
+    def __init__(self, n, rank, world, device=None):
+        import torch
+        from . import _native
+        self._native = _native
+        self.n, self.rank, self.world = n, rank, world
+        self.device = torch.cuda.current_device() if device is None else device
+        self.ctx = _native.context(self.device)
+        self.ld = local_cols(n, rank, world)
+        dev = torch.device('cuda', self.device)
+        self.S = torch.empty((n, self.ld), dtype=torch.float64, device=dev)
+        self.A = torch.empty((n, self.ld), dtype=torch.float64, device=dev)
+        pe = panel_elems(n, 0)
+        self.panels = [torch.empty(pe, dtype=torch.float64, device=dev) for _ in range(2)]
+        h = ctypes.c_void_p()
+        rc = self.ctx.lib.mdb_dist_create(self.ctx.handle, n, rank, world, ctypes.c_void_p(self.S.data_ptr()),
+                                          ctypes.c_void_p(self.A.data_ptr()), self.ld,
+                                          ctypes.c_void_p(self.panels[0].data_ptr()),
+                                          ctypes.c_void_p(self.panels[1].data_ptr()), ctypes.byref(h))
+        self.ctx.check(rc, 'mdb_dist_create')
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.mdb_dist_destroy(self.handle)
+            self.handle = None
+
+    def _on(self, stream):
+        self.ctx.set_stream(stream.stream.cuda_stream)
+
+    def generate_f2(self, seed, mu, p, stream):
+        self._on(stream)
+        p64 = None if p is None else np.ascontiguousarray(p, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.mdb_dist_generate_f2(self.handle, seed, mu, self._native.ptr(p64)), 'mdb_dist_generate_f2')
+
+    def set_matrix(self, Ap, stream):
+        self._on(stream)
+        Ap = np.ascontiguousarray(Ap, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.mdb_dist_set_matrix(self.handle, self._native.ptr(Ap), Ap.shape[1]), 'mdb_dist_set_matrix')
+
+    def set_bounds(self, bounds, p, stream):
+        self._on(stream)
+        p64 = None if p is None else np.ascontiguousarray(p, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.mdb_dist_set_bounds(self.handle, ctypes.byref(bounds), self._native.ptr(p64)),
+                       'mdb_dist_set_bounds')
+
+    def panel_tensor(self, slot, k):
+        return self.panels[slot][:panel_elems(self.n, k)]
+
+    def factor_panel(self, k, slot, stream):
+        self._on(stream)
+        self.ctx.check(self.ctx.lib.mdb_dist_factor_panel(self.handle, k, slot), 'mdb_dist_factor_panel')
+
+    def absorb_panel(self, k, slot, stream):
+        self._on(stream)
+        self.ctx.check(self.ctx.lib.mdb_dist_absorb_panel(self.handle, k, slot), 'mdb_dist_absorb_panel')
+
+    def apply_panel(self, k, slot, only_block, skip_block, stream):
+        self._on(stream)
+        self.ctx.check(self.ctx.lib.mdb_dist_apply_panel(self.handle, k, slot, only_block, skip_block), 'mdb_dist_apply_panel')
+
+    def finalize(self, stream):
+        self._on(stream)
+        n = self.n
+        d, omega, delta = np.empty(n), np.empty(n), np.empty(n)
+        clamped = np.zeros(n, dtype=np.uint8)
+        P = self._native.ptr
+        self.ctx.check(self.ctx.lib.mdb_dist_finalize(self.handle, P(d), P(omega), P(delta), P(clamped)), 'mdb_dist_finalize')
+        return d, omega, delta, clamped.astype(bool)
+
+
+def _streams(device):
+    import torch
+    lo, hi = -1, 0
+    main = TorchStream(torch.cuda.Stream(device=device, priority=-1))
+    bulk = TorchStream(torch.cuda.Stream(device=device, priority=0))
+    return main, bulk
+
+
+def approximate_distributed(Ap_or_none, n, bounds_kwargs, p=None, generator=None, lookahead=True):
+    """Factorizes over all ranks of the default process group (NCCL).
+
+    Ap_or_none : host matrix already permuted (A[p][:, p]) on every rank, or None with
+                 generator = (seed, mu) to use the device generator of family F2 permuted by p.
+    Returns (steps, d, omega_pos, delta_pos, clamped): `steps.S` holds this rank's columns of L.
+    omega / delta are returned in POSITION order here (scatter with p for the reference's original order).
+    """
+    import torch
+    import torch.distributed as dist
+    from . import _native
+    rank, world = dist.get_rank(), dist.get_world_size()
+    device = torch.cuda.current_device()
+    main, bulk = _streams(device)
+    steps = CudaSteps(n, rank, world, device)
+    if Ap_or_none is not None:
+        steps.set_matrix(Ap_or_none, main)
+    else:
+        steps.generate_f2(generator[0], generator[1], p, main)
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, bounds_kwargs.get('min_diag_D'), bounds_kwargs.get('max_diag_D'),
+                                       bounds_kwargs['min_abs_value_D'], bounds_kwargs['min_abs_value_L'],
+                                       bounds_kwargs.get('min_diag_B'), bounds_kwargs.get('max_diag_B'))
+    steps.set_bounds(bounds, p, main)
+    torch.cuda.synchronize()
+    factorize(n, rank, world, steps, NcclComm(), main, bulk, lookahead=lookahead)
+    torch.cuda.synchronize()
+    d, omega, delta, clamped = steps.finalize(main)
+    return steps, d, omega, delta, clamped
+
+
+def identity_residual(steps, d, omega, delta, nprobe=2, seed=5):
+    """Oracle-free check at any n (Reimer.py:947-957): L D L^T v == (A o Omega + diag(gamma + delta)) v in
+    position order, with L and A as local column slabs and one all-reduce per side.  Test / bench helper
+    (plain torch products on the slabs), not part of the factorization path."""
+    import torch
+    import torch.distributed as dist
+    n, ld, rank, world = steps.n, steps.ld, steps.rank, steps.world
+    dev = steps.S.device
+    g = torch.Generator(device='cpu')
+    g.manual_seed(seed)
+    V = torch.rand((n, nprobe), generator=g, dtype=torch.float64).to(dev) * 2 - 1
+    lc = torch.arange(ld, device=dev)
+    gc = ((lc // NB) * world + rank) * NB + lc % NB
+    valid = gc < n
+    gcv = gc.clamp(max=n - 1)
+    d_t = torch.as_tensor(d, device=dev)
+    w_t = torch.as_tensor(omega, device=dev)
+    de_t = torch.as_tensor(delta, device=dev)
+    L = steps.S                                   # local columns of L after finalize
+    z = (L.T @ V) * (d_t[gcv] * valid)[:, None]   # d_k (L[:, k] . v) for local k
+    lhs = L @ z
+    # (A o Omega)[i, k] = A[i, k] * omega[max(i, k)], diagonal replaced by gamma + delta
+    rows = torch.arange(n, device=dev)
+    rhs = torch.zeros((n, nprobe), dtype=torch.float64, device=dev)
+    av = torch.zeros((n, nprobe), dtype=torch.float64, device=dev)
+    chunk = 4096
+    for c0 in range(0, ld, chunk):
+        c1 = min(c0 + chunk, ld)
+        Ablk = steps.A[:, c0:c1]
+        g_blk = gcv[c0:c1]
+        W = torch.maximum(rows[:, None], g_blk[None, :])
+        Om = w_t[W]
+        diag_mask = rows[:, None] == g_blk[None, :]
+        M = torch.where(diag_mask, (Ablk + de_t[g_blk][None, :]), Ablk * Om) * valid[c0:c1][None, :]
+        rhs += M @ V[g_blk] * 1.0
+        av += (Ablk * valid[c0:c1][None, :]) @ V[g_blk]
+        del W, Om, M
+    dist.all_reduce(lhs)
+    dist.all_reduce(rhs)
+    dist.all_reduce(av)
+    return float((lhs - rhs).abs().max() / av.abs().max())
+
+
+def bench_f2(n, s, steps, warmup, seed):
+    """bench.py's N > 1 leg: family F2 generated on the devices, timed with CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from . import _native
+    rank, world = dist.get_rank(), dist.get_world_size()
+    device = torch.cuda.current_device()
+    ctx = _native.context(device)
+    mu = s * math.sqrt(2 * n)
+    diag = np.empty(n)
+    ctx.check(ctx.lib.mdb_generate_diag_f2(ctx.handle, n, seed, mu, _native.ptr(diag)), 'mdb_generate_diag_f2')
+    p = np.argsort(-diag).astype(np.int64)
+    main, bulk = _streams(device)
+    st = CudaSteps(n, rank, world, device)
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, 0.015 * mu, 0.9 * mu, 0.015 * mu,
+                                       float(np.finfo(np.float64).eps), None, 2 * mu)
+    comm = NcclComm()
+    times = []
+    launches = 0
+    for it in range(warmup + steps):
+        st.generate_f2(seed, mu, p, main)
+        st.set_bounds(bounds, p, main)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main.stream)
+        factorize(n, rank, world, st, comm, main, bulk, lookahead=True)
+        e1.record(main.stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=torch.device('cuda', device))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it >= warmup:
+            times.append(float(t.item()))
+            launches += ctx.launch_count() - l0
+    d, omega, delta, clamped = st.finalize(main)
+    ident = identity_residual(st, d, omega, delta)
+    out = dict(ms_per_step=float(np.mean(times)), gpu_launches=int(launches), identity=ident,
+               n_clamped=int(clamped.sum()))
+    st.close()
+    return out

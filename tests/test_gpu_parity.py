@@ -1,0 +1,464 @@
+"""GPU parity tests (pytest -m gpu, on the B200 box).  Everything goes through the public Python API,
+i.e. through the C ABI of libmdb200.so, and is compared with the CPU oracle on the same seeded inputs,
+with the golden vectors produced by the unmodified reference, and -- at BASELINE's full size -- with the
+size-independent identity of Reimer.py:947-957.  /root/reference is never read here.
+
+Tolerances (BASELINE.json north_star): permutation vector and clamped-index set bit-exact; L, d, omega,
+solve results within 1e-10 (|dL| <= 1e-10 max(1, |L|), relative for d / x) in the benign regime;
+||B - B_ref||_F / ||B_ref||_F <= 1e-12 for the composed matrix B = L D L^T in every regime (in the
+explosive regime d / L individually are decided by rounding noise in the reference itself).
+"""
+import ctypes
+import json
+import math
+
+import numpy as np
+import pytest
+
+import workloads
+from conftest import load_golden, ld_join
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+TOL_B = 1e-12
+
+
+@pytest.fixture(scope='module')
+def matrix():
+    import matrix_decomposition_b200 as m
+    from matrix_decomposition_b200 import _native
+    _native.context()          # fails loudly without a GPU / libmdb200.so
+    return m
+
+
+@pytest.fixture(scope='module')
+def orc():
+    from oracle import cpu_oracle
+    return cpu_oracle
+
+
+def _kw_from_json(kw):
+    out = {}
+    for k, v in kw.items():
+        out[k] = np.asarray(v, dtype=float) if isinstance(v, list) and k != 'permutation' else v
+        if k == 'permutation' and isinstance(v, list):
+            out[k] = np.asarray(v, dtype=np.int64)
+    return out
+
+
+def _composed(L, d):
+    d = np.asarray(d, dtype=np.float64)
+    return L @ (d[:, None] * L.T)
+
+
+def _compare(dec, ref_L, ref_d, ref_p, ref_clamped, ref_omega=None, ref_delta=None, benign=True, scale=1.0):
+    np.testing.assert_array_equal(np.asarray(dec.p), ref_p)
+    np.testing.assert_array_equal(dec.clamped, ref_clamped)
+    L, d = dec.L, np.asarray(dec.d, dtype=np.float64)
+    ref_d = np.asarray(ref_d, dtype=np.float64)
+    B, B_ref = _composed(L, d), _composed(ref_L, ref_d)
+    assert np.linalg.norm(B - B_ref) <= TOL_B * np.linalg.norm(B_ref)
+    if benign:
+        assert np.all(np.abs(L - ref_L) <= TOL * np.maximum(1.0, np.abs(ref_L)))
+        np.testing.assert_allclose(d, ref_d, rtol=TOL)
+        if ref_omega is not None:
+            np.testing.assert_allclose(np.asarray(dec.omega, dtype=float), np.asarray(ref_omega, dtype=float), rtol=TOL,
+                                       atol=1e-14)
+        if ref_delta is not None:
+            np.testing.assert_allclose(np.asarray(dec.delta, dtype=float), np.asarray(ref_delta, dtype=float),
+                                       rtol=1e-9, atol=1e-11 * scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# approximate: golden vectors of the reference
+# ---------------------------------------------------------------------------------------------
+def test_known_answer_2x2(matrix):
+    dec = matrix.approximation.positive_semidefinite.decomposition(
+        np.array([[2.0, 1.0], [1.0, -3.0]]), min_diag_D=1e-6, permutation='decreasing_diagonal_values')
+    np.testing.assert_array_equal(dec.p, [0, 1])
+    np.testing.assert_allclose(np.asarray(dec.d, dtype=float), [2, 1e-6], rtol=1e-15)
+    np.testing.assert_allclose(np.asarray(dec.omega, dtype=float), [1, 0.3938888], rtol=1e-6)
+    np.testing.assert_allclose(np.asarray(dec.delta, dtype=float), [0, 3.07757519], rtol=1e-7, atol=1e-15)
+    np.testing.assert_allclose(dec.L[1, 0], 0.1969444, rtol=1e-6)
+    assert list(dec.clamped) == [False, True]
+
+
+def test_reference_test_grid_n10_static_permutations(matrix):
+    """Every static-permutation parametrisation of matrix/tests/test_approximate.py (dense, real) that the
+    reference completes on its own fixture: 500+ cases against the reference's own outputs."""
+    z = load_golden('approx_fixture10.npz')
+    A = z['A']
+    manifest = json.loads(str(z['manifest']))
+    n_run = n_ties = 0
+    for m in manifest:
+        kw = _kw_from_json(m['kwargs'])
+        perm = kw['permutation']
+        if not m['ok'] or (isinstance(perm, str) and perm in ('minimal_difference', 'maximal_stability')) or perm is None:
+            continue
+        key = m['key']
+        dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+        d_ref = ld_join(z, key + '/d').astype(np.float64)
+        np.testing.assert_array_equal(np.asarray(dec.p), z[key + '/p'])
+        np.testing.assert_array_equal(dec.clamped, z[key + '/clamped'])
+        B, B_ref = _composed(dec.L, dec.d), _composed(z[key + '/L'], d_ref)
+        assert np.linalg.norm(B - B_ref) <= TOL_B * np.linalg.norm(B_ref), key
+        d = np.asarray(dec.d, dtype=np.float64)
+        if np.all(np.abs(d - d_ref) <= 1e-9 * np.abs(d_ref)):
+            assert np.all(np.abs(dec.L - z[key + '/L']) <= 1e-9 * np.maximum(1.0, np.abs(z[key + '/L']))), key
+        else:
+            n_ties += 1          # degenerate (d, omega) tie of SURVEY fact 7: B and the clamped set still agree
+        n_run += 1
+    assert n_run >= 500
+    assert n_ties <= 0.05 * n_run
+
+
+@pytest.mark.parametrize('key,benign', [('goe64', False), ('f2_n200_s1.05', True), ('f2_n200_s0.9', False),
+                                        ('f3_n128_nearpsd', True), ('f3_n128_nearpsd_default', True)])
+def test_families_against_reference_goldens(matrix, key, benign):
+    z = load_golden('approx_families.npz')
+    m = {e['key']: e for e in json.loads(str(z['manifest']))}[key]
+    fam = m['family']
+    if fam['kind'] == 'goe':
+        A = workloads.goe(fam['n'], fam['seed'])
+    elif fam['kind'] == 'shifted_goe':
+        A = workloads.shifted_goe(fam['n'], fam['seed'], fam['s'])[0]
+    else:
+        A = workloads.lowrank_plus_diag(fam['n'], fam['seed'], fam['lo'], fam['hi'])
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, **_kw_from_json(m['kwargs']))
+    _compare(dec, z[key + '/L'], ld_join(z, key + '/d'), z[key + '/p'], z[key + '/clamped'],
+             ld_join(z, key + '/omega'), ld_join(z, key + '/delta'), benign=benign, scale=np.abs(A).max())
+
+
+@pytest.mark.parametrize('key,benign', [('f2_n1000_s1.05', True), ('f2_n600_s0.9', False), ('c1_goe2000', False)])
+def test_large_goldens_decisions_and_probes(matrix, key, benign):
+    """BASELINE config 1 (GOE n=2000, min_diag_D=1e-6) and two F2 cases: decisions and B v probes of the reference."""
+    z = load_golden('approx_families.npz')
+    m = {e['key']: e for e in json.loads(str(z['manifest']))}[key]
+    fam = m['family']
+    A = workloads.goe(fam['n'], fam['seed']) if fam['kind'] == 'goe' else workloads.shifted_goe(fam['n'], fam['seed'], fam['s'])[0]
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, **_kw_from_json(m['kwargs']))
+    np.testing.assert_array_equal(np.asarray(dec.p), z[key + '/p'])
+    np.testing.assert_array_equal(dec.clamped, z[key + '/clamped'])
+    d = np.asarray(dec.d, dtype=np.float64)
+    V = z[key + '/probes']
+    Bv = dec.L @ (d[:, None] * (dec.L.T @ V))
+    assert np.max(np.abs(Bv - z[key + '/Bv'])) <= 1e-11 * np.max(np.abs(z[key + '/Bv']))
+    if benign:
+        np.testing.assert_allclose(d, ld_join(z, key + '/d').astype(float), rtol=TOL)
+        rows = z[key + '/L_rows_idx']
+        assert np.all(np.abs(dec.L[rows] - z[key + '/L_rows']) <= TOL * np.maximum(1.0, np.abs(z[key + '/L_rows'])))
+    # solve with the resident factor reproduces A_approx x = b
+    b = np.random.default_rng(1).standard_normal(A.shape[0])
+    x = dec.solve(b)
+    r = dec.matrix_right_side_multiplication(x) - b
+    assert np.max(np.abs(r)) <= 1e-8 * max(1.0, np.max(np.abs(b))) or not benign
+
+
+# ---------------------------------------------------------------------------------------------
+# approximate: oracle on seeded inputs, edge shapes, options
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [1, 2, 3, 127, 128, 129, 255, 257, 384, 700])
+def test_sizes_around_block_boundaries(matrix, orc, n):
+    A, kw = workloads.shifted_goe(n, 100 + n, 1.05)
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+    ref = orc.approximate(A, **kw)
+    _compare(dec, ref['L'], ref['d'], ref['p'], ref['clamped'], ref['omega'], ref['delta'], scale=np.abs(A).max())
+    assert np.all(np.triu(dec.L, 1) == 0) and np.all(dec.L.diagonal() == 1)
+
+
+def test_empty_matrix(matrix):
+    dec = matrix.approximation.positive_semidefinite.decomposition(np.zeros((0, 0)), permutation='none')
+    assert dec.n == 0 and dec.L.shape == (0, 0)
+
+
+@pytest.mark.parametrize('perm', ['none', 'decreasing_diagonal_values', 'increasing_diagonal_values',
+                                  'decreasing_absolute_diagonal_values', 'increasing_absolute_diagonal_values', 'vector'])
+@pytest.mark.parametrize('rt', [None, 'LDL', 'LDL_compressed', 'LL'])
+def test_permutations_and_return_types(matrix, orc, perm, rt):
+    n = 150
+    A = workloads.goe(n, 77) + 3.0 * np.eye(n)
+    p_arg = np.random.default_rng(5).permutation(n) if perm == 'vector' else perm
+    kw = dict(min_diag_D=0.5, max_diag_D=40.0, max_diag_B=60.0, permutation=p_arg)
+    A_copy = A.copy()
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, return_type=rt, **kw)
+    assert np.array_equal(A, A_copy)                                  # A untouched (test_approximate.py:68)
+    assert dec.type_str == (rt or 'LDL')
+    ref = orc.approximate(A, **kw)
+    ldl = dec.as_type('LDL')
+    np.testing.assert_array_equal(np.asarray(dec.p), ref['p'])
+    np.testing.assert_array_equal(dec.clamped, ref['clamped'])
+    B, B_ref = _composed(ldl.L, ldl.d), _composed(ref['L'], ref['d'])
+    assert np.linalg.norm(B - B_ref) <= TOL_B * np.linalg.norm(B_ref)
+    assert np.all(np.abs(ldl.L - ref['L']) <= 1e-9 * np.maximum(1.0, np.abs(ref['L'])))
+    # value checks of test_approximate.py:187-250
+    d = np.asarray(ldl.d, dtype=float)
+    assert np.all(np.isfinite(d)) and np.all(d >= 0.5 * (1 - 1e-12)) and np.all(d <= 40.0 * (1 + 1e-12))
+    assert np.all(B.diagonal() <= 60.0 * (1 + 1e-10))
+    # omega / delta identity of test_approximate.py:476-506 on the composed matrix
+    Bfull = ldl.composed_matrix
+    np.testing.assert_allclose(Bfull.diagonal(), A.diagonal() + np.asarray(dec.delta, dtype=float), rtol=1e-9, atol=1e-9)
+    q = np.asarray(dec.p)
+    om = np.asarray(dec.omega, dtype=float)
+    i, j = 7, 3
+    np.testing.assert_allclose(Bfull[q[i], q[j]], A[q[i], q[j]] * om[q[i]], rtol=1e-8, atol=1e-10)
+
+
+def test_vector_bounds_and_default_min_diag_D(matrix, orc):
+    n = 96
+    A = workloads.reference_fixture(n)
+    kw = dict(min_diag_D=None, min_diag_B=np.arange(n) / n, max_diag_B=np.arange(n) + 30.0, permutation='none')
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+    ref = orc.approximate(A, **kw)
+    _compare(dec, ref['L'], ref['d'], ref['p'], ref['clamped'], benign=False)
+    B = _composed(dec.L, dec.d)
+    assert np.all(B.diagonal() >= kw['min_diag_B'] - 1e-9) and np.all(B.diagonal() <= kw['max_diag_B'] + 1e-9)
+
+
+def test_explosive_regime_clamped_set_and_B(matrix, orc):
+    """min_diag_D = 1e-6 on a strongly indefinite matrix: Lu grows to 1e60; clamped set and B must still match."""
+    A = workloads.goe(500, 9)
+    kw = dict(min_diag_D=1e-6, permutation='decreasing_diagonal_values')
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+    ref = orc.approximate(A, **kw)
+    _compare(dec, ref['L'], ref['d'], ref['p'], ref['clamped'], benign=False)
+    assert np.all(np.isfinite(dec.L))
+
+
+def test_positive_semidefinite_matrix(matrix, orc):
+    z = load_golden('decompose_solve_permute.npz')
+    manifest = json.loads(str(z['manifest']))
+    A = workloads.reference_fixture(10)
+    n_run = 0
+    for m in manifest:
+        if not m['key'].startswith('psd10/'):
+            continue
+        kw = _kw_from_json(m['kwargs'])
+        if kw.get('permutation') in ('maximal_stability', 'minimal_difference'):
+            continue
+        B = matrix.approximation.positive_semidefinite.positive_semidefinite_matrix(A, **kw)
+        np.testing.assert_allclose(B, z[m['key'] + '/B'], rtol=1e-10, atol=1e-10)
+        n_run += 1
+    assert n_run >= 2
+    A, kw = workloads.shifted_goe(200, 8, 1.05)
+    B = matrix.approximation.positive_semidefinite.positive_semidefinite_matrix(A, **kw)
+    ref = orc.approximate(A, **kw)
+    np.testing.assert_allclose(B, orc.psd_matrix(A, ref, None, kw['max_diag_B']), rtol=1e-10, atol=1e-10)
+
+
+def test_batched_many_small_matrices(matrix, orc):
+    """BASELINE config 5 shape (independent 512 x 512 problems), a small batch through the batched C-ABI call."""
+    from matrix_decomposition_b200 import _native
+    ctx = _native.context()
+    batch, n = 6, 512
+    As = np.stack([workloads.shifted_goe(n, 1000 + b, 1.05)[0] for b in range(batch)])
+    kw = workloads.f2_bounds(n)
+    ps = np.stack([np.argsort(-As[b].diagonal()) for b in range(batch)]).astype(np.int64)
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
+                                       float(np.finfo(float).eps), None, kw['max_diag_B'])
+    L = np.empty((batch, n, n))
+    d, om, de = np.empty((batch, n)), np.empty((batch, n)), np.empty((batch, n))
+    cl = np.zeros((batch, n), dtype=np.uint8)
+    P = _native.ptr
+    rc = ctx.lib.mdb_approximate_batched_f64(ctx.handle, batch, n, P(As), n, P(ps), ctypes.byref(bounds), P(L), n, P(d),
+                                             P(om), P(de), P(cl), _native.HOST)
+    ctx.check(rc, 'mdb_approximate_batched_f64')
+    for b in range(batch):
+        ref = orc.approximate(As[b], **kw)
+        np.testing.assert_array_equal(ps[b], ref['p'])
+        np.testing.assert_array_equal(cl[b].astype(bool), ref['clamped'])
+        assert np.all(np.abs(L[b] - ref['L']) <= TOL * np.maximum(1.0, np.abs(ref['L'])))
+        np.testing.assert_allclose(d[b], ref['d'].astype(float), rtol=TOL)
+        np.testing.assert_allclose(om[b], ref['omega'].astype(float), rtol=TOL, atol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------
+# decompose, solve, multiply, permute
+# ---------------------------------------------------------------------------------------------
+def test_decompose_solve_multiply_against_reference_goldens(matrix):
+    z = load_golden('decompose_solve_permute.npz')
+    manifest = json.loads(str(z['manifest']))
+    A = z['spd10/A']
+    for m in manifest:
+        key = m['key']
+        if not key.startswith('spd10/'):
+            continue
+        perm = m['permutation']
+        perm = np.asarray(perm, dtype=np.int64) if isinstance(perm, list) else perm
+        A_copy = A.copy()
+        dec = matrix.decompose(A, permutation=perm, return_type=m['return_type'])
+        assert np.array_equal(A, A_copy)
+        np.testing.assert_array_equal(np.asarray(dec.p), z[key + '/p'])
+        if m['return_type'] == 'LL':
+            np.testing.assert_allclose(dec.L, z[key + '/L'], rtol=TOL, atol=1e-13)
+        elif m['return_type'] == 'LDL':
+            np.testing.assert_allclose(dec.L, z[key + '/L'], rtol=TOL, atol=1e-13)
+            np.testing.assert_allclose(dec.d, z[key + '/d'], rtol=TOL)
+        else:
+            np.testing.assert_allclose(dec.LD, z[key + '/LD'], rtol=TOL, atol=1e-13)
+        np.testing.assert_allclose(dec.solve(z['spd10/b1']), z[key + '/x1'], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(dec.solve(z['spd10/b2']), z[key + '/x2'], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(dec.matrix_right_side_multiplication(z['spd10/b2']), z[key + '/Ab2'], rtol=1e-11,
+                                   atol=1e-11)
+        assert matrix.util.is_almost_equal(dec.composed_matrix, A, atol=1e-6)          # test_decompose.py:40
+    A = workloads.lowrank_plus_diag(128, 5)
+    dec = matrix.decompose(A, permutation='decreasing_diagonal_values', return_type='LDL')
+    np.testing.assert_array_equal(np.asarray(dec.p), z['f3_128/p'])
+    np.testing.assert_allclose(dec.L, z['f3_128/L'], rtol=TOL, atol=1e-13)
+    np.testing.assert_allclose(dec.d, z['f3_128/d'], rtol=TOL)
+    np.testing.assert_allclose(dec.solve(z['f3_128/b']), z['f3_128/x'], rtol=TOL, atol=1e-12)
+    np.testing.assert_allclose(dec.solve(z['f3_128/b'][:, 0]), z['f3_128/x0'], rtol=TOL, atol=1e-12)
+
+
+def test_decompose_failure_index(matrix):
+    z = load_golden('decompose_solve_permute.npz')
+    with pytest.raises(matrix.errors.NoDecompositionPossibleWithProblematicSubdecompositionError) as ei:
+        matrix.decompose(z['indef10/A'], permutation='none')
+    assert ei.value.problematic_leading_principal_submatrix_index == int(z['indef10/bad_index'])
+    assert not matrix.is_positive_definite(z['indef10/A'])
+    assert matrix.is_positive_definite(z['spd10/A']) and matrix.is_invertible(z['spd10/A'])
+
+
+@pytest.mark.parametrize('n,nrhs', [(300, 1), (300, 2), (300, 9), (1000, 1), (1000, 130), (2500, 1), (2500, 24)])
+def test_solve_and_multiply_against_oracle(matrix, orc, n, nrhs):
+    A = workloads.lowrank_plus_diag(n, n)
+    for rt in ('LDL', 'LL'):
+        dec = matrix.decompose(A, permutation='decreasing_diagonal_values', return_type=rt)
+        rng = np.random.default_rng(nrhs)
+        b = rng.standard_normal(n) if nrhs == 1 else rng.standard_normal((n, nrhs))
+        x = dec.solve(b)
+        d = dec.d if rt == 'LDL' else None
+        x_ref = orc.solve(dec.L, d, np.asarray(dec.p), b)
+        assert x.shape == b.shape
+        assert np.max(np.abs(x - x_ref)) <= TOL * np.max(np.abs(x_ref))
+        assert np.max(np.abs(A @ x - b)) <= 1e-9 * np.max(np.abs(b))                    # test_solve.py:31
+        y = dec.matrix_right_side_multiplication(b)
+        assert np.max(np.abs(y - A @ b)) <= 1e-10 * np.max(np.abs(A @ b))               # test_multiply.py:30
+        # an uploaded factor (no resident handle) gives the same answer
+        fresh = dec.copy()
+        assert np.array_equal(fresh.solve(b), x)
+
+
+def test_solve_zero_and_integer_rhs_and_singular(matrix):
+    A = workloads.reference_fixture_spd(10)
+    dec = matrix.decompose(A, return_type='LDL')
+    assert np.all(dec.solve(np.zeros(10)) == 0)
+    x = dec.solve(np.arange(10))
+    np.testing.assert_allclose(A @ x, np.arange(10), rtol=1e-9, atol=1e-9)
+    sing = matrix.decompositions.LDL_Decomposition(np.eye(4), np.array([1.0, 0.0, 1.0, 1.0]))
+    with pytest.raises(matrix.errors.DecompositionSingularError):
+        sing.solve(np.ones(4))
+    both = dec.inverse_matrix_both_sides_multiplication(np.arange(10.0))
+    np.testing.assert_allclose(both, np.arange(10.0) @ np.linalg.solve(A, np.arange(10.0)), rtol=1e-9)
+    both = dec.matrix_both_sides_multiplication(np.arange(10.0), np.ones(10))
+    np.testing.assert_allclose(both, np.ones(10) @ A @ np.arange(10.0), rtol=1e-10)
+
+
+def test_permute_symmetric_bit_exact(matrix):
+    z = load_golden('decompose_solve_permute.npz')
+    np.testing.assert_array_equal(matrix.permute.symmetric(z['permute10/A'], z['permute10/p']), z['permute10/B'])
+    for n in (1, 33, 1024, 1500):
+        A = workloads.goe(n, n)
+        p = np.random.default_rng(n).permutation(n)
+        B = matrix.permute.symmetric(A, p)
+        assert np.array_equal(B, A[p[:, None], p[None, :]])                              # test_permute.py:60
+        assert np.array_equal(matrix.permute.symmetric(B, matrix.permute.invert_permutation_vector(p)), A)
+
+
+# ---------------------------------------------------------------------------------------------
+# the tile kernel, the device generator, and the full-size identity
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,N,K,lower,beta1,neg', [(128, 64, 16, 0, 0, 0), (1, 1, 16, 0, 1, 0), (257, 191, 128, 0, 1, 1),
+                                                   (1000, 1000, 128, 1, 1, 0), (333, 777, 48, 1, 1, 0)])
+def test_dmma_tile_kernel(M, N, K, lower, beta1, neg):
+    from matrix_decomposition_b200 import _native
+    ctx = _native.context()
+    rng = np.random.default_rng(M + N + K)
+    A, B, C0 = rng.standard_normal((M, K)), rng.standard_normal((N, K)), rng.standard_normal((M, N))
+    C = C0.copy()
+    ms = ctypes.c_double()
+    rg, cg = (64, 0) if lower else (0, 0)
+    P = _native.ptr
+    ctx.check(ctx.lib.mdb_debug_gemm_tn(ctx.handle, M, N, K, P(A), K, P(B), K, P(C), N, lower, beta1, neg, rg, cg, 1,
+                                        ctypes.byref(ms)), 'mdb_debug_gemm_tn')
+    prod = A @ B.T
+    want = (C0 if beta1 else 0) + (-prod if neg else prod)
+    if lower:
+        want = np.where((rg + np.arange(M))[:, None] > (cg + np.arange(N))[None, :], want, C0)
+    assert np.max(np.abs(C - want)) <= 1e-12 * K
+
+
+def test_device_generator_and_identity_at_scale():
+    """Family F2 generated on the device at n = 8192: symmetric, right statistics; the factorization of it
+    satisfies the oracle-free identity L D L^T = A o Omega + diag(delta) (Reimer.py:947-957) to rounding."""
+    from matrix_decomposition_b200 import _native
+    ctx = _native.context()
+    lib = ctx.lib
+    n = 8192
+    mu = 1.05 * math.sqrt(2 * n)
+    dA = ctx.malloc(n * n * 8)
+    ctx.check(lib.mdb_generate_f2(ctx.handle, n, 11, mu, ctypes.c_void_p(dA), n), 'gen')
+    A = np.empty((n, n))
+    ctx.check(lib.mdb_memcpy(ctx.handle, _native.ptr(A), ctypes.c_void_p(dA), n * n * 8, _native.HOST, _native.DEVICE), 'copy')
+    ctx.free(dA)
+    assert np.array_equal(A, A.T)
+    off = A[np.triu_indices(n, 1)]
+    assert abs(off.mean()) < 2e-3 and abs(off.var() - 0.5) < 5e-3
+    assert abs((A.diagonal() - mu).var() - 1.0) < 0.1
+    diag = np.empty(n)
+    ctx.check(lib.mdb_generate_diag_f2(ctx.handle, n, 11, mu, _native.ptr(diag)), 'diag')
+    assert np.array_equal(diag, A.diagonal())
+    p = np.argsort(-diag).astype(np.int64)
+    f = ctypes.c_void_p()
+    ctx.check(lib.mdb_factor_create(ctx.handle, n, 1, ctypes.byref(f)), 'create')
+    ctx.check(lib.mdb_factor_generate_f2(f, 11, mu, _native.ptr(p)), 'gen2')
+    kw = workloads.f2_bounds(n)
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
+                                       float(np.finfo(float).eps), None, kw['max_diag_B'])
+    ctx.check(lib.mdb_factor_run(f, ctypes.byref(bounds)), 'run')
+    res = ctypes.c_double()
+    ctx.check(lib.mdb_factor_identity_residual(f, 3, 5, ctypes.byref(res)), 'identity')
+    assert res.value <= 1e-12
+    # same matrix through the host API gives the same decisions as the device-resident path
+    d = np.empty(n)
+    cl = np.zeros(n, dtype=np.uint8)
+    ctx.check(lib.mdb_factor_get(f, _native.TYPE_LDL, None, 0, _native.HOST, _native.ptr(d), None, None, _native.ptr(cl),
+                                 None), 'get')
+    lib.mdb_factor_destroy(f)
+    import matrix_decomposition_b200 as matrix
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+    assert np.array_equal(dec.clamped, cl.astype(bool)) and np.array_equal(np.asarray(dec.d, dtype=float), d)
+    assert 0.2 * n < cl.sum() < 0.6 * n
+
+
+def test_distributed_steps_single_rank_equal_single_gpu_path(matrix, orc):
+    """The multi-GPU step functions with world = 1 (no collective) reproduce the single-GPU path bit for bit."""
+    import torch
+    from matrix_decomposition_b200 import distributed as md, _native
+    n = 700
+    A, kw = workloads.shifted_goe(n, 3, 1.05)
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+    p = np.asarray(dec.p)
+    Ap = A[p[:, None], p[None, :]]
+
+    class LocalComm:
+        def broadcast(self, tensor, src, stream):
+            class H:
+                def wait(self, s):
+                    pass
+            return H()
+
+    main, bulk = md._streams(torch.cuda.current_device())
+    steps = md.CudaSteps(n, 0, 1)
+    steps.set_matrix(Ap, main)
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
+                                       float(np.finfo(float).eps), None, kw['max_diag_B'])
+    steps.set_bounds(bounds, p, main)
+    md.factorize(n, 0, 1, steps, LocalComm(), main, bulk, lookahead=True)
+    torch.cuda.synchronize()
+    d, omega, delta, clamped = steps.finalize(main)
+    L = steps.S.cpu().numpy()[:, :n]
+    steps.close()
+    assert np.array_equal(clamped, dec.clamped)
+    assert np.array_equal(d, np.asarray(dec.d, dtype=float))
+    assert np.array_equal(L, dec.L)

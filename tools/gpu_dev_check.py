@@ -149,7 +149,7 @@ def check_decompose_failure():
 
 
 @guarded
-def timing(n, s=1.05):
+def timing(n, s=1.05, exact=False):
     """HBM-resident factorization timing with the device generator (family F2)."""
     ctx = _native.context()
     lib = ctx.lib
@@ -162,17 +162,19 @@ def timing(n, s=1.05):
     kw = workloads.f2_bounds(n, s)
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
                                        np.finfo(float).eps, None, kw['max_diag_B'])
+    if exact:
+        bounds, keep = _native.make_bounds(_native.RULE_EXACT, 0.0, None, 0.0, 0.0)
     out = {}
-    for rep in range(2):
+    for rep in range(3):
         ctx.check(lib.mdb_factor_generate_f2(f, 1234, mu, _native.ptr(p)), 'gen')
         ctx.synchronize()
-        ctx.set_profiling(rep == 1)
+        ctx.set_profiling(rep == 2)
         t = time.perf_counter()
         ctx.check(lib.mdb_factor_run(f, ctypes.byref(bounds)), 'run')
         ctx.synchronize()
         dt = time.perf_counter() - t
-        out['profiled' if rep else 'plain'] = dt
-        if rep:
+        out['profiled' if rep == 2 else 'plain'] = dt
+        if rep == 2:
             out['phases_ms'] = ctx.phase_ms()
     ctx.set_profiling(False)
     res = ctypes.c_double()
@@ -183,7 +185,7 @@ def timing(n, s=1.05):
                                  _native.ptr(clamped), None), 'get')
     lib.mdb_factor_destroy(f)
     gflops = n ** 3 / 3 / out['plain'] / 1e9
-    report(f'timing n{n}', res.value < 1e-10, seconds=out['plain'], gflops=gflops, frac_of_37_1=gflops / 37100,
+    report(f'timing n{n} exact{int(exact)} lookahead{os.environ.get("MDB200_LOOKAHEAD", "1")}', res.value < 1e-10, seconds=out['plain'], gflops=gflops, frac_of_37_1=gflops / 37100,
            phases_ms=out.get('phases_ms'), identity_residual=res.value, n_clamped=int(clamped.sum()),
            d_min=float(d.min()), d_max=float(d.max()))
 
@@ -191,6 +193,12 @@ def timing(n, s=1.05):
 def main():
     quick = '--quick' in sys.argv
     print('device context:', _native.context().device, flush=True)
+    if '--timing-only' in sys.argv:
+        sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [4096, 16384]
+        for n in sizes:
+            timing(n)
+            timing(n, exact=True)
+        return 0
     # 1. the tile kernel
     check_gemm(128, 64, 16, False, False, False)
     check_gemm(128, 64, 128, False, True, False)
