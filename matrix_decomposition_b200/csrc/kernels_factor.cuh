@@ -51,8 +51,10 @@ __device__ __forceinline__ double mdb_f2_element(int64_t i, int64_t j, uint64_t 
   const uint64_t h2 = mdb_splitmix64(h1);
   const double u1 = ((double)(h1 >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0, 1)
   const double u2 = ((double)(h2 >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-  const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-  return (i == j) ? z + mu : z * 0.70710678118654752440;
+  // explicit roundings: no FMA contraction across the select, so every kernel that evaluates an element
+  // (matrix, permuted matrix, diagonal only) produces the same bits
+  const double z = __dmul_rn(sqrt(-2.0 * log(u1)), cospi(2.0 * u2));
+  return (i == j) ? __dadd_rn(z, mu) : __dmul_rn(z, 0.70710678118654752440);
 }
 
 // out[r, c] = elem(prow[row0 + r], pcol[c]) for r < rows, c < cols (p null = identity)
@@ -105,11 +107,13 @@ __device__ __forceinline__ void mdb_cp_async_wait_all() {
 // Sblk / Ablk point at element (k0, k0) of the storage that holds S (lower part is read and written) and
 // the permuted original A (upper part is read): the same array W on one GPU, S_loc / A_loc when distributed.
 template <int NB>
-__global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
-                                                   int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
+__global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
+                                                       int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
+  // 4 threads per row: thread (j, h) = (tid >> 2, tid & 3) sums the terms m = h (mod 4) of row j's dot product;
+  // the h == 0 thread owns the row's state (alpha, beta, rowmax) and evaluates the rule when its column comes up.
   extern __shared__ double smem_d[];
-  constexpr int LDT = NB + 1;
-  double* T = smem_d;           // T[r * LDT + c] = W[k0 + r, k0 + c]
+  constexpr int LDT = NB + 4;   // 264 j words: the 4 rows of a half warp land in 4 disjoint groups of 8 banks
+  double* T = smem_d;           // T[r * LDT + c] = block element (r, c)
   double* s_u = T + NB * LDT;   // NB
   double* s_d = s_u + NB;       // NB
   __shared__ double s_dec[3];   // d, omega, drop of the current column
@@ -121,33 +125,38 @@ __global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int 
   double* Ut = F.Ut + b * F.sUt;
   double* hdr = F.hdr + b * F.sHdr;
   const int tid = threadIdx.x;
+  const int j = tid >> 2, h = tid & 3;
+  const bool owner = (h == 0) && (j < kb);
   const double mavL = F.prm.min_abs_value_L;
 
-  // whole block in flight at once (kb asynchronous 8-byte copies per thread, coalesced per row):
+  // whole block in flight at once (asynchronous 8-byte copies, coalesced per row):
   // strict lower part from S, diagonal and upper part from A
-  if (tid < kb)
-    for (int r = 0; r < kb; ++r)
-      mdb_cp_async8(&T[r * LDT + tid], (tid < r) ? &Sblk[r * ldS + tid] : &Ablk[r * ldA + tid]);
-
+  {
+    const int c = tid & (NB - 1);
+    if (c < kb)
+      for (int r = tid / NB; r < kb; r += 4)
+        mdb_cp_async8(&T[r * LDT + c], (c < r) ? &Sblk[r * ldS + c] : &Ablk[r * ldA + c]);
+  }
   double alpha_j = 0, beta_j = 0, rowmax_j = 0, gamma_j = 0, mB = F.prm.min_diag_B, MB = F.prm.max_diag_B;
-  if (tid < kb) {
-    alpha_j = F.alpha[vo + k0 + tid];
-    beta_j = F.beta[vo + k0 + tid];
-    rowmax_j = F.rowmax[vo + k0 + tid];
-    gamma_j = F.gamma[vo + k0 + tid];
-    if (F.minB) mB = F.minB[vo + k0 + tid];
-    if (F.maxB) MB = F.maxB[vo + k0 + tid];
+  if (owner) {
+    alpha_j = F.alpha[vo + k0 + j];
+    beta_j = F.beta[vo + k0 + j];
+    rowmax_j = F.rowmax[vo + k0 + j];
+    gamma_j = F.gamma[vo + k0 + j];
+    if (F.minB) mB = F.minB[vo + k0 + j];
+    if (F.maxB) MB = F.maxB[vo + k0 + j];
   }
   mdb_cp_async_wait_all();
   __syncthreads();
 
   for (int k = 0; k < kb; ++k) {
-    if (tid == k) {
+    if (owner && j == k) {
       const MdDecision dec = md_decide(F.prm, alpha_j, beta_j, gamma_j, mB, MB);
       const int64_t K = k0 + k;
+      const double delta = (dec.d - gamma_j) + (dec.omega != 0 ? dec.omega * dec.omega * alpha_j : 0.0);  // :541-545
       F.d[vo + K] = dec.d;
       F.omega[vo + K] = dec.omega;
-      F.delta[vo + K] = (dec.d - gamma_j) + (dec.omega != 0 ? dec.omega * dec.omega * alpha_j : 0.0);  // :541-545
+      F.delta[vo + K] = delta;
       F.clamped[vo + K] = (uint8_t)dec.clamped;
       if (F.prm.rule == MD_RULE_EXACT && dec.clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
       const double drop = (dec.omega == 0 || dec.omega * rowmax_j < mavL) ? 1.0 : 0.0;
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int 
       hdr[k] = dec.d;
       hdr[NB + k] = dec.omega;
       hdr[2 * NB + k] = drop;
-      hdr[3 * NB + k] = F.delta[vo + K];
+      hdr[3 * NB + k] = delta;
       hdr[4 * NB + k] = (double)dec.clamped;
     }
     __syncthreads();
@@ -172,39 +181,48 @@ __global__ void __launch_bounds__(NB) k_diag_block(FactorDev F, int64_t k0, int 
       Ut[tid * NB + k] = u;
     }
     __syncthreads();
-    if (tid > k && tid < kb) {
-      const double a = T[k * LDT + tid];
-      double r = a;
-      if (!drop) r = (1.0 - wk) * a + wk * T[tid * LDT + k];
-      // four interleaved partial sums: breaks the DFMA dependency chain (4x shorter critical path)
-      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      const double* Trow = T + tid * LDT;
-      int m = 0;
-      for (; m + 4 <= k; m += 4) {
+    const bool active = (j > k && j < kb);
+    const double* Trow = T + j * LDT;
+    double acc = 0;
+    if (active) {
+      double a0 = 0, a1 = 0;
+      int m = h;
+      for (; m + 4 < k; m += 8) {
         a0 += Trow[m] * s_u[m];
-        a1 += Trow[m + 1] * s_u[m + 1];
-        a2 += Trow[m + 2] * s_u[m + 2];
-        a3 += Trow[m + 3] * s_u[m + 3];
+        a1 += Trow[m + 4] * s_u[m + 4];
       }
-      for (; m < k; ++m) a0 += Trow[m] * s_u[m];
-      const double acc = (a0 + a1) + (a2 + a3);
-      const double x = (dk != 0) ? (r - acc) / dk : 0.0;
-      T[tid * LDT + k] = x;
-      alpha_j += x * x * dk;
-      beta_j += 2.0 * a * a;
-      rowmax_j = fmax(rowmax_j, fabs(x));
+      if (m < k) a0 += Trow[m] * s_u[m];
+      acc = a0 + a1;
+    }
+    // every lane takes part in the shuffles (rows of one warp become active at different k)
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (active) {
+      if (h == 0) {
+        const double a = T[k * LDT + j];
+        double r = a;
+        if (!drop) r = (1.0 - wk) * a + wk * Trow[k];
+        const double x = (dk != 0) ? (r - acc) / dk : 0.0;
+        T[j * LDT + k] = x;
+        alpha_j += x * x * dk;
+        beta_j += 2.0 * a * a;
+        rowmax_j = fmax(rowmax_j, fabs(x));
+      }
     }
     // no barrier needed here: the next iteration's first barrier orders these writes before any read
   }
   __syncthreads();
-  if (tid < kb) {
-    F.alpha[vo + k0 + tid] = alpha_j;
-    F.beta[vo + k0 + tid] = beta_j;
-    F.rowmax[vo + k0 + tid] = rowmax_j;
+  if (owner) {
+    F.alpha[vo + k0 + j] = alpha_j;
+    F.beta[vo + k0 + j] = beta_j;
+    F.rowmax[vo + k0 + j] = rowmax_j;
   }
-  // strict lower part of the block back to W (unscaled rows Lu)
-  for (int r = 1; r < kb; ++r)
-    for (int c = tid; c < r; c += NB) Sblk[r * ldS + c] = T[r * LDT + c];
+  // strict lower part of the block back to S (unscaled rows Lu)
+  {
+    const int c = tid & (NB - 1);
+    for (int r = tid / NB; r < kb; r += 4)
+      if (c < r) Sblk[r * ldS + c] = T[r * LDT + c];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -228,6 +246,8 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
   double* s_d = xs + NB * LDX;  // NB
   double* s_w = s_d + NB;       // NB
   double* s_drop = s_w + NB;    // NB
+  double* us = s_drop + NB;     // 2 x (NB x 8): double-buffered 8-column slices of U (L1 is too small to hold U
+                                // next to the X tiles, so U is staged through shared memory with cp.async)
 
   const int64_t b = blockIdx.z;
   const int64_t vo = b * F.sVec;
@@ -243,11 +263,23 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
   const int64_t j = jbase + tid;
   const bool valid = j < jend;
 
+  // slice sb = columns [8 sb, 8 sb + 8) of U, rows m < 8 sb + 8 (rows m >= column hold stale data and are not used)
+  auto load_slice = [&](int sb, int buf) {
+    const int c0 = sb * 8;
+    const int chunks = (c0 + 8) * 4;  // 16-byte chunks
+    for (int idx = tid; idx < chunks; idx += R) {
+      const int m = idx >> 2, q = idx & 3;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(us + buf * (NB * 8) + m * 8 + q * 2);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ut + m * NB + c0 + q * 2));
+    }
+  };
+
   for (int c = tid; c < NB; c += R) {
     s_d[c] = hdr[c];
     s_w[c] = hdr[NB + c];
     s_drop[c] = hdr[2 * NB + c];
   }
+  load_slice(0, 0);
   // S0 tile, transposed into shared memory: coalesced row segments, all rows in flight at once
   for (int rr = 0; rr < R; ++rr) {
     const int64_t jj = jbase + rr;
@@ -279,15 +311,22 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
         beta_j += 2.0 * a * a;
       }
     }
-    // forward substitution, 8 columns at a time
-    for (int c0 = 0; c0 < NB; c0 += 8) {
+  }
+  // forward substitution, 8 columns at a time; the next U slice streams in while this one is used
+  for (int sb = 0; sb < NB / 8; ++sb) {
+    const int c0 = sb * 8;
+    if (sb + 1 < NB / 8) load_slice(sb + 1, (sb + 1) & 1);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (valid) {
+      const double* U = us + (sb & 1) * (NB * 8);
       double acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = xs[(c0 + i) * LDX + tid];
+#pragma unroll 4
       for (int m = 0; m < c0; ++m) {
         const double xm = xs[m * LDX + tid];
-        const double2* up = reinterpret_cast<const double2*>(Ut + m * NB + c0);
-        const double2 u0 = __ldg(up), u1 = __ldg(up + 1), u2 = __ldg(up + 2), u3 = __ldg(up + 3);
+        const double2* up = reinterpret_cast<const double2*>(U + m * 8);
+        const double2 u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
         acc[0] -= xm * u0.x; acc[1] -= xm * u0.y; acc[2] -= xm * u1.x; acc[3] -= xm * u1.y;
         acc[4] -= xm * u2.x; acc[5] -= xm * u2.y; acc[6] -= xm * u3.x; acc[7] -= xm * u3.y;
       }
@@ -300,14 +339,17 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
         alpha_j += x * x * dk;
         rowmax_j = fmax(rowmax_j, fabs(x));
 #pragma unroll
-        for (int i2 = i + 1; i2 < 8; ++i2) acc[i2] -= x * __ldg(Ut + c * NB + c0 + i2);
+        for (int i2 = i + 1; i2 < 8; ++i2) acc[i2] -= x * U[c * 8 + i2];
       }
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+  }
+  if (valid) {
     F.alpha[vo + j] = alpha_j;
     F.beta[vo + j] = beta_j;
     F.rowmax[vo + j] = rowmax_j;
   }
-  __syncthreads();
   // write back (coalesced rows): Lu into W, X and Y = -X d into the compact panel buffers
   for (int rr = 0; rr < R; ++rr) {
     const int64_t jj = jbase + rr;

@@ -375,8 +375,8 @@ static FactorDev make_dev(mdb_factor* f) {
 static int configure_kernels(mdb_ctx* ctx) {
   static bool done = false;
   if (done) return MDB_OK;
-  const int diag_smem = (NB * (NB + 1) + 2 * NB) * 8;
-  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB) * 8;
+  const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
+  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB + 2 * NB * 8) * 8;
   const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel<NB, PANEL_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
@@ -451,8 +451,8 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
     MDB_CUDA(ctx, cudaMemsetAsync(f->alpha, 0, (size_t)3 * bn * 8, ctx->stream));  // alpha, beta, rowmax contiguous
     MDB_CUDA(ctx, cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream));
   }
-  const int diag_smem = (NB * (NB + 1) + 2 * NB) * 8;
-  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB) * 8;
+  const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
+  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB + 2 * NB * 8) * 8;
   // Lookahead-1 (default): the trailing update of panel k is split into (a) the next column block, done on
   // the main stream, and (b) the rest, done on the side stream while the main stream already factors
   // diagonal block + panel k+1.  Panel operands are double buffered.  With profiling on, everything runs
@@ -468,7 +468,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
     double* PY = buf ? f->PY2 : f->PY;
     {
       PhaseTimer t(ctx, 0);
-      k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), NB, diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
+      k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), 4 * NB, diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
                                                                                 f->W + k0 * f->ld + k0, f->ld);
       MDB_LAUNCHED(ctx);
     }

