@@ -99,6 +99,16 @@ int mdb_approximate_f64(mdb_ctx *ctx, int64_t n, const double *A, int64_t lda, c
                         const mdb_bounds *bounds, int out_type, double *L, int64_t ldl, double *d, double *omega,
                         double *delta, uint8_t *clamped, int loc, mdb_factor **factor_out);
 
+/* Dynamic pivoting, Reimer.py:497-523: method 1 = 'minimal_difference' (key (f, -d, omega, j)), 2 =
+ * 'maximal_stability' (key (-d, f, omega, j); the reference's default for permutation=None, Reimer.py:415-416).
+ * Every step evaluates the rule for all remaining rows, so this is an unblocked right-looking factorization
+ * (n^2/2 rule evaluations, rank-1 updates), meant for n up to ~10^4.  p_out (n, host) receives the permutation
+ * chosen; everything else as mdb_approximate_f64. */
+int mdb_approximate_dynamic_f64(mdb_ctx *ctx, int64_t n, const double *A, int64_t lda, int method,
+                                const mdb_bounds *bounds, int out_type, double *L, int64_t ldl, int64_t *p_out,
+                                double *d, double *omega, double *delta, uint8_t *clamped, int loc,
+                                mdb_factor **factor_out);
+
 /* Replaces dense.calculate._decompose (dense/calculate.py:15-126): permute + potrf + as_type.
  * info: 0 or failing leading minor (LAPACK convention, dense/calculate.py:115-119); the status is
  * MDB_ERR_NOT_POSITIVE_DEFINITE when info > 0 (L then holds the partial factor). */

@@ -70,6 +70,8 @@ SIGNATURES = {
     'mdb_permute_sym_f64': (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _int]),
     'mdb_approximate_f64': (_int, [_vp, _i64, _vp, _i64, _vp, ctypes.POINTER(Bounds), _int, _vp, _i64, _vp, _vp, _vp,
                                    _vp, _int, _pp]),
+    'mdb_approximate_dynamic_f64': (_int, [_vp, _i64, _vp, _i64, _int, ctypes.POINTER(Bounds), _int, _vp, _i64, _vp, _vp, _vp,
+                                           _vp, _vp, _int, _pp]),
     'mdb_decompose_f64': (_int, [_vp, _i64, _vp, _i64, _vp, _int, _vp, _i64, _vp, _vp, _int, _pp]),
     'mdb_approximate_batched_f64': (_int, [_vp, _i64, _i64, _vp, _i64, _vp, ctypes.POINTER(Bounds), _vp, _i64, _vp,
                                            _vp, _vp, _vp, _int]),

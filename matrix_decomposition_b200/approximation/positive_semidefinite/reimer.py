@@ -122,6 +122,7 @@ def _prepare(A, min_diag_B, max_diag_B, min_diag_D, max_diag_D, min_abs_value_D,
                                           lower_bound=0, upper_bound=1)
     min_abs_value_L = max(min_abs_value_L, L_eps)
 
+    dynamic = 0
     if permutation is None:  # R.py:415-416
         permutation = MAXIMAL_STABILITY_PERMUTATION_METHOD
     if isinstance(permutation, str):
@@ -137,11 +138,11 @@ def _prepare(A, min_diag_B, max_diag_B, min_diag_D, max_diag_D, min_abs_value_D,
                     and min_diag_D is not None and min_diag_D <= 0):  # R.py:437-441
                 raise ValueError(f'The permutation method {MINIMAL_DIFFERENCE_PERMUTATION_METHOD} is '
                                  f'only available if min_diag_D is greater zero.')
-            raise NotImplementedError(
-                f'The dynamic pivoting method "{permutation_method}" (R.py:497-523) is not built yet in '
-                f'matrix_decomposition_b200; pass one of {constants.UNIVERSAL_PERMUTATION_METHODS} or a '
-                f'permutation vector (see DESIGN.md, "next").')
-        p = permute.permutation_vector(A, permutation_method=permutation_method)
+            # dynamic pivoting starts from the identity (R.py:443) and is resolved on the device
+            p = None
+            dynamic = 1 if permutation_method == MINIMAL_DIFFERENCE_PERMUTATION_METHOD else 2
+        else:
+            p = permute.permutation_vector(A, permutation_method=permutation_method)
     else:
         p = np.asanyarray(permutation)
         if p.ndim != 1 or p.shape[0] != n:
@@ -149,13 +150,13 @@ def _prepare(A, min_diag_B, max_diag_B, min_diag_D, max_diag_D, min_abs_value_D,
                                f'A. Its shape is {p.shape} and the shape of A is {A.shape}.')
             logger.error(error)
             raise error
-    return A, n, p, min_diag_B, max_diag_B, min_diag_D, max_diag_D, float(min_abs_value_D), float(min_abs_value_L)
+    return (A, n, p, dynamic, min_diag_B, max_diag_B, min_diag_D, max_diag_D, float(min_abs_value_D),
+            float(min_abs_value_L))
 
 
 def _run(A, out_type_str, keep_factor, **kw):
-    A, n, p, min_diag_B, max_diag_B, min_diag_D, max_diag_D, mavD, mavL = _prepare(A, **kw)
+    A, n, p, dynamic, min_diag_B, max_diag_B, min_diag_D, max_diag_D, mavD, mavL = _prepare(A, **kw)
     A64 = np.ascontiguousarray(A, dtype=np.float64)
-    p64 = np.ascontiguousarray(p, dtype=np.int64)
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, min_diag_D, max_diag_D, mavD, mavL, min_diag_B, max_diag_B)
     Lout = np.empty((n, n), dtype=np.float64)
     d = np.empty(n, dtype=np.float64)
@@ -164,11 +165,21 @@ def _run(A, out_type_str, keep_factor, **kw):
     clamped = np.zeros(n, dtype=np.uint8)
     handle = ctypes.c_void_p()
     ctx = _native.context()
-    rc = ctx.lib.mdb_approximate_f64(ctx.handle, n, _native.ptr(A64), n, _native.ptr(p64), ctypes.byref(bounds),
-                                     _native.TYPE_CODES[out_type_str], _native.ptr(Lout), n, _native.ptr(d),
-                                     _native.ptr(omega), _native.ptr(delta), _native.ptr(clamped), _native.HOST,
-                                     ctypes.byref(handle) if keep_factor else None)
-    ctx.check(rc, 'mdb_approximate_f64')
+    P = _native.ptr
+    if dynamic:
+        p = np.empty(n, dtype=np.int64)
+        rc = ctx.lib.mdb_approximate_dynamic_f64(ctx.handle, n, P(A64), n, dynamic, ctypes.byref(bounds),
+                                                 _native.TYPE_CODES[out_type_str], P(Lout), n, P(p), P(d), P(omega),
+                                                 P(delta), P(clamped), _native.HOST,
+                                                 ctypes.byref(handle) if keep_factor else None)
+        ctx.check(rc, 'mdb_approximate_dynamic_f64')
+        p = p.astype(np.min_scalar_type(n)) if n > 0 else p   # dtype of the reference's arange (R.py:443)
+    else:
+        p64 = np.ascontiguousarray(p, dtype=np.int64)
+        rc = ctx.lib.mdb_approximate_f64(ctx.handle, n, P(A64), n, P(p64), ctypes.byref(bounds),
+                                         _native.TYPE_CODES[out_type_str], P(Lout), n, P(d), P(omega), P(delta),
+                                         P(clamped), _native.HOST, ctypes.byref(handle) if keep_factor else None)
+        ctx.check(rc, 'mdb_approximate_f64')
     del keep
     factor = _native.Factor(ctx, handle) if keep_factor else None
     return Lout, d, p, omega, delta, clamped.astype(bool), factor
@@ -186,8 +197,9 @@ def decomposition(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag
     holds the boolean mask (by position) of the columns whose (d, omega) left the unclamped branch of
     R.py:68.  `A` is never modified (`overwrite_A` only documents permission).
 
-    Deviation: the dynamic pivoting methods 'maximal_stability' (the reference's default for
-    permutation=None) and 'minimal_difference' are not built yet and raise NotImplementedError.
+    The dynamic pivoting methods 'maximal_stability' (the default for permutation=None, R.py:415-416) and
+    'minimal_difference' run as an unblocked right-looking factorization with a device-wide arg-min per
+    column (mdb_approximate_dynamic_f64); they need n^2/2 rule evaluations and are meant for n up to ~10^4.
     """
     supported_return_types = constants.DECOMPOSITION_TYPES
     if return_type is not None and return_type not in supported_return_types:

@@ -29,11 +29,13 @@ struct GemmArgs {
   int64_t m_tile0;       // first M tile (units of 128) this launch covers (grid.y bands start here)
   int64_t n_tiles;       // number of N tiles (units of 64) this launch covers, starting at n_tile0
   int64_t n_tile0;
-  // 1-D block-cyclic columns (multi GPU): C holds the local column slab, local N tile nt belongs to global
-  // column ((nt / 2) * cyc_G + cyc_r) * 128 + (nt % 2) * 64 and its B rows start at that column - b_glob0.
-  // cyc_G <= 1: plain mapping (global column = col_glob0 + local column, B row = local column).
+  // Column mapping.  Local N tile nt (C columns nt*64 ...) has the global column
+  //   cyc_G <= 1 : col_glob0 + nt*64                                  (one GPU)
+  //   cyc_G  > 1 : ((nt / 2) * cyc_G + cyc_r) * 128 + (nt % 2) * 64   (1-D block-cyclic column slab)
+  // and its B rows start at (global column - b_glob0); b_rows = number of valid B rows (0: N).
   int cyc_G, cyc_r;
   int64_t b_glob0;
+  int64_t b_rows;
 };
 
 namespace gemm {
@@ -76,8 +78,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) k_gemm_tn(GemmArgs g) {
   // global column of the tile's first column, and the B row that belongs to it
   const int64_t gj0 = (g.cyc_G > 1) ? ((nt / (MDB_NB / BN)) * g.cyc_G + g.cyc_r) * MDB_NB + (nt % (MDB_NB / BN)) * BN
                                     : g.col_glob0 + j0;
-  const int64_t brow0 = (g.cyc_G > 1) ? gj0 - g.b_glob0 : j0;
-  const int64_t Nb = (g.cyc_G > 1) ? g.M : g.N;  // number of valid B rows (cyclic: the panel has M rows)
+  const int64_t brow0 = gj0 - g.b_glob0;
+  const int64_t Nb = g.b_rows > 0 ? g.b_rows : g.N;  // number of valid B rows
   if (LOWER && (g.row_glob0 + i0 + BM - 1) <= gj0) return;  // tile entirely on/above the diagonal
   if (brow0 < 0) return;                                     // column block already factored
 

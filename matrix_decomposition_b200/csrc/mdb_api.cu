@@ -8,7 +8,9 @@
 
 #include "kernels_factor.cuh"
 #include "kernels_gemm.cuh"
+#include "kernels_gemm_tma.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_dynamic.cuh"
 
 #define NB MDB_NB
 #define PANEL_R 64
@@ -63,6 +65,8 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
     }
     const char* la = getenv("MDB200_LOOKAHEAD");
     ctx->lookahead = !(la && la[0] == '0');
+    const char* tm = getenv("MDB200_TMA");
+    ctx->use_tma = !(tm && tm[0] == '0');
   }
   ctx->stream = ctx->own_stream;
   MDB_CUDA(ctx, cudaEventCreate(&ctx->ev[0]));
@@ -487,10 +491,18 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       g.B = PY; g.ldb = NB; g.sB = F.sPanel;
       g.C = f->W + k1 * f->ld + k1; g.ldc = f->ld; g.sC = F.sW;
       g.M = rows; g.N = rows; g.K = NB;
-      g.row_glob0 = k1; g.col_glob0 = k1;
+      g.row_glob0 = k1; g.col_glob0 = k1; g.b_glob0 = k1; g.b_rows = rows;
+      // TMA-fed kernel when it applies (one matrix), else the cp.async kernel
+      auto trailing = [&](const GemmArgs& ga) -> int {
+        if (batch == 1) {
+          const int r = launch_gemm_tn_tma(ctx, ga, rows, rows);
+          if (r != -1) return r;
+        }
+        return launch_gemm_tn<true, true, false>(ctx, ga, batch);
+      };
       if (!lookahead) {
         PhaseTimer t(ctx, 2);
-        rc = launch_gemm_tn<true, true, false>(ctx, g, batch);
+        rc = trailing(g);
         if (rc) return rc;
       } else {
         const int64_t nt_block = NB / gemm::BN;  // N tiles of one column block
@@ -498,7 +510,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
         if (kidx >= 1) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(kidx - 1) & 1], 0));
         GemmArgs ga = g;
         ga.n_tile0 = 0; ga.n_tiles = nt_block;
-        rc = launch_gemm_tn<true, true, false>(ctx, ga, batch);  // (a) next column block, main stream
+        rc = trailing(ga);  // (a) next column block, main stream
         if (rc) return rc;
         MDB_CUDA(ctx, cudaEventRecord(ctx->ev_panel[kidx & 1], main_s));
         if (rows > NB) {
@@ -507,7 +519,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
           gb.n_tile0 = nt_block; gb.n_tiles = 0; gb.m_tile0 = 1;
           cudaStream_t saved = ctx->stream;
           ctx->stream = side_s;
-          rc = launch_gemm_tn<true, true, false>(ctx, gb, batch);  // (b) the rest, side stream
+          rc = trailing(gb);  // (b) the rest, side stream
           ctx->stream = saved;
           if (rc) return rc;
         }
@@ -609,6 +621,90 @@ extern "C" int mdb_approximate_f64(mdb_ctx* ctx, int64_t n, const double* A, int
   if (!ctx || !bounds) return MDB_ERR_INVALID;
   MDB_CHECK(ctx, bounds->rule == MDB_RULE_REIMER, "mdb_approximate_f64: bounds->rule must be MDB_RULE_REIMER");
   return one_shot(ctx, 1, n, A, lda, p, bounds, out_type, L, ldl, d, omega, delta, clamped, nullptr, loc, factor_out);
+}
+
+extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda, int method,
+                                           const mdb_bounds* bnd, int out_type, double* L, int64_t ldl, int64_t* p_out,
+                                           double* d, double* omega, double* delta, uint8_t* clamped, int loc,
+                                           mdb_factor** factor_out) {
+  if (!ctx || !bnd) return MDB_ERR_INVALID;
+  if (factor_out) *factor_out = nullptr;
+  MDB_CHECK(ctx, method == 1 || method == 2, "mdb_approximate_dynamic_f64: method must be 1 or 2");
+  MDB_CHECK(ctx, bnd->rule == MDB_RULE_REIMER, "mdb_approximate_dynamic_f64: bounds->rule must be MDB_RULE_REIMER");
+  MDB_CHECK(ctx, out_type == MDB_TYPE_LDL || out_type == MDB_TYPE_LDL_COMPRESSED || out_type == MDB_TYPE_LL,
+            "unknown decomposition type");
+  mdb_factor* f = nullptr;
+  int rc = mdb_factor_create(ctx, n, 1, &f);
+  if (rc) return rc;
+  rc = mdb_factor_set_matrix(f, A, lda, nullptr, loc);
+  double *minB = nullptr, *maxB = nullptr, *xcol = nullptr, *ycol = nullptr;
+  DynCand* cand = nullptr;
+  DynSel* sel = nullptr;
+  std::vector<int64_t> pfin((size_t)std::max<int64_t>(n, 1));
+  if (!rc && n > 0) {
+    // per-index B bounds in position order (the start permutation is the identity, Reimer.py:443)
+    std::vector<double> mb((size_t)n), Mb((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+      mb[(size_t)i] = bnd->min_diag_B ? bnd->min_diag_B[i * bnd->stride_B] : -INFINITY;
+      Mb[(size_t)i] = bnd->max_diag_B ? bnd->max_diag_B[i * bnd->stride_B] : INFINITY;
+    }
+    const int nb_max = (int)((n + 255) / 256);
+    cudaError_t e = cudaMalloc((void**)&minB, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&maxB, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&xcol, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ycol, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&cand, (size_t)nb_max * sizeof(DynCand));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sel, sizeof(DynSel));
+    if (e == cudaSuccess && !f->p_dev) e = cudaMalloc((void**)&f->p_dev, (size_t)n * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(minB, mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(maxB, Mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(f->alpha, 0, (size_t)3 * n * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = mdb_fail(ctx, MDB_ERR_CUDA, "mdb_approximate_dynamic_f64: %s", cudaGetErrorString(e));
+    if (!rc) {
+      k_fill_iota<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->p_dev);
+      FactorDev F = make_dev(f);
+      F.minB = minB; F.maxB = maxB;
+      F.prm.rule = MD_RULE_REIMER;
+      F.prm.min_diag_D = bnd->min_diag_D; F.prm.max_diag_D = bnd->max_diag_D;
+      F.prm.min_abs_value_D = bnd->min_abs_value_D; F.prm.min_abs_value_L = bnd->min_abs_value_L;
+      F.prm.min_diag_B = -INFINITY; F.prm.max_diag_B = INFINITY;
+      f->rule = MDB_RULE_REIMER;
+      f->mavL = bnd->min_abs_value_L;
+      for (int64_t i = 0; i < n; ++i) {
+        const int64_t rem = n - i;
+        const int nblk = (int)((rem + 255) / 256);
+        k_dyn_select1<<<nblk, 256, 0, ctx->stream>>>(F, method, i, cand);
+        k_dyn_select2<<<1, 256, 0, ctx->stream>>>(F, method, i, nblk, cand, minB, maxB, f->p_dev, sel);
+        k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, sel);
+        ctx->launches += 3;
+        if (rem > 1) {
+          k_dyn_column<<<(unsigned)((rem - 1 + 255) / 256), 256, 0, ctx->stream>>>(F, i, sel, xcol, ycol);
+          const unsigned t32 = (unsigned)((rem - 1 + 31) / 32);
+          k_dyn_rank1<<<dim3(t32, t32), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, xcol, ycol);
+          ctx->launches += 2;
+        }
+      }
+      cudaError_t e2 = cudaGetLastError();
+      if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(pfin.data(), f->p_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+      if (e2 != cudaSuccess) rc = mdb_fail(ctx, MDB_ERR_CUDA, "mdb_approximate_dynamic_f64: %s", cudaGetErrorString(e2));
+      f->p_host.assign(pfin.begin(), pfin.begin() + n);
+      f->state = ST_FACTORED;
+    }
+  } else if (!rc) {
+    f->state = ST_FACTORED;
+  }
+  cudaFree(minB); cudaFree(maxB); cudaFree(xcol); cudaFree(ycol); cudaFree(cand); cudaFree(sel);
+  if (!rc) rc = mdb_factor_get(f, out_type, L, ldl, loc, d, omega, delta, clamped, nullptr);
+  if (!rc && p_out)
+    for (int64_t i = 0; i < n; ++i) p_out[i] = pfin[(size_t)i];
+  if (rc || !factor_out) {
+    mdb_factor_destroy(f);
+    f = nullptr;
+  }
+  if (factor_out) *factor_out = f;
+  return rc;
 }
 
 extern "C" int mdb_approximate_batched_f64(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int64_t lda,
@@ -997,7 +1093,10 @@ extern "C" int mdb_debug_gemm_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
   if (reps < 1) reps = 1;
   cudaEventRecord(ctx->ev[0], ctx->stream);
   for (int r = 0; r < reps && !rc; ++r) {
-    if (lower) rc = launch_gemm_tn<true, true, false>(ctx, g, 1);
+    if (lower) {
+      rc = launch_gemm_tn_tma(ctx, g, M, N);
+      if (rc == -1) rc = launch_gemm_tn<true, true, false>(ctx, g, 1);
+    }
     else if (beta1 && neg) rc = launch_gemm_tn<false, true, true>(ctx, g, 1);
     else if (beta1) rc = launch_gemm_tn<false, true, false>(ctx, g, 1);
     else rc = launch_gemm_tn<false, false, false>(ctx, g, 1);

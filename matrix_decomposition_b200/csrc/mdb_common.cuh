@@ -20,6 +20,7 @@ struct mdb_ctx {
   cudaStream_t side_stream;  // low priority: the bulk of the trailing update under lookahead
   cudaEvent_t ev_panel[2], ev_upd[2];
   int lookahead;
+  int use_tma;  // MDB200_TMA=0 falls back to the cp.async tile kernel
   char err[512];
   int64_t launches;
   int profiling;

@@ -289,15 +289,15 @@ extern "C" int mdb_dist_apply_panel(mdb_dist* s, int64_t k, int slot, int64_t on
   g.A = PX; g.lda = NB; g.B = PY; g.ldb = NB;
   g.C = s->S + k1 * s->ld; g.ldc = s->ld;
   g.M = rows; g.N = s->nblk_loc * NB; g.K = NB;
-  g.row_glob0 = k1; g.col_glob0 = 0; g.b_glob0 = k1;
-  g.cyc_G = s->world; g.cyc_r = s->rank;
-  // one rank: the plain mapping (global column = local column); B is indexed by global column, so shift it
-  if (s->world == 1) { g.cyc_G = 1; g.b_glob0 = 0; g.B = PY - k1 * NB; }
+  g.row_glob0 = k1; g.col_glob0 = 0; g.b_glob0 = k1; g.b_rows = rows;
+  g.cyc_G = s->world; g.cyc_r = s->rank;  // one rank: plain mapping, global column = local column
   auto launch = [&](int64_t b0, int64_t b1) -> int {  // local blocks [b0, b1)
     if (b1 <= b0) return MDB_OK;
     GemmArgs gg = g;
     gg.n_tile0 = b0 * tpb;
     gg.n_tiles = (b1 - b0) * tpb;
+    const int r = launch_gemm_tn_tma(ctx, gg, rows, rows);
+    if (r != -1) return r;
     return launch_gemm_tn<true, true, false>(ctx, gg, 1);
   };
   int rc = MDB_OK;
