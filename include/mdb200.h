@@ -71,6 +71,11 @@ int64_t mdb_launch_count(const mdb_ctx *ctx);
 /* Per-phase device time of the last mdb_factor_run with profiling on: ms[0..3] = diag, panel, trailing, other */
 int mdb_ctx_set_profiling(mdb_ctx *ctx, int on);
 int mdb_ctx_get_phase_ms(const mdb_ctx *ctx, double ms[4]);
+/* Blocking of the factorization (tuning / tests; the defaults are chosen for B200).  Panels are 128 columns; the
+ * trailing update is applied per outer block of `fixed` = 1, 2, 4 or 8 panels, or, with fixed = 0, of 2 / 4 / 8
+ * panels while at least t2 / t4 / t8 rows remain (else 1).  ms[2] above then is the bulk (per outer block) update,
+ * ms[3] the inner (per panel, within the outer block) update.  Environment: MDB200_AGG, MDB200_AGG_THRESH. */
+int mdb_ctx_set_blocking(mdb_ctx *ctx, int fixed, int64_t t2, int64_t t4, int64_t t8);
 
 /* ---- device memory (so that a host language without CUDA bindings can stage buffers) ---- */
 int mdb_malloc(mdb_ctx *ctx, size_t bytes, void **dptr);

@@ -61,6 +61,7 @@ SIGNATURES = {
     'mdb_launch_count': (_i64, [_vp]),
     'mdb_ctx_set_profiling': (_int, [_vp, _int]),
     'mdb_ctx_get_phase_ms': (_int, [_vp, _vp]),
+    'mdb_ctx_set_blocking': (_int, [_vp, _int, _i64, _i64, _i64]),
     'mdb_malloc': (_int, [_vp, _sz, _pp]),
     'mdb_free': (_int, [_vp, _vp]),
     'mdb_malloc_host': (_int, [_vp, _sz, _pp]),
@@ -169,6 +170,10 @@ class Context:
 
     def set_profiling(self, on):
         self.check(self.lib.mdb_ctx_set_profiling(self.handle, int(bool(on))), 'mdb_ctx_set_profiling')
+
+    def set_blocking(self, fixed=0, t2=8192, t4=16384, t8=32768):
+        """Outer-block width of the factorization (see mdb_ctx_set_blocking in include/mdb200.h)."""
+        self.check(self.lib.mdb_ctx_set_blocking(self.handle, int(fixed), int(t2), int(t4), int(t8)), 'mdb_ctx_set_blocking')
 
     def phase_ms(self):
         out = (ctypes.c_double * 4)()

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
 // substitution X (D Ltilde^T) = R with the mix R = (1 - omega) A + omega S0 applied on load; one
 // thread per row, 8 columns at a time, U broadcast through L1, the row's X staged in shared memory.
 // Epilogue accumulates alpha / beta / rowmax in column order (like Reimer.py:604,684) and writes
-//   W[j, k0:k1] = X (unscaled Lu),  PX[j - k1, :] = X,  PY[j - k1, :] = -X d   (trailing-update operands).
+//   W[j, k0:k1] = X (unscaled Lu),  PX[j - p_row0, :] = X,  PY[j - p_row0, :] = -X d   (trailing-update operands).
 // A[j, k] for the mix comes from (Asrc, a_rs, a_cs): element (j, k) at Asrc[j * a_rs + k * a_cs]
 // (single GPU: the upper triangle of W, a_rs = 1, a_cs = ldw; multi GPU: the local copy of A).
 // ------------------------------------------------------------------------------------------------
@@ -238,8 +238,11 @@ template <int NB, int R>
 __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t row_begin, int64_t n_rows,
                                              const double* __restrict__ Asrc, int64_t a_rs, int64_t a_cs,
                                              double* __restrict__ Wcol, int64_t w_ld,
-                                             double* __restrict__ PX, double* __restrict__ PY, int64_t p_row0) {
+                                             double* __restrict__ PX, double* __restrict__ PY, int64_t p_row0,
+                                             int64_t p_ld) {
   // Wcol: pointer such that S0[j, k0 + c] lives at Wcol[j * w_ld + c]  (j = global row)
+  // PX / PY: row (j - p_row0) of the operand buffers, leading dimension p_ld (>= NB: the buffers hold the
+  // panels of one outer block side by side so that the bulk trailing update contracts over all of them)
   extern __shared__ double smem_d[];
   constexpr int LDX = R + 1;
   double* xs = smem_d;          // xs[c * LDX + r]
@@ -358,8 +361,8 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
       for (int c = tid; c < NB; c += R) {
         const double x = xs[c * LDX + rr];
         Wcol[jj * w_ld + c] = x;
-        PX[pr * NB + c] = x;
-        PY[pr * NB + c] = -x * s_d[c];
+        PX[pr * p_ld + c] = x;
+        PY[pr * p_ld + c] = -x * s_d[c];
       }
     }
   }

@@ -28,9 +28,10 @@ struct mdb_factor {
   int64_t* p_dev;    // batch x n (null = identity)
   int* info;         // batch
   double *Ut, *hdr;  // batch x NB*NB, batch x 3*NB
-  double *PX, *PY;   // batch x panel_rows x NB
+  double *PX, *PY;   // batch x panel_rows x (agg * NB): operands of one outer block
   double *PX2, *PY2; // second pair for lookahead
   int64_t panel_rows;
+  int agg;           // panels per outer block (1 for batched small matrices)
   int state, out_type, rule;
   double mavL;
   bool prepared;
@@ -67,6 +68,19 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
     ctx->lookahead = !(la && la[0] == '0');
     const char* tm = getenv("MDB200_TMA");
     ctx->use_tma = !(tm && tm[0] == '0');
+    // outer block width of the factorization: MDB200_AGG = 1, 2, 4, 8 panels (fixed) or unset = by remaining size,
+    // thresholds MDB200_AGG_THRESH = "t2,t4,t8" (remaining rows from which 2, 4, 8 panels are aggregated)
+    const char* ag = getenv("MDB200_AGG");
+    ctx->agg_fixed = ag ? atoi(ag) : 0;
+    if (ctx->agg_fixed != 1 && ctx->agg_fixed != 2 && ctx->agg_fixed != 4 && ctx->agg_fixed != 8) ctx->agg_fixed = 0;
+    ctx->agg_thresh[0] = 8192; ctx->agg_thresh[1] = 16384; ctx->agg_thresh[2] = 32768;
+    const char* at = getenv("MDB200_AGG_THRESH");
+    if (at) {
+      long long a = 0, b = 0, c = 0;
+      if (sscanf(at, "%lld,%lld,%lld", &a, &b, &c) == 3 && a > 0 && b >= a && c >= b) {
+        ctx->agg_thresh[0] = a; ctx->agg_thresh[1] = b; ctx->agg_thresh[2] = c;
+      }
+    }
   }
   ctx->stream = ctx->own_stream;
   MDB_CUDA(ctx, cudaEventCreate(&ctx->ev[0]));
@@ -117,6 +131,14 @@ extern "C" int64_t mdb_launch_count(const mdb_ctx* ctx) { return ctx ? ctx->laun
 extern "C" int mdb_ctx_set_profiling(mdb_ctx* ctx, int on) {
   if (!ctx) return MDB_ERR_INVALID;
   ctx->profiling = on;
+  return MDB_OK;
+}
+extern "C" int mdb_ctx_set_blocking(mdb_ctx* ctx, int fixed, int64_t t2, int64_t t4, int64_t t8) {
+  if (!ctx) return MDB_ERR_INVALID;
+  MDB_CHECK(ctx, fixed == 0 || fixed == 1 || fixed == 2 || fixed == 4 || fixed == 8, "mdb_ctx_set_blocking: fixed must be 0, 1, 2, 4 or 8");
+  MDB_CHECK(ctx, fixed != 0 || (t2 > 0 && t4 >= t2 && t8 >= t4), "mdb_ctx_set_blocking: need 0 < t2 <= t4 <= t8");
+  ctx->agg_fixed = fixed;
+  if (fixed == 0) { ctx->agg_thresh[0] = t2; ctx->agg_thresh[1] = t4; ctx->agg_thresh[2] = t8; }
   return MDB_OK;
 }
 extern "C" int mdb_ctx_get_phase_ms(const mdb_ctx* ctx, double ms[4]) {
@@ -204,6 +226,13 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
   const int64_t nn = std::max<int64_t>(n, 1);
   f->panel_rows = std::max<int64_t>(mdb_round_up(nn, NB), NB);
+  // widest outer block this factor can use (operand buffer width): 1 for batched small matrices
+  f->agg = 1;
+  if (batch == 1) {
+    if (ctx->agg_fixed) f->agg = ctx->agg_fixed;
+    else f->agg = nn >= ctx->agg_thresh[2] ? 8 : nn >= ctx->agg_thresh[1] ? 4 : nn >= ctx->agg_thresh[0] ? 2 : 1;
+  }
+  const size_t panel_bytes = (size_t)batch * f->panel_rows * f->agg * NB * 8;
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8); };
   A((void**)&f->W, (size_t)batch * nn * f->ld * 8);
@@ -212,10 +241,10 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   A((void**)&f->info, (size_t)batch * sizeof(int));
   A((void**)&f->Ut, (size_t)batch * NB * NB * 8);
   A((void**)&f->hdr, (size_t)batch * 5 * NB * 8);
-  A((void**)&f->PX, (size_t)batch * f->panel_rows * NB * 8);
-  A((void**)&f->PY, (size_t)batch * f->panel_rows * NB * 8);
-  A((void**)&f->PX2, (size_t)batch * f->panel_rows * NB * 8);
-  A((void**)&f->PY2, (size_t)batch * f->panel_rows * NB * 8);
+  A((void**)&f->PX, panel_bytes);
+  A((void**)&f->PY, panel_bytes);
+  A((void**)&f->PX2, panel_bytes);
+  A((void**)&f->PY2, panel_bytes);
   if (e != cudaSuccess) {
     snprintf(ctx->err, sizeof(ctx->err), "mdb_factor_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     factor_release(f);
@@ -230,8 +259,10 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   MDB_CUDA(ctx, cudaMemsetAsync(f->clamped, 0, (size_t)bn, ctx->stream));
   MDB_CUDA(ctx, cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream));
   MDB_CUDA(ctx, cudaMemsetAsync(f->Ut, 0, (size_t)batch * NB * NB * 8, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->PX, 0, (size_t)batch * f->panel_rows * NB * 8, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->PY, 0, (size_t)batch * f->panel_rows * NB * 8, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->PX, 0, panel_bytes, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->PY, 0, panel_bytes, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->PX2, 0, panel_bytes, ctx->stream));
+  MDB_CUDA(ctx, cudaMemsetAsync(f->PY2, 0, panel_bytes, ctx->stream));
   *out = f;
   return MDB_OK;
 }
@@ -372,7 +403,7 @@ static FactorDev make_dev(mdb_factor* f) {
   F.gamma = f->gamma; F.alpha = f->alpha; F.beta = f->beta; F.rowmax = f->rowmax;
   F.d = f->d; F.omega = f->omega; F.delta = f->delta; F.clamped = f->clamped;
   F.minB = f->minB; F.maxB = f->maxB; F.info = f->info; F.Ut = f->Ut; F.hdr = f->hdr;
-  F.sW = f->n * f->ld; F.sVec = f->n; F.sUt = NB * NB; F.sHdr = 5 * NB; F.sPanel = f->panel_rows * NB;
+  F.sW = f->n * f->ld; F.sVec = f->n; F.sUt = NB * NB; F.sHdr = 5 * NB; F.sPanel = f->panel_rows * f->agg * NB;
   return F;
 }
 
@@ -457,79 +488,113 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
   }
   const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
   const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB + 2 * NB * 8) * 8;
-  // Lookahead-1 (default): the trailing update of panel k is split into (a) the next column block, done on
-  // the main stream, and (b) the rest, done on the side stream while the main stream already factors
-  // diagonal block + panel k+1.  Panel operands are double buffered.  With profiling on, everything runs
-  // serialised on the main stream so that the per-phase timers mean something.
+  // Two-level blocking.  Panels are NB = 128 columns wide (diagonal block + row-parallel panel kernel); `agg`
+  // consecutive panels form an outer block of KB = agg * NB columns whose operands X, Y sit side by side in one
+  // (rows x KB) buffer.  After panel j only the remaining columns of its outer block are updated (K = 128,
+  // "inner" update); the rest of the trailing matrix gets one update per outer block with K = KB ("bulk"), which
+  // is where n^3/3 of the flops go: the C tile is read and written once per KB instead of once per NB, and the
+  // DMMA pipeline of a tile runs 4 x longer between its prologue and epilogue.
+  // Lookahead-1 (default): while the side (low priority) stream runs the bulk update (b) of outer block O-1 on
+  // the columns beyond outer block O, the main stream factors outer block O; then (a) = the bulk update of O on
+  // the columns of outer block O+1 goes to the main stream and (b) to the side stream, concurrently (they touch
+  // disjoint columns).  Operand buffers are double buffered by outer-block parity.  With profiling on,
+  // everything runs serialised on the main stream so that the per-phase timers mean something.
+  // The outer block width shrinks with the remaining size (agg_for): a wide block makes the bulk kernel more
+  // efficient but lengthens the sequential work (agg diagonal blocks + panels) that one bulk update has to hide.
+  const int64_t LDP = (int64_t)f->agg * NB;  // leading dimension of the operand buffers (widest outer block)
+  auto agg_for = [&](int64_t remaining) -> int64_t {
+    int a = 1;
+    if (ctx->agg_fixed) a = ctx->agg_fixed;
+    else if (remaining >= ctx->agg_thresh[2]) a = 8;
+    else if (remaining >= ctx->agg_thresh[1]) a = 4;
+    else if (remaining >= ctx->agg_thresh[0]) a = 2;
+    return std::min<int64_t>(a, f->agg);
+  };
   const bool lookahead = !ctx->profiling && ctx->lookahead && n > 2 * NB;
   cudaStream_t main_s = ctx->stream, side_s = ctx->side_stream;
-  int64_t kidx = 0;
-  for (int64_t k0 = 0; k0 < n; k0 += NB, ++kidx) {
-    const int kb = (int)std::min<int64_t>(NB, n - k0);
-    const int64_t k1 = k0 + kb;
-    const int buf = lookahead ? (int)(kidx & 1) : 0;
+  auto trailing = [&](const GemmArgs& ga, cudaStream_t st) -> int {  // TMA-fed kernel when it applies, else cp.async
+    cudaStream_t saved = ctx->stream;
+    ctx->stream = st;
+    int r = -1;
+    if (batch == 1) r = launch_gemm_tn_tma(ctx, ga, ga.M, ga.b_rows);
+    if (r == -1) r = launch_gemm_tn<true, true, false>(ctx, ga, batch);
+    ctx->stream = saved;
+    return r;
+  };
+  int64_t oidx = 0;
+  for (int64_t ob = 0, KB = 0; ob < n; ob += KB, ++oidx) {
+    KB = agg_for(n - ob) * NB;
+    const int64_t oe = std::min<int64_t>(ob + KB, n);
+    const int buf = lookahead ? (int)(oidx & 1) : 0;
     double* PX = buf ? f->PX2 : f->PX;
     double* PY = buf ? f->PY2 : f->PY;
-    {
-      PhaseTimer t(ctx, 0);
-      k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), 4 * NB, diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
-                                                                                f->W + k0 * f->ld + k0, f->ld);
-      MDB_LAUNCHED(ctx);
-    }
-    if (k1 < n) {
+    for (int64_t k0 = ob; k0 < oe; k0 += NB) {
+      const int kb = (int)std::min<int64_t>(NB, n - k0);
+      const int64_t k1 = k0 + kb;
+      {
+        PhaseTimer t(ctx, 0);
+        k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), 4 * NB, diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
+                                                                                  f->W + k0 * f->ld + k0, f->ld);
+        MDB_LAUNCHED(ctx);
+      }
+      if (k1 >= n) break;
       const int64_t rows = n - k1;
       {
         PhaseTimer t(ctx, 1);
         dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, (unsigned)batch);
         k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, main_s>>>(F, k0, k1, rows, f->W, 1, f->ld, f->W + k0, f->ld,
-                                                                    PX, PY, k1);
+                                                                    PX + (k0 - ob), PY + (k0 - ob), ob, LDP);
         MDB_LAUNCHED(ctx);
       }
-      GemmArgs g;
-      memset(&g, 0, sizeof(g));
-      g.A = PX; g.lda = NB; g.sA = F.sPanel;
-      g.B = PY; g.ldb = NB; g.sB = F.sPanel;
-      g.C = f->W + k1 * f->ld + k1; g.ldc = f->ld; g.sC = F.sW;
-      g.M = rows; g.N = rows; g.K = NB;
-      g.row_glob0 = k1; g.col_glob0 = k1; g.b_glob0 = k1; g.b_rows = rows;
-      // TMA-fed kernel when it applies (one matrix), else the cp.async kernel
-      auto trailing = [&](const GemmArgs& ga) -> int {
-        if (batch == 1) {
-          const int r = launch_gemm_tn_tma(ctx, ga, rows, rows);
-          if (r != -1) return r;
-        }
-        return launch_gemm_tn<true, true, false>(ctx, ga, batch);
-      };
-      if (!lookahead) {
-        PhaseTimer t(ctx, 2);
-        rc = trailing(g);
+      if (k1 < oe) {  // inner update: columns [k1, oe) of the outer block, K = NB
+        PhaseTimer t(ctx, 3);
+        GemmArgs gi;
+        memset(&gi, 0, sizeof(gi));
+        gi.A = PX + (k1 - ob) * LDP + (k0 - ob); gi.lda = LDP; gi.sA = F.sPanel;
+        gi.B = PY + (k1 - ob) * LDP + (k0 - ob); gi.ldb = LDP; gi.sB = F.sPanel;
+        gi.C = f->W + k1 * f->ld + k1; gi.ldc = f->ld; gi.sC = F.sW;
+        gi.M = rows; gi.N = oe - k1; gi.K = NB;
+        gi.row_glob0 = k1; gi.col_glob0 = k1; gi.b_glob0 = k1; gi.b_rows = rows;
+        rc = trailing(gi, main_s);
         if (rc) return rc;
-      } else {
-        const int64_t nt_block = NB / gemm::BN;  // N tiles of one column block
-        // all earlier (b) updates must have reached the next column block (and released this panel buffer's twin)
-        if (kidx >= 1) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(kidx - 1) & 1], 0));
-        GemmArgs ga = g;
-        ga.n_tile0 = 0; ga.n_tiles = nt_block;
-        rc = trailing(ga);  // (a) next column block, main stream
-        if (rc) return rc;
-        MDB_CUDA(ctx, cudaEventRecord(ctx->ev_panel[kidx & 1], main_s));
-        if (rows > NB) {
-          MDB_CUDA(ctx, cudaStreamWaitEvent(side_s, ctx->ev_panel[kidx & 1], 0));
-          GemmArgs gb = g;
-          gb.n_tile0 = nt_block; gb.n_tiles = 0; gb.m_tile0 = 1;
-          cudaStream_t saved = ctx->stream;
-          ctx->stream = side_s;
-          rc = trailing(gb);  // (b) the rest, side stream
-          ctx->stream = saved;
-          if (rc) return rc;
-        }
-        MDB_CUDA(ctx, cudaEventRecord(ctx->ev_upd[kidx & 1], side_s));
       }
     }
+    if (oe >= n) break;
+    // bulk update of everything beyond the outer block, K = KB
+    const int64_t rows = n - oe;
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = PX + (oe - ob) * LDP; g.lda = LDP; g.sA = F.sPanel;
+    g.B = PY + (oe - ob) * LDP; g.ldb = LDP; g.sB = F.sPanel;
+    g.C = f->W + oe * f->ld + oe; g.ldc = f->ld; g.sC = F.sW;
+    g.M = rows; g.N = rows; g.K = (int)(oe - ob);
+    g.row_glob0 = oe; g.col_glob0 = oe; g.b_glob0 = oe; g.b_rows = rows;
+    if (!lookahead) {
+      PhaseTimer t(ctx, 2);
+      rc = trailing(g, main_s);
+      if (rc) return rc;
+    } else {
+      MDB_CUDA(ctx, cudaEventRecord(ctx->ev_panel[oidx & 1], main_s));  // operands of outer block O complete
+      // (b) of O-1 must have reached the columns of outer block O+1 (and released the other operand buffer)
+      if (oidx >= 1) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(oidx - 1) & 1], 0));
+      const int64_t KBn = agg_for(rows) * NB;  // width of the next outer block
+      GemmArgs ga = g;
+      ga.n_tile0 = 0; ga.n_tiles = KBn / gemm::BN;
+      rc = trailing(ga, main_s);  // (a) columns of the next outer block, main stream
+      if (rc) return rc;
+      if (rows > KBn) {
+        MDB_CUDA(ctx, cudaStreamWaitEvent(side_s, ctx->ev_panel[oidx & 1], 0));
+        GemmArgs gb = g;
+        gb.n_tile0 = KBn / gemm::BN; gb.n_tiles = 0; gb.m_tile0 = KBn / gemm::BM;
+        rc = trailing(gb, side_s);  // (b) the rest, side stream, concurrently with (a)
+        if (rc) return rc;
+      }
+      MDB_CUDA(ctx, cudaEventRecord(ctx->ev_upd[oidx & 1], side_s));
+    }
   }
-  if (lookahead && kidx >= 1) {
-    MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(kidx - 1) & 1], 0));
-    if (kidx >= 2) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(kidx - 2) & 1], 0));
+  if (lookahead && oidx >= 1) {
+    MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(oidx - 1) & 1], 0));
+    if (oidx >= 2) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(oidx - 2) & 1], 0));
   }
   MDB_CUDA(ctx, cudaGetLastError());
   f->state = ST_FACTORED;

@@ -21,6 +21,8 @@ struct mdb_ctx {
   cudaEvent_t ev_panel[2], ev_upd[2];
   int lookahead;
   int use_tma;  // MDB200_TMA=0 falls back to the cp.async tile kernel
+  int agg_fixed;            // panels per outer block forced by MDB200_AGG (0 = choose by remaining size)
+  int64_t agg_thresh[3];    // remaining sizes from which 2, 4, 8 panels are aggregated
   char err[512];
   int64_t launches;
   int profiling;

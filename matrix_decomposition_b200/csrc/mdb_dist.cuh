@@ -227,7 +227,7 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot) {
     dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, 1);
     // A[j, k0 + c] = A_loc[j * ld + lc0 + c]  ->  Asrc + j * a_rs + k0 * a_cs with a_rs = ld, a_cs = 1
     k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
-                                                                     s->S + lc0, s->ld, PX, PY, k1);
+                                                                     s->S + lc0, s->ld, PX, PY, k1, NB);
     MDB_LAUNCHED(ctx);
     MDB_CUDA(ctx, cudaMemcpyAsync(vecs, s->alpha + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     MDB_CUDA(ctx, cudaMemcpyAsync(vecs + rows, s->beta + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -167,6 +167,27 @@ def test_sizes_around_block_boundaries(matrix, orc, n):
     assert np.all(np.triu(dec.L, 1) == 0) and np.all(dec.L.diagonal() == 1)
 
 
+@pytest.mark.parametrize('blocking', [dict(fixed=2), dict(fixed=4), dict(fixed=8), dict(fixed=0, t2=300, t4=600, t8=1100)])
+@pytest.mark.parametrize('n', [640, 1500])
+def test_outer_block_aggregation_matches_oracle(matrix, orc, n, blocking):
+    """Two-level blocking (bulk trailing update per outer block of 2 / 4 / 8 panels, shrinking with the remaining
+    size) is what large n uses by default; forced here at sizes the oracle finishes in seconds."""
+    from matrix_decomposition_b200 import _native
+    ctx = _native.context()
+    A, kw = workloads.shifted_goe(n, 900 + n, 1.05)
+    ref = orc.approximate(A, **kw)
+    try:
+        ctx.set_blocking(**blocking)
+        dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+        S = workloads.lowrank_plus_diag(n, 5)
+        dd = matrix.decompose(S, permutation='decreasing_diagonal_values', return_type='LL')
+    finally:
+        ctx.set_blocking()
+    _compare(dec, ref['L'], ref['d'], ref['p'], ref['clamped'], ref['omega'], ref['delta'], scale=np.abs(A).max())
+    rr = orc.decompose(S, 'decreasing_diagonal_values', 'LL')
+    np.testing.assert_allclose(dd.L, rr['L'], rtol=1e-10, atol=1e-12)
+
+
 def test_empty_matrix(matrix):
     dec = matrix.approximation.positive_semidefinite.decomposition(np.zeros((0, 0)), permutation='none')
     assert dec.n == 0 and dec.L.shape == (0, 0)
