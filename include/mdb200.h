@@ -178,7 +178,11 @@ int mdb_debug_gemm_tn(mdb_ctx *ctx, int64_t M, int64_t N, int64_t K, const doubl
  *                  (Schur complement / unscaled rows Lu below the diagonal) and the permuted original A.
  *   panel0/1     : two broadcast buffers of mdb_dist_panel_elems(s, 0) doubles each.  Layout for panel k with
  *                  rows = n - k1: [5 x 128 header: d, omega, drop, delta, clamped] [3 x rows: alpha, beta, rowmax
- *                  of rows >= k1] [rows x 128: X] [rows x 128: Y = -X D]. */
+ *                  of rows >= k1] [rows x 128: X].  (Y = -X D is rebuilt by every receiver.)
+ * Two-level blocking as on one GPU: mdb_dist_outer_width(s, k) consecutive panels starting at panel k form an outer
+ * block; their operands X, Y are collected side by side in per-rank operand buffers (two, `oslot` = outer-block
+ * parity), inner updates (one panel, K = 128) stay inside the outer block, and everything beyond it gets one bulk
+ * update per outer block (K = 128 * width). */
 typedef struct mdb_dist mdb_dist;
 int mdb_dist_create(mdb_ctx *ctx, int64_t n, int rank, int world, double *S_loc, double *A_loc, int64_t ld_loc,
                     double *panel0, double *panel1, mdb_dist **out);
@@ -192,14 +196,18 @@ int mdb_dist_set_matrix(mdb_dist *s, const double *Ap, int64_t ld);
 /* bounds as in mdb_factor_run; p (host, may be NULL) maps position -> original index for vector B bounds.
  * Resets alpha / beta / rowmax. */
 int mdb_dist_set_bounds(mdb_dist *s, const mdb_bounds *bounds, const int64_t *p);
-/* owner of panel k only: diagonal block + panel into panel buffer `slot` (asynchronous on the ctx stream) */
-int mdb_dist_factor_panel(mdb_dist *s, int64_t k, int slot);
-/* every rank, once per panel, after the broadcast: take d / omega / delta / clamped and the alpha / beta /
- * rowmax slices out of the panel buffer (asynchronous) */
-int mdb_dist_absorb_panel(mdb_dist *s, int64_t k, int slot);
-/* every rank: apply panel k (in buffer `slot`) to the local trailing columns.  only_block >= 0 restricts the
- * update to that global column block (lookahead); skip_block >= 0 leaves that block out. */
-int mdb_dist_apply_panel(mdb_dist *s, int64_t k, int slot, int64_t only_block, int64_t skip_block);
+int64_t mdb_dist_outer_width(const mdb_dist *s, int64_t k); /* panels in the outer block starting at panel k */
+/* owner of panel k only: diagonal block + panel; operands into operand buffer `oslot` of the outer block starting
+ * at panel k_outer, message into panel buffer `slot` (asynchronous on the ctx stream) */
+int mdb_dist_factor_panel(mdb_dist *s, int64_t k, int slot, int64_t k_outer, int oslot);
+/* every rank, once per panel, after the broadcast: take d / omega / delta / clamped, the alpha / beta / rowmax
+ * slices and the operands X, Y = -X D out of panel buffer `slot` (asynchronous; no-op on the owner) */
+int mdb_dist_absorb_panel(mdb_dist *s, int64_t k, int slot, int64_t k_outer, int oslot);
+/* every rank: S[rows >= r0, local blocks J in [blk_lo, blk_hi)] += X Y^T over the panels [k_first, k_first + k_count)
+ * of the outer block starting at k_outer (operand buffer `oslot`), r0 = 128 (k_first + k_count); blk_hi < 0 = to the
+ * end; strict lower triangle only. */
+int mdb_dist_apply_update(mdb_dist *s, int64_t k_outer, int oslot, int64_t k_first, int64_t k_count, int64_t blk_lo,
+                          int64_t blk_hi);
 /* finalises the local columns in place (S_loc then holds the local columns of L: scaled, thresholded, unit
  * diagonal, zeros above) and copies the replicated vectors to the host (position order; any may be NULL) */
 int mdb_dist_finalize(mdb_dist *s, double *d, double *omega, double *delta, uint8_t *clamped);

@@ -10,6 +10,8 @@ struct mdb_dist {
   int64_t nblk_glob, nblk_loc;
   double *S, *A;       // n x ld, owned by the caller (torch tensors)
   double* panel[2];    // broadcast buffers, owned by the caller
+  double *OPX[2], *OPY[2];  // operands of one outer block, (n x ldp) each, double buffered by outer-block parity
+  int64_t ldp;         // = (widest outer block) * NB
   double* vec;         // 7 x n: gamma, alpha, beta, rowmax, d, omega, delta (position order, full length)
   double *gamma, *alpha, *beta, *rowmax, *d, *omega, *delta;
   uint8_t* clamped;
@@ -31,11 +33,26 @@ extern "C" int64_t mdb_dist_local_cols(int64_t n, int rank, int world) {
   return std::max<int64_t>(dist_local_blocks(n, rank, world), 1) * NB;
 }
 
-// header 5 x NB | vectors 3 x rows | X rows x NB | Y rows x NB
+// header 5 x NB | vectors 3 x rows | X rows x NB   (Y = -X D is rebuilt by the receivers)
 static inline int64_t dist_panel_elems(int64_t n, int64_t k) {
   const int64_t k1 = std::min<int64_t>((k + 1) * NB, n);
   const int64_t rows = n - k1;
-  return 5 * NB + 3 * rows + 2 * rows * NB;
+  return 5 * NB + 3 * rows + rows * NB;
+}
+
+// number of panels in the outer block that starts at panel k (same rule as mdb_factor_run)
+static inline int64_t dist_outer_width(const mdb_ctx* ctx, int64_t n, int64_t k) {
+  const int64_t remaining = n - k * NB;
+  int64_t a = 1;
+  if (ctx->agg_fixed) a = ctx->agg_fixed;
+  else if (remaining >= ctx->agg_thresh[2]) a = 8;
+  else if (remaining >= ctx->agg_thresh[1]) a = 4;
+  else if (remaining >= ctx->agg_thresh[0]) a = 2;
+  const int64_t left = (n + NB - 1) / NB - k;
+  return std::max<int64_t>(1, std::min<int64_t>(a, left));
+}
+extern "C" int64_t mdb_dist_outer_width(const mdb_dist* s, int64_t k) {
+  return (s && k >= 0 && k < s->nblk_glob) ? std::min<int64_t>(dist_outer_width(s->ctx, s->n, k), s->ldp / NB) : 0;
 }
 extern "C" int64_t mdb_dist_panel_elems(const mdb_dist* s, int64_t k) { return s ? dist_panel_elems(s->n, k) : 0; }
 
@@ -57,7 +74,15 @@ extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, dou
   s->S = S_loc; s->A = A_loc; s->panel[0] = panel0; s->panel[1] = panel1;
   s->vec = nullptr; s->clamped = nullptr; s->minB = s->maxB = nullptr; s->info = nullptr; s->Ut = nullptr;
   s->pcol_dev = nullptr; s->have_bounds = false;
+  s->OPX[0] = s->OPX[1] = s->OPY[0] = s->OPY[1] = nullptr;
+  s->ldp = dist_outer_width(ctx, n, 0) * NB;  // the first outer block is the widest
   cudaError_t e = cudaMalloc((void**)&s->vec, (size_t)7 * n * 8);
+  for (int i = 0; i < 2; ++i) {
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->OPX[i], (size_t)n * s->ldp * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->OPY[i], (size_t)n * s->ldp * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->OPX[i], 0, (size_t)n * s->ldp * 8, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->OPY[i], 0, (size_t)n * s->ldp * 8, ctx->stream);
+  }
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->clamped, (size_t)n);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->info, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->Ut, (size_t)NB * NB * 8);
@@ -83,6 +108,7 @@ extern "C" int mdb_dist_destroy(mdb_dist* s) {
   cudaStreamSynchronize(s->ctx->stream);
   cudaFree(s->vec); cudaFree(s->clamped); cudaFree(s->minB); cudaFree(s->maxB); cudaFree(s->info); cudaFree(s->Ut);
   cudaFree(s->pcol_dev);
+  for (int i = 0; i < 2; ++i) { cudaFree(s->OPX[i]); cudaFree(s->OPY[i]); }
   delete s;
   return MDB_OK;
 }
@@ -202,21 +228,22 @@ static FactorDev dist_make_dev(mdb_dist* s, double* hdr) {
   return F;
 }
 
-extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot) {
+extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot, int64_t k_outer, int oslot) {
   if (!s) return MDB_ERR_INVALID;
   mdb_ctx* ctx = s->ctx;
   MDB_CHECK(ctx, s->have_bounds, "mdb_dist_factor_panel: call mdb_dist_set_bounds first");
   MDB_CHECK(ctx, k >= 0 && k < s->nblk_glob && (k % s->world) == s->rank, "mdb_dist_factor_panel: not the owner of panel k");
-  MDB_CHECK(ctx, slot == 0 || slot == 1, "bad slot");
+  MDB_CHECK(ctx, (slot == 0 || slot == 1) && (oslot == 0 || oslot == 1), "bad slot");
+  MDB_CHECK(ctx, k_outer >= 0 && k_outer <= k && (k - k_outer + 1) * NB <= s->ldp, "mdb_dist_factor_panel: bad outer block");
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1;
   const int kb = (int)(k1 - k0);
   const int64_t lc0 = (k / s->world) * NB;
+  const int64_t ob = k_outer * NB;
   double* buf = s->panel[slot];
   double* hdr = buf;
   double* vecs = buf + 5 * NB;
-  double* PX = vecs + 3 * rows;
-  double* PY = PX + rows * NB;
+  double* MX = vecs + 3 * rows;  // X part of the message
   FactorDev F = dist_make_dev(s, hdr);
   const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
   const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB + 2 * NB * 8) * 8;
@@ -225,10 +252,15 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot) {
   MDB_LAUNCHED(ctx);
   if (rows > 0) {
     dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, 1);
-    // A[j, k0 + c] = A_loc[j * ld + lc0 + c]  ->  Asrc + j * a_rs + k0 * a_cs with a_rs = ld, a_cs = 1
+    // A[j, k0 + c] = A_loc[j * ld + lc0 + c]  ->  Asrc + j * a_rs + k0 * a_cs with a_rs = ld, a_cs = 1.
+    // The owner's operands go straight into the outer-block buffers; X is then copied into the message.
+    double* PX = s->OPX[oslot] + (k0 - ob);
+    double* PY = s->OPY[oslot] + (k0 - ob);
     k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
-                                                                     s->S + lc0, s->ld, PX, PY, k1, NB);
+                                                                     s->S + lc0, s->ld, PX, PY, ob, s->ldp);
     MDB_LAUNCHED(ctx);
+    MDB_CUDA(ctx, cudaMemcpy2DAsync(MX, (size_t)NB * 8, PX + (k1 - ob) * s->ldp, (size_t)s->ldp * 8, (size_t)NB * 8,
+                                    (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
     MDB_CUDA(ctx, cudaMemcpyAsync(vecs, s->alpha + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     MDB_CUDA(ctx, cudaMemcpyAsync(vecs + rows, s->beta + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     MDB_CUDA(ctx, cudaMemcpyAsync(vecs + 2 * rows, s->rowmax + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -249,13 +281,29 @@ __global__ void k_dist_absorb_hdr(int kb, int64_t k0, const double* __restrict__
   }
 }
 
-extern "C" int mdb_dist_absorb_panel(mdb_dist* s, int64_t k, int slot) {
+// message X (rows x NB, compact) -> operand buffers: OX = X, OY = -X d (the same expression as k_panel, so the
+// owner's and the receivers' operands are identical bit for bit).  HBM bound: 24 * rows * NB bytes.
+__global__ void __launch_bounds__(256) k_dist_absorb_x(int64_t rows, const double* __restrict__ X,
+                                                       const double* __restrict__ hdr, double* __restrict__ OX,
+                                                       double* __restrict__ OY, int64_t ldp) {
+  const int c = threadIdx.x & (MDB_NB - 1);
+  const double dc = hdr[c];
+  for (int64_t r = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7); r < rows; r += (int64_t)gridDim.x * 2) {
+    const double x = X[r * MDB_NB + c];
+    OX[r * ldp + c] = x;
+    OY[r * ldp + c] = -x * dc;
+  }
+}
+
+extern "C" int mdb_dist_absorb_panel(mdb_dist* s, int64_t k, int slot, int64_t k_outer, int oslot) {
   if (!s) return MDB_ERR_INVALID;
   mdb_ctx* ctx = s->ctx;
-  MDB_CHECK(ctx, k >= 0 && k < s->nblk_glob && (slot == 0 || slot == 1), "mdb_dist_absorb_panel: bad panel / slot");
+  MDB_CHECK(ctx, k >= 0 && k < s->nblk_glob && (slot == 0 || slot == 1) && (oslot == 0 || oslot == 1),
+            "mdb_dist_absorb_panel: bad panel / slot");
+  MDB_CHECK(ctx, k_outer >= 0 && k_outer <= k && (k - k_outer + 1) * NB <= s->ldp, "mdb_dist_absorb_panel: bad outer block");
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
-  if ((k % s->world) == s->rank) return MDB_OK;  // the owner's arrays are already up to date
-  const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1;
+  if ((k % s->world) == s->rank) return MDB_OK;  // the owner's arrays and operands are already in place
+  const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1, ob = k_outer * NB;
   double* buf = s->panel[slot];
   k_dist_absorb_hdr<<<1, NB, 0, ctx->stream>>>((int)(k1 - k0), k0, buf, s->d, s->omega, s->delta, s->clamped);
   MDB_LAUNCHED(ctx);
@@ -264,55 +312,47 @@ extern "C" int mdb_dist_absorb_panel(mdb_dist* s, int64_t k, int slot) {
     MDB_CUDA(ctx, cudaMemcpyAsync(s->alpha + k1, vecs, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     MDB_CUDA(ctx, cudaMemcpyAsync(s->beta + k1, vecs + rows, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     MDB_CUDA(ctx, cudaMemcpyAsync(s->rowmax + k1, vecs + 2 * rows, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    const int64_t off = (k1 - ob) * s->ldp + (k0 - ob);
+    const unsigned grid = (unsigned)std::min<int64_t>((rows + 1) / 2, (int64_t)ctx->num_sms * 8);
+    k_dist_absorb_x<<<grid, 256, 0, ctx->stream>>>(rows, vecs + 3 * rows, buf, s->OPX[oslot] + off, s->OPY[oslot] + off, s->ldp);
+    MDB_LAUNCHED(ctx);
   }
   MDB_CUDA(ctx, cudaGetLastError());
   return MDB_OK;
 }
 
-extern "C" int mdb_dist_apply_panel(mdb_dist* s, int64_t k, int slot, int64_t only_block, int64_t skip_block) {
+extern "C" int mdb_dist_apply_update(mdb_dist* s, int64_t k_outer, int oslot, int64_t k_first, int64_t k_count,
+                                     int64_t blk_lo, int64_t blk_hi) {
   if (!s) return MDB_ERR_INVALID;
   mdb_ctx* ctx = s->ctx;
-  MDB_CHECK(ctx, k >= 0 && k < s->nblk_glob && (slot == 0 || slot == 1), "mdb_dist_apply_panel: bad panel / slot");
+  MDB_CHECK(ctx, oslot == 0 || oslot == 1, "mdb_dist_apply_update: bad slot");
+  MDB_CHECK(ctx, k_outer >= 0 && k_first >= k_outer && k_count >= 1 && (k_first + k_count - k_outer) * NB <= s->ldp &&
+                     k_first + k_count <= s->nblk_glob,
+            "mdb_dist_apply_update: bad panel range");
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1;
-  if (rows <= 0) return MDB_OK;
-  double* buf = s->panel[slot];
-  double* PX = buf + 5 * NB + 3 * rows;
-  double* PY = PX + rows * NB;
+  if (blk_hi < 0 || blk_hi > s->nblk_glob) blk_hi = s->nblk_glob;
+  if (blk_lo < k_first + k_count) blk_lo = k_first + k_count;
+  const int64_t n = s->n, ob = k_outer * NB, r0 = (k_first + k_count) * NB, rows = n - r0;
+  if (rows <= 0 || blk_hi <= blk_lo) return MDB_OK;
   const int64_t tpb = NB / gemm::BN;  // N tiles per column block
-  // local blocks with global index > k:  lb >= first
-  int64_t first = (k + 1 - s->rank + s->world - 1) / s->world;
-  if (first < 0) first = 0;
-  int64_t lb_begin = first, lb_end = s->nblk_loc;  // [begin, end)
+  // local blocks lb with global index lb * world + rank in [blk_lo, blk_hi)
+  auto first_local = [&](int64_t J) { return std::max<int64_t>((J - s->rank + s->world - 1) / s->world, 0); };
+  const int64_t lb_begin = first_local(blk_lo), lb_end = std::min<int64_t>(first_local(blk_hi), s->nblk_loc);
+  if (lb_end <= lb_begin) return MDB_OK;
   GemmArgs g;
   memset(&g, 0, sizeof(g));
-  g.A = PX; g.lda = NB; g.B = PY; g.ldb = NB;
-  g.C = s->S + k1 * s->ld; g.ldc = s->ld;
-  g.M = rows; g.N = s->nblk_loc * NB; g.K = NB;
-  g.row_glob0 = k1; g.col_glob0 = 0; g.b_glob0 = k1; g.b_rows = rows;
+  const int64_t off = (r0 - ob) * s->ldp + (k_first - k_outer) * NB;
+  g.A = s->OPX[oslot] + off; g.lda = s->ldp;
+  g.B = s->OPY[oslot] + off; g.ldb = s->ldp;
+  g.C = s->S + r0 * s->ld; g.ldc = s->ld;
+  g.M = rows; g.N = s->nblk_loc * NB; g.K = (int)(k_count * NB);
+  g.row_glob0 = r0; g.col_glob0 = 0; g.b_glob0 = r0; g.b_rows = rows;
   g.cyc_G = s->world; g.cyc_r = s->rank;  // one rank: plain mapping, global column = local column
-  auto launch = [&](int64_t b0, int64_t b1) -> int {  // local blocks [b0, b1)
-    if (b1 <= b0) return MDB_OK;
-    GemmArgs gg = g;
-    gg.n_tile0 = b0 * tpb;
-    gg.n_tiles = (b1 - b0) * tpb;
-    const int r = launch_gemm_tn_tma(ctx, gg, rows, rows);
-    if (r != -1) return r;
-    return launch_gemm_tn<true, true, false>(ctx, gg, 1);
-  };
-  int rc = MDB_OK;
-  if (only_block >= 0) {
-    if ((only_block % s->world) != s->rank || only_block <= k) return MDB_OK;
-    const int64_t lb = only_block / s->world;
-    rc = launch(lb, lb + 1);
-  } else if (skip_block >= 0 && (skip_block % s->world) == s->rank && skip_block > k) {
-    const int64_t lb = skip_block / s->world;
-    rc = launch(lb_begin, std::min(lb, lb_end));
-    if (!rc) rc = launch(std::max(lb + 1, lb_begin), lb_end);
-  } else {
-    rc = launch(lb_begin, lb_end);
-  }
-  return rc;
+  g.n_tile0 = lb_begin * tpb;
+  g.n_tiles = (lb_end - lb_begin) * tpb;
+  const int r = launch_gemm_tn_tma(ctx, g, rows, rows);
+  if (r != -1) return r;
+  return launch_gemm_tn<true, true, false>(ctx, g, 1);
 }
 
 extern "C" int mdb_dist_finalize(mdb_dist* s, double* d, double* omega, double* delta, uint8_t* clamped) {

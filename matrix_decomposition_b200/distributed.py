@@ -1,12 +1,16 @@
 """Multi-GPU factorization: 1-D block-cyclic column distribution, one process per GPU.
 
 Global column block J (width 128, in elimination order) lives on rank J % world.  Per panel k the owner
-factors the diagonal block and the panel on its GPU (mdb_dist_factor_panel), the result -- the unscaled
-rows X, Y = -X D, the (d, omega, ...) header and the alpha / beta / rowmax slices -- is broadcast with
-torch.distributed (NCCL over NVLink / NVSwitch), and every rank applies it to its own trailing column
-blocks with the FP64 DMMA tile kernel (mdb_dist_apply_panel).  Lookahead-1: the owner of panel k+1 updates
-that column block first and factors + broadcasts it while all ranks are still busy with the bulk of
-update k on a second stream, so the broadcast and the sequential panel work hide under the update.
+factors the diagonal block and the panel on its GPU (mdb_dist_factor_panel); the result -- the unscaled
+rows X, the (d, omega, ...) header and the alpha / beta / rowmax slices -- is broadcast with
+torch.distributed (NCCL over NVLink / NVSwitch) and absorbed by every rank into its operand buffers
+(X and Y = -X D, mdb_dist_absorb_panel).  Updates use the same two-level blocking as the single-GPU path:
+`outer_width` consecutive panels form an outer block; after panel k only the remaining column blocks of
+its outer block are updated (K = 128), and everything beyond the outer block gets one bulk update per
+outer block with K = 128 * width on the FP64 DMMA tile kernel (mdb_dist_apply_update), each rank on its own
+column blocks.  Lookahead: the owner of the next panel updates that column block first, then factors and
+broadcasts it while all ranks are still busy with the bulk update on a second stream, so the broadcast and
+the sequential panel work hide under the update.
 
 The orchestration below is backend-neutral: `Steps` is the per-rank device work, `Comm` the broadcast.
 The product backend is CudaSteps (libmdb200.so + torch.cuda streams) with NcclComm; the CPU tests in
@@ -37,7 +41,7 @@ def local_cols(n, rank, world):
 def panel_elems(n, k):
     k1 = min((k + 1) * NB, n)
     rows = n - k1
-    return 5 * NB + 3 * rows + 2 * rows * NB
+    return 5 * NB + 3 * rows + rows * NB
 
 
 class NullStream:
@@ -51,7 +55,7 @@ class NullStream:
 
 
 def factorize(n, rank, world, steps, comm, main=None, bulk=None, lookahead=True):
-    """The panel loop.  `steps` provides factor_panel / absorb_panel / apply_panel / panel_tensor,
+    """The panel loop.  `steps` provides outer_width / factor_panel / absorb_panel / apply_update / panel_tensor,
     `comm.broadcast(tensor, src, stream)` returns a handle whose wait(stream) makes `stream` wait for it.
     `main` / `bulk` are stream objects with record() -> event and wait(event)."""
     main = main or NullStream()
@@ -62,31 +66,43 @@ def factorize(n, rank, world, steps, comm, main=None, bulk=None, lookahead=True)
     works = {}
     bulk_done = {}
 
-    def issue_factor_and_broadcast(k):
+    def issue_factor_and_broadcast(k, k_outer, oslot):
         slot = k % 2
         if owner_of(k, world) == rank:
-            steps.factor_panel(k, slot, main)
+            steps.factor_panel(k, slot, k_outer, oslot, main)
         works[k] = comm.broadcast(steps.panel_tensor(slot, k), owner_of(k, world), main)
 
-    issue_factor_and_broadcast(0)
-    for k in range(T):
-        slot = k % 2
-        works.pop(k).wait(main)                      # panel k has arrived
-        steps.absorb_panel(k, slot, main)
-        if k + 1 < T:
-            if k - 1 in bulk_done:
-                main.wait(bulk_done.pop(k - 1))      # bulk update k-1 reached block k+1 and released slot (k+1) % 2
+    issue_factor_and_broadcast(0, 0, 0)
+    kO, oidx = 0, 0
+    while kO < T:
+        cnt = steps.outer_width(kO)
+        kE = kO + cnt
+        oslot = oidx % 2
+        for k in range(kO, kE):
+            works.pop(k).wait(main)                                   # panel k has arrived
+            steps.absorb_panel(k, k % 2, kO, oslot, main)
+            if k + 1 < kE:                                            # inner updates: stay inside the outer block
+                steps.apply_update(kO, oslot, k, 1, k + 1, k + 2, main)   # next column block first
+                issue_factor_and_broadcast(k + 1, kO, oslot)
+                steps.apply_update(kO, oslot, k, 1, k + 2, kE, main)
+        if kE < T:
+            cntn = steps.outer_width(kE)
+            if oidx - 1 in bulk_done:
+                # bulk update O-1 reached the next outer block and released the other operand buffer
+                main.wait(bulk_done.pop(oidx - 1))
             if lookahead:
-                steps.apply_panel(k, slot, k + 1, -1, main)     # next column block first
-                ready = main.record()
-                issue_factor_and_broadcast(k + 1)                # overlaps with the bulk update below
+                ready = main.record()                                 # operands of this outer block complete
+                steps.apply_update(kO, oslot, kO, cnt, kE, kE + 1, main)          # next panel's block first
+                issue_factor_and_broadcast(kE, kE, (oidx + 1) % 2)               # overlaps with the bulk update
+                steps.apply_update(kO, oslot, kO, cnt, kE + 1, kE + cntn, main)   # rest of the next outer block
                 bulk.wait(ready)
-                steps.apply_panel(k, slot, -1, k + 1, bulk)     # the rest
-                bulk_done[k] = bulk.record()
+                steps.apply_update(kO, oslot, kO, cnt, kE + cntn, -1, bulk)       # everything beyond
+                bulk_done[oidx] = bulk.record()
             else:
-                steps.apply_panel(k, slot, -1, -1, main)
-                bulk_done[k] = main.record()
-                issue_factor_and_broadcast(k + 1)
+                steps.apply_update(kO, oslot, kO, cnt, kE, -1, main)
+                bulk_done[oidx] = main.record()
+                issue_factor_and_broadcast(kE, kE, (oidx + 1) % 2)
+        kO, oidx = kE, oidx + 1
     for ev in bulk_done.values():
         main.wait(ev)
 
@@ -174,17 +190,21 @@ class CudaSteps:
     def panel_tensor(self, slot, k):
         return self.panels[slot][:panel_elems(self.n, k)]
 
-    def factor_panel(self, k, slot, stream):
-        self._on(stream)
-        self.ctx.check(self.ctx.lib.mdb_dist_factor_panel(self.handle, k, slot), 'mdb_dist_factor_panel')
+    def outer_width(self, k):
+        return int(self.ctx.lib.mdb_dist_outer_width(self.handle, k))
 
-    def absorb_panel(self, k, slot, stream):
+    def factor_panel(self, k, slot, k_outer, oslot, stream):
         self._on(stream)
-        self.ctx.check(self.ctx.lib.mdb_dist_absorb_panel(self.handle, k, slot), 'mdb_dist_absorb_panel')
+        self.ctx.check(self.ctx.lib.mdb_dist_factor_panel(self.handle, k, slot, k_outer, oslot), 'mdb_dist_factor_panel')
 
-    def apply_panel(self, k, slot, only_block, skip_block, stream):
+    def absorb_panel(self, k, slot, k_outer, oslot, stream):
         self._on(stream)
-        self.ctx.check(self.ctx.lib.mdb_dist_apply_panel(self.handle, k, slot, only_block, skip_block), 'mdb_dist_apply_panel')
+        self.ctx.check(self.ctx.lib.mdb_dist_absorb_panel(self.handle, k, slot, k_outer, oslot), 'mdb_dist_absorb_panel')
+
+    def apply_update(self, k_outer, oslot, k_first, k_count, blk_lo, blk_hi, stream):
+        self._on(stream)
+        self.ctx.check(self.ctx.lib.mdb_dist_apply_update(self.handle, k_outer, oslot, k_first, k_count, blk_lo, blk_hi),
+                       'mdb_dist_apply_update')
 
     def finalize(self, stream):
         self._on(stream)

@@ -24,7 +24,7 @@ class GlooComm:
 
 class NumpySteps:
     def __init__(self, n, rank, world, Ap, rule=bm.RULE_REIMER, min_diag_D=None, max_diag_D=None, min_abs_value_D=None,
-                 min_abs_value_L=None, min_diag_B=-math.inf, max_diag_B=math.inf):
+                 min_abs_value_L=None, min_diag_B=-math.inf, max_diag_B=math.inf, agg=2):
         self.n, self.rank, self.world = n, rank, world
         self.ld = local_cols(n, rank, world)
         self.nloc = local_blocks(n, rank, world)
@@ -45,7 +45,14 @@ class NumpySteps:
         self.mavL = float(np.finfo(np.float64).eps) if min_abs_value_L is None else float(min_abs_value_L)
         self.mB, self.MB = float(min_diag_B), float(max_diag_B)
         self.panels = [torch.zeros(panel_elems(n, 0), dtype=torch.float64) for _ in range(2)]
+        self.agg = agg
+        self.OPX = [np.zeros((n, agg * NB)) for _ in range(2)]      # operands of one outer block, rows = global - ob
+        self.OPY = [np.zeros((n, agg * NB)) for _ in range(2)]
         self.log = []
+
+    def outer_width(self, k):
+        T = (self.n + NB - 1) // NB
+        return max(1, min(self.agg, T - k))
 
     def panel_tensor(self, slot, k):
         return self.panels[slot][:panel_elems(self.n, k)]
@@ -57,18 +64,17 @@ class NumpySteps:
         buf = self.panels[slot].numpy()
         hdr = buf[:5 * NB].reshape(5, NB)
         vec = buf[5 * NB:5 * NB + 3 * rows].reshape(3, rows)
-        PX = buf[5 * NB + 3 * rows: 5 * NB + 3 * rows + rows * NB].reshape(rows, NB)
-        PY = buf[5 * NB + 3 * rows + rows * NB: 5 * NB + 3 * rows + 2 * rows * NB].reshape(rows, NB)
-        return hdr, vec, PX, PY
+        MX = buf[5 * NB + 3 * rows: 5 * NB + 3 * rows + rows * NB].reshape(rows, NB)
+        return hdr, vec, MX
 
-    def factor_panel(self, k, slot, stream):
+    def factor_panel(self, k, slot, k_outer, oslot, stream):
         assert owner_of(k, self.world) == self.rank
-        self.log.append(('factor', k, slot))
+        self.log.append(('factor', k, slot, k_outer, oslot))
         n = self.n
         k0, k1 = k * NB, min((k + 1) * NB, n)
         kb = k1 - k0
         lc0 = (k // self.world) * NB
-        hdr, vec, PX, PY = self._views(slot, k)
+        hdr, vec, MX = self._views(slot, k)
         X = np.zeros((n - k0, kb))
         Lt = np.zeros((kb, kb))
         for c in range(kb):
@@ -97,40 +103,51 @@ class NumpySteps:
         for c in range(kb):
             self.S[k0 + c + 1:, lc0 + c] = X[c + 1:, c]
         if k1 < n:
-            PX[:] = X[kb:, :]
-            PY[:] = -X[kb:, :] * self.d[k0:k1][None, :]
+            ob, c0 = k_outer * NB, k0 - k_outer * NB
+            self.OPX[oslot][k1 - ob: n - ob, c0:c0 + NB] = X[kb:, :]
+            self.OPY[oslot][k1 - ob: n - ob, c0:c0 + NB] = -X[kb:, :] * self.d[k0:k1][None, :]
+            MX[:] = X[kb:, :]
             vec[0], vec[1], vec[2] = self.alpha[k1:], self.beta[k1:], self.rowmax[k1:]
 
-    def absorb_panel(self, k, slot, stream):
-        self.log.append(('absorb', k, slot))
+    def absorb_panel(self, k, slot, k_outer, oslot, stream):
+        self.log.append(('absorb', k, slot, k_outer, oslot))
         if owner_of(k, self.world) == self.rank:
             return
         n = self.n
         k0, k1 = k * NB, min((k + 1) * NB, n)
-        hdr, vec, PX, PY = self._views(slot, k)
+        hdr, vec, MX = self._views(slot, k)
         kb = k1 - k0
         self.d[k0:k1], self.omega[k0:k1], self.delta[k0:k1] = hdr[0, :kb], hdr[1, :kb], hdr[3, :kb]
         self.clamped[k0:k1] = hdr[4, :kb] != 0
         if k1 < n:
             self.alpha[k1:], self.beta[k1:], self.rowmax[k1:] = vec[0], vec[1], vec[2]
+            ob, c0 = k_outer * NB, k0 - k_outer * NB
+            self.OPX[oslot][k1 - ob: n - ob, c0:c0 + NB] = MX
+            self.OPY[oslot][k1 - ob: n - ob, c0:c0 + NB] = -MX * hdr[0][None, :]
 
-    def apply_panel(self, k, slot, only_block, skip_block, stream):
-        self.log.append(('apply', k, slot, only_block, skip_block))
+    def apply_update(self, k_outer, oslot, k_first, k_count, blk_lo, blk_hi, stream):
+        self.log.append(('apply', k_outer, oslot, k_first, k_count, blk_lo, blk_hi))
         n = self.n
-        k1 = min((k + 1) * NB, n)
-        if k1 >= n:
+        T = (n + NB - 1) // NB
+        if blk_hi < 0 or blk_hi > T:
+            blk_hi = T
+        blk_lo = max(blk_lo, k_first + k_count)
+        r0, ob = (k_first + k_count) * NB, k_outer * NB
+        if r0 >= n:
             return
-        hdr, vec, PX, PY = self._views(slot, k)
+        c0, c1 = (k_first - k_outer) * NB, (k_first + k_count - k_outer) * NB
+        PX = self.OPX[oslot][r0 - ob: n - ob, c0:c1]
+        PY = self.OPY[oslot][r0 - ob: n - ob, c0:c1]
         for lb in range(self.nloc):
             J = lb * self.world + self.rank
-            if J <= k or (only_block >= 0 and J != only_block) or (skip_block >= 0 and J == skip_block):
+            if J < blk_lo or J >= blk_hi:
                 continue
             g0 = J * NB
             w = min(NB, n - g0)
-            upd = PX @ PY[g0 - k1: g0 - k1 + w].T          # rows k1.., columns g0..g0+w
-            rows = np.arange(k1, n)[:, None]
+            upd = PX @ PY[g0 - r0: g0 - r0 + w].T          # rows r0.., columns g0..g0+w
+            rows = np.arange(r0, n)[:, None]
             cols = np.arange(g0, g0 + w)[None, :]
-            blk = self.S[k1:, lb * NB: lb * NB + w]
+            blk = self.S[r0:, lb * NB: lb * NB + w]
             blk += np.where(rows > cols, upd, 0.0)
 
     def local_L(self):

@@ -549,15 +549,14 @@ def test_device_generator_and_identity_at_scale():
     assert 0.2 * n < cl.sum() < 0.6 * n
 
 
-def test_distributed_steps_single_rank_equal_single_gpu_path(matrix, orc):
-    """The multi-GPU step functions with world = 1 (no collective) reproduce the single-GPU path bit for bit."""
+@pytest.mark.parametrize('n,fixed', [(700, 1), (1500, 4), (1100, 8)])
+def test_distributed_steps_single_rank_equal_single_gpu_path(matrix, orc, n, fixed):
+    """The multi-GPU step functions with world = 1 (no collective) reproduce the single-GPU path bit for bit,
+    with and without outer-block aggregation."""
     import torch
     from matrix_decomposition_b200 import distributed as md, _native
-    n = 700
+    ctx = _native.context()
     A, kw = workloads.shifted_goe(n, 3, 1.05)
-    dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
-    p = np.asarray(dec.p)
-    Ap = A[p[:, None], p[None, :]]
 
     class LocalComm:
         def broadcast(self, tensor, src, stream):
@@ -566,17 +565,25 @@ def test_distributed_steps_single_rank_equal_single_gpu_path(matrix, orc):
                     pass
             return H()
 
-    main, bulk = md._streams(torch.cuda.current_device())
-    steps = md.CudaSteps(n, 0, 1)
-    steps.set_matrix(Ap, main)
-    bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
-                                       float(np.finfo(float).eps), None, kw['max_diag_B'])
-    steps.set_bounds(bounds, p, main)
-    md.factorize(n, 0, 1, steps, LocalComm(), main, bulk, lookahead=True)
-    torch.cuda.synchronize()
-    d, omega, delta, clamped = steps.finalize(main)
-    L = steps.S.cpu().numpy()[:, :n]
-    steps.close()
+    try:
+        ctx.set_blocking(fixed=fixed)
+        dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+        p = np.asarray(dec.p)
+        Ap = A[p[:, None], p[None, :]]
+        main, bulk = md._streams(torch.cuda.current_device())
+        steps = md.CudaSteps(n, 0, 1)
+        assert steps.outer_width(0) == fixed
+        steps.set_matrix(Ap, main)
+        bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
+                                           float(np.finfo(float).eps), None, kw['max_diag_B'])
+        steps.set_bounds(bounds, p, main)
+        md.factorize(n, 0, 1, steps, LocalComm(), main, bulk, lookahead=True)
+        torch.cuda.synchronize()
+        d, omega, delta, clamped = steps.finalize(main)
+        L = steps.S.cpu().numpy()[:, :n]
+        steps.close()
+    finally:
+        ctx.set_blocking()
     assert np.array_equal(clamped, dec.clamped)
     assert np.array_equal(d, np.asarray(dec.d, dtype=float))
     assert np.array_equal(L, dec.L)

@@ -24,7 +24,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     out = {}
-    for n in (700, 1500):
+    from matrix_decomposition_b200 import _native
+    for n, fixed in ((700, 1), (1500, 2), (1500, 4)):
+        _native.context(local).set_blocking(fixed=fixed)
         A, kw = workloads.shifted_goe(n, 3, 1.05)
         p = np.argsort(-A.diagonal()).astype(np.int64)
         Ap = A[p[:, None], p[None, :]]
@@ -41,9 +43,10 @@ def main():
                     g0 = (lb * world) * md.NB
                     w = min(md.NB, n - g0)
                     ok = ok and np.array_equal(Lloc[:, lb * md.NB: lb * md.NB + w], dec.L[:, g0:g0 + w])
-                out[f'n{n}_lookahead{int(la)}'] = dict(bitwise_equal_single_gpu=bool(ok), identity=ident)
+                out[f'n{n}_agg{fixed}_lookahead{int(la)}'] = dict(bitwise_equal_single_gpu=bool(ok), identity=ident)
             steps.close()
             del steps
+    _native.context(local).set_blocking()
     big = int(os.environ.get('DIST_N', '32768'))
     t = time.time()
     res = md.bench_f2(big, 1.05, steps=1, warmup=1, seed=7)
