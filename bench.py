@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native matrix-decomposition hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n SIZE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size SIZE]
 
 A "step" is one modified LDL^T factorization (matrix.approximate /
 approximation.positive_semidefinite.decomposition) of one synthetic dense symmetric float64 matrix of
@@ -38,6 +38,9 @@ METRIC = 'approximate FP64 GFLOP/s (n^3/3)'
 UNIT = 'GFLOP/s'
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl);
                                # MEASURED_PEAKS.json holds only HBM and bf16 peaks
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the bulk kernel from one `ncu --set full` capture
+# (profiles/r01_ncu_summary.txt); None until captured for the current kernel
+NCU_TRAFFIC = None
 CPU_SAMPLE_N = 6144
 S_SHIFT = 1.05
 
@@ -104,6 +107,8 @@ def cpu_baseline(n=CPU_SAMPLE_N, reps=1):
     import workloads
     from oracle import cpu_oracle as orc
     A, kw = workloads.shifted_goe(n, 4242, S_SHIFT)
+    # all host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+    cores = orc.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
     orc.approximate(A[:256, :256].copy(), **f2_bounds(256))  # build + warm the library
     best = None
     for _ in range(reps):
@@ -111,11 +116,21 @@ def cpu_baseline(n=CPU_SAMPLE_N, reps=1):
         res = orc.approximate(A, **kw)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
-    cores = os.cpu_count() or 1
     return dict(value=n ** 3 / 3 / best / 1e9, unit=UNIT, cores=cores, kind='port',
                 sample='oracle/mdo_oracle.c (x87 long double column loop of Reimer.py:476-686, OpenMP over rows) on one '
                        'F2 matrix n=%d, %.1f s, %d clamped columns; the Python reference itself measured 0.19-0.23 '
                        'GFLOP/s in the build container (BASELINE.md)' % (n, best, int(res['clamped'].sum()))), best
+
+
+def cpu_baseline_subprocess():
+    """cpu_baseline() in a fresh interpreter with a clean OpenMP environment: under torchrun the ranks inherit
+    OMP_NUM_THREADS=1 and the x87 row loops ran 15 x slower than on the same box outside torchrun."""
+    env = dict(os.environ)
+    for k in ('OMP_NUM_THREADS', 'OMP_PROC_BIND', 'OMP_PLACES', 'GOMP_CPU_AFFINITY', 'KMP_AFFINITY'):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-baseline-json'], env=env, check=True,
+                         stdout=subprocess.PIPE, text=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
 
 
 def run_reference(args):
@@ -152,7 +167,7 @@ def run_single(args):
     torch.cuda.set_device(0)
     ctx = _native.context(0)
     lib = ctx.lib
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.Stream(priority=-1)   # high priority: panels overtake the bulk update on the side stream
     ctx.set_stream(stream.cuda_stream)
     mu = S_SHIFT * math.sqrt(2 * n)
     kw = f2_bounds(n)
@@ -201,23 +216,29 @@ def run_single(args):
     res = ctypes.c_double()
     ctx.check(lib.mdb_factor_identity_residual(f, 2, 7, ctypes.byref(res)), 'mdb_factor_identity_residual')
 
-    # ---- roofline of the dominant kernel (k_gemm_tn<LOWER>, the trailing update), serialised profiling pass ----
+    # ---- roofline of the dominant kernel (k_gemm_tn_tma: the bulk trailing update, one launch per outer block),
+    #      serialised profiling pass with CUDA events around every phase on the launching stream ----
     regenerate()
     ctx.set_profiling(True)
     factor()
     ctx.synchronize()
     ctx.set_profiling(False)
     phases = ctx.phase_ms()
-    NB = 128
-    trailing_flop = sum(float(n - k1) ** 2 * NB for k1 in range(NB, n, NB))   # 2 * (rows^2 / 2) * NB per launch
-    n_launch = len(range(NB, n, NB))
-    achieved = trailing_flop / (phases['trailing'] * 1e-3) / 1e12 if phases['trailing'] > 0 else None
-    roofline = dict(bound='tensor', kernel='k_gemm_tn<LOWER,BETA1> (FP64 DMMA trailing update)', achieved=achieved,
-                    peak=FP64_DMMA_PEAK_TFLOPS, unit='TFLOP/s', frac=(achieved / FP64_DMMA_PEAK_TFLOPS if achieved else None),
+    st = ctx.update_stats()
+    achieved = st['bulk_flop'] / (phases['trailing'] * 1e-3) / 1e12 if phases['trailing'] > 0 else None
+    roofline = dict(bound='tensor', kernel='k_gemm_tn_tma (TMA-fed FP64 DMMA tile kernel; bulk trailing update, strict lower '
+                                           'triangle, K = 128 x panels of the outer block)',
+                    achieved=achieved, peak=FP64_DMMA_PEAK_TFLOPS, unit='TFLOP/s',
+                    frac=(achieved / FP64_DMMA_PEAK_TFLOPS if achieved else None),
                     peak_source='measured FP64 DMMA peak (tools/fp64_peak.cu, profiles/r01_fp64_peak.jsonl); '
                                 'MEASURED_PEAKS.json has no FP64 entry',
-                    launches=n_launch, avg_launch_ms=phases['trailing'] / max(n_launch, 1),
-                    algorithmic_flop_per_launch='(n - k1)^2 * 128', phases_ms=phases, traffic=None)
+                    launches=st['bulk_launches'], avg_launch_ms=phases['trailing'] / max(st['bulk_launches'], 1),
+                    algorithmic_flop_per_launch='K * rows * (rows - 1), rows = n - end of the outer block, K = its width '
+                                                '(1024 / 512 / 256 / 128 while >= 32768 / 16384 / 8192 / 0 rows remain)',
+                    algorithmic_flop_total=st['bulk_flop'], share_of_n3_over_3=st['bulk_flop'] / (n ** 3 / 3),
+                    inner_update=dict(flop=st['inner_flop'], launches=st['inner_launches'], ms=phases['inner'],
+                                      tflops=(st['inner_flop'] / (phases['inner'] * 1e-3) / 1e12 if phases['inner'] > 0 else None)),
+                    phases_ms=phases, traffic=NCU_TRAFFIC)
     lib.mdb_factor_destroy(f)
 
     # ---- end-to-end leg: C-ABI one-shot call with pinned host buffers ----
@@ -233,7 +254,8 @@ def run_single(args):
                                      'decreasing_diagonal_values' % n,
                             n=n, l2='inputs (%.1f GB) far larger than L2; matrix regenerated between steps' % (8e-9 * n * n),
                             frac_of_fp64_dmma_peak=value / 1e3 / FP64_DMMA_PEAK_TFLOPS,
-                            identity_residual=res.value, lookahead=os.environ.get('MDB200_LOOKAHEAD', '1')),
+                            identity_residual=res.value, lookahead=os.environ.get('MDB200_LOOKAHEAD', '1'),
+                            blocking='panels of 128 columns; outer blocks of 8/4/2/1 panels by remaining size'),
                 clocks=clocks, gpu_launches=int(launches_per_step * args.steps), roofline=roofline, cpu_baseline=base)
     if e2e is not None:
         line['e2e'] = e2e
@@ -287,13 +309,18 @@ def run_distributed(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', str(rank)))
     torch.cuda.set_device(local)
+    base = cpu_baseline_subprocess() if rank == 0 else None   # before the ranks start spinning on collectives
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     n = args.n or 131072
-    out = mdist.bench_f2(n, S_SHIFT, steps=args.steps, warmup=args.warmup, seed=20261019)
+    sampler = ClockSampler(local)
     if rank == 0:
+        sampler.start()
+    out = mdist.bench_f2(n, S_SHIFT, steps=args.steps, warmup=args.warmup, seed=20261019, e2e=not args.no_e2e,
+                         peak_tflops=FP64_DMMA_PEAK_TFLOPS)
+    if rank == 0:
+        out['clocks'] = sampler.stop()
         ms = out['ms_per_step']
         value = n ** 3 / 3 / (ms * 1e-3) / 1e9
-        base, _ = cpu_baseline()
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64',
                     data='synthetic',
@@ -302,7 +329,8 @@ def run_distributed(args):
                                          (n, 8e-9 * n * n, world), n=n,
                                 l2='inputs far larger than L2; matrix regenerated between steps',
                                 frac_of_fp64_dmma_peak=value / 1e3 / (FP64_DMMA_PEAK_TFLOPS * world),
-                                identity=out.get('identity')),
+                                identity=out.get('identity'), n_clamped=out.get('n_clamped'),
+                                e2e_skipped=out.get('e2e_skipped')),
                     clocks=out.get('clocks'), gpu_launches=out.get('gpu_launches'), roofline=out.get('roofline'),
                     cpu_baseline=base, e2e=out.get('e2e'))
         print(json.dumps(line))
@@ -317,9 +345,13 @@ def main():
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--n', type=int, default=0, help='override the matrix size (debugging only)')
+    ap.add_argument('--size', dest='n', type=int, default=0, help='override the matrix size (debugging only)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cpu-baseline-json', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_baseline_json:
+        print(json.dumps(cpu_baseline()[0]))
+        return 0
     if args.impl == 'reference':
         return run_reference(args)
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -68,7 +68,8 @@ int mdb_ctx_synchronize(mdb_ctx *ctx);
 const char *mdb_last_error(const mdb_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 int64_t mdb_launch_count(const mdb_ctx *ctx);
-/* Per-phase device time of the last mdb_factor_run with profiling on: ms[0..3] = diag, panel, trailing, other */
+/* Per-phase device time of the last mdb_factor_run with profiling on (serialised, CUDA events per phase):
+ * ms[0..3] = diagonal blocks, panels, bulk trailing updates, inner (within the outer block) updates */
 int mdb_ctx_set_profiling(mdb_ctx *ctx, int on);
 int mdb_ctx_get_phase_ms(const mdb_ctx *ctx, double ms[4]);
 /* Blocking of the factorization (tuning / tests; the defaults are chosen for B200).  Panels are 128 columns; the
@@ -76,6 +77,10 @@ int mdb_ctx_get_phase_ms(const mdb_ctx *ctx, double ms[4]);
  * panels while at least t2 / t4 / t8 rows remain (else 1).  ms[2] above then is the bulk (per outer block) update,
  * ms[3] the inner (per panel, within the outer block) update.  Environment: MDB200_AGG, MDB200_AGG_THRESH. */
 int mdb_ctx_set_blocking(mdb_ctx *ctx, int fixed, int64_t t2, int64_t t4, int64_t t8);
+/* Algorithmic work of the trailing updates of the last mdb_factor_run: out = {bulk flop, bulk launches (one per
+ * outer block; with lookahead each is issued as two kernels), inner flop, inner launches}; flop = 2 K per updated
+ * element of the strict lower triangle. */
+int mdb_ctx_get_update_stats(const mdb_ctx *ctx, double out[4]);
 
 /* ---- device memory (so that a host language without CUDA bindings can stage buffers) ---- */
 int mdb_malloc(mdb_ctx *ctx, size_t bytes, void **dptr);
@@ -193,6 +198,9 @@ int64_t mdb_dist_panel_elems(const mdb_dist *s, int64_t k);  /* doubles to broad
 int mdb_dist_generate_f2(mdb_dist *s, uint64_t seed, double mu, const int64_t *p);
 /* local columns from a host matrix that is already permuted: Ap (n x n, ld) */
 int mdb_dist_set_matrix(mdb_dist *s, const double *Ap, int64_t ld);
+/* this rank's slab from a buffer that already has the slab layout (n x ld_src, local column lc at [i * ld_src + lc];
+ * loc = MDB_HOST / MDB_DEVICE): the end-to-end entry when every rank holds its own columns on the host */
+int mdb_dist_set_local(mdb_dist *s, const double *A_loc_src, int64_t ld_src, int loc);
 /* bounds as in mdb_factor_run; p (host, may be NULL) maps position -> original index for vector B bounds.
  * Resets alpha / beta / rowmax. */
 int mdb_dist_set_bounds(mdb_dist *s, const mdb_bounds *bounds, const int64_t *p);

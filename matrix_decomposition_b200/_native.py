@@ -62,6 +62,7 @@ SIGNATURES = {
     'mdb_ctx_set_profiling': (_int, [_vp, _int]),
     'mdb_ctx_get_phase_ms': (_int, [_vp, _vp]),
     'mdb_ctx_set_blocking': (_int, [_vp, _int, _i64, _i64, _i64]),
+    'mdb_ctx_get_update_stats': (_int, [_vp, _vp]),
     'mdb_malloc': (_int, [_vp, _sz, _pp]),
     'mdb_free': (_int, [_vp, _vp]),
     'mdb_malloc_host': (_int, [_vp, _sz, _pp]),
@@ -98,6 +99,7 @@ SIGNATURES = {
     'mdb_dist_panel_elems': (_i64, [_vp, _i64]),
     'mdb_dist_generate_f2': (_int, [_vp, _u64, _dbl, _vp]),
     'mdb_dist_set_matrix': (_int, [_vp, _vp, _i64]),
+    'mdb_dist_set_local': (_int, [_vp, _vp, _i64, _int]),
     'mdb_dist_set_bounds': (_int, [_vp, ctypes.POINTER(Bounds), _vp]),
     'mdb_dist_outer_width': (_i64, [_vp, _i64]),
     'mdb_dist_factor_panel': (_int, [_vp, _i64, _int, _i64, _int]),
@@ -176,10 +178,15 @@ class Context:
         """Outer-block width of the factorization (see mdb_ctx_set_blocking in include/mdb200.h)."""
         self.check(self.lib.mdb_ctx_set_blocking(self.handle, int(fixed), int(t2), int(t4), int(t8)), 'mdb_ctx_set_blocking')
 
+    def update_stats(self):
+        out = (ctypes.c_double * 4)()
+        self.check(self.lib.mdb_ctx_get_update_stats(self.handle, out), 'mdb_ctx_get_update_stats')
+        return dict(bulk_flop=out[0], bulk_launches=int(out[1]), inner_flop=out[2], inner_launches=int(out[3]))
+
     def phase_ms(self):
         out = (ctypes.c_double * 4)()
         self.check(self.lib.mdb_ctx_get_phase_ms(self.handle, out), 'mdb_ctx_get_phase_ms')
-        return dict(diag=out[0], panel=out[1], trailing=out[2], other=out[3])
+        return dict(diag=out[0], panel=out[1], trailing=out[2], inner=out[3])
 
     # --- raw device memory (used by bench.py and the distributed driver) ---
     def malloc(self, nbytes):

@@ -123,46 +123,64 @@ MD_HD double md_difference_frobenius_norm(double d, double omega, double alpha, 
   return t * t + (omega - 1) * (omega - 1) * beta;
 }
 
-// Reimer.py:42-176
-MD_HD MdDecision md_minimal_change(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
-                                   double min_diag_B, double max_diag_B, double min_abs_value_D) {
-  MdDecision r;
+// Candidate order of the reference: min over the list by the key (f, -d, omega), Reimer.py:156-160.
+MD_HD bool md_candidate_better(double cf, double cd, double cw, double bf, double bd, double bw) {
+  if (cf != bf) return cf < bf;
+  if (cd != bd) return cd > bd;
+  return cw < bw;
+}
+
+// Best candidate of a subset of the candidate list of Reimer.py:42-176 (clamped branch only):
+//   part bit 0: (a, 1) / (b, 1) (:82-88) and the cubic roots for d = lo (:95-96, :103-135)
+//   part bit 1: the cubic roots for d = max_diag_D (:97-98), the omega = 0 fallback (:146-148), (0, 0) (:151-152)
+// have = 0 when the subset is empty.  min over the union of both parts = the reference's choice (the key is a
+// total order when no f is NaN), so the two cubic solves can run in two threads and be merged afterwards.
+struct MdBest {
+  double d, w, f;
+  int have;
+};
+
+MD_HD MdBest md_merge_best(const MdBest& x, const MdBest& y) {  // y is "later in the list" than x
+  if (!x.have) return y;
+  if (!y.have) return x;
+  return md_candidate_better(y.f, y.d, y.w, x.f, x.d, x.w) ? y : x;
+}
+
+MD_HD MdBest md_minimal_change_part(int part, double alpha, double beta, double gamma, double min_diag_D,
+                                    double max_diag_D, double min_diag_B, double max_diag_B, double min_abs_value_D) {
   const double lo = md_pymax(min_diag_D, min_abs_value_D);  // :64
   const double a = md_pymax(lo, min_diag_B - alpha);        // :65
   const double b = md_pymin(max_diag_D, max_diag_B - alpha);  // :66
   const double dstar = gamma - alpha;                       // :67
-  if (a <= dstar && dstar <= b) {                           // :68-72
-    r.d = dstar; r.omega = 1; r.f = 0; r.clamped = 0;
-    return r;
-  }
   double best_d = 0, best_w = 0, best_f = 0;
   int have = 0;
 #define MD_CONSIDER(dd_, ww_)                                                        \
   do {                                                                               \
     const double cd_ = (dd_), cw_ = (ww_);                                           \
     const double cf_ = md_difference_frobenius_norm(cd_, cw_, alpha, beta, gamma);   \
-    int better_;                                                                     \
-    if (!have) better_ = 1;                                                          \
-    else if (cf_ != best_f) better_ = cf_ < best_f;                                  \
-    else if (cd_ != best_d) better_ = cd_ > best_d;                                  \
-    else better_ = cw_ < best_w;                                                     \
-    if (better_) { best_d = cd_; best_w = cw_; best_f = cf_; have = 1; }             \
+    if (!have || md_candidate_better(cf_, cd_, cw_, best_f, best_d, best_w)) {       \
+      best_d = cd_; best_w = cw_; best_f = cf_; have = 1;                            \
+    }                                                                                \
   } while (0)
 
   int add_best_d_omega_zero = 0;
   if (isfinite(alpha)) {
-    if (a <= b) {  // :82-88
+    if ((part & 1) && a <= b) {  // :82-88
       if (dstar < a) MD_CONSIDER(a, 1.0);
       else if (dstar > b) MD_CONSIDER(b, 1.0);
     }
     if (isfinite(beta)) {
       if (alpha != 0) {
-        double dv[2];
-        int nd = 0;
-        if (min_diag_B - alpha <= lo) dv[nd++] = lo;                                  // :95-96
-        if (isfinite(max_diag_D) && max_diag_D <= max_diag_B) dv[nd++] = max_diag_D;  // :97-98
-        for (int t = 0; t < nd; ++t) {
-          const double dd = dv[t];
+        for (int t = 0; t < 2; ++t) {
+          if (!((part >> t) & 1)) continue;
+          double dd;
+          if (t == 0) {
+            if (!(min_diag_B - alpha <= lo)) continue;  // :95-96
+            dd = lo;
+          } else {
+            if (!(isfinite(max_diag_D) && max_diag_D <= max_diag_B)) continue;  // :97-98
+            dd = max_diag_D;
+          }
           const double q = (-0.5 * beta / alpha) / alpha;  // :103
           const double p = (dd - gamma) / alpha - q;       // :104
           if (!isfinite(q) || !isfinite(p)) { add_best_d_omega_zero = 1; continue; }  // :105-110
@@ -187,15 +205,54 @@ MD_HD MdDecision md_minimal_change(double alpha, double beta, double gamma, doub
   } else {
     add_best_d_omega_zero = 1;  // :140-143
   }
+  // the fallback is one and the same candidate whoever adds it; a flag raised by the d = lo solve (part bit 0
+  // only) still has to produce it
   if (add_best_d_omega_zero) {  // :146-148
     const double dd = md_pymax(md_pymax(lo, min_diag_B), md_pymin(md_pymin(gamma, max_diag_D), max_diag_B));
     MD_CONSIDER(dd, 0.0);
   }
-  if (min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D) MD_CONSIDER(0.0, 0.0);  // :151-152
+  if ((part & 2) && min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D) MD_CONSIDER(0.0, 0.0);  // :151-152
 #undef MD_CONSIDER
-  if (!have) { best_d = NAN; best_w = NAN; best_f = NAN; }
-  r.d = best_d; r.omega = best_w; r.f = best_f; r.clamped = 1;
+  MdBest r;
+  r.d = best_d; r.w = best_w; r.f = best_f; r.have = have;
   return r;
+}
+
+// Reimer.py:68-72: the unclamped branch
+MD_HD bool md_unclamped(double alpha, double gamma, double min_diag_D, double max_diag_D, double min_diag_B,
+                        double max_diag_B, double min_abs_value_D) {
+  const double lo = md_pymax(min_diag_D, min_abs_value_D);
+  const double a = md_pymax(lo, min_diag_B - alpha);
+  const double b = md_pymin(max_diag_D, max_diag_B - alpha);
+  const double dstar = gamma - alpha;
+  return a <= dstar && dstar <= b;
+}
+
+MD_HD MdDecision md_decision_from_best(const MdBest& m) {
+  MdDecision r;
+  if (m.have) { r.d = m.d; r.omega = m.w; r.f = m.f; }
+  else { r.d = NAN; r.omega = NAN; r.f = NAN; }
+  r.clamped = 1;
+  return r;
+}
+
+// Reimer.py:42-176
+MD_HD MdDecision md_minimal_change(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
+                                   double min_diag_B, double max_diag_B, double min_abs_value_D) {
+  if (md_unclamped(alpha, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, min_abs_value_D)) {  // :68-72
+    MdDecision r;
+    r.d = gamma - alpha; r.omega = 1; r.f = 0; r.clamped = 0;
+    return r;
+  }
+  return md_decision_from_best(
+      md_minimal_change_part(3, alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, min_abs_value_D));
+}
+
+// effective min_diag_D of Reimer.py:488-491 (NaN = "None": per-index default)
+MD_HD double md_effective_min_diag_D(const MdRuleParams& prm, double gamma, double min_diag_B_i, double max_diag_B_i) {
+  double mD = prm.min_diag_D;
+  if (isnan(mD)) mD = md_pymin(0.5 * md_pymin(md_pymax(gamma, min_diag_B_i), max_diag_B_i), prm.max_diag_D);
+  return mD;
 }
 
 // Decision for one column given its accumulated (alpha, beta, gamma) and per-index B bounds.
@@ -208,8 +265,6 @@ MD_HD MdDecision md_decide(const MdRuleParams& prm, double alpha, double beta, d
     r.clamped = !(r.d > 0);
     return r;
   }
-  double mD = prm.min_diag_D;
-  if (isnan(mD))  // Reimer.py:488-491
-    mD = md_pymin(0.5 * md_pymin(md_pymax(gamma, min_diag_B_i), max_diag_B_i), prm.max_diag_D);
+  const double mD = md_effective_min_diag_D(prm, gamma, min_diag_B_i, max_diag_B_i);  // Reimer.py:488-491
   return md_minimal_change(alpha, beta, gamma, mD, prm.max_diag_D, min_diag_B_i, max_diag_B_i, prm.min_abs_value_D);
 }

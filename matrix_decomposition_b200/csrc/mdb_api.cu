@@ -133,6 +133,12 @@ extern "C" int mdb_ctx_set_profiling(mdb_ctx* ctx, int on) {
   ctx->profiling = on;
   return MDB_OK;
 }
+extern "C" int mdb_ctx_get_update_stats(const mdb_ctx* ctx, double out[4]) {
+  if (!ctx || !out) return MDB_ERR_INVALID;
+  out[0] = ctx->gemm_flop[0]; out[1] = (double)ctx->gemm_launches[0];
+  out[2] = ctx->gemm_flop[1]; out[3] = (double)ctx->gemm_launches[1];
+  return MDB_OK;
+}
 extern "C" int mdb_ctx_set_blocking(mdb_ctx* ctx, int fixed, int64_t t2, int64_t t4, int64_t t8) {
   if (!ctx) return MDB_ERR_INVALID;
   MDB_CHECK(ctx, fixed == 0 || fixed == 1 || fixed == 2 || fixed == 4 || fixed == 8, "mdb_ctx_set_blocking: fixed must be 0, 1, 2, 4 or 8");
@@ -481,6 +487,8 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
   f->rule = bnd->rule;
   f->mavL = F.prm.min_abs_value_L;
   for (int i = 0; i < 4; ++i) ctx->phase_ms[i] = 0;
+  ctx->gemm_flop[0] = ctx->gemm_flop[1] = 0;
+  ctx->gemm_launches[0] = ctx->gemm_launches[1] = 0;
 
   if (bn > 0) {
     MDB_CUDA(ctx, cudaMemsetAsync(f->alpha, 0, (size_t)3 * bn * 8, ctx->stream));  // alpha, beta, rowmax contiguous
@@ -557,6 +565,11 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
         gi.row_glob0 = k1; gi.col_glob0 = k1; gi.b_glob0 = k1; gi.b_rows = rows;
         rc = trailing(gi, main_s);
         if (rc) return rc;
+        {  // strictly-lower elements of the rows x (oe - k1) region, 2 K flop each
+          const double M = (double)rows, N = (double)(oe - k1);
+          ctx->gemm_flop[1] += 2.0 * NB * (N * M - 0.5 * N * (N + 1)) * (double)batch;
+          ctx->gemm_launches[1] += 1;
+        }
       }
     }
     if (oe >= n) break;
@@ -569,6 +582,8 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
     g.C = f->W + oe * f->ld + oe; g.ldc = f->ld; g.sC = F.sW;
     g.M = rows; g.N = rows; g.K = (int)(oe - ob);
     g.row_glob0 = oe; g.col_glob0 = oe; g.b_glob0 = oe; g.b_rows = rows;
+    ctx->gemm_flop[0] += (double)g.K * (double)rows * (double)(rows - 1) * (double)batch;  // 2 K flop per element i > j
+    ctx->gemm_launches[0] += 1;
     if (!lookahead) {
       PhaseTimer t(ctx, 2);
       rc = trailing(g, main_s);

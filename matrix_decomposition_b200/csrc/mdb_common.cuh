@@ -27,6 +27,8 @@ struct mdb_ctx {
   int64_t launches;
   int profiling;
   double phase_ms[4];
+  double gemm_flop[2];        // algorithmic flop of the bulk / inner trailing updates of the last mdb_factor_run
+  int64_t gemm_launches[2];
   int num_sms;
   cudaEvent_t ev[2];
 };

@@ -177,6 +177,20 @@ extern "C" int mdb_dist_set_matrix(mdb_dist* s, const double* Ap, int64_t ld) {
   return MDB_OK;
 }
 
+// this rank's column slab from a host (or device) buffer that already has the slab layout: A_loc_src is n x ld_src
+// with local column lc at A_loc_src[i * ld_src + lc]  (the reverse of reading S_loc after mdb_dist_finalize)
+extern "C" int mdb_dist_set_local(mdb_dist* s, const double* A_loc_src, int64_t ld_src, int loc) {
+  if (!s || !A_loc_src) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CHECK(ctx, ld_src >= s->ld, "mdb_dist_set_local: ld_src < local columns");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = copy2d_async(ctx, s->A, s->ld, A_loc_src, ld_src, s->n, s->ld, MDB_DEVICE, loc);
+  if (!rc) rc = dist_after_matrix(s);
+  if (rc) return rc;
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MDB_OK;
+}
+
 extern "C" int mdb_dist_set_bounds(mdb_dist* s, const mdb_bounds* bnd, const int64_t* p) {
   if (!s || !bnd) return MDB_ERR_INVALID;
   mdb_ctx* ctx = s->ctx;
@@ -213,6 +227,8 @@ extern "C" int mdb_dist_set_bounds(mdb_dist* s, const mdb_bounds* bnd, const int
   s->prm.max_diag_B = sc_maxB;
   MDB_CUDA(ctx, cudaMemsetAsync(s->alpha, 0, (size_t)3 * n * 8, ctx->stream));
   MDB_CUDA(ctx, cudaMemsetAsync(s->info, 0, sizeof(int), ctx->stream));
+  ctx->gemm_flop[0] = ctx->gemm_flop[1] = 0;  // mdb_ctx_get_update_stats counts this rank's share from here on
+  ctx->gemm_launches[0] = ctx->gemm_launches[1] = 0;
   s->have_bounds = true;
   return MDB_OK;
 }
@@ -350,6 +366,19 @@ extern "C" int mdb_dist_apply_update(mdb_dist* s, int64_t k_outer, int oslot, in
   g.cyc_G = s->world; g.cyc_r = s->rank;  // one rank: plain mapping, global column = local column
   g.n_tile0 = lb_begin * tpb;
   g.n_tiles = (lb_end - lb_begin) * tpb;
+  {  // this rank's algorithmic work: 2 K flop per strictly-lower element of its column blocks (bulk = the whole
+     // outer block is contracted at once)
+    double elems = 0;
+    for (int64_t lb = lb_begin; lb < lb_end; ++lb) {
+      const int64_t g0 = (lb * s->world + s->rank) * NB;         // first global column of the block
+      const int64_t w = std::min<int64_t>(NB, n - g0);
+      const double first = (double)(n - std::max<int64_t>(r0, g0 + 1));  // rows below the diagonal in column g0
+      elems += w * first - 0.5 * (double)w * (double)(w - 1) * (g0 + 1 >= r0 ? 1.0 : 0.0);
+    }
+    const bool bulk = k_first == k_outer && k_count == mdb_dist_outer_width(s, k_outer);
+    ctx->gemm_flop[bulk ? 0 : 1] += 2.0 * (double)g.K * elems;
+    ctx->gemm_launches[bulk ? 0 : 1] += 1;
+  }
   const int r = launch_gemm_tn_tma(ctx, g, rows, rows);
   if (r != -1) return r;
   return launch_gemm_tn<true, true, false>(ctx, g, 1);

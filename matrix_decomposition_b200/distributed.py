@@ -162,6 +162,7 @@ class CudaSteps:
                                           ctypes.c_void_p(self.panels[1].data_ptr()), ctypes.byref(h))
         self.ctx.check(rc, 'mdb_dist_create')
         self.handle = h
+        self.bulk_events = None
 
     def close(self):
         if self.handle:
@@ -203,8 +204,23 @@ class CudaSteps:
 
     def apply_update(self, k_outer, oslot, k_first, k_count, blk_lo, blk_hi, stream):
         self._on(stream)
+        timed = self.bulk_events is not None and k_first == k_outer and k_count == self.outer_width(k_outer)
+        if timed:       # serialised profiling pass: CUDA events around every bulk update on its launching stream
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream.stream)
         self.ctx.check(self.ctx.lib.mdb_dist_apply_update(self.handle, k_outer, oslot, k_first, k_count, blk_lo, blk_hi),
                        'mdb_dist_apply_update')
+        if timed:
+            e1.record(stream.stream)
+            self.bulk_events.append((e0, e1))
+
+    def set_local(self, A_loc_host, stream):
+        """This rank's column slab from a host array in slab layout (n x ld_loc)."""
+        self._on(stream)
+        assert A_loc_host.shape == (self.n, self.ld) and A_loc_host.dtype == np.float64 and A_loc_host.flags.c_contiguous
+        self.ctx.check(self.ctx.lib.mdb_dist_set_local(self.handle, self._native.ptr(A_loc_host), self.ld, self._native.HOST),
+                       'mdb_dist_set_local')
 
     def finalize(self, stream):
         self._on(stream)
@@ -297,13 +313,26 @@ def identity_residual(steps, d, omega, delta, nprobe=2, seed=5):
     return float((lhs - rhs).abs().max() / av.abs().max())
 
 
-def bench_f2(n, s, steps, warmup, seed):
-    """bench.py's N > 1 leg: family F2 generated on the devices, timed with CUDA events, max over ranks."""
+def _mem_available_bytes():
+    try:
+        for line in open('/proc/meminfo'):
+            if line.startswith('MemAvailable:'):
+                return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
+def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None):
+    """bench.py's N > 1 leg: family F2 generated on the devices, timed with CUDA events, max over ranks.
+    Adds a serialised profiling pass (roofline of the bulk update kernel on this rank's share) and an
+    end-to-end leg in which every rank starts from its own column slab in pinned HOST memory."""
     import torch
     import torch.distributed as dist
     from . import _native
     rank, world = dist.get_rank(), dist.get_world_size()
     device = torch.cuda.current_device()
+    dev = torch.device('cuda', device)
     ctx = _native.context(device)
     mu = s * math.sqrt(2 * n)
     diag = np.empty(n)
@@ -314,6 +343,12 @@ def bench_f2(n, s, steps, warmup, seed):
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, 0.015 * mu, 0.9 * mu, 0.015 * mu,
                                        float(np.finfo(np.float64).eps), None, 2 * mu)
     comm = NcclComm()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     times = []
     launches = 0
     for it in range(warmup + steps):
@@ -329,14 +364,78 @@ def bench_f2(n, s, steps, warmup, seed):
         e1.record(main.stream)
         torch.cuda.synchronize()
         dist.barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=torch.device('cuda', device))
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = max_over_ranks(e0.elapsed_time(e1))
         if it >= warmup:
-            times.append(float(t.item()))
+            times.append(t)
             launches += ctx.launch_count() - l0
     d, omega, delta, clamped = st.finalize(main)
     ident = identity_residual(st, d, omega, delta)
     out = dict(ms_per_step=float(np.mean(times)), gpu_launches=int(launches), identity=ident,
                n_clamped=int(clamped.sum()))
+
+    # ---- roofline: one serialised pass (no lookahead, everything on the main stream), events per bulk update ----
+    st.generate_f2(seed, mu, p, main)
+    st.set_bounds(bounds, p, main)
+    torch.cuda.synchronize()
+    dist.barrier()
+    st.bulk_events = []
+    factorize(n, rank, world, st, comm, main, bulk, lookahead=False)
+    torch.cuda.synchronize()
+    bulk_ms = sum(a.elapsed_time(b) for a, b in st.bulk_events)
+    n_bulk = len(st.bulk_events)
+    st.bulk_events = None
+    stats = ctx.update_stats()
+    dist.barrier()
+    if bulk_ms > 0 and n_bulk:
+        achieved = stats['bulk_flop'] / (bulk_ms * 1e-3) / 1e12
+        out['roofline'] = dict(bound='tensor', kernel='k_gemm_tn_tma (bulk trailing update on rank 0\'s column blocks)',
+                               achieved=achieved, peak=peak_tflops, unit='TFLOP/s',
+                               frac=(achieved / peak_tflops if peak_tflops else None), launches=n_bulk,
+                               avg_launch_ms=bulk_ms / n_bulk,
+                               algorithmic_flop_per_launch='2 K x (strictly-lower elements of this rank\'s column blocks '
+                                                           'beyond the outer block), K = 128 x its panels',
+                               algorithmic_flop_total=stats['bulk_flop'],
+                               share_of_n3_over_3=stats['bulk_flop'] * world / (n ** 3 / 3), traffic=None,
+                               note='per rank (rank 0); serialised pass without lookahead')
+
+    # ---- end to end: every rank starts from its own column slab in pinned host memory ----
+    out['e2e'] = None
+    if e2e:
+        slab_bytes = n * st.ld * 8
+        local_ranks = int(os.environ.get('LOCAL_WORLD_SIZE', world))
+        ok = _mem_available_bytes() > 1.5 * slab_bytes * local_ranks + (16 << 30)
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() > 0:
+            host = ctx.pinned_array((n, st.ld))
+            st.generate_f2(seed, mu, p, main)            # fill the host slab once, untimed
+            torch.cuda.synchronize()
+            ctx.check(ctx.lib.mdb_memcpy(ctx.handle, _native.ptr(host), ctypes.c_void_p(st.A.data_ptr()), slab_bytes,
+                                         _native.HOST, _native.DEVICE), 'mdb_memcpy')
+            e2e_times = []
+            import time
+            for it in range(2):                          # one warm-up call, one timed
+                torch.cuda.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+                st.set_local(host, main)                 # H2D of the slab (+ device copy into the working array)
+                st.set_bounds(bounds, p, main)
+                factorize(n, rank, world, st, comm, main, bulk, lookahead=True)
+                dv, ov, de, cl = st.finalize(main)       # D2H of d, omega, delta, clamped; L stays distributed on the GPUs
+                torch.cuda.synchronize()
+                dt = max_over_ranks(time.perf_counter() - t0)
+                if it > 0:
+                    e2e_times.append(dt)
+            _native.free_pinned(host)
+            sec = float(np.mean(e2e_times))
+            out['e2e'] = dict(value=n ** 3 / 3 / sec / 1e9, unit='GFLOP/s',
+                              h2d_bytes_per_step=int(sum(n * local_cols(n, r, world) * 8 for r in range(world))),
+                              d2h_bytes_per_step=int(world * (3 * n * 8 + n)), seconds_per_step=sec, steps=1,
+                              call='distributed.CudaSteps.set_local (pinned host column slabs) + factorize + finalize; '
+                                   'L stays distributed on the devices (SURVEY 8e), the vectors d/omega/delta/clamped '
+                                   'return to every host', n_clamped=int(cl.sum()), results_finite=bool(np.all(np.isfinite(dv))))
+        else:
+            out['e2e_skipped'] = ('host memory: %.0f GB available for %d x %.0f GB pinned slabs'
+                                  % (_mem_available_bytes() / 1e9, local_ranks, slab_bytes / 1e9))
     st.close()
     return out

@@ -50,6 +50,8 @@ def rule_shim():
         s.mdh_cubic.restype = ctypes.c_int
         s.mdh_minimal_change.argtypes = [dbl] * 8 + [vp]
         s.mdh_minimal_change.restype = ctypes.c_int
+        s.mdh_minimal_change_split.argtypes = [dbl] * 8 + [vp]
+        s.mdh_minimal_change_split.restype = ctypes.c_int
         s.mdh_decide.argtypes = [ctypes.c_int] + [dbl] * 8 + [vp]
         s.mdh_decide.restype = ctypes.c_int
         _shim = s

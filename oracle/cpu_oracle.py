@@ -64,6 +64,14 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """OpenMP threads of the row loops (timing harness only); returns the number now in use."""
+    L = lib()
+    L.mdo_set_threads.argtypes = [ctypes.c_int]
+    L.mdo_set_threads.restype = ctypes.c_int
+    return int(L.mdo_set_threads(int(n)))
+
+
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 

@@ -11,6 +11,19 @@ int mdh_minimal_change(double alpha, double beta, double gamma, double min_diag_
   out3[0] = r.d; out3[1] = r.omega; out3[2] = r.f;
   return r.clamped;
 }
+// the two-thread evaluation of the kernels: both halves of the candidate list, merged
+int mdh_minimal_change_split(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
+                             double min_diag_B, double max_diag_B, double mav, double* out3) {
+  if (md_unclamped(alpha, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav)) {
+    out3[0] = gamma - alpha; out3[1] = 1; out3[2] = 0;
+    return 0;
+  }
+  const MdBest x = md_minimal_change_part(1, alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav);
+  const MdBest y = md_minimal_change_part(2, alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav);
+  MdDecision r = md_decision_from_best(md_merge_best(x, y));
+  out3[0] = r.d; out3[1] = r.omega; out3[2] = r.f;
+  return r.clamped;
+}
 int mdh_decide(int rule, double min_diag_D, double max_diag_D, double mavD, double alpha, double beta, double gamma,
                double mB, double MB, double* out3) {
   MdRuleParams prm;

@@ -26,6 +26,9 @@ def test_fp64_rule_against_reference_vectors():
         assert abs(out[2] - w[2]) <= 1e-12 * max(1.0, abs(w[2]))       # same minimum
         if abs(out[0] - w[0]) > 1e-12 * abs(w[0]) or abs(out[1] - w[1]) > 1e-9:
             n_far += 1                                                   # degenerate ties only
+        out2 = np.zeros(3)                                               # two-thread split used by k_diag_block
+        cl2 = shim.mdh_minimal_change_split(*[float(v) for v in row], out2.ctypes.data_as(ctypes.c_void_p))
+        assert cl2 == cl and (np.array_equal(out, out2) or (np.isnan(out).any() and np.isnan(out2).any()))
     assert n_far <= 4
 
 
