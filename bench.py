@@ -310,7 +310,7 @@ def run_distributed(args):
     local = int(os.environ.get('LOCAL_RANK', str(rank)))
     torch.cuda.set_device(local)
     base = cpu_baseline_subprocess() if rank == 0 else None   # before the ranks start spinning on collectives
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    mdist.init_process_group(local)
     n = args.n or 131072
     sampler = ClockSampler(local)
     if rank == 0:

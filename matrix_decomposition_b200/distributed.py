@@ -125,6 +125,19 @@ class TorchStream:
             self.stream.wait_event(event)
 
 
+def init_process_group(device_index=None, **kw):
+    """torch.distributed.init_process_group('nccl') with NCCL's internal stream at HIGH priority.  The panel
+    broadcast is on the critical path while the bulk update keeps every SM busy on a low-priority stream; at the
+    default priority the broadcast kernel queues behind the ~10^4 CTAs of that update and the lookahead is lost."""
+    import torch
+    import torch.distributed as dist
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return dist.init_process_group('nccl', device_id=torch.device('cuda', device_index), pg_options=opts, **kw)
+
+
 class NcclComm:
     def broadcast(self, tensor, src, stream):
         import torch

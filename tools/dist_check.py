@@ -22,7 +22,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', str(rank)))
     torch.cuda.set_device(local)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    md.init_process_group(local)
     out = {}
     from matrix_decomposition_b200 import _native
     for n, fixed in ((700, 1), (1500, 2), (1500, 4)):
