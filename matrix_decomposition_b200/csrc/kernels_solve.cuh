@@ -245,3 +245,208 @@ __global__ void k_max_abs_diff(int64_t n, const double* __restrict__ a, const do
     atomicMax(&out[1], (unsigned long long)__double_as_longlong(m));
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Persistent triangular sweep for up to 8 right-hand sides (the bandwidth-bound solve, decompositions.py:987-989):
+//   forward  (reverse = 0):  z_I = Linv_I  (b_I - sum_{J < I} L[I, J] z_J)        L  = lower triangle of W
+//   backward (reverse = 1):  x_I = LinvT_I (y_I - sum_{J > I} U[I, J] x_J)        U  = L^T = mirrored upper triangle
+// in ONE launch per sweep instead of two launches per 128-row block.  L is streamed exactly once (8 n^2 bytes per
+// solve, both sweeps): the work is cut into tasks that CTAs claim from a global counter in dependency order,
+//   partial (I, c) : p[I][c] = sum over the column blocks J of chunk c (8 blocks, J < I - 1) of L[I, J] z_J
+//   diag I         : z_I = Linv_I (b_I - sum_c p[I][c] - L[I, I-1] z_{I-1}),  then publishes flag[I]
+// Each block L[I, J] (128 x 128) is loaded into REGISTERS before the task waits for z_J, so after the flag arrives
+// only the arithmetic is left; the diag task also holds Linv_I (transposed) in shared memory ahead of time.  That
+// keeps the dependency chain z_0 -> z_1 -> ... at one flag round trip + two small products per block.  A task only
+// waits for tasks earlier in the claim order, so resident CTAs always make progress (no co-residency assumption);
+// spins are bounded and raise *err instead of hanging the device.  Partial sums are combined in a fixed order:
+// results are deterministic.  In reversed mode block index I stands for T - 1 - I.
+// ------------------------------------------------------------------------------------------------
+struct TrsvArgs {
+  const double* W; int64_t ldw; int64_t n; int T;
+  const double* DinvT;    // per block: TRANSPOSE of the inverse diagonal block to apply (forward: LinvT, backward: Linv)
+  const double* in;       // nrhs x ldt
+  double* out;            // nrhs x ldt
+  int64_t ldt; int nrhs;
+  const double* scale_d;  // backward sweep of an LDL factor: the input is divided by d first (decompositions.py:988)
+  double* partial;        // [T][NC][nrhs][128]
+  int NC;
+  unsigned int* flags;    // [T]   z_I published
+  unsigned int* counters; // [T]   partial tasks of row block I done
+  const int2* tasks;      // (I, c) with c = -1 for the diag task
+  int ntasks;
+  unsigned int* next_task;
+  int reverse;
+  int* err;
+};
+
+namespace trsv {
+constexpr int NB = MDB_NB, CH = 8, THREADS = 256;
+constexpr unsigned int SPIN_LIMIT = 1u << 27;
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool spin_until(const unsigned int* p, unsigned int want, int* err) {
+  unsigned int it = 0;
+  while (ld_acquire(p) < want) {
+    if (++it > SPIN_LIMIT) { atomicExch(err, 1); return false; }
+    __nanosleep(20);
+  }
+  return true;
+}
+}  // namespace trsv
+
+template <int MR>
+__global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a) {
+  using namespace trsv;
+  extern __shared__ double smem_d[];
+  double* sD = smem_d;              // NB x NB: DinvT of the current diag task, sD[c * NB + r]
+  double* zs = sD + NB * NB;        // MR x NB: z of the block being applied
+  double* vs = zs + MR * NB;        // MR x NB: right-hand side of the diag task
+  __shared__ int s_task;
+  __shared__ int s_ok;
+  const int tid = threadIdx.x, r = tid >> 1, h = tid & 1;
+  const int nrhs = a.nrhs;
+  const int T = a.T;
+
+  // element (row block I, column block J) of the triangle being swept, as global (row, col) of W
+  auto blk_row = [&](int I) { return (int64_t)(a.reverse ? T - 1 - I : I) * NB; };
+
+  for (;;) {
+    if (tid == 0) s_task = (int)atomicAdd(a.next_task, 1u);
+    __syncthreads();
+    const int t = s_task;
+    __syncthreads();
+    if (t >= a.ntasks) break;
+    const int I = a.tasks[t].x, c = a.tasks[t].y;
+    const int64_t row0 = blk_row(I);
+    const int64_t grow = row0 + r;
+    const bool rowok = grow < a.n;
+    const double* Wrow = a.W + (rowok ? grow : 0) * a.ldw;
+    double blk[64];
+    double acc[MR];
+
+    // registers <- block (I, J): thread (r, h) holds the 16-byte chunks q = 2 i + h of row r
+    auto load_block = [&](int J) {
+      const double* src = Wrow + blk_row(J);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        double2 v = make_double2(0.0, 0.0);
+        if (rowok) v = *reinterpret_cast<const double2*>(src + 4 * i + 2 * h);
+        blk[2 * i] = v.x;
+        blk[2 * i + 1] = v.y;
+      }
+    };
+    // zs <- z_J (all right-hand sides)
+    auto load_z = [&](int J) {
+      const int64_t c0 = blk_row(J);
+      for (int e = tid; e < nrhs * NB; e += THREADS) zs[e] = a.out[(int64_t)(e / NB) * a.ldt + c0 + (e % NB)];
+    };
+    auto apply_block = [&]() {  // acc[m] += sum over this thread's chunks
+#pragma unroll
+      for (int m = 0; m < MR; ++m) {
+        if (m < nrhs) {
+          double s0 = 0, s1 = 0;
+          const double* z = zs + m * NB + 2 * h;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const double2 zz = *reinterpret_cast<const double2*>(z + 4 * i);
+            s0 = fma(blk[2 * i], zz.x, s0);
+            s1 = fma(blk[2 * i + 1], zz.y, s1);
+          }
+          acc[m] += s0 + s1;
+        }
+      }
+    };
+    auto wait = [&](const unsigned int* p, unsigned int want) -> bool {
+      if (tid == 0) s_ok = spin_until(p, want, a.err) ? 1 : 0;
+      __syncthreads();
+      const bool ok = s_ok != 0;
+      __syncthreads();
+      return ok;
+    };
+#pragma unroll
+    for (int m = 0; m < MR; ++m) acc[m] = 0.0;
+
+    if (c >= 0) {
+      // ---- partial task: column blocks [c CH, min(c CH + CH, I - 1)) ----
+      const int J0 = c * CH, J1 = min(J0 + CH, I - 1);
+      for (int J = J0; J < J1; ++J) {
+        load_block(J);
+        if (!wait(a.flags + J, 1u)) return;
+        load_z(J);
+        __syncthreads();
+        apply_block();
+        __syncthreads();
+      }
+      double* out = a.partial + ((int64_t)I * a.NC + c) * nrhs * NB;
+#pragma unroll
+      for (int m = 0; m < MR; ++m) {
+        if (m < nrhs) {
+          const double v = acc[m] + __shfl_xor_sync(0xffffffffu, acc[m], 1);
+          if (h == 0) out[m * NB + r] = v;
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(a.counters + I, 1u);
+    } else {
+      // ---- diag task ----
+      const int nparts = (I - 1 > 0) ? (I - 1 + CH - 1) / CH : 0;
+      {  // the inverse diagonal block (already transposed in memory) -> shared, 16-byte copies
+        const double* src = a.DinvT + (int64_t)(a.reverse ? T - 1 - I : I) * NB * NB;
+        for (int e = tid; e < NB * NB / 2; e += THREADS)
+          reinterpret_cast<double2*>(sD)[e] = reinterpret_cast<const double2*>(src)[e];
+      }
+      if (I >= 1) load_block(I - 1);
+      if (nparts > 0 && !wait(a.counters + I, (unsigned int)nparts)) return;
+      // vs = b_I - sum_c partial[I][c]   (fixed order)
+      for (int e = tid; e < nrhs * NB; e += THREADS) {
+        const int m = e / NB, rr = e % NB;
+        const int64_t gi = row0 + rr;
+        double v = a.in[(int64_t)m * a.ldt + gi];
+        if (a.scale_d) v = (gi < a.n) ? v / a.scale_d[gi] : 0.0;
+        const double* ps = a.partial + (int64_t)I * a.NC * nrhs * NB + m * NB + rr;
+        for (int cc = 0; cc < nparts; ++cc) v -= ps[(int64_t)cc * nrhs * NB];
+        vs[e] = v;
+      }
+      if (I >= 1) {
+        if (!wait(a.flags + (I - 1), 1u)) return;
+        load_z(I - 1);
+        __syncthreads();
+        apply_block();
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+          if (m < nrhs) {
+            const double v = acc[m] + __shfl_xor_sync(0xffffffffu, acc[m], 1);
+            if (h == 0) vs[m * NB + r] -= v;
+          }
+        }
+      }
+      __syncthreads();
+      // z_I = Dinv v: thread (r, h) sums the columns cc = 4 i + 2 h, 4 i + 2 h + 1
+#pragma unroll
+      for (int m = 0; m < MR; ++m) {
+        if (m < nrhs) {
+          double s0 = 0, s1 = 0;
+          const double* v = vs + m * NB + 2 * h;
+          const double* dcol = sD + (2 * h) * NB + r;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const double2 vv = *reinterpret_cast<const double2*>(v + 4 * i);
+            s0 = fma(dcol[(4 * i) * NB], vv.x, s0);
+            s1 = fma(dcol[(4 * i + 1) * NB], vv.y, s1);
+          }
+          double z = s0 + s1;
+          z += __shfl_xor_sync(0xffffffffu, z, 1);
+          if (h == 0) a.out[(int64_t)m * a.ldt + row0 + r] = z;
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicExch(a.flags + I, 1u);
+    }
+  }
+}

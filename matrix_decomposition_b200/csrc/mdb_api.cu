@@ -36,6 +36,8 @@ struct mdb_factor {
   double mavL;
   bool prepared;
   double *Linv, *LinvT, *Ltri, *Utri;
+  // persistent triangular sweep (<= 8 right-hand sides): task list, flags, partial sums
+  int2* trsv_tasks; int trsv_ntasks; unsigned int* trsv_sync; double* trsv_partial; int trsv_partial_rhs;
   std::vector<int64_t> p_host;
 };
 
@@ -68,6 +70,8 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
     ctx->lookahead = !(la && la[0] == '0');
     const char* tm = getenv("MDB200_TMA");
     ctx->use_tma = !(tm && tm[0] == '0');
+    const char* tv = getenv("MDB200_TRSV");
+    ctx->use_trsv = !(tv && tv[0] == '0');
     // outer block width of the factorization: MDB200_AGG = 1, 2, 4, 8 panels (fixed) or unset = by remaining size,
     // thresholds MDB200_AGG_THRESH = "t2,t4,t8" (remaining rows from which 2, 4, 8 panels are aggregated)
     const char* ag = getenv("MDB200_AGG");
@@ -215,6 +219,7 @@ static void factor_release(mdb_factor* f) {
   cudaFree(f->W); cudaFree(f->vec); cudaFree(f->clamped); cudaFree(f->minB); cudaFree(f->maxB);
   cudaFree(f->p_dev); cudaFree(f->info); cudaFree(f->Ut); cudaFree(f->hdr); cudaFree(f->PX); cudaFree(f->PY); cudaFree(f->PX2); cudaFree(f->PY2);
   cudaFree(f->Linv); cudaFree(f->LinvT); cudaFree(f->Ltri); cudaFree(f->Utri);
+  cudaFree(f->trsv_tasks); cudaFree(f->trsv_sync); cudaFree(f->trsv_partial);
   delete f;
 }
 
@@ -230,6 +235,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   f->W = nullptr; f->vec = nullptr; f->clamped = nullptr; f->minB = f->maxB = nullptr; f->p_dev = nullptr;
   f->info = nullptr; f->Ut = f->hdr = f->PX = f->PY = f->PX2 = f->PY2 = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
   f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
+  f->trsv_tasks = nullptr; f->trsv_ntasks = 0; f->trsv_sync = nullptr; f->trsv_partial = nullptr; f->trsv_partial_rhs = 0;
   const int64_t nn = std::max<int64_t>(n, 1);
   f->panel_rows = std::max<int64_t>(mdb_round_up(nn, NB), NB);
   // widest outer block this factor can use (operand buffer width): 1 for batched small matrices
@@ -936,6 +942,78 @@ static int product_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, const doubl
   return launch_gemm_tn<false, false, false>(ctx, g, 1);  // neg without beta is never needed
 }
 
+// One persistent launch per triangular sweep (kernels_solve.cuh, k_trsv_persistent).
+static int trsv_prepare(mdb_factor* f, int nrhs) {
+  mdb_ctx* ctx = f->ctx;
+  const int T = (int)((f->n + NB - 1) / NB);
+  const int NC = (T + trsv::CH - 1) / trsv::CH;
+  if (!f->trsv_tasks) {
+    // claim order: diag(t), then every partial task whose last needed block is t (so that a task only ever
+    // waits for tasks claimed before it)
+    std::vector<int2> tasks;
+    for (int t = 0; t < T; ++t) {
+      tasks.push_back(make_int2(t, -1));
+      if ((t + 1) % trsv::CH == 0) {
+        for (int I = t + 2; I < T; ++I) tasks.push_back(make_int2(I, (t + 1) / trsv::CH - 1));
+      } else if (t + 2 < T) {
+        tasks.push_back(make_int2(t + 2, t / trsv::CH));
+      }
+    }
+    f->trsv_ntasks = (int)tasks.size();
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_tasks, tasks.size() * sizeof(int2)));
+    MDB_CUDA(ctx, cudaMemcpyAsync(f->trsv_tasks, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `tasks` goes out of scope
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_sync, (size_t)(2 * T + 2) * sizeof(unsigned int)));
+  }
+  if (f->trsv_partial_rhs < nrhs) {
+    if (f->trsv_partial) cudaFree(f->trsv_partial);
+    f->trsv_partial = nullptr;
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_partial, (size_t)T * NC * nrhs * NB * 8));
+    f->trsv_partial_rhs = nrhs;
+  }
+  static bool configured = false;
+  if (!configured) {
+    const int smem = (NB * NB + 2 * 8 * NB) * 8;
+    MDB_CUDA(ctx, cudaFuncSetAttribute(k_trsv_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MDB_CUDA(ctx, cudaFuncSetAttribute(k_trsv_persistent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  return MDB_OK;
+}
+
+static int trsv_sweep(mdb_factor* f, int nrhs, bool reverse, const double* in, double* out, int64_t ldt,
+                      const double* scale_d) {
+  mdb_ctx* ctx = f->ctx;
+  const int T = (int)((f->n + NB - 1) / NB);
+  TrsvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.W = f->W; a.ldw = f->ld; a.n = f->n; a.T = T;
+  a.DinvT = reverse ? f->Linv : f->LinvT;
+  a.in = in; a.out = out; a.ldt = ldt; a.nrhs = nrhs; a.scale_d = scale_d;
+  a.partial = f->trsv_partial; a.NC = (T + trsv::CH - 1) / trsv::CH;
+  a.flags = f->trsv_sync; a.counters = f->trsv_sync + T; a.next_task = f->trsv_sync + 2 * T;
+  a.err = (int*)(f->trsv_sync + 2 * T + 1);
+  a.tasks = f->trsv_tasks; a.ntasks = f->trsv_ntasks; a.reverse = reverse ? 1 : 0;
+  MDB_CUDA(ctx, cudaMemsetAsync(f->trsv_sync, 0, (size_t)(2 * T + 2) * sizeof(unsigned int), ctx->stream));
+  const int grid = std::min(ctx->num_sms, f->trsv_ntasks);
+  const int smem = (NB * NB + 2 * 8 * NB) * 8;
+  if (nrhs == 1) k_trsv_persistent<1><<<grid, trsv::THREADS, smem, ctx->stream>>>(a);
+  else k_trsv_persistent<8><<<grid, trsv::THREADS, smem, ctx->stream>>>(a);
+  MDB_LAUNCHED(ctx);
+  MDB_CUDA(ctx, cudaGetLastError());
+  return MDB_OK;
+}
+
+static int trsv_check(mdb_factor* f) {
+  mdb_ctx* ctx = f->ctx;
+  const int T = (int)((f->n + NB - 1) / NB);
+  int err = 0;
+  MDB_CUDA(ctx, cudaMemcpyAsync(&err, f->trsv_sync + 2 * T + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (err) return mdb_fail(ctx, MDB_ERR_CUDA, "%s", "k_trsv_persistent: a dependency wait ran into its spin limit");
+  return MDB_OK;
+}
+
 static int rhs_in(mdb_factor* f, const double* B, int64_t ldb, int64_t nrhs, int loc, double** Bt, double** Yt,
                   int64_t* ldt_out, double** stage) {
   mdb_ctx* ctx = f->ctx;
@@ -996,12 +1074,44 @@ extern "C" int mdb_factor_solve(mdb_factor* f, const double* B, int64_t ldb, int
   int64_t ldt = 0;
   rc = rhs_in(f, B, ldb, nrhs, loc, &Bt, &Yt, &ldt, &stage);
   const int64_t T = (n + NB - 1) / NB;
+  if (!rc && nrhs <= 8 && ctx->use_trsv && T >= 2) {
+    // bandwidth-bound case: one persistent launch per sweep, L streamed once
+    rc = trsv_prepare(f, (int)nrhs);
+    if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (!rc) rc = trsv_sweep(f, (int)nrhs, false, Bt, Yt, ldt, nullptr);                                   // L z = b
+    if (!rc) rc = trsv_sweep(f, (int)nrhs, true, Yt, Bt, ldt, f->out_type != MDB_TYPE_LL ? f->d : nullptr);  // L^T x = z / d
+    if (ctx->profiling) {  // device time of the two sweeps -> mdb_ctx_get_phase_ms()[0]
+      cudaEventRecord(ctx->ev[1], ctx->stream);
+      cudaEventSynchronize(ctx->ev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+      ctx->phase_ms[0] = ms;
+    }
+    if (!rc) rc = rhs_out(f, Bt, ldt, nrhs, X, ldx, loc, stage);
+    if (!rc) rc = trsv_check(f);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(Bt); cudaFree(Yt); cudaFree(stage);
+    if (rc) return rc;
+    MDB_CUDA(ctx, e2);
+    return MDB_OK;
+  }
+  if (ctx->profiling) cudaEventRecord(ctx->ev[0], ctx->stream);
+  // Many right-hand sides: blocked sweeps on the DMMA tile kernel, two-level like the factorization.  Inside a
+  // super block of SB diagonal blocks the updates have K = 128; everything beyond it gets ONE update with
+  // K = 128 SB, so the right-hand sides are read and written once per super block.
+  const int64_t SB = 4;
   // forward sweep  L z = b  (decompositions.py:987 / :1349)
-  for (int64_t J = 0; J < T && !rc; ++J) {
-    const int64_t j0 = J * NB, j1 = std::min<int64_t>(j0 + NB, n);
-    rc = product_tn(ctx, nrhs, NB, NB, Bt + j0, ldt, f->Linv + J * NB * NB, NB, Yt + j0, ldt, false, false);
-    if (!rc && j1 < n)
-      rc = product_tn(ctx, nrhs, n - j1, NB, Yt + j0, ldt, f->W + j1 * f->ld + j0, f->ld, Bt + j1, ldt, true, true);
+  for (int64_t S0 = 0; S0 < T && !rc; S0 += SB) {
+    const int64_t S1 = std::min<int64_t>(S0 + SB, T);
+    const int64_t s0 = S0 * NB, s1 = std::min<int64_t>(S1 * NB, n);
+    for (int64_t J = S0; J < S1 && !rc; ++J) {
+      const int64_t j0 = J * NB, j1 = std::min<int64_t>(j0 + NB, n);
+      rc = product_tn(ctx, nrhs, NB, NB, Bt + j0, ldt, f->Linv + J * NB * NB, NB, Yt + j0, ldt, false, false);
+      if (!rc && j1 < s1)
+        rc = product_tn(ctx, nrhs, s1 - j1, NB, Yt + j0, ldt, f->W + j1 * f->ld + j0, f->ld, Bt + j1, ldt, true, true);
+    }
+    if (!rc && s1 < n)
+      rc = product_tn(ctx, nrhs, n - s1, (S1 - S0) * NB, Yt + s0, ldt, f->W + s1 * f->ld + s0, f->ld, Bt + s1, ldt, true, true);
   }
   if (!rc && f->out_type != MDB_TYPE_LL) {  // x / d  (decompositions.py:988)
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)nrhs);
@@ -1009,10 +1119,24 @@ extern "C" int mdb_factor_solve(mdb_factor* f, const double* B, int64_t ldb, int
     MDB_LAUNCHED(ctx);
   }
   // backward sweep  L^T x = z  (decompositions.py:989 / :1350): rows of U = L^T from the mirrored upper triangle
-  for (int64_t J = T - 1; J >= 0 && !rc; --J) {
-    const int64_t j0 = J * NB;
-    rc = product_tn(ctx, nrhs, NB, NB, Yt + j0, ldt, f->LinvT + J * NB * NB, NB, Bt + j0, ldt, false, false);
-    if (!rc && j0 > 0) rc = product_tn(ctx, nrhs, j0, NB, Bt + j0, ldt, f->W + j0, f->ld, Yt, ldt, true, true);
+  for (int64_t S1 = T; S1 > 0 && !rc; S1 -= std::min<int64_t>(SB, S1)) {
+    const int64_t S0 = S1 > SB ? S1 - SB : 0;
+    const int64_t s0 = S0 * NB;
+    for (int64_t J = S1 - 1; J >= S0 && !rc; --J) {
+      const int64_t j0 = J * NB;
+      rc = product_tn(ctx, nrhs, NB, NB, Yt + j0, ldt, f->LinvT + J * NB * NB, NB, Bt + j0, ldt, false, false);
+      if (!rc && j0 > s0)
+        rc = product_tn(ctx, nrhs, j0 - s0, NB, Bt + j0, ldt, f->W + s0 * f->ld + j0, f->ld, Yt + s0, ldt, true, true);
+    }
+    if (!rc && s0 > 0)
+      rc = product_tn(ctx, nrhs, s0, (S1 - S0) * NB, Bt + s0, ldt, f->W + s0, f->ld, Yt, ldt, true, true);
+  }
+  if (ctx->profiling) {  // device time of the two sweeps -> mdb_ctx_get_phase_ms()[0]
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    cudaEventSynchronize(ctx->ev[1]);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->phase_ms[0] = ms;
   }
   if (!rc) rc = rhs_out(f, Bt, ldt, nrhs, X, ldx, loc, stage);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);

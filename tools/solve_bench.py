@@ -48,6 +48,13 @@ def main():
     out['solve1_s'] = t1
     out['solve1_gbs'] = 8.0 * n * n / t1 / 1e9
     out['solve1_frac_hbm'] = out['solve1_gbs'] / HBM_PEAK_GBS
+    ctx.set_profiling(True)
+    dec.solve(b1)
+    ms = ctx.phase_ms()['diag']      # device time of the two sweeps (CUDA events on the launching stream)
+    out['solve1_device_ms'] = ms
+    out['solve1_device_gbs'] = 8.0 * n * n / (ms * 1e-3) / 1e9
+    out['solve1_device_frac_hbm'] = out['solve1_device_gbs'] / HBM_PEAK_GBS
+    ctx.set_profiling(False)
     out['solve1_residual'] = float(np.max(np.abs(A @ x1 - b1)) / np.max(np.abs(b1)))
     k = 1024
     Bk = rng.standard_normal((n, k))
@@ -55,6 +62,13 @@ def main():
     out['solve1024_s'] = tk
     out['solve1024_tflops'] = 2.0 * n * n * k / tk / 1e12
     out['solve1024_frac_fp64_peak'] = out['solve1024_tflops'] / FP64_PEAK_TFLOPS
+    ctx.set_profiling(True)
+    dec.solve(Bk)
+    ms = ctx.phase_ms()['diag']
+    out['solve1024_device_ms'] = ms
+    out['solve1024_device_tflops'] = 2.0 * n * n * k / (ms * 1e-3) / 1e12
+    out['solve1024_device_frac_fp64_peak'] = out['solve1024_device_tflops'] / FP64_PEAK_TFLOPS
+    ctx.set_profiling(False)
     out['solve1024_residual'] = float(np.max(np.abs(A @ Xk[:, :4] - Bk[:, :4])) / np.max(np.abs(Bk[:, :4])))
     if '--cpu' in sys.argv:
         import scipy.linalg
