@@ -81,6 +81,10 @@ int mdb_ctx_set_blocking(mdb_ctx *ctx, int fixed, int64_t t2, int64_t t4, int64_
  * outer block; with lookahead each is issued as two kernels), inner flop, inner launches}; flop = 2 K per updated
  * element of the strict lower triangle. */
 int mdb_ctx_get_update_stats(const mdb_ctx *ctx, double out[4]);
+/* 1 when the matrix of the last mdb_factor_set_matrix / one-shot call on this context held an inf or NaN: the
+ * reference's check_finite scan (dense/util.py:15-21, dense/calculate.py:76), done on the device while the matrix
+ * is gathered instead of as a separate pass over host memory. */
+int mdb_ctx_last_input_nonfinite(const mdb_ctx *ctx);
 
 /* ---- device memory (so that a host language without CUDA bindings can stage buffers) ---- */
 int mdb_malloc(mdb_ctx *ctx, size_t bytes, void **dptr);

@@ -63,6 +63,7 @@ SIGNATURES = {
     'mdb_ctx_get_phase_ms': (_int, [_vp, _vp]),
     'mdb_ctx_set_blocking': (_int, [_vp, _int, _i64, _i64, _i64]),
     'mdb_ctx_get_update_stats': (_int, [_vp, _vp]),
+    'mdb_ctx_last_input_nonfinite': (_int, [_vp]),
     'mdb_malloc': (_int, [_vp, _sz, _pp]),
     'mdb_free': (_int, [_vp, _vp]),
     'mdb_malloc_host': (_int, [_vp, _sz, _pp]),
@@ -281,6 +282,13 @@ class Factor:
             self.close()
         except Exception:
             pass
+
+    def download(self, n, type_code):
+        """The n x n factor matrix (L or LD, in the type the factor was finalised with) as a fresh numpy array."""
+        out = np.empty((n, n), dtype=np.float64)
+        rc = self.ctx.lib.mdb_factor_get(self.handle, int(type_code), ptr(out), n, HOST, None, None, None, None, None)
+        self.ctx.check(rc, 'mdb_factor_get')
+        return out
 
     def solve(self, b):
         b = np.asarray(b)

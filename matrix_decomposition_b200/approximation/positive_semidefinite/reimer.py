@@ -154,11 +154,12 @@ def _prepare(A, min_diag_B, max_diag_B, min_diag_D, max_diag_D, min_abs_value_D,
             float(min_abs_value_L))
 
 
-def _run(A, out_type_str, keep_factor, **kw):
+def _run(A, out_type_str, keep_factor, download_L=True, **kw):
+    """download_L=False leaves the n x n factor in HBM (returned Lout is None; needs keep_factor)."""
     A, n, p, dynamic, min_diag_B, max_diag_B, min_diag_D, max_diag_D, mavD, mavL = _prepare(A, **kw)
     A64 = np.ascontiguousarray(A, dtype=np.float64)
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, min_diag_D, max_diag_D, mavD, mavL, min_diag_B, max_diag_B)
-    Lout = np.empty((n, n), dtype=np.float64)
+    Lout = np.empty((n, n), dtype=np.float64) if download_L else None
     d = np.empty(n, dtype=np.float64)
     omega = np.empty(n, dtype=np.float64)
     delta = np.empty(n, dtype=np.float64)
@@ -208,22 +209,26 @@ def decomposition(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag
         logger.error(error)
         raise error
     type_str = constants.LDL_DECOMPOSITION_TYPE if return_type is None else return_type
-    Lout, d, p, omega, delta, clamped, factor = _run(
-        A, type_str, True, min_diag_B=min_diag_B, max_diag_B=max_diag_B, min_diag_D=min_diag_D,
+    # the factor stays in HBM: dec.L / dec.LD download it on first access, solve / multiply never need to
+    _, d64, p, omega, delta, clamped, factor = _run(
+        A, type_str, True, download_L=False, min_diag_B=min_diag_B, max_diag_B=max_diag_B, min_diag_D=min_diag_D,
         max_diag_D=max_diag_D, min_abs_value_D=min_abs_value_D, min_abs_value_L=min_abs_value_L,
         permutation=permutation)
-    d = d.astype(RESULT_DTYPE)
+    d = d64.astype(RESULT_DTYPE)
+    n = len(d)
     if type_str == constants.LL_DECOMPOSITION_TYPE:
         for i, d_i in enumerate(d):  # decompositions.py:903-908 (cannot happen: min_diag_D >= 0)
             if d_i < 0:
                 raise errors.NoDecompositionPossibleWithProblematicSubdecompositionError(
                     decompositions.LDL_Decomposition(np.eye(len(d)), d, p), constants.LL_DECOMPOSITION_TYPE, p[i])
-        dec = decompositions.LL_Decomposition(Lout, p=p)
+        dec = decompositions.LL_Decomposition(None, p=p)
+        dec._attach_lazy_matrix(factor, n, np.sqrt(d64))
     elif type_str == constants.LDL_DECOMPOSITION_COMPRESSED_TYPE:
-        dec = decompositions.LDL_DecompositionCompressed(Lout, p=p)
+        dec = decompositions.LDL_DecompositionCompressed(None, p=p)
+        dec._attach_lazy_matrix(factor, n, d64)
     else:
-        dec = decompositions.LDL_Decomposition(Lout, d, p=p)
-    dec._attach_device_factor(factor)
+        dec = decompositions.LDL_Decomposition(None, d, p=p)
+        dec._attach_lazy_matrix(factor, n, np.ones(n))
     dec.omega = omega.astype(RESULT_DTYPE)
     dec.delta = delta.astype(RESULT_DTYPE)
     dec.clamped = clamped

@@ -24,6 +24,9 @@ def _resolve_permutation(A, permutation, supported_methods):
     return p
 
 
+_HOST_FINITE_SCAN_MAX = 1 << 20   # elements
+
+
 def _make_decomposition(type_str, Lout, d, p):
     if type_str == constants.LL_DECOMPOSITION_TYPE:
         return decompositions.LL_Decomposition(Lout, p=p)
@@ -52,7 +55,10 @@ def decompose(A, permutation=None, return_type=None, check_finite=True, overwrit
     util.check_square_matrix(A)
     if np.iscomplexobj(A):
         raise ValueError('complex matrices are outside the dense real (float64) path of this package.')
-    util.check_finite(A, check_finite=check_finite)
+    # dense/calculate.py:76.  Small inputs are scanned here; for large ones the scan (a pass over n^2 host doubles
+    # plus an n^2 temporary) rides on the device-side gather instead (checked right after the call below).
+    host_scan = A.size <= _HOST_FINITE_SCAN_MAX
+    util.check_finite(A, check_finite=check_finite and host_scan)
     p = _resolve_permutation(A, permutation, constants.UNIVERSAL_PERMUTATION_METHODS)
     supported_return_type = constants.DECOMPOSITION_TYPES
     if return_type is not None and return_type not in supported_return_type:
@@ -63,25 +69,41 @@ def decompose(A, permutation=None, return_type=None, check_finite=True, overwrit
     n = A.shape[0]
     A64 = np.ascontiguousarray(A, dtype=np.float64)
     p64 = np.ascontiguousarray(p, dtype=np.int64)
-    Lout = np.empty((n, n), dtype=np.float64)
     d = np.empty(n, dtype=np.float64)
     info = ctypes.c_int64(0)
     handle = ctypes.c_void_p()
     ctx = _native.context()
+    # The factor stays in HBM (L = NULL: no n x n download); .L / .LD fetch it on first access.
     rc = ctx.lib.mdb_decompose_f64(ctx.handle, n, _native.ptr(A64), n, _native.ptr(p64), _native.TYPE_CODES[type_str],
-                                   _native.ptr(Lout), n, _native.ptr(d), ctypes.byref(info), _native.HOST,
-                                   ctypes.byref(handle))
+                                   None, n, _native.ptr(d), ctypes.byref(info), _native.HOST, ctypes.byref(handle))
+    # dense/calculate.py:76: the finite check of A, evaluated on the device while A was gathered
+    if check_finite and ctx.lib.mdb_ctx_last_input_nonfinite(ctx.handle):
+        if handle:
+            ctx.lib.mdb_factor_destroy(handle)
+        raise errors.MatrixNotFiniteError(A)
     if rc == _native.MDB_ERR_NOT_POSITIVE_DEFINITE:
         bad_index = int(info.value) - 1
         # like dense/calculate.py:112-119: hand back the partial Cholesky factor with NaN at the bad pivot
+        # (rare path: run again, this time downloading the partial factor)
+        Lout = np.empty((n, n), dtype=np.float64)
+        ctx.lib.mdb_decompose_f64(ctx.handle, n, _native.ptr(A64), n, _native.ptr(p64), _native.TYPE_CODES[type_str],
+                                  _native.ptr(Lout), n, _native.ptr(d), ctypes.byref(info), _native.HOST, None)
         Lpart = np.tril(Lout)
         Lpart[bad_index, bad_index] = np.nan
         sub = decompositions.LL_Decomposition(Lpart, p=p)
         raise errors.NoDecompositionPossibleWithProblematicSubdecompositionError(
             A, constants.LL_DECOMPOSITION_TYPE, bad_index, sub)
     ctx.check(rc, 'mdb_decompose_f64')
-    dec = _make_decomposition(type_str, Lout, d, p)
-    dec._attach_device_factor(_native.Factor(ctx, handle))
+    factor = _native.Factor(ctx, handle)
+    if type_str == constants.LL_DECOMPOSITION_TYPE:
+        dec = decompositions.LL_Decomposition(None, p=p)
+        dec._attach_lazy_matrix(factor, n, np.sqrt(d))
+    elif type_str == constants.LDL_DECOMPOSITION_COMPRESSED_TYPE:
+        dec = decompositions.LDL_DecompositionCompressed(None, p=p)
+        dec._attach_lazy_matrix(factor, n, d)
+    else:
+        dec = decompositions.LDL_Decomposition(None, d, p=p)
+        dec._attach_lazy_matrix(factor, n, np.ones(n))
     return dec
 
 

@@ -6,13 +6,16 @@
 // ------------------------------------------------------------------------------------------------
 // Symmetric gather  W[i, j] = A[p[i], p[j]]   (dense/permute.py:26), gamma[i] = A[p[i], p[i]].
 // HBM bound: 8 n^2 written coalesced; reads are 8-byte gathers inside row p[i] (sector efficiency 1/4
-// for a random p, 1 for the identity).  grid = (n rows, column chunks of 1024, batch).
+// for a random p, 1 for the identity).  grid = (n rows, column chunks of 1024, batch).  Also raises
+// *nonfinite when an element is inf / NaN (the reference's check_finite scan, dense/util.py:15-21).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gather_sym(int64_t n, const double* __restrict__ A, int64_t lda,
                                                     int64_t sA, const int64_t* __restrict__ p, int64_t sP,
                                                     double* __restrict__ W, int64_t ldw, int64_t sW,
-                                                    double* __restrict__ gamma, int64_t sVec) {
+                                                    double* __restrict__ gamma, int64_t sVec,
+                                                    int* __restrict__ nonfinite) {
   const int64_t b = blockIdx.z;
+  bool bad = false;
   const int64_t i = blockIdx.x;
   A += b * sA;
   W += b * sW;
@@ -28,9 +31,11 @@ __global__ void __launch_bounds__(256) k_gather_sym(int64_t n, const double* __r
       const int64_t pj = pb ? pb[j] : j;
       const double v = Arow[pj];
       Wrow[j] = v;
+      bad |= !isfinite(v);
       if (gamma && j == i) gamma[b * sVec + i] = v;
     }
   }
+  if (bad && nonfinite) *nonfinite = 1;  // dense/util.py:15-21 (is_finite), evaluated where the data already is
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -30,6 +30,17 @@ __global__ void __launch_bounds__(256) k_symmetrize(int64_t n, double* __restric
   }
 }
 
+// undo k_symmetrize: W[i, j] = 0 for i < j (before the factor is copied out again)
+__global__ void __launch_bounds__(256) k_zero_upper(int64_t n, double* __restrict__ W, int64_t ldw) {
+  const int64_t i = blockIdx.x;
+  const int64_t j0 = (int64_t)blockIdx.y * 1024 + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t j = j0 + 256 * e;
+    if (j < n && j > i) W[i * ldw + j] = 0.0;
+  }
+}
+
 // Per diagonal block J (NB x NB, lower triangular with diagonal; unit_diag forces a unit diagonal):
 //   Linv[J]  = inverse (lower),  LinvT[J] = its transpose (= inverse of the upper block U_JJ = L_JJ^T)
 //   Ltri[J]  = the lower triangle incl. diagonal, zeros above;  Utri[J] = its transpose

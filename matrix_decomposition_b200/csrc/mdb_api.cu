@@ -137,6 +137,7 @@ extern "C" int mdb_ctx_set_profiling(mdb_ctx* ctx, int on) {
   ctx->profiling = on;
   return MDB_OK;
 }
+extern "C" int mdb_ctx_last_input_nonfinite(const mdb_ctx* ctx) { return ctx ? ctx->last_input_nonfinite : 0; }
 extern "C" int mdb_ctx_get_update_stats(const mdb_ctx* ctx, double out[4]) {
   if (!ctx || !out) return MDB_ERR_INVALID;
   out[0] = ctx->gemm_flop[0]; out[1] = (double)ctx->gemm_launches[0];
@@ -250,7 +251,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   A((void**)&f->W, (size_t)batch * nn * f->ld * 8);
   A((void**)&f->vec, (size_t)7 * batch * nn * 8);
   A((void**)&f->clamped, (size_t)batch * nn);
-  A((void**)&f->info, (size_t)batch * sizeof(int));
+  A((void**)&f->info, (size_t)(batch + 1) * sizeof(int));
   A((void**)&f->Ut, (size_t)batch * NB * NB * 8);
   A((void**)&f->hdr, (size_t)batch * 5 * NB * 8);
   A((void**)&f->PX, panel_bytes);
@@ -311,10 +312,10 @@ static int factor_set_p(mdb_factor* f, const int64_t* p) {
 }
 
 static int gather_sym(mdb_ctx* ctx, int64_t n, int64_t batch, const double* A_dev, int64_t lda, int64_t sA,
-                      const int64_t* p_dev, double* W, int64_t ldw, int64_t sW, double* gamma) {
+                      const int64_t* p_dev, double* W, int64_t ldw, int64_t sW, double* gamma, int* nonfinite = nullptr) {
   if (n == 0) return MDB_OK;
   dim3 grid((unsigned)n, (unsigned)((n + 1023) / 1024), (unsigned)batch);
-  k_gather_sym<<<grid, 256, 0, ctx->stream>>>(n, A_dev, lda, sA, p_dev, n, W, ldw, sW, gamma, n);
+  k_gather_sym<<<grid, 256, 0, ctx->stream>>>(n, A_dev, lda, sA, p_dev, n, W, ldw, sW, gamma, n, nonfinite);
   MDB_LAUNCHED(ctx);
   MDB_CUDA(ctx, cudaGetLastError());
   return MDB_OK;
@@ -340,12 +341,17 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
     A_dev = staging;
     lds = n;
   }
-  rc = gather_sym(ctx, n, f->batch, A_dev, lds, n * lds, f->p_dev, f->W, f->ld, n * f->ld, f->gamma);
-  if (staging) {
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(staging);
-  }
+  // the finite check of the input rides on the gather: flag = the int after the per-matrix info entries
+  int* flag = f->info + f->batch;
+  MDB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+  rc = gather_sym(ctx, n, f->batch, A_dev, lds, n * lds, f->p_dev, f->W, f->ld, n * f->ld, f->gamma, flag);
+  int bad = 0;
+  cudaError_t ef = cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (ef == cudaSuccess) ef = cudaStreamSynchronize(ctx->stream);
+  if (staging) cudaFree(staging);
   if (rc) return rc;
+  MDB_CUDA(ctx, ef);
+  ctx->last_input_nonfinite = bad;
   f->state = ST_MATRIX;
   f->prepared = false;
   return MDB_OK;
@@ -652,6 +658,12 @@ extern "C" int mdb_factor_get(mdb_factor* f, int out_type, double* L, int64_t ld
   const int64_t n = f->n, batch = f->batch, bn = batch * n;
   if (L && n > 0) {
     MDB_CHECK(ctx, ldl >= n, "mdb_factor_get: ldl < n");
+    if (f->prepared) {  // a solve mirrored L into the upper triangle: undo that (the next solve mirrors it again)
+      dim3 grid((unsigned)n, (unsigned)((n + 1023) / 1024));
+      k_zero_upper<<<grid, 256, 0, ctx->stream>>>(n, f->W, f->ld);
+      MDB_LAUNCHED(ctx);
+      f->prepared = false;
+    }
     // rows of consecutive batch members are contiguous in both layouts when viewed as (batch*n) x n
     rc = copy2d_async(ctx, L, ldl, f->W, f->ld, bn, n, l_loc, MDB_DEVICE);
     if (rc) return rc;

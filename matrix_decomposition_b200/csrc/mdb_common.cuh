@@ -28,6 +28,7 @@ struct mdb_ctx {
   int64_t launches;
   int profiling;
   double phase_ms[4];
+  int last_input_nonfinite;   // set by mdb_factor_set_matrix: the matrix held an inf / NaN
   double gemm_flop[2];        // algorithmic flop of the bulk / inner trailing updates of the last mdb_factor_run
   int64_t gemm_launches[2];
   int num_sms;

@@ -39,8 +39,16 @@ class DecompositionBase(metaclass=abc.ABCMeta):
         return '{type_str} decomposition of matrix with shape ({n}, {n})'.format(type_str=self.type_str, n=self.n)
 
     # *** device residency *** #
+    # A decomposition produced by this package's factorizations keeps its n x n factor in HBM: solve, multiply and
+    # composed_matrix work on it there, and the numpy array behind .L / .LD is only downloaded when it is first
+    # read ("lazy").  At n = 65536 that is 34 GB of device -> host copy the reference's users of solve() never see.
+
+    _matrix_attr = None      # '_L' or '_LD'
+    _matrix_type_code = None
 
     def _drop_device_factor(self):
+        if '_lazy_matrix' in self.__dict__:      # the only copy of the factor lives on the device: fetch it first
+            self._matrix()
         f = self.__dict__.pop('_device_factor', None)
         if f is not None:
             f.close()
@@ -49,6 +57,38 @@ class DecompositionBase(metaclass=abc.ABCMeta):
         """Called by the factorization routines: the factor is already resident in HBM."""
         self._drop_device_factor()
         self.__dict__['_device_factor'] = factor
+
+    def _attach_lazy_matrix(self, factor, n, diagonal):
+        """Called by the factorization routines instead of passing the matrix: it stays in HBM until read.
+        `diagonal` is the diagonal of the matrix attribute (known without downloading it)."""
+        self._drop_device_factor()
+        self.__dict__.pop(self._matrix_attr, None)
+        self.__dict__['_device_factor'] = factor
+        self.__dict__['_lazy_matrix'] = dict(n=int(n), diagonal=np.asarray(diagonal, dtype=np.float64))
+
+    @property
+    def is_device_resident_only(self):
+        """True while the factor matrix has not been downloaded into a numpy array yet."""
+        return '_lazy_matrix' in self.__dict__
+
+    def _matrix(self):
+        M = self.__dict__.get(self._matrix_attr)
+        if M is None:
+            lazy = self.__dict__.get('_lazy_matrix')
+            if lazy is None:
+                raise AttributeError(self._matrix_attr[1:])
+            M = self.__dict__['_device_factor'].download(lazy['n'], self._matrix_type_code)
+            self.__dict__[self._matrix_attr] = M
+            del self.__dict__['_lazy_matrix']
+        return M
+
+    def _matrix_n(self):
+        lazy = self.__dict__.get('_lazy_matrix')
+        return lazy['n'] if lazy is not None else self._matrix().shape[0]
+
+    def _matrix_diagonal(self):
+        lazy = self.__dict__.get('_lazy_matrix')
+        return lazy['diagonal'] if lazy is not None else np.asarray(self._matrix()).diagonal()
 
     @abc.abstractmethod
     def _upload(self, ctx):
@@ -62,6 +102,8 @@ class DecompositionBase(metaclass=abc.ABCMeta):
         return f
 
     def __deepcopy__(self, memo):
+        if '_lazy_matrix' in self.__dict__:
+            self._matrix()
         new = self.__class__.__new__(self.__class__)
         for k, v in self.__dict__.items():
             if k != '_device_factor':  # device handles are not shared between copies
@@ -69,6 +111,8 @@ class DecompositionBase(metaclass=abc.ABCMeta):
         return new
 
     def __getstate__(self):
+        if '_lazy_matrix' in self.__dict__:
+            self._matrix()
         return {k: v for k, v in self.__dict__.items() if k != '_device_factor'}
 
     # *** permutation (decompositions.py:49-171) *** #
@@ -325,6 +369,8 @@ class LDL_Decomposition(DecompositionBase):
     """ `L D L^H` of the permuted matrix; L unit lower triangular, d = diag(D)  (decompositions.py:790-1013). """
 
     type_str = constants.LDL_DECOMPOSITION_TYPE
+    _matrix_attr = '_L'
+    _matrix_type_code = _native.TYPE_LDL
 
     def __init__(self, L=None, d=None, p=None):
         self.L = L
@@ -333,11 +379,11 @@ class LDL_Decomposition(DecompositionBase):
 
     @property
     def n(self):
-        return self.L.shape[0]
+        return self._matrix_n()
 
     @property
     def L(self):
-        return self._L
+        return self._matrix()
 
     @L.setter
     def L(self, L):
@@ -441,6 +487,8 @@ class LDL_DecompositionCompressed(DecompositionBase):
     """ `L D L^H` with L and D stored in one matrix LD  (decompositions.py:1016-1167). """
 
     type_str = constants.LDL_DECOMPOSITION_COMPRESSED_TYPE
+    _matrix_attr = '_LD'
+    _matrix_type_code = _native.TYPE_LDL_COMPRESSED
 
     def __init__(self, LD=None, p=None):
         self.LD = LD
@@ -448,11 +496,11 @@ class LDL_DecompositionCompressed(DecompositionBase):
 
     @property
     def n(self):
-        return self.LD.shape[0]
+        return self._matrix_n()
 
     @property
     def LD(self):
-        return self._LD
+        return self._matrix()
 
     @LD.setter
     def LD(self, LD):
@@ -464,7 +512,7 @@ class LDL_DecompositionCompressed(DecompositionBase):
 
     @property
     def d(self):
-        d = np.asarray(self.LD).diagonal()
+        d = self._matrix_diagonal()
         if np.iscomplexobj(d) and np.all(np.isreal(d)):
             d = d.real
         return d
@@ -528,6 +576,8 @@ class LL_Decomposition(DecompositionBase):
     """ `L L^H` (Cholesky) of the permuted matrix  (decompositions.py:1170-1373). """
 
     type_str = constants.LL_DECOMPOSITION_TYPE
+    _matrix_attr = '_L'
+    _matrix_type_code = _native.TYPE_LL
 
     def __init__(self, L=None, p=None):
         self.L = L
@@ -535,11 +585,11 @@ class LL_Decomposition(DecompositionBase):
 
     @property
     def n(self):
-        return self.L.shape[0]
+        return self._matrix_n()
 
     @property
     def L(self):
-        return self._L
+        return self._matrix()
 
     @L.setter
     def L(self, L):
@@ -557,7 +607,7 @@ class LL_Decomposition(DecompositionBase):
 
     @property
     def _d(self):
-        d = np.asarray(self.L).diagonal()
+        d = self._matrix_diagonal()
         if np.iscomplexobj(d) and np.all(np.isreal(d)):
             d = d.real
         return d

@@ -428,6 +428,52 @@ def test_decompose_solve_multiply_against_reference_goldens(matrix):
     np.testing.assert_allclose(dec.solve(z['f3_128/b'][:, 0]), z['f3_128/x0'], rtol=TOL, atol=1e-12)
 
 
+def test_factor_stays_on_device_until_read(matrix, orc):
+    """decompose / approximate keep the n x n factor in HBM: solve and multiply work on it there, .L downloads
+    it on first access -- also after a solve has mirrored it into the upper triangle on the device."""
+    n = 700
+    S = workloads.lowrank_plus_diag(n, 8)
+    b = np.random.default_rng(1).standard_normal(n)
+    for rt in ('LDL', 'LL', 'LDL_compressed'):
+        dec = matrix.decompose(S, permutation='decreasing_diagonal_values', return_type=rt)
+        assert dec.is_device_resident_only and dec.n == n
+        x = dec.solve(b)
+        assert dec.is_device_resident_only                      # solve did not need the host copy
+        np.testing.assert_allclose(S @ x, b, rtol=0, atol=1e-9)
+        ref = orc.decompose(S, 'decreasing_diagonal_values', rt)
+        M = dec.LD if rt == 'LDL_compressed' else dec.L         # first access: download (after the solve)
+        assert not dec.is_device_resident_only
+        assert np.all(np.triu(M, 1) == 0)
+        if rt == 'LDL_compressed':
+            np.testing.assert_allclose(np.tril(M, -1), np.tril(ref['L'], -1), rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(M.diagonal(), ref['d'], rtol=1e-10)
+        else:
+            np.testing.assert_allclose(M, ref['L'], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(dec.solve(b), x, rtol=1e-12, atol=1e-14)   # still solves after the download
+        import copy
+        dec2 = matrix.decompose(S, permutation='decreasing_diagonal_values', return_type=rt)
+        dec3 = copy.deepcopy(dec2)                               # copying materialises
+        assert not dec2.is_device_resident_only and dec3.is_equal(dec)
+    A, kw = workloads.shifted_goe(300, 4, 1.05)
+    dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+    assert dec.is_device_resident_only
+    ref = orc.approximate(A, **kw)
+    np.testing.assert_allclose(np.asarray(dec.d, dtype=float), ref['d'].astype(float), rtol=1e-10)
+    assert np.all(np.abs(dec.L - ref['L']) <= 1e-10 * np.maximum(1.0, np.abs(ref['L'])))
+    # the finite check of large inputs happens on the device (small ones are scanned on the host)
+    from matrix_decomposition_b200 import calculate
+    S2 = workloads.lowrank_plus_diag(1100, 9)
+    assert S2.size > calculate._HOST_FINITE_SCAN_MAX
+    with pytest.raises(matrix.errors.MatrixNotFiniteError):
+        Sbad = S2.copy()
+        Sbad[5, 7] = Sbad[7, 5] = np.inf
+        matrix.decompose(Sbad)
+    Sbad = S2.copy()
+    Sbad[3, 3] = np.nan
+    with pytest.raises(matrix.errors.MatrixNotFiniteError):
+        matrix.decompose(Sbad, permutation='none')
+
+
 def test_decompose_failure_index(matrix):
     z = load_golden('decompose_solve_permute.npz')
     with pytest.raises(matrix.errors.NoDecompositionPossibleWithProblematicSubdecompositionError) as ei:
