@@ -40,7 +40,7 @@ FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_pe
                                # MEASURED_PEAKS.json holds only HBM and bf16 peaks
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the bulk kernel from one `ncu --set full` capture
 # (profiles/r01_ncu_summary.txt); None until captured for the current kernel
-NCU_TRAFFIC = None
+NCU_TRAFFIC = 46.01e9   # bulk update part (b), grid 234240 tiles, 109.3 ms: read 30.94 GB + write 15.08 GB (profiles/r01b_ncu_summary.txt)
 CPU_SAMPLE_N = 6144
 S_SHIFT = 1.05
 
@@ -238,7 +238,11 @@ def run_single(args):
                     algorithmic_flop_total=st['bulk_flop'], share_of_n3_over_3=st['bulk_flop'] / (n ** 3 / 3),
                     inner_update=dict(flop=st['inner_flop'], launches=st['inner_launches'], ms=phases['inner'],
                                       tflops=(st['inner_flop'] / (phases['inner'] * 1e-3) / 1e12 if phases['inner'] > 0 else None)),
-                    phases_ms=phases, traffic=NCU_TRAFFIC)
+                    phases_ms=phases, traffic=NCU_TRAFFIC,
+                    traffic_note='ncu --set full capture of the LARGEST bulk launch (part (b) of the first outer block, grid '
+                                 '234240 tiles, 109.3 ms, DMMA pipe 95.4 % active): dram read 30.94 GB + write 15.08 GB vs '
+                                 'algorithmic 31.7 GB (C triangle read + written 30.7 GB, operands 1.0 GB); the excess are '
+                                 'operand re-reads that missed L2 (profiles/r01b_ncu_summary.txt)')
     lib.mdb_factor_destroy(f)
 
     # ---- end-to-end leg: C-ABI one-shot call with pinned host buffers ----

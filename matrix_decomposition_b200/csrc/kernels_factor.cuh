@@ -13,7 +13,8 @@ __global__ void __launch_bounds__(256) k_gather_sym(int64_t n, const double* __r
                                                     int64_t sA, const int64_t* __restrict__ p, int64_t sP,
                                                     double* __restrict__ W, int64_t ldw, int64_t sW,
                                                     double* __restrict__ gamma, int64_t sVec,
-                                                    int* __restrict__ nonfinite) {
+                                                    int* __restrict__ nonfinite, int upper_only) {
+  // upper_only: A is symmetric and only its upper triangle (row <= column) is valid in the source buffer
   const int64_t b = blockIdx.z;
   bool bad = false;
   const int64_t i = blockIdx.x;
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(256) k_gather_sym(int64_t n, const double* __r
     const int64_t j = j0 + 256 * e;
     if (j < n) {
       const int64_t pj = pb ? pb[j] : j;
-      const double v = Arow[pj];
+      const double v = (upper_only && pj < pi) ? A[pj * lda + pi] : Arow[pj];
       Wrow[j] = v;
       bad |= !isfinite(v);
       if (gamma && j == i) gamma[b * sVec + i] = v;
@@ -382,9 +383,9 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
 __global__ void __launch_bounds__(256) k_finalize(int64_t n, double* __restrict__ W, int64_t ldw, int64_t sW,
                                                   const double* __restrict__ d, const double* __restrict__ omega,
                                                   int64_t sVec, double mavL, int out_type, double* __restrict__ out,
-                                                  int64_t ldo, int64_t sOut) {
+                                                  int64_t ldo, int64_t sOut, int64_t row0) {
   const int64_t b = blockIdx.z;
-  const int64_t i = blockIdx.x;
+  const int64_t i = row0 + blockIdx.x;   // rows [row0, row0 + gridDim.x)
   const double* Wrow = W + b * sW + i * ldw;
   double* Orow = out + b * sOut + i * ldo;
   const double w = omega[b * sVec + i];

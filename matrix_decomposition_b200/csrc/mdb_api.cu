@@ -36,6 +36,8 @@ struct mdb_factor {
   double mavL;
   bool prepared;
   double *Linv, *LinvT, *Ltri, *Utri;
+  // streamed output (one-shot calls with a host L): rows of L are finalised and copied out per outer block
+  double* out_host; int64_t out_ld; int out_stream_type;
   // persistent triangular sweep (<= 8 right-hand sides): task list, flags, partial sums
   int2* trsv_tasks; int trsv_ntasks; unsigned int* trsv_sync; double* trsv_partial; int trsv_partial_rhs;
   std::vector<int64_t> p_host;
@@ -62,6 +64,8 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
     MDB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
     MDB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, hi_pri));
     MDB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, lo_pri));
+    MDB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, hi_pri));
+    MDB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       MDB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_panel[i], cudaEventDisableTiming));
       MDB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_upd[i], cudaEventDisableTiming));
@@ -108,6 +112,8 @@ extern "C" int mdb_ctx_destroy(mdb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_panel[i]) cudaEventDestroy(ctx->ev_panel[i]);
     if (ctx->ev_upd[i]) cudaEventDestroy(ctx->ev_upd[i]);
@@ -236,6 +242,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   f->W = nullptr; f->vec = nullptr; f->clamped = nullptr; f->minB = f->maxB = nullptr; f->p_dev = nullptr;
   f->info = nullptr; f->Ut = f->hdr = f->PX = f->PY = f->PX2 = f->PY2 = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
   f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
+  f->out_host = nullptr; f->out_ld = 0; f->out_stream_type = MDB_TYPE_LDL;
   f->trsv_tasks = nullptr; f->trsv_ntasks = 0; f->trsv_sync = nullptr; f->trsv_partial = nullptr; f->trsv_partial_rhs = 0;
   const int64_t nn = std::max<int64_t>(n, 1);
   f->panel_rows = std::max<int64_t>(mdb_round_up(nn, NB), NB);
@@ -312,10 +319,11 @@ static int factor_set_p(mdb_factor* f, const int64_t* p) {
 }
 
 static int gather_sym(mdb_ctx* ctx, int64_t n, int64_t batch, const double* A_dev, int64_t lda, int64_t sA,
-                      const int64_t* p_dev, double* W, int64_t ldw, int64_t sW, double* gamma, int* nonfinite = nullptr) {
+                      const int64_t* p_dev, double* W, int64_t ldw, int64_t sW, double* gamma, int* nonfinite = nullptr,
+                      int upper_only = 0) {
   if (n == 0) return MDB_OK;
   dim3 grid((unsigned)n, (unsigned)((n + 1023) / 1024), (unsigned)batch);
-  k_gather_sym<<<grid, 256, 0, ctx->stream>>>(n, A_dev, lda, sA, p_dev, n, W, ldw, sW, gamma, n, nonfinite);
+  k_gather_sym<<<grid, 256, 0, ctx->stream>>>(n, A_dev, lda, sA, p_dev, n, W, ldw, sW, gamma, n, nonfinite, upper_only);
   MDB_LAUNCHED(ctx);
   MDB_CUDA(ctx, cudaGetLastError());
   return MDB_OK;
@@ -334,9 +342,20 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
   const double* A_dev = A;
   double* staging = nullptr;
   int64_t lds = lda;
+  int upper_only = 0;
   if (a_loc == MDB_HOST) {
     MDB_CUDA(ctx, cudaMalloc((void**)&staging, (size_t)f->batch * n * n * 8));
-    rc = copy2d_async(ctx, staging, n, A, lda, f->batch * n, n, MDB_DEVICE, MDB_HOST);  // batch stride = n*lda
+    if (f->batch == 1 && n >= 4096) {
+      // A is symmetric: only its upper triangle crosses PCIe (row blocks [r0, r0 + RB) x columns [r0, n)),
+      // the gather mirrors it.  Half the bytes of the full copy.
+      const int64_t RB = 2048;
+      for (int64_t r0 = 0; r0 < n && !rc; r0 += RB)
+        rc = copy2d_async(ctx, staging + r0 * n + r0, n, A + r0 * lda + r0, lda, std::min<int64_t>(RB, n - r0), n - r0,
+                          MDB_DEVICE, MDB_HOST);
+      upper_only = 1;
+    } else {
+      rc = copy2d_async(ctx, staging, n, A, lda, f->batch * n, n, MDB_DEVICE, MDB_HOST);  // batch stride = n*lda
+    }
     if (rc) { cudaFree(staging); return rc; }
     A_dev = staging;
     lds = n;
@@ -344,7 +363,7 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
   // the finite check of the input rides on the gather: flag = the int after the per-matrix info entries
   int* flag = f->info + f->batch;
   MDB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
-  rc = gather_sym(ctx, n, f->batch, A_dev, lds, n * lds, f->p_dev, f->W, f->ld, n * f->ld, f->gamma, flag);
+  rc = gather_sym(ctx, n, f->batch, A_dev, lds, n * lds, f->p_dev, f->W, f->ld, n * f->ld, f->gamma, flag, upper_only);
   int bad = 0;
   cudaError_t ef = cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   if (ef == cudaSuccess) ef = cudaStreamSynchronize(ctx->stream);
@@ -584,6 +603,19 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
         }
       }
     }
+    if (f->out_host) {
+      // rows [ob, oe) of L are final (nothing reads them or the A entries above their diagonal again): scale /
+      // threshold them in place and send them home while the factorization goes on
+      MDB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, main_s));
+      MDB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+      dim3 grid((unsigned)(oe - ob), (unsigned)((n + 1023) / 1024), 1);
+      k_finalize<<<grid, 256, 0, ctx->copy_stream>>>(n, f->W, f->ld, F.sW, f->d, f->omega, n, f->mavL, f->out_stream_type,
+                                                     f->W, f->ld, F.sW, ob);
+      MDB_LAUNCHED(ctx);
+      MDB_CUDA(ctx, cudaMemcpy2DAsync(f->out_host + ob * f->out_ld, (size_t)f->out_ld * 8, f->W + ob * f->ld,
+                                      (size_t)f->ld * 8, (size_t)n * 8, (size_t)(oe - ob), cudaMemcpyDeviceToHost,
+                                      ctx->copy_stream));
+    }
     if (oe >= n) break;
     // bulk update of everything beyond the outer block, K = KB
     const int64_t rows = n - oe;
@@ -626,6 +658,13 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
   MDB_CUDA(ctx, cudaGetLastError());
   f->state = ST_FACTORED;
   f->prepared = false;
+  if (f->out_host) {  // every row has been finalised and copied by the copy stream
+    MDB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_copy, 0));
+    f->state = ST_FINAL;
+    f->out_type = f->out_stream_type;
+    f->out_host = nullptr;
+  }
   return MDB_OK;
 }
 
@@ -639,7 +678,7 @@ static int factor_finalize(mdb_factor* f, int out_type) {
   if (f->n > 0) {
     dim3 grid((unsigned)f->n, (unsigned)((f->n + 1023) / 1024), (unsigned)f->batch);
     k_finalize<<<grid, 256, 0, ctx->stream>>>(f->n, f->W, f->ld, f->n * f->ld, f->d, f->omega, f->n, f->mavL, out_type,
-                                              f->W, f->ld, f->n * f->ld);
+                                              f->W, f->ld, f->n * f->ld, 0);
     MDB_LAUNCHED(ctx);
     MDB_CUDA(ctx, cudaGetLastError());
   }
@@ -703,8 +742,13 @@ static int one_shot(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int
   int rc = mdb_factor_create(ctx, n, batch, &f);
   if (rc) return rc;
   rc = mdb_factor_set_matrix(f, A, lda, p, loc);
+  bool streamed = false;
+  if (!rc && loc == MDB_HOST && L && batch == 1 && n >= 4096 && ldl >= n) {
+    f->out_host = L; f->out_ld = ldl; f->out_stream_type = out_type;  // L leaves the device row block by row block
+    streamed = true;
+  }
   if (!rc) rc = mdb_factor_run(f, bounds);
-  if (!rc) rc = mdb_factor_get(f, out_type, L, ldl, loc, d, omega, delta, clamped, info);
+  if (!rc) rc = mdb_factor_get(f, out_type, streamed ? nullptr : L, ldl, loc, d, omega, delta, clamped, info);
   if (rc || !factor_out) {
     mdb_factor_destroy(f);
     f = nullptr;

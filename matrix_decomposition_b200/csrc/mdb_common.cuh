@@ -18,6 +18,8 @@ struct mdb_ctx {
   cudaStream_t stream;
   cudaStream_t own_stream;
   cudaStream_t side_stream;  // low priority: the bulk of the trailing update under lookahead
+  cudaStream_t copy_stream;  // finalize + device -> host copy of finished rows of L while the factorization goes on
+  cudaEvent_t ev_copy;
   cudaEvent_t ev_panel[2], ev_upd[2];
   int lookahead;
   int use_tma;  // MDB200_TMA=0 falls back to the cp.async tile kernel
