@@ -474,6 +474,43 @@ def test_factor_stays_on_device_until_read(matrix, orc):
         matrix.decompose(Sbad, permutation='none')
 
 
+@pytest.mark.parametrize('rt', ['LDL', 'LL'])
+def test_one_shot_streamed_output_equals_resident_factor(matrix, rt):
+    """From n = 4096 on the one-shot C-ABI calls upload only the upper triangle of A and stream finished rows of L
+    to the host while the factorization is still running; the result must equal the factor that stayed on the
+    device (downloaded afterwards), bit for bit, and satisfy the oracle-free identity of Reimer.py:947-957."""
+    from matrix_decomposition_b200 import _native
+    ctx = _native.context()
+    lib = ctx.lib
+    n = 4300
+    A, kw = workloads.shifted_goe(n, 77, 1.05)
+    p = np.argsort(-A.diagonal()).astype(np.int64)
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
+                                       float(np.finfo(float).eps), None, kw['max_diag_B'])
+    L = np.full((n, n), np.nan)
+    d, om, de = np.empty(n), np.empty(n), np.empty(n)
+    cl = np.zeros(n, dtype=np.uint8)
+    h = ctypes.c_void_p()
+    P = _native.ptr
+    ctx.check(lib.mdb_approximate_f64(ctx.handle, n, P(A), n, P(p), ctypes.byref(bounds), _native.TYPE_CODES[rt], P(L), n,
+                                      P(d), P(om), P(de), P(cl), _native.HOST, ctypes.byref(h)), 'one-shot')
+    resident = _native.Factor(ctx, h).download(n, _native.TYPE_CODES[rt])
+    assert np.array_equal(L, resident)
+    assert np.all(np.triu(L, 1) == 0)
+    # identity: P^T L D L^T P = A o Omega + diag(delta)  on a probe vector
+    v = np.random.default_rng(3).standard_normal(n)
+    Lu = L if rt == 'LDL' else L / np.sqrt(d)[None, :]
+    lhs = Lu @ (d * (Lu.T @ v))
+    Ap = A[p[:, None], p[None, :]]
+    om_pos, de_pos = om[p], de[p]
+    later = np.maximum(np.arange(n)[:, None], np.arange(n)[None, :])
+    M = Ap * om_pos[later]
+    M[np.diag_indices(n)] = Ap.diagonal() + de_pos
+    rhs = M @ v
+    assert np.max(np.abs(lhs - rhs)) <= 1e-11 * np.max(np.abs(Ap @ v))
+    assert 0.2 * n < cl.sum() < 0.7 * n
+
+
 def test_decompose_failure_index(matrix):
     z = load_golden('decompose_solve_permute.npz')
     with pytest.raises(matrix.errors.NoDecompositionPossibleWithProblematicSubdecompositionError) as ei:
