@@ -38,6 +38,8 @@ extern "C" {
 #define MDB_TYPE_LDL 0            /* constants.py:5  'LDL'            */
 #define MDB_TYPE_LDL_COMPRESSED 1 /* constants.py:6  'LDL_compressed' */
 #define MDB_TYPE_LL 2             /* constants.py:7  'LL'             */
+#define MDB_TYPE_NONE (-1)        /* leave the factor un-finalised on the device (needs factor_out, L == NULL):
+                                     input of mdb_factor_psd_matrix */
 
 #define MDB_HOST 0   /* pointer refers to host memory   */
 #define MDB_DEVICE 1 /* pointer refers to device memory */
@@ -166,6 +168,14 @@ int mdb_factor_multiply(mdb_factor *f, const double *B, int64_t ldb, int64_t nrh
  * returns max over `nprobe` random vectors v of |P^T L D L^T P v - (A o Omega + diag(delta)) v|_inf /
  * |A v|_inf, all evaluated on the device from the resident W (which still holds A in its upper triangle). */
 int mdb_factor_identity_residual(mdb_factor *f, int nprobe, uint64_t seed, double *residual);
+
+/* Replaces the formation of B in positive_semidefinite_matrix (Reimer.py:899-992) from a factor that has been
+ * run but not finalised (one-shot calls with out_type = MDB_TYPE_NONE, or mdb_factor_run): B (n x n, ORIGINAL index
+ * order) = A o Omega with the diagonal A_ii + delta_i clipped to [min_diag_B_i, max_diag_B_i] (host pointers, scalar
+ * for stride_B = 0, n-vectors indexed by original index for stride_B = 1, NULL = no bound) and the inner-product
+ * fallback where d == 0 (:958-975). */
+int mdb_factor_psd_matrix(mdb_factor *f, const double *min_diag_B, const double *max_diag_B, int64_t stride_B, double *B,
+                          int64_t ldb, int loc);
 
 /* ---- introspection / unit-test hooks (used by tests/ and bench.py, not by the drop-in path) ----
  * mdb_factor_device_ptr: which = 0 W, 1 gamma, 2 alpha, 3 beta, 4 rowmax, 5 d, 6 omega, 7 delta (device addresses

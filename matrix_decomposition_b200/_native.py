@@ -28,6 +28,7 @@ RULE_EXACT = 1
 TYPE_LDL = 0
 TYPE_LDL_COMPRESSED = 1
 TYPE_LL = 2
+TYPE_NONE = -1
 HOST = 0
 DEVICE = 1
 
@@ -85,6 +86,7 @@ SIGNATURES = {
     'mdb_factor_generate_f2': (_int, [_vp, _u64, _dbl, _vp]),
     'mdb_generate_f2': (_int, [_vp, _i64, _u64, _dbl, _vp, _i64]),
     'mdb_factor_run': (_int, [_vp, ctypes.POINTER(Bounds)]),
+    'mdb_factor_psd_matrix': (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _int]),
     'mdb_factor_get': (_int, [_vp, _int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     'mdb_factor_upload': (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _pp]),
     'mdb_factor_solve': (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _int]),

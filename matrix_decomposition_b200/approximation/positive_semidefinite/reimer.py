@@ -154,6 +154,10 @@ def _prepare(A, min_diag_B, max_diag_B, min_diag_D, max_diag_D, min_abs_value_D,
             float(min_abs_value_L))
 
 
+def _type_code(out_type_str):
+    return _native.TYPE_NONE if out_type_str is None else _native.TYPE_CODES[out_type_str]
+
+
 def _run(A, out_type_str, keep_factor, download_L=True, **kw):
     """download_L=False leaves the n x n factor in HBM (returned Lout is None; needs keep_factor)."""
     A, n, p, dynamic, min_diag_B, max_diag_B, min_diag_D, max_diag_D, mavD, mavL = _prepare(A, **kw)
@@ -170,7 +174,7 @@ def _run(A, out_type_str, keep_factor, download_L=True, **kw):
     if dynamic:
         p = np.empty(n, dtype=np.int64)
         rc = ctx.lib.mdb_approximate_dynamic_f64(ctx.handle, n, P(A64), n, dynamic, ctypes.byref(bounds),
-                                                 _native.TYPE_CODES[out_type_str], P(Lout), n, P(p), P(d), P(omega),
+                                                 _type_code(out_type_str), P(Lout), n, P(p), P(d), P(omega),
                                                  P(delta), P(clamped), _native.HOST,
                                                  ctypes.byref(handle) if keep_factor else None)
         ctx.check(rc, 'mdb_approximate_dynamic_f64')
@@ -178,7 +182,7 @@ def _run(A, out_type_str, keep_factor, download_L=True, **kw):
     else:
         p64 = np.ascontiguousarray(p, dtype=np.int64)
         rc = ctx.lib.mdb_approximate_f64(ctx.handle, n, P(A64), n, P(p64), ctypes.byref(bounds),
-                                         _native.TYPE_CODES[out_type_str], P(Lout), n, P(d), P(omega), P(delta),
+                                         _type_code(out_type_str), P(Lout), n, P(d), P(omega), P(delta),
                                          P(clamped), _native.HOST, ctypes.byref(handle) if keep_factor else None)
         ctx.check(rc, 'mdb_approximate_f64')
     del keep
@@ -240,34 +244,37 @@ def positive_semidefinite_matrix(A, min_diag_B=None, max_diag_B=None, min_diag_D
     """
     Computes an approximation `B` of `A` which has a LDL^H decomposition with the specified properties
     (R.py:819-992): B[i, i] = A[i, i] + delta[i] clipped to [min_diag_B, max_diag_B] (R.py:924-945),
-    B[i, j] = A[i, j] * omega[later of (i, j) in elimination order] (R.py:947-957).
+    B[i, j] = A[i, j] * omega[later of (i, j) in elimination order] (R.py:947-957), with the inner-product
+    fallback where d == 0 (R.py:958-975).
 
-    Status: the factorization runs on the device; the O(n^2) element-wise formation of B (an n^2 Python
-    double loop in the reference) is vectorised on the host here and is next in line for a device kernel
-    ("next").  The inner-product fallback for d == 0 (R.py:958-975) is included.
+    Both the factorization and the formation of B (an n^2 Python double loop in the reference) run on the
+    device: the factor is left un-finalised in HBM (its upper triangle still holds the permuted A) and
+    mdb_factor_psd_matrix writes B in original index order.
     """
-    Lout, d, p, omega, delta, clamped, _ = _run(
-        A, constants.LDL_DECOMPOSITION_TYPE, False, min_diag_B=min_diag_B, max_diag_B=max_diag_B,
+    _, d, p, omega, delta, clamped, factor = _run(
+        A, None, True, download_L=False, min_diag_B=min_diag_B, max_diag_B=max_diag_B,
         min_diag_D=min_diag_D, max_diag_D=max_diag_D, min_abs_value_D=min_abs_value_D,
         min_abs_value_L=min_abs_value_L, permutation=permutation)
-    A = np.asarray(A)
-    n = A.shape[0]
-    q = permute.invert_permutation_vector(np.asarray(p, dtype=np.int64))
-    later = np.where(q[:, None] > q[None, :], np.arange(n)[:, None], np.arange(n)[None, :])   # b of R.py:949-955
-    earlier_pos = np.minimum(q[:, None], q[None, :])                                            # q[a]
-    B = A.astype(np.float64) * omega[later]
-    zero_d = d[earlier_pos] == 0
-    if np.any(zero_d):
-        LD = Lout * d[None, :]
-        for i, j in zip(*np.nonzero(np.triu(zero_d, 1))):
-            b = later[i, j]
-            m = earlier_pos[i, j]
-            val = 0.0 if omega[b] == 0 or m == 0 else float(LD[q[i], :m] @ Lout[q[j], :m])
-            B[i, j] = B[j, i] = val
-    diag = A.diagonal().astype(np.float64) + delta
-    if min_diag_B is not None:
-        diag = np.maximum(diag, np.asarray(min_diag_B, dtype=np.float64))
-    if max_diag_B is not None:
-        diag = np.minimum(diag, np.asarray(max_diag_B, dtype=np.float64))
-    B[np.diag_indices(n)] = diag
+    n = len(d)
+    B = np.empty((n, n), dtype=np.float64)
+    ctx = factor.ctx
+
+    def bound(x):
+        if x is None:
+            return None, 0
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 0:   # (np.ascontiguousarray would silently turn a scalar into a 1-vector)
+            return np.full(1, float(x)), 0
+        return np.ascontiguousarray(x), 1
+    mB, s1 = bound(min_diag_B)
+    MB, s2 = bound(max_diag_B)
+    stride = max(s1, s2)
+    if stride:   # mixed scalar / vector bounds: broadcast the scalar one
+        if mB is not None and s1 == 0:
+            mB = np.full(n, mB[0])
+        if MB is not None and s2 == 0:
+            MB = np.full(n, MB[0])
+    rc = ctx.lib.mdb_factor_psd_matrix(factor.handle, _native.ptr(mB), _native.ptr(MB), stride, _native.ptr(B), n, _native.HOST)
+    ctx.check(rc, 'mdb_factor_psd_matrix')
+    factor.close()
     return B

@@ -410,6 +410,66 @@ __global__ void __launch_bounds__(256) k_finalize(int64_t n, double* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// B of positive_semidefinite_matrix (Reimer.py:899-992) from the UN-finalised state (upper triangle of W = the
+// permuted A, strict lower = unscaled rows Lu), in ORIGINAL index order:
+//   B[i, i] = A[i, i] + delta_i clipped to [min_diag_B_i, max_diag_B_i]                       :924-945
+//   B[i, j] = A[i, j] * omega[later of (i, j)]          when d[earlier] != 0                  :947-957
+//           = 0                                          when omega[later] == 0
+//           = sum_{k < earlier} L[q_i, k] d_k L[q_j, k]  otherwise (rows of the scaled, thresholded L)  :958-975
+// q = inverse permutation (position of an original index).  HBM bound: 8 n^2 written coalesced, reads are
+// 8-byte gathers from the upper triangle.  grid = (n rows, column chunks of 1024).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_psd_matrix(int64_t n, const double* __restrict__ W, int64_t ldw,
+                                                    const double* __restrict__ gamma, const double* __restrict__ delta,
+                                                    const double* __restrict__ omega, const double* __restrict__ d,
+                                                    const int64_t* __restrict__ q, const double* __restrict__ minB,
+                                                    const double* __restrict__ maxB, int64_t strideB, double mavL,
+                                                    double* __restrict__ B, int64_t ldb) {
+  const int64_t i = blockIdx.x;
+  const int64_t qi = q ? q[i] : i;
+  const int64_t j0 = (int64_t)blockIdx.y * 1024 + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int64_t j = j0 + 256 * e;
+    if (j >= n) continue;
+    double v;
+    if (j == i) {
+      v = gamma[qi] + delta[qi];
+      if (minB) { const double m = minB[i * strideB]; if (v < m) v = m; }
+      if (maxB) { const double m = maxB[i * strideB]; if (v > m) v = m; }
+    } else {
+      const int64_t qj = q ? q[j] : j;
+      const int64_t lo = qi < qj ? qi : qj, hi = qi < qj ? qj : qi;
+      const double om = omega[hi];
+      if (d[lo] != 0) {
+        v = W[lo * ldw + hi] * om;
+      } else if (om == 0) {
+        v = 0.0;
+      } else {  // rare: inner product of two rows of the scaled, thresholded L over the columns before `lo`
+        const double wi = omega[qi], wj = omega[qj];
+        const double* Li = W + qi * ldw;
+        const double* Lj = W + qj * ldw;
+        double acc = 0;
+        for (int64_t k = 0; k < lo; ++k) {
+          double a = wi * Li[k], bb = wj * Lj[k];
+          if (wi == 0 || fabs(a) < mavL) a = 0;
+          if (wj == 0 || fabs(bb) < mavL) bb = 0;
+          acc += a * d[k] * bb;
+        }
+        v = acc;
+      }
+    }
+    B[i * ldb + j] = v;
+  }
+}
+
+// q[p[i]] = i
+__global__ void k_invert_permutation(int64_t n, const int64_t* __restrict__ p, int64_t* __restrict__ q) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) q[p[i]] = i;
+}
+
 // position-indexed -> original-indexed scatter of omega / delta (Reimer.py:538,545): out[p[i]] = in[i]
 __global__ void k_scatter_by_p(int64_t n, const int64_t* __restrict__ p, const double* __restrict__ in,
                                double* __restrict__ out) {

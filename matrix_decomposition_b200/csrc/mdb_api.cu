@@ -692,7 +692,9 @@ extern "C" int mdb_factor_get(mdb_factor* f, int out_type, double* L, int64_t ld
   if (!f) return MDB_ERR_INVALID;
   mdb_ctx* ctx = f->ctx;
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
-  int rc = factor_finalize(f, out_type);
+  int rc = MDB_OK;
+  if (out_type != MDB_TYPE_NONE) rc = factor_finalize(f, out_type);   // MDB_TYPE_NONE: vectors only, W stays un-finalised
+  else if (L) return mdb_fail(ctx, MDB_ERR_INVALID, "%s", "mdb_factor_get: MDB_TYPE_NONE cannot return L");
   if (rc) return rc;
   const int64_t n = f->n, batch = f->batch, bn = batch * n;
   if (L && n > 0) {
@@ -728,6 +730,54 @@ extern "C" int mdb_factor_get(mdb_factor* f, int out_type, double* L, int64_t ld
   return MDB_OK;
 }
 
+// B of positive_semidefinite_matrix from an un-finalised factor (Reimer.py:899-992)
+extern "C" int mdb_factor_psd_matrix(mdb_factor* f, const double* min_diag_B, const double* max_diag_B, int64_t stride_B,
+                                     double* B, int64_t ldb, int loc) {
+  if (!f || !B) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CHECK(ctx, f->state == ST_FACTORED, "mdb_factor_psd_matrix: needs a factorised, not yet finalised factor");
+  MDB_CHECK(ctx, f->batch == 1 && f->rule == MDB_RULE_REIMER, "mdb_factor_psd_matrix: one approximate factorization");
+  MDB_CHECK(ctx, ldb >= f->n, "mdb_factor_psd_matrix: ldb < n");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t n = f->n;
+  if (n == 0) return MDB_OK;
+  double *mB = nullptr, *MB = nullptr, *Bd = (loc == MDB_DEVICE) ? B : nullptr;
+  int64_t* q = nullptr;
+  const int64_t nb = stride_B != 0 ? n : 1, ldd = (loc == MDB_DEVICE) ? ldb : n;
+  cudaError_t e = cudaSuccess;
+  if (min_diag_B) {
+    e = cudaMalloc((void**)&mB, (size_t)nb * 8);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(mB, 8, min_diag_B, (size_t)std::max<int64_t>(stride_B, 1) * 8, 8, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess && max_diag_B) {
+    e = cudaMalloc((void**)&MB, (size_t)nb * 8);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(MB, 8, max_diag_B, (size_t)std::max<int64_t>(stride_B, 1) * 8, 8, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess && f->p_dev) {
+    e = cudaMalloc((void**)&q, (size_t)n * 8);
+    if (e == cudaSuccess) {
+      k_invert_permutation<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->p_dev, q);
+      MDB_LAUNCHED(ctx);
+    }
+  }
+  if (e == cudaSuccess && !Bd) e = cudaMalloc((void**)&Bd, (size_t)n * n * 8);
+  int rc = MDB_OK;
+  if (e == cudaSuccess) {
+    dim3 grid((unsigned)n, (unsigned)((n + 1023) / 1024));
+    k_psd_matrix<<<grid, 256, 0, ctx->stream>>>(n, f->W, f->ld, f->gamma, f->delta, f->omega, f->d, q, mB, MB,
+                                                stride_B != 0 ? 1 : 0, f->mavL, Bd, ldd);
+    MDB_LAUNCHED(ctx);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && loc != MDB_DEVICE) rc = copy2d_async(ctx, B, ldb, Bd, ldd, n, n, MDB_HOST, MDB_DEVICE);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(mB); cudaFree(MB); cudaFree(q);
+  if (loc != MDB_DEVICE) cudaFree(Bd);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // one-shot entry points
 // ------------------------------------------------------------------------------------------------
@@ -736,7 +786,8 @@ static int one_shot(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int
                     double* delta, uint8_t* clamped, int64_t* info, int loc, mdb_factor** factor_out) {
   if (!ctx) return MDB_ERR_INVALID;
   MDB_CHECK(ctx, n >= 0, "n < 0");
-  MDB_CHECK(ctx, out_type == MDB_TYPE_LDL || out_type == MDB_TYPE_LDL_COMPRESSED || out_type == MDB_TYPE_LL,
+  MDB_CHECK(ctx, out_type == MDB_TYPE_LDL || out_type == MDB_TYPE_LDL_COMPRESSED || out_type == MDB_TYPE_LL ||
+                     (out_type == MDB_TYPE_NONE && factor_out && !L),
             "unknown decomposition type");
   mdb_factor* f = nullptr;
   int rc = mdb_factor_create(ctx, n, batch, &f);
@@ -773,7 +824,8 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
   if (factor_out) *factor_out = nullptr;
   MDB_CHECK(ctx, method == 1 || method == 2, "mdb_approximate_dynamic_f64: method must be 1 or 2");
   MDB_CHECK(ctx, bnd->rule == MDB_RULE_REIMER, "mdb_approximate_dynamic_f64: bounds->rule must be MDB_RULE_REIMER");
-  MDB_CHECK(ctx, out_type == MDB_TYPE_LDL || out_type == MDB_TYPE_LDL_COMPRESSED || out_type == MDB_TYPE_LL,
+  MDB_CHECK(ctx, out_type == MDB_TYPE_LDL || out_type == MDB_TYPE_LDL_COMPRESSED || out_type == MDB_TYPE_LL ||
+                     (out_type == MDB_TYPE_NONE && factor_out && !L),
             "unknown decomposition type");
   mdb_factor* f = nullptr;
   int rc = mdb_factor_create(ctx, n, 1, &f);
