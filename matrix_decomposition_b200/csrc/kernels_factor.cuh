@@ -1,6 +1,8 @@
 // kernels_factor.cuh -- gather, generator, diagonal-block, panel and finalize kernels of the blocked
 // right-looking modified LDL^T (the restatement validated by oracle/blocked_model.py).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "mdb_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -37,6 +39,91 @@ __global__ void __launch_bounds__(256) k_gather_sym(int64_t n, const double* __r
     }
   }
   if (bad && nonfinite) *nonfinite = 1;  // dense/util.py:15-21 (is_finite), evaluated where the data already is
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same gather with the source row staged in shared memory.  A thread-block cluster of C CTAs owns one output row:
+// CTA r loads chunk r of source row p[i] with coalesced loads (the row is read from HBM exactly once), then every
+// CTA writes its slice of the output row, fetching A[p[i], p[j]] from whichever CTA of the cluster holds column p[j]
+// (distributed shared memory).  Traffic = the algorithmic 16 n^2 bytes for any permutation; the 8-byte gathers of
+// k_gather_sym (sector efficiency 1/4) become shared-memory reads.  Chunks are 2^shift doubles (64 KB, three CTAs
+// per SM, for n <= 65536; 128 KB beyond), C = 1, 2, 4, 8.  grid = (n * C, 1, batch), cluster (C, 1, 1).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_sym_cluster(int64_t n, const double* __restrict__ A, int64_t lda,
+                                                            int64_t sA, const int64_t* __restrict__ p, int64_t sP,
+                                                            double* __restrict__ W, int64_t ldw, int64_t sW,
+                                                            double* __restrict__ gamma, int64_t sVec,
+                                                            int* __restrict__ nonfinite, int shift) {
+  namespace cg = cooperative_groups;
+  extern __shared__ double smem_d[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int r = (int)cluster.block_rank();
+  const int64_t chunk = (int64_t)1 << shift;
+  const int64_t b = blockIdx.z;
+  const int64_t i = blockIdx.x / C;
+  A += b * sA;
+  W += b * sW;
+  const int64_t* pb = p ? p + b * sP : nullptr;
+  const int64_t pi = pb ? pb[i] : i;
+  const double* Arow = A + pi * lda;
+  bool bad = false;
+  {  // my chunk of the source row: coalesced, 4 independent loads in flight per thread
+    const int64_t c0 = (int64_t)r * chunk;
+    const int64_t len = (c0 < n) ? ((n - c0 < chunk) ? n - c0 : chunk) : 0;
+    const double* src = Arow + c0;
+    int64_t k = threadIdx.x;
+    for (; k + 3 * 256 < len; k += 4 * 256) {
+      const double v0 = src[k], v1 = src[k + 256], v2 = src[k + 512], v3 = src[k + 768];
+      smem_d[k] = v0; smem_d[k + 256] = v1; smem_d[k + 512] = v2; smem_d[k + 768] = v3;
+      bad |= !(isfinite(v0) && isfinite(v1) && isfinite(v2) && isfinite(v3));
+    }
+    for (; k < len; k += 256) {
+      const double v = src[k];
+      smem_d[k] = v;
+      bad |= !isfinite(v);
+    }
+  }
+  cluster.sync();
+  {  // my slice of the output row
+    const int64_t per = (((n + C - 1) / C) + 3) & ~(int64_t)3;
+    const int64_t j0 = (int64_t)r * per, j1 = (j0 + per < n) ? j0 + per : n;
+    double* Wrow = W + i * ldw;
+    const int64_t mask = chunk - 1;
+    auto fetch = [&](int64_t pj) -> double {
+      const int owner = (int)(pj >> shift);
+      const double* src = (owner == r) ? smem_d : cluster.map_shared_rank(smem_d, owner);
+      return src[pj & mask];
+    };
+    int64_t j = j0 + threadIdx.x;
+    for (; j + 3 * 256 < j1; j += 4 * 256) {
+      const int64_t q0 = pb ? pb[j] : j, q1 = pb ? pb[j + 256] : j + 256, q2 = pb ? pb[j + 512] : j + 512,
+                    q3 = pb ? pb[j + 768] : j + 768;
+      const double v0 = fetch(q0), v1 = fetch(q1), v2 = fetch(q2), v3 = fetch(q3);
+      Wrow[j] = v0; Wrow[j + 256] = v1; Wrow[j + 512] = v2; Wrow[j + 768] = v3;
+    }
+    for (; j < j1; j += 256) Wrow[j] = fetch(pb ? pb[j] : j);
+    if (gamma && i >= j0 && i < j1 && threadIdx.x == 0) gamma[b * sVec + i] = fetch(pi);
+  }
+  if (bad && nonfinite) *nonfinite = 1;
+  cluster.sync();  // nobody leaves while its shared memory may still be read
+}
+
+// lower triangle <- transpose of the upper triangle (the host upload sends only the upper triangle of a symmetric A)
+__global__ void __launch_bounds__(256) k_mirror_upper_to_lower(int64_t n, double* __restrict__ A, int64_t lda) {
+  __shared__ double tile[32][33];
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;  // tile (bi, bj) of the UPPER triangle, bi <= bj
+  if (bi > bj) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int64_t i = bi * 32 + rr, j = bj * 32 + tx;
+    tile[rr][tx] = (i < n && j < n) ? A[i * lda + j] : 0.0;
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int64_t i = bj * 32 + rr, j = bi * 32 + tx;  // destination (row in block bj, column in block bi)
+    if (i < n && j < n && i > j) A[i * lda + j] = tile[tx][rr];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -76,6 +76,8 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
     ctx->use_tma = !(tm && tm[0] == '0');
     const char* tv = getenv("MDB200_TRSV");
     ctx->use_trsv = !(tv && tv[0] == '0');
+    const char* cgv = getenv("MDB200_CLUSTER_GATHER");
+    ctx->use_cluster_gather = !(cgv && cgv[0] == '0');
     // outer block width of the factorization: MDB200_AGG = 1, 2, 4, 8 panels (fixed) or unset = by remaining size,
     // thresholds MDB200_AGG_THRESH = "t2,t4,t8" (remaining rows from which 2, 4, 8 panels are aggregated)
     const char* ag = getenv("MDB200_AGG");
@@ -322,6 +324,37 @@ static int gather_sym(mdb_ctx* ctx, int64_t n, int64_t batch, const double* A_de
                       const int64_t* p_dev, double* W, int64_t ldw, int64_t sW, double* gamma, int* nonfinite = nullptr,
                       int upper_only = 0) {
   if (n == 0) return MDB_OK;
+  // cluster kernel: source row staged in (distributed) shared memory, row read once
+  const int shift = (n <= 8 * 8192) ? 13 : 14;  // chunk of 8192 doubles (64 KB) or 16384 (128 KB)
+  const int64_t chunk = (int64_t)1 << shift;
+  int C = 1;
+  while (C < 8 && (int64_t)C * chunk < n) C *= 2;
+  if (!upper_only && ctx->use_cluster_gather && (int64_t)C * chunk >= n && n * C <= 0x7fffffff) {
+    static bool configured = false;
+    if (!configured) {
+      MDB_CUDA(ctx, cudaFuncSetAttribute(k_gather_sym_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+      configured = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(n * C), 1, (unsigned)batch);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)std::min<int64_t>(chunk, n) * 8;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int64_t sP = n, sVec = n;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_gather_sym_cluster, n, A_dev, lda, sA, p_dev, sP, W, ldw, sW, gamma, sVec,
+                                       nonfinite, shift);
+    if (e == cudaSuccess) {
+      MDB_LAUNCHED(ctx);
+      return MDB_OK;
+    }
+    cudaGetLastError();  // fall through to the plain gather
+  }
   dim3 grid((unsigned)n, (unsigned)((n + 1023) / 1024), (unsigned)batch);
   k_gather_sym<<<grid, 256, 0, ctx->stream>>>(n, A_dev, lda, sA, p_dev, n, W, ldw, sW, gamma, n, nonfinite, upper_only);
   MDB_LAUNCHED(ctx);
@@ -352,7 +385,11 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
       for (int64_t r0 = 0; r0 < n && !rc; r0 += RB)
         rc = copy2d_async(ctx, staging + r0 * n + r0, n, A + r0 * lda + r0, lda, std::min<int64_t>(RB, n - r0), n - r0,
                           MDB_DEVICE, MDB_HOST);
-      upper_only = 1;
+      if (!rc) {
+        const unsigned t32 = (unsigned)((n + 31) / 32);
+        k_mirror_upper_to_lower<<<dim3(t32, t32), 256, 0, ctx->stream>>>(n, staging, n);
+        MDB_LAUNCHED(ctx);
+      }
     } else {
       rc = copy2d_async(ctx, staging, n, A, lda, f->batch * n, n, MDB_DEVICE, MDB_HOST);  // batch stride = n*lda
     }

@@ -23,6 +23,7 @@ struct mdb_ctx {
   cudaEvent_t ev_panel[2], ev_upd[2];
   int lookahead;
   int use_tma;  // MDB200_TMA=0 falls back to the cp.async tile kernel
+  int use_cluster_gather;  // MDB200_CLUSTER_GATHER=0: plain 8-byte gather instead of the cluster / DSMEM kernel
   int use_trsv; // MDB200_TRSV=0: per-block launches instead of the persistent triangular sweep (<= 8 right-hand sides)
   int agg_fixed;            // panels per outer block forced by MDB200_AGG (0 = choose by remaining size)
   int64_t agg_thresh[3];    // remaining sizes from which 2, 4, 8 panels are aggregated
