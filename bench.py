@@ -137,6 +137,19 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    if os.environ.get('OMP_NUM_THREADS') and not os.environ.get('MDB200_REF_CHILD'):
+        # launched under torchrun (it exports OMP_NUM_THREADS=1): run the CPU arm in a fresh interpreter with a clean
+        # OpenMP environment so that it really uses all host cores, and relay its line
+        env = dict(os.environ)
+        for k in ('OMP_NUM_THREADS', 'OMP_PROC_BIND', 'OMP_PLACES', 'GOMP_CPU_AFFINITY', 'KMP_AFFINITY', 'RANK', 'WORLD_SIZE',
+                  'LOCAL_RANK', 'LOCAL_WORLD_SIZE'):
+            env.pop(k, None)
+        env['MDB200_REF_CHILD'] = '1'
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--gpus', str(args.gpus),
+                              '--steps', str(args.steps), '--warmup', str(args.warmup)], env=env, check=True,
+                             stdout=subprocess.PIPE, text=True).stdout
+        print(out.strip().splitlines()[-1])
+        return 0
     n = CPU_SAMPLE_N
     times = []
     base = None

@@ -2,6 +2,7 @@
 // right-looking modified LDL^T, the permutation gather, and solve / multiply with a resident factor.
 #include <math.h>
 #include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
@@ -46,6 +47,15 @@ struct mdb_factor {
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+// Wait for the background release of an earlier one-shot call (before anything that allocates device memory).
+static void ctx_reap(mdb_ctx* ctx) {
+  if (ctx && ctx->reaper) {
+    ctx->reaper->join();
+    delete ctx->reaper;
+    ctx->reaper = nullptr;
+  }
+}
+
 extern "C" int mdb_version(void) { return 100; }
 
 extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
@@ -111,6 +121,7 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
 
 extern "C" int mdb_ctx_destroy(mdb_ctx* ctx) {
   if (!ctx) return MDB_OK;
+  ctx_reap(ctx);
   cudaSetDevice(ctx->device);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
@@ -171,6 +182,7 @@ extern "C" int mdb_ctx_get_phase_ms(const mdb_ctx* ctx, double ms[4]) {
 // ------------------------------------------------------------------------------------------------
 extern "C" int mdb_malloc(mdb_ctx* ctx, size_t bytes, void** dptr) {
   if (!ctx || !dptr) return MDB_ERR_INVALID;
+  ctx_reap(ctx);
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   MDB_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 8));
   return MDB_OK;
@@ -236,6 +248,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   if (!ctx || !out) return MDB_ERR_INVALID;
   *out = nullptr;
   MDB_CHECK(ctx, n >= 0 && batch >= 1, "mdb_factor_create: n >= 0 and batch >= 1 required");
+  ctx_reap(ctx);
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   mdb_factor* f = new (std::nothrow) mdb_factor();
   if (!f) return mdb_fail(ctx, MDB_ERR_INVALID, "%s", "out of host memory");
@@ -827,20 +840,39 @@ static int one_shot(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int
                      (out_type == MDB_TYPE_NONE && factor_out && !L),
             "unknown decomposition type");
   mdb_factor* f = nullptr;
+  // MDB200_TIMING=1: wall-clock of the stages of a one-shot call on stderr (debugging aid)
+  static const bool timing = getenv("MDB200_TIMING") != nullptr;
+  auto now = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+  const double t0 = now();
   int rc = mdb_factor_create(ctx, n, batch, &f);
   if (rc) return rc;
+  if (timing) cudaStreamSynchronize(ctx->stream);
+  const double t1 = now();
   rc = mdb_factor_set_matrix(f, A, lda, p, loc);
+  if (timing) cudaStreamSynchronize(ctx->stream);
+  const double t2 = now();
   bool streamed = false;
   if (!rc && loc == MDB_HOST && L && batch == 1 && n >= 4096 && ldl >= n) {
     f->out_host = L; f->out_ld = ldl; f->out_stream_type = out_type;  // L leaves the device row block by row block
     streamed = true;
   }
   if (!rc) rc = mdb_factor_run(f, bounds);
+  if (timing) cudaStreamSynchronize(ctx->stream);
+  const double t3 = now();
   if (!rc) rc = mdb_factor_get(f, out_type, streamed ? nullptr : L, ldl, loc, d, omega, delta, clamped, info);
+  const double t4 = now();
   if (rc || !factor_out) {
-    mdb_factor_destroy(f);
+    // the results are complete; the tens of GB of device buffers are released in the background
+    cudaStreamSynchronize(ctx->stream);
+    ctx_reap(ctx);
+    mdb_factor* dead = f;
+    ctx->reaper = new (std::nothrow) std::thread([dead]() { factor_release(dead); });
+    if (!ctx->reaper) factor_release(dead);
     f = nullptr;
   }
+  if (timing)
+    fprintf(stderr, "[mdb200] one-shot n=%lld: create %.3f s, set_matrix %.3f s, run %.3f s, get %.3f s, destroy %.3f s\n",
+            (long long)n, t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4);
   if (factor_out) *factor_out = f;
   return rc;
 }
@@ -977,6 +1009,7 @@ extern "C" int mdb_permute_sym_f64(mdb_ctx* ctx, int64_t n, const double* A, int
   MDB_CHECK(ctx, n >= 0 && lda >= n && ldb >= n, "mdb_permute_sym_f64: bad dimensions");
   if (n == 0) return MDB_OK;
   MDB_CHECK(ctx, A && B, "mdb_permute_sym_f64: null matrix");
+  ctx_reap(ctx);
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   int64_t* p_dev = nullptr;
   double *A_dev = nullptr, *B_dev = nullptr;

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mdb200.h"
@@ -31,6 +32,8 @@ struct mdb_ctx {
   int64_t launches;
   int profiling;
   double phase_ms[4];
+  std::thread* reaper;        // background release of the previous one-shot call's device buffers (cudaFree of tens
+                              // of GB takes 0.2-0.4 s and nothing the caller waits for depends on it)
   int last_input_nonfinite;   // set by mdb_factor_set_matrix: the matrix held an inf / NaN
   double gemm_flop[2];        // algorithmic flop of the bulk / inner trailing updates of the last mdb_factor_run
   int64_t gemm_launches[2];

@@ -63,6 +63,7 @@ extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, dou
   MDB_CHECK(ctx, n > 0 && world >= 1 && rank >= 0 && rank < world, "mdb_dist_create: bad n / rank / world");
   MDB_CHECK(ctx, S_loc && A_loc && panel0 && panel1, "mdb_dist_create: null buffer");
   MDB_CHECK(ctx, ld_loc == mdb_dist_local_cols(n, rank, world), "mdb_dist_create: ld_loc must be mdb_dist_local_cols()");
+  ctx_reap(ctx);
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc = configure_kernels(ctx);
   if (rc) return rc;
