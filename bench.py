@@ -161,8 +161,8 @@ def run_reference(args):
     value = n ** 3 / 3 / (ms * 1e-3) / 1e9
     base['value'] = value
     line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='f64 (x87 long double accumulators, like the reference)', data='synthetic',
+                warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak' if args.gpus == 1 else 'strong',
+                vs_baseline=None, dtype='f64 (x87 long double accumulators, like the reference)', data='synthetic',
                 config=dict(workload='matrix.approximate (modified LDL^T), F2 shifted GOE s=1.05, bounded CPU sample n=%d '
                                      'of the n=%d GPU workload' % (n, 65536 if args.gpus == 1 else 131072)),
                 cpu_baseline=base,
