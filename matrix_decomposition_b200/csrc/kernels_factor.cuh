@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
 // A[j, k] for the mix comes from (Asrc, a_rs, a_cs): element (j, k) at Asrc[j * a_rs + k * a_cs]
 // (single GPU: the upper triangle of W, a_rs = 1, a_cs = ldw; multi GPU: the local copy of A).
 // ------------------------------------------------------------------------------------------------
+#define MDB_PANEL_LDX(R) ((R) + 8)
+#define MDB_PANEL_SMEM_DOUBLES(NB, R) ((NB) * MDB_PANEL_LDX(R) + 4 * (NB) + 2 * (NB) * 8)
+
 template <int NB, int R>
 __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t row_begin, int64_t n_rows,
                                              const double* __restrict__ Asrc, int64_t a_rs, int64_t a_cs,
@@ -337,12 +340,13 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
   // PX / PY: row (j - p_row0) of the operand buffers, leading dimension p_ld (>= NB: the buffers hold the
   // panels of one outer block side by side so that the bulk trailing update contracts over all of them)
   extern __shared__ double smem_d[];
-  constexpr int LDX = R + 1;
+  constexpr int LDX = MDB_PANEL_LDX(R);  // 72: the DMMA fragment loads below then take the minimal two wavefronts
   double* xs = smem_d;          // xs[c * LDX + r]
   double* s_d = xs + NB * LDX;  // NB
   double* s_w = s_d + NB;       // NB
   double* s_drop = s_w + NB;    // NB
-  double* us = s_drop + NB;     // 2 x (NB x 8): double-buffered 8-column slices of U (L1 is too small to hold U
+  double* s_inv = s_drop + NB;  // NB: 1 / d (0 where d == 0): x = r * (1 / d), <= 1 ulp from r / d, one division per column
+  double* us = s_inv + NB;      // 2 x (NB x 8): double-buffered 8-column slices of U (L1 is too small to hold U
                                 // next to the X tiles, so U is staged through shared memory with cp.async)
 
   const int64_t b = blockIdx.z;
@@ -371,7 +375,9 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
   };
 
   for (int c = tid; c < NB; c += R) {
-    s_d[c] = hdr[c];
+    const double dc = hdr[c];
+    s_d[c] = dc;
+    s_inv[c] = (dc != 0) ? 1.0 / dc : 0.0;
     s_w[c] = hdr[NB + c];
     s_drop[c] = hdr[2 * NB + c];
   }
@@ -392,12 +398,12 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
     rowmax_j = F.rowmax[vo + j];
     // mix with the original A column entries; beta in column order
     const double* Aj = Asrc + j * a_rs + k0 * a_cs;
-    for (int cb = 0; cb < NB; cb += 16) {
-      double av[16];
+    for (int cb = 0; cb < NB; cb += 32) {
+      double av[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) av[i] = Aj[(int64_t)(cb + i) * a_cs];  // 16 independent loads in flight
+      for (int i = 0; i < 32; ++i) av[i] = Aj[(int64_t)(cb + i) * a_cs];  // 32 independent loads in flight
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 32; ++i) {
         const int c = cb + i;
         const double a = av[i];
         const double w = s_w[c];
@@ -413,30 +419,56 @@ __global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t ro
     const int c0 = sb * 8;
     if (sb + 1 < NB / 8) load_slice(sb + 1, (sb + 1) & 1);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    if (valid) {
+    {
+      // acc = R - X U on the FP64 tensor cores: each warp owns its 32 rows (two 16 x 8 tiles), K = c0.
+      // mma.m16n8k4: a0 = A[g][t4], a1 = A[g+8][t4], b0 = B[t4][g], c = C[g | g+8][2 t4 | 2 t4 + 1].
       const double* U = us + (sb & 1) * (NB * 8);
-      double acc[8];
+      const int lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+      const int rb = (tid & ~31);  // first row of this warp inside the CTA tile
+      if (jbase + rb < jend && c0 > 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = xs[(c0 + i) * LDX + tid];
+        for (int mt = 0; mt < 2; ++mt) {
+          const int r0 = rb + 16 * mt + g;
+          double cfrag[4];
+          cfrag[0] = xs[(c0 + 2 * t4) * LDX + r0];
+          cfrag[1] = xs[(c0 + 2 * t4 + 1) * LDX + r0];
+          cfrag[2] = xs[(c0 + 2 * t4) * LDX + r0 + 8];
+          cfrag[3] = xs[(c0 + 2 * t4 + 1) * LDX + r0 + 8];
 #pragma unroll 4
-      for (int m = 0; m < c0; ++m) {
-        const double xm = xs[m * LDX + tid];
-        const double2* up = reinterpret_cast<const double2*>(U + m * 8);
-        const double2 u0 = up[0], u1 = up[1], u2 = up[2], u3 = up[3];
-        acc[0] -= xm * u0.x; acc[1] -= xm * u0.y; acc[2] -= xm * u1.x; acc[3] -= xm * u1.y;
-        acc[4] -= xm * u2.x; acc[5] -= xm * u2.y; acc[6] -= xm * u3.x; acc[7] -= xm * u3.y;
+          for (int k = 0; k < c0; k += 4) {
+            const double a0 = xs[(k + t4) * LDX + r0];
+            const double a1 = xs[(k + t4) * LDX + r0 + 8];
+            const double b0 = -U[(k + t4) * 8 + g];
+            asm volatile(
+                "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+                : "+d"(cfrag[0]), "+d"(cfrag[1]), "+d"(cfrag[2]), "+d"(cfrag[3])
+                : "d"(a0), "d"(a1), "d"(b0));
+          }
+          xs[(c0 + 2 * t4) * LDX + r0] = cfrag[0];
+          xs[(c0 + 2 * t4 + 1) * LDX + r0] = cfrag[1];
+          xs[(c0 + 2 * t4) * LDX + r0 + 8] = cfrag[2];
+          xs[(c0 + 2 * t4 + 1) * LDX + r0 + 8] = cfrag[3];
+        }
       }
+      __syncwarp();
+      if (valid) {
+        // the 8 x 8 triangle of the slice, one thread per row
+        double acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        const double dk = s_d[c];
-        const double x = (dk != 0) ? acc[i] / dk : 0.0;
-        xs[c * LDX + tid] = x;
-        alpha_j += x * x * dk;
-        rowmax_j = fmax(rowmax_j, fabs(x));
+        for (int i = 0; i < 8; ++i) acc[i] = xs[(c0 + i) * LDX + tid];
 #pragma unroll
-        for (int i2 = i + 1; i2 < 8; ++i2) acc[i2] -= x * U[c * 8 + i2];
+        for (int i = 0; i < 8; ++i) {
+          const int c = c0 + i;
+          const double dk = s_d[c];
+          const double x = (dk != 0) ? acc[i] * s_inv[c] : 0.0;
+          xs[c * LDX + tid] = x;
+          alpha_j += x * x * dk;          // Reimer.py:679-684
+          rowmax_j = fmax(rowmax_j, fabs(x));
+#pragma unroll
+          for (int i2 = i + 1; i2 < 8; ++i2) acc[i2] -= x * U[c * 8 + i2];
+        }
       }
+      __syncwarp();
     }
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();

@@ -498,7 +498,7 @@ static int configure_kernels(mdb_ctx* ctx) {
   static bool done = false;
   if (done) return MDB_OK;
   const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
-  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB + 2 * NB * 8) * 8;
+  const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
   const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel<NB, PANEL_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
@@ -576,7 +576,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
     MDB_CUDA(ctx, cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream));
   }
   const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
-  const int panel_smem = (NB * (PANEL_R + 1) + 3 * NB + 2 * NB * 8) * 8;
+  const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
   // Two-level blocking.  Panels are NB = 128 columns wide (diagonal block + row-parallel panel kernel); `agg`
   // consecutive panels form an outer block of KB = agg * NB columns whose operands X, Y sit side by side in one
   // (rows x KB) buffer.  After panel j only the remaining columns of its outer block are updated (K = 128,
