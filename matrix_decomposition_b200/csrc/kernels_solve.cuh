@@ -303,7 +303,7 @@ __device__ __forceinline__ bool spin_until(const unsigned int* p, unsigned int w
   unsigned int it = 0;
   while (ld_acquire(p) < want) {
     if (++it > SPIN_LIMIT) { atomicExch(err, 1); return false; }
-    __nanosleep(20);
+    if (it > 64) __nanosleep(32);  // the first polls are back to back: the wait is usually on the dependency chain
   }
   return true;
 }
