@@ -148,7 +148,7 @@ def run_reference(args):
         out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--gpus', str(args.gpus),
                               '--steps', str(args.steps), '--warmup', str(args.warmup)], env=env, check=True,
                              stdout=subprocess.PIPE, text=True).stdout
-        print(out.strip().splitlines()[-1])
+        _RESULT.append(out.strip().splitlines()[-1])
         return 0
     n = CPU_SAMPLE_N
     times = []
@@ -167,7 +167,7 @@ def run_reference(args):
                                      'of the n=%d GPU workload' % (n, 65536 if args.gpus == 1 else 131072)),
                 cpu_baseline=base,
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -276,7 +276,7 @@ def run_single(args):
                 clocks=clocks, gpu_launches=int(launches_per_step * args.steps), roofline=roofline, cpu_baseline=base)
     if e2e is not None:
         line['e2e'] = e2e
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -350,13 +350,46 @@ def run_distributed(args):
                                 e2e_skipped=out.get('e2e_skipped')),
                     clocks=out.get('clocks'), gpu_launches=out.get('gpu_launches'), roofline=out.get('roofline'),
                     cpu_baseline=base, e2e=out.get('e2e'))
-        print(json.dumps(line))
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
     return 0
 
 
+class _QuietStdout:
+    """Everything libraries print to stdout while the benchmark runs (e.g. NCCL's version banner) goes to stderr, so
+    that stdout carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+def emit(line):
+    """The one JSON line, on the real stdout."""
+    _RESULT.append(json.dumps(line))
+
+
+_RESULT = []
+
+
 def main():
+    with _QuietStdout():
+        rc = _main()
+    for line in _RESULT:
+        print(line, flush=True)
+    return rc
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=2)
@@ -367,7 +400,7 @@ def main():
     ap.add_argument('--cpu-baseline-json', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline_json:
-        print(json.dumps(cpu_baseline()[0]))
+        _RESULT.append(json.dumps(cpu_baseline()[0]))
         return 0
     if args.impl == 'reference':
         return run_reference(args)
