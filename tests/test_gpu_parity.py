@@ -511,6 +511,33 @@ def test_one_shot_streamed_output_equals_resident_factor(matrix, rt):
     assert 0.2 * n < cl.sum() < 0.7 * n
 
 
+def test_config2_size_decompose_and_solve_properties(matrix):
+    """BASELINE config 2 at full size (SPD, n = 16384, LDL, solve with 1 and 64 right-hand sides), checked through
+    size-independent properties: A x = b, the composed matrix applied to probes equals A applied to them, d > 0,
+    L unit lower triangular; the factor never leaves the device except for the final look at L."""
+    n = 16384
+    A = workloads.lowrank_plus_diag(n, 12)
+    dec = matrix.decompose(A, permutation='decreasing_diagonal_values', return_type='LDL')
+    assert dec.is_device_resident_only
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal(n)
+    x = dec.solve(b)                                            # persistent triangular sweeps (1 rhs)
+    assert np.max(np.abs(A @ x - b)) <= 1e-10 * np.max(np.abs(b)) * n ** 0.5
+    Bk = rng.standard_normal((n, 64))
+    Xk = dec.solve(Bk)                                          # blocked DMMA sweeps
+    assert np.max(np.abs(A @ Xk - Bk)) <= 1e-10 * np.max(np.abs(Bk)) * n ** 0.5
+    np.testing.assert_allclose(dec.solve(Bk[:, 0]), Xk[:, 0], rtol=1e-9, atol=1e-12)   # both paths agree
+    V = rng.standard_normal((n, 3))
+    AV = dec.matrix_right_side_multiplication(V)                # (P^T L D L^T P) V on the device
+    assert np.max(np.abs(AV - A @ V)) <= 1e-11 * np.max(np.abs(A @ V))
+    d = np.asarray(dec.d, dtype=float)
+    assert np.all(d > 0) and dec.is_positive_definite()
+    assert sorted(np.asarray(dec.p).tolist()) == list(range(n))
+    assert np.all(np.diff(A.diagonal()[np.asarray(dec.p)]) <= 0)     # 'decreasing_diagonal_values'
+    L = dec.L
+    assert np.all(L.diagonal() == 1) and np.all(np.triu(L[:2048, :2048], 1) == 0) and L[5, n - 1] == 0
+
+
 def test_decompose_failure_index(matrix):
     z = load_golden('decompose_solve_permute.npz')
     with pytest.raises(matrix.errors.NoDecompositionPossibleWithProblematicSubdecompositionError) as ei:
