@@ -264,27 +264,29 @@ __global__ void k_max_abs_diff(int64_t n, const double* __restrict__ a, const do
 // in ONE launch per sweep instead of two launches per 128-row block.  L is streamed exactly once (8 n^2 bytes per
 // solve, both sweeps): the work is cut into tasks that CTAs claim from a global counter in dependency order,
 //   partial (I, c) : p[I][c] = sum over the column blocks J of chunk c (8 blocks, J < I - 1) of L[I, J] z_J
-//   diag I         : z_I = Linv_I (b_I - sum_c p[I][c] - L[I, I-1] z_{I-1}),  then publishes flag[I]
-// Each block L[I, J] (128 x 128) is loaded into REGISTERS before the task waits for z_J, so after the flag arrives
-// only the arithmetic is left; the diag task also holds Linv_I (transposed) in shared memory ahead of time.  That
-// keeps the dependency chain z_0 -> z_1 -> ... at one flag round trip + two small products per block.  A task only
-// waits for tasks earlier in the claim order, so resident CTAs always make progress (no co-residency assumption);
-// spins are bounded and raise *err instead of hanging the device.  Partial sums are combined in a fixed order:
-// results are deterministic.  In reversed mode block index I stands for T - 1 - I.
+//   diag I         : z_I = Linv_I (b_I - sum_c p[I][c] - L[I, I-1] z_{I-1})
+// Each block L[I, J] (128 x 128) is loaded into REGISTERS before the task waits for z_J, so after z_J arrives only
+// the arithmetic is left; the diag task also holds Linv_I (transposed) in shared memory ahead of time.
+// Synchronisation is on the DATA: the output vector and the partial sums are pre-filled with a sentinel (a NaN with
+// a private payload) and a consumer polls the very doubles it needs until they are no longer the sentinel -- no
+// flags, no fences, one L2 round trip per step of the dependency chain z_0 -> z_1 -> ...  (a right-hand side that
+// contains exactly that NaN pattern runs into the bounded spin and is reported as an error).  A task only waits
+// for tasks earlier in the claim order, so resident CTAs always make progress (no co-residency assumption).
+// Partial sums are combined in a fixed order: results are deterministic.  In reversed mode block index I stands
+// for T - 1 - I.
 // ------------------------------------------------------------------------------------------------
 struct TrsvArgs {
   const double* W; int64_t ldw; int64_t n; int T;
   const double* DinvT;    // per block: TRANSPOSE of the inverse diagonal block to apply (forward: LinvT, backward: Linv)
   const double* in;       // nrhs x ldt
-  double* out;            // nrhs x ldt
+  double* out;            // nrhs x ldt, pre-filled with the sentinel
   int64_t ldt; int nrhs;
   const double* scale_d;  // backward sweep of an LDL factor: the input is divided by d first (decompositions.py:988)
-  double* partial;        // [T][NC][nrhs][128]
+  double* partial;        // [T][NC][nrhs][128], pre-filled with the sentinel
   int NC;
-  unsigned int* flags;    // [T]   z_I published
-  unsigned int* counters; // [T]   partial tasks of row block I done
-  const int2* tasks;      // (I, c) with c = -1 for the diag task
+  const int2* tasks;      // partial tasks (I, c) in claim order
   int ntasks;
+  int nd;                 // CTAs dedicated to the diag tasks
   unsigned int* next_task;
   int reverse;
   int* err;
@@ -292,22 +294,30 @@ struct TrsvArgs {
 
 namespace trsv {
 constexpr int NB = MDB_NB, CH = 8, THREADS = 256;
-constexpr unsigned int SPIN_LIMIT = 1u << 27;
+constexpr unsigned int SPIN_LIMIT = 1u << 26;
+constexpr unsigned long long SENTINEL = 0x7ff8dead5eed0001ull;
 
-__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ bool spin_until(const unsigned int* p, unsigned int want, int* err) {
+// polls one double until the producer has overwritten the sentinel
+__device__ __forceinline__ double poll(const double* p, int* err, bool* ok) {
+  unsigned long long bits;
   unsigned int it = 0;
-  while (ld_acquire(p) < want) {
-    if (++it > SPIN_LIMIT) { atomicExch(err, 1); return false; }
-    if (it > 64) __nanosleep(32);  // the first polls are back to back: the wait is usually on the dependency chain
+  for (;;) {
+    asm volatile("ld.volatile.global.u64 %0, [%1];\n" : "=l"(bits) : "l"(p) : "memory");
+    if (bits != SENTINEL) break;
+    if (++it > SPIN_LIMIT) { atomicExch(err, 1); *ok = false; break; }
+    if (it > 256) __nanosleep(32);
   }
-  return true;
+  return __longlong_as_double((long long)bits);
+}
+__device__ __forceinline__ void publish(double* p, double v) {
+  asm volatile("st.volatile.global.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
 }
 }  // namespace trsv
+
+__global__ void k_fill_sentinel(int64_t n, double* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) reinterpret_cast<unsigned long long*>(x)[i] = trsv::SENTINEL;
+}
 
 template <int MR>
 __global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a) {
@@ -317,21 +327,36 @@ __global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a
   double* zs = sD + NB * NB;        // MR x NB: z of the block being applied
   double* vs = zs + MR * NB;        // MR x NB: right-hand side of the diag task
   __shared__ int s_task;
-  __shared__ int s_ok;
+  __shared__ int s_fail;
   const int tid = threadIdx.x, r = tid >> 1, h = tid & 1;
   const int nrhs = a.nrhs;
   const int T = a.T;
+  if (tid == 0) s_fail = 0;
 
   // element (row block I, column block J) of the triangle being swept, as global (row, col) of W
   auto blk_row = [&](int I) { return (int64_t)(a.reverse ? T - 1 - I : I) * NB; };
 
+  // The first ND CTAs own the dependency chain: CTA b runs the diag tasks I = b, b + ND, ... and nothing else, so
+  // a diag task never queues behind a long partial task and the next one is already prefetching (its L block and
+  // inverse diagonal block) while the current one computes.  All other CTAs claim partial tasks in order.
+  const bool diag_cta = (int)blockIdx.x < a.nd;
+  int my_diag = (int)blockIdx.x;
   for (;;) {
-    if (tid == 0) s_task = (int)atomicAdd(a.next_task, 1u);
-    __syncthreads();
-    const int t = s_task;
-    __syncthreads();
-    if (t >= a.ntasks) break;
-    const int I = a.tasks[t].x, c = a.tasks[t].y;
+    int I, c;
+    if (diag_cta) {
+      __syncthreads();
+      if (my_diag >= T || s_fail != 0) break;
+      I = my_diag; c = -1;
+      my_diag += a.nd;
+    } else {
+      if (tid == 0) s_task = (int)atomicAdd(a.next_task, 1u);
+      __syncthreads();
+      const int t = s_task;
+      const bool failed = s_fail != 0;
+      __syncthreads();
+      if (t >= a.ntasks || failed) break;
+      I = a.tasks[t].x; c = a.tasks[t].y;
+    }
     const int64_t row0 = blk_row(I);
     const int64_t grow = row0 + r;
     const bool rowok = grow < a.n;
@@ -350,10 +375,13 @@ __global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a
         blk[2 * i + 1] = v.y;
       }
     };
-    // zs <- z_J (all right-hand sides)
+    // zs <- z_J (all right-hand sides), polling the data itself
     auto load_z = [&](int J) {
       const int64_t c0 = blk_row(J);
-      for (int e = tid; e < nrhs * NB; e += THREADS) zs[e] = a.out[(int64_t)(e / NB) * a.ldt + c0 + (e % NB)];
+      bool ok = true;
+      for (int e = tid; e < nrhs * NB; e += THREADS)
+        zs[e] = poll(a.out + (int64_t)(e / NB) * a.ldt + c0 + (e % NB), a.err, &ok);
+      if (!ok) s_fail = 1;
     };
     auto apply_block = [&]() {  // acc[m] += sum over this thread's chunks
 #pragma unroll
@@ -371,13 +399,6 @@ __global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a
         }
       }
     };
-    auto wait = [&](const unsigned int* p, unsigned int want) -> bool {
-      if (tid == 0) s_ok = spin_until(p, want, a.err) ? 1 : 0;
-      __syncthreads();
-      const bool ok = s_ok != 0;
-      __syncthreads();
-      return ok;
-    };
 #pragma unroll
     for (int m = 0; m < MR; ++m) acc[m] = 0.0;
 
@@ -386,7 +407,6 @@ __global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a
       const int J0 = c * CH, J1 = min(J0 + CH, I - 1);
       for (int J = J0; J < J1; ++J) {
         load_block(J);
-        if (!wait(a.flags + J, 1u)) return;
         load_z(J);
         __syncthreads();
         apply_block();
@@ -397,12 +417,9 @@ __global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a
       for (int m = 0; m < MR; ++m) {
         if (m < nrhs) {
           const double v = acc[m] + __shfl_xor_sync(0xffffffffu, acc[m], 1);
-          if (h == 0) out[m * NB + r] = v;
+          if (h == 0) publish(out + m * NB + r, v);
         }
       }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) atomicAdd(a.counters + I, 1u);
     } else {
       // ---- diag task ----
       const int nparts = (I - 1 > 0) ? (I - 1 + CH - 1) / CH : 0;
@@ -412,19 +429,21 @@ __global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a
           reinterpret_cast<double2*>(sD)[e] = reinterpret_cast<const double2*>(src)[e];
       }
       if (I >= 1) load_block(I - 1);
-      if (nparts > 0 && !wait(a.counters + I, (unsigned int)nparts)) return;
-      // vs = b_I - sum_c partial[I][c]   (fixed order)
-      for (int e = tid; e < nrhs * NB; e += THREADS) {
-        const int m = e / NB, rr = e % NB;
-        const int64_t gi = row0 + rr;
-        double v = a.in[(int64_t)m * a.ldt + gi];
-        if (a.scale_d) v = (gi < a.n) ? v / a.scale_d[gi] : 0.0;
-        const double* ps = a.partial + (int64_t)I * a.NC * nrhs * NB + m * NB + rr;
-        for (int cc = 0; cc < nparts; ++cc) v -= ps[(int64_t)cc * nrhs * NB];
-        vs[e] = v;
+      // vs = b_I - sum_c partial[I][c]   (fixed order; each partial is polled until it has been produced)
+      {
+        bool ok = true;
+        for (int e = tid; e < nrhs * NB; e += THREADS) {
+          const int m = e / NB, rr = e % NB;
+          const int64_t gi = row0 + rr;
+          double v = a.in[(int64_t)m * a.ldt + gi];
+          if (a.scale_d) v = (gi < a.n) ? v / a.scale_d[gi] : 0.0;
+          const double* ps = a.partial + (int64_t)I * a.NC * nrhs * NB + m * NB + rr;
+          for (int cc = 0; cc < nparts; ++cc) v -= poll(ps + (int64_t)cc * nrhs * NB, a.err, &ok);
+          vs[e] = v;
+        }
+        if (!ok) s_fail = 1;
       }
       if (I >= 1) {
-        if (!wait(a.flags + (I - 1), 1u)) return;
         load_z(I - 1);
         __syncthreads();
         apply_block();
@@ -452,12 +471,9 @@ __global__ void __launch_bounds__(trsv::THREADS, 1) k_trsv_persistent(TrsvArgs a
           }
           double z = s0 + s1;
           z += __shfl_xor_sync(0xffffffffu, z, 1);
-          if (h == 0) a.out[(int64_t)m * a.ldt + row0 + r] = z;
+          if (h == 0) publish(a.out + (int64_t)m * a.ldt + row0 + r, z);
         }
       }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) atomicExch(a.flags + I, 1u);
     }
   }
 }

@@ -1129,8 +1129,7 @@ static int trsv_prepare(mdb_factor* f, int nrhs) {
     // claim order: diag(t), then every partial task whose last needed block is t (so that a task only ever
     // waits for tasks claimed before it)
     std::vector<int2> tasks;
-    for (int t = 0; t < T; ++t) {
-      tasks.push_back(make_int2(t, -1));
+    for (int t = 0; t < T; ++t) {  // (the diag tasks themselves run on dedicated CTAs)
       if ((t + 1) % trsv::CH == 0) {
         for (int I = t + 2; I < T; ++I) tasks.push_back(make_int2(I, (t + 1) / trsv::CH - 1));
       } else if (t + 2 < T) {
@@ -1138,10 +1137,10 @@ static int trsv_prepare(mdb_factor* f, int nrhs) {
       }
     }
     f->trsv_ntasks = (int)tasks.size();
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_tasks, tasks.size() * sizeof(int2)));
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(int2)));
     MDB_CUDA(ctx, cudaMemcpyAsync(f->trsv_tasks, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `tasks` goes out of scope
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_sync, (size_t)(2 * T + 2) * sizeof(unsigned int)));
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_sync, 2 * sizeof(unsigned int)));
   }
   if (f->trsv_partial_rhs < nrhs) {
     if (f->trsv_partial) cudaFree(f->trsv_partial);
@@ -1169,11 +1168,18 @@ static int trsv_sweep(mdb_factor* f, int nrhs, bool reverse, const double* in, d
   a.DinvT = reverse ? f->Linv : f->LinvT;
   a.in = in; a.out = out; a.ldt = ldt; a.nrhs = nrhs; a.scale_d = scale_d;
   a.partial = f->trsv_partial; a.NC = (T + trsv::CH - 1) / trsv::CH;
-  a.flags = f->trsv_sync; a.counters = f->trsv_sync + T; a.next_task = f->trsv_sync + 2 * T;
-  a.err = (int*)(f->trsv_sync + 2 * T + 1);
+  a.next_task = f->trsv_sync;
+  a.err = (int*)(f->trsv_sync + 1);
   a.tasks = f->trsv_tasks; a.ntasks = f->trsv_ntasks; a.reverse = reverse ? 1 : 0;
-  MDB_CUDA(ctx, cudaMemsetAsync(f->trsv_sync, 0, (size_t)(2 * T + 2) * sizeof(unsigned int), ctx->stream));
-  const int grid = std::min(ctx->num_sms, f->trsv_ntasks);
+  MDB_CUDA(ctx, cudaMemsetAsync(f->trsv_sync, 0, 2 * sizeof(unsigned int), ctx->stream));
+  {  // the data is its own "ready" flag: output and partial sums start out as the sentinel
+    const int64_t n_out = (int64_t)nrhs * ldt, n_part = (int64_t)T * a.NC * nrhs * NB;
+    k_fill_sentinel<<<(unsigned)((n_out + 255) / 256), 256, 0, ctx->stream>>>(n_out, out);
+    k_fill_sentinel<<<(unsigned)((n_part + 255) / 256), 256, 0, ctx->stream>>>(n_part, f->trsv_partial);
+    ctx->launches += 2;
+  }
+  { const char* e = getenv("MDB200_TRSV_ND"); a.nd = e ? atoi(e) : 16; if (a.nd < 1) a.nd = 1; if (a.nd > 64) a.nd = 64; }
+  const int grid = std::max(a.nd + 1, std::min(ctx->num_sms, f->trsv_ntasks + a.nd));
   const int smem = (NB * NB + 2 * 8 * NB) * 8;
   if (nrhs == 1) k_trsv_persistent<1><<<grid, trsv::THREADS, smem, ctx->stream>>>(a);
   else k_trsv_persistent<8><<<grid, trsv::THREADS, smem, ctx->stream>>>(a);
@@ -1184,11 +1190,11 @@ static int trsv_sweep(mdb_factor* f, int nrhs, bool reverse, const double* in, d
 
 static int trsv_check(mdb_factor* f) {
   mdb_ctx* ctx = f->ctx;
-  const int T = (int)((f->n + NB - 1) / NB);
   int err = 0;
-  MDB_CUDA(ctx, cudaMemcpyAsync(&err, f->trsv_sync + 2 * T + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MDB_CUDA(ctx, cudaMemcpyAsync(&err, f->trsv_sync + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (err) return mdb_fail(ctx, MDB_ERR_CUDA, "%s", "k_trsv_persistent: a dependency wait ran into its spin limit");
+  if (err) return mdb_fail(ctx, MDB_ERR_CUDA, "%s", "k_trsv_persistent: a dependency wait ran into its spin limit "
+                                                    "(a right-hand side holding the kernel's sentinel NaN would do that)");
   return MDB_OK;
 }
 
