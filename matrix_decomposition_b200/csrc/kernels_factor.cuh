@@ -191,7 +191,11 @@ __device__ __forceinline__ void mdb_cp_async_wait_all() {
 // Diagonal block: columns K = k0 .. k0+kb-1, rows of the block only.  One CTA (NB threads, thread j
 // owns row j of the block), the whole block in shared memory.  Sequential over the columns because
 // the decision for column k needs alpha_k, which contains Lu[k, k0:k]^2 d from this very block:
-//   thread k : (d, omega) = rule(alpha_k, beta_k, gamma_k)                 Reimer.py:479-494 / :42-176
+//   threads (k, 0..1) : (d, omega) = rule(alpha_k, beta_k, gamma_k)        Reimer.py:479-494 / :42-176
+//                       the rule is ~1300 dependent scalar instructions when the column is clamped (two cubic solves,
+//                       Reimer.py:95-115); the two values of d (lo, max_diag_D) are evaluated by two lanes of the
+//                       warp running the SAME instruction stream (md_candidates_for_d) and merged with the
+//                       reference's key
 //   threads m < k : u[m] = d_m * thresh(omega Lu[k, m])                    Reimer.py:553-560
 //   threads j > k : Lu[j, k] = (r_j - sum_m Lu[j, m] u[m]) / d,  alpha_j, beta_j, rowmax_j updates
 // with r_j = A[j, k] when the whole scaled row k is dropped, else (1 - omega) A[j, k] + omega S0[j, k].
@@ -203,7 +207,7 @@ template <int NB>
 __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
                                                        int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
   // 4 threads per row: thread (j, h) = (tid >> 2, tid & 3) sums the terms m = h (mod 4) of row j's dot product;
-  // the h == 0 thread owns the row's state (alpha, beta, rowmax) and evaluates the rule when its column comes up.
+  // the h == 0 thread owns the row's state (alpha, beta, rowmax; mirrored in h == 1 for the two-lane rule).
   extern __shared__ double smem_d[];
   constexpr int LDT = NB + 4;   // 264 j words: the 4 rows of a half warp land in 4 disjoint groups of 8 banks
   double* T = smem_d;           // T[r * LDT + c] = block element (r, c)
@@ -219,7 +223,10 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
   double* hdr = F.hdr + b * F.sHdr;
   const int tid = threadIdx.x;
   const int j = tid >> 2, h = tid & 3;
+  const int lane = tid & 31;
   const bool owner = (h == 0) && (j < kb);
+  const bool tracks = (h < 2) && (j < kb);
+  const bool exact = F.prm.rule == MD_RULE_EXACT;
   const double mavL = F.prm.min_abs_value_L;
 
   // whole block in flight at once (asynchronous 8-byte copies, coalesced per row):
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
         mdb_cp_async8(&T[r * LDT + c], (c < r) ? &Sblk[r * ldS + c] : &Ablk[r * ldA + c]);
   }
   double alpha_j = 0, beta_j = 0, rowmax_j = 0, gamma_j = 0, mB = F.prm.min_diag_B, MB = F.prm.max_diag_B;
-  if (owner) {
+  if (tracks) {
     alpha_j = F.alpha[vo + k0 + j];
     beta_j = F.beta[vo + k0 + j];
     rowmax_j = F.rowmax[vo + k0 + j];
@@ -243,15 +250,45 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
   __syncthreads();
 
   for (int k = 0; k < kb; ++k) {
+    // rule: lanes (k, 0) and (k, 1) evaluate the candidates of d = lo and d = max_diag_D side by side
+    MdBest cand;
+    cand.d = cand.w = cand.f = 0;
+    cand.have = 0;
+    int fb = 0;
+    bool uncl = true;
+    double mD = 0;
+    if (tracks && j == k && !exact) {
+      mD = md_effective_min_diag_D(F.prm, gamma_j, mB, MB);
+      uncl = md_unclamped(alpha_j, gamma_j, mD, F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D);
+      if (!uncl) {
+        double dd;
+        const bool en = md_d_candidate(h, alpha_j, beta_j, mD, F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D, &dd);
+        cand = md_candidates_for_d(en, dd, alpha_j, beta_j, gamma_j, mB, MB, &fb);
+      }
+    }
+    MdBest other;
+    const int src = (lane & ~3) | 1;
+    other.d = __shfl_sync(0xffffffffu, cand.d, src);
+    other.w = __shfl_sync(0xffffffffu, cand.w, src);
+    other.f = __shfl_sync(0xffffffffu, cand.f, src);
+    other.have = __shfl_sync(0xffffffffu, cand.have, src);
+    const int fb1 = __shfl_sync(0xffffffffu, fb, src);
     if (owner && j == k) {
-      const MdDecision dec = md_decide(F.prm, alpha_j, beta_j, gamma_j, mB, MB);
+      MdDecision dec;
+      if (exact || uncl) {
+        dec.d = gamma_j - alpha_j; dec.omega = 1; dec.f = 0;
+        dec.clamped = exact ? !(dec.d > 0) : 0;
+      } else {
+        dec = md_decision_from_best(md_assemble_minimal_change(cand, other, fb | fb1, alpha_j, beta_j, gamma_j, mD,
+                                                               F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D));
+      }
       const int64_t K = k0 + k;
       const double delta = (dec.d - gamma_j) + (dec.omega != 0 ? dec.omega * dec.omega * alpha_j : 0.0);  // :541-545
       F.d[vo + K] = dec.d;
       F.omega[vo + K] = dec.omega;
       F.delta[vo + K] = delta;
       F.clamped[vo + K] = (uint8_t)dec.clamped;
-      if (F.prm.rule == MD_RULE_EXACT && dec.clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
+      if (exact && dec.clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
       const double drop = (dec.omega == 0 || dec.omega * rowmax_j < mavL) ? 1.0 : 0.0;
       s_dec[0] = dec.d;
       s_dec[1] = dec.omega;
@@ -276,8 +313,10 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
     __syncthreads();
     const bool active = (j > k && j < kb);
     const double* Trow = T + j * LDT;
-    double acc = 0;
+    double acc = 0, a = 0, s0k = 0;
     if (active) {
+      a = T[k * LDT + j];   // read before the shuffles: thread (j, 0) overwrites T[j][k] after them
+      s0k = Trow[k];
       double a0 = 0, a1 = 0;
       int m = h;
       for (; m + 4 < k; m += 8) {
@@ -291,12 +330,11 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     if (active) {
-      if (h == 0) {
-        const double a = T[k * LDT + j];
+      if (h < 2) {
         double r = a;
-        if (!drop) r = (1.0 - wk) * a + wk * Trow[k];
+        if (!drop) r = (1.0 - wk) * a + wk * s0k;
         const double x = (dk != 0) ? (r - acc) / dk : 0.0;
-        T[j * LDT + k] = x;
+        if (h == 0) T[j * LDT + k] = x;
         alpha_j += x * x * dk;
         beta_j += 2.0 * a * a;
         rowmax_j = fmax(rowmax_j, fabs(x));

@@ -146,12 +146,12 @@ MD_HD MdBest md_merge_best(const MdBest& x, const MdBest& y) {  // y is "later i
   return md_candidate_better(y.f, y.d, y.w, x.f, x.d, x.w) ? y : x;
 }
 
-MD_HD MdBest md_minimal_change_part(int part, double alpha, double beta, double gamma, double min_diag_D,
-                                    double max_diag_D, double min_diag_B, double max_diag_B, double min_abs_value_D) {
-  const double lo = md_pymax(min_diag_D, min_abs_value_D);  // :64
-  const double a = md_pymax(lo, min_diag_B - alpha);        // :65
-  const double b = md_pymin(max_diag_D, max_diag_B - alpha);  // :66
-  const double dstar = gamma - alpha;                       // :67
+// The candidates that one value dd of d contributes (Reimer.py:103-135): the real roots of the cubic in omega,
+// clipped to [omega_lower, omega_upper].  *fallback is raised when p or q is not finite (:105-110).  Branch-free
+// in its arguments apart from the cubic itself, so that two lanes of a warp can evaluate the two values of dd
+// (lo and max_diag_D) side by side without diverging.
+MD_HD MdBest md_candidates_for_d(bool enabled, double dd, double alpha, double beta, double gamma, double min_diag_B,
+                                 double max_diag_B, int* fallback) {
   double best_d = 0, best_w = 0, best_f = 0;
   int have = 0;
 #define MD_CONSIDER(dd_, ww_)                                                        \
@@ -162,60 +162,132 @@ MD_HD MdBest md_minimal_change_part(int part, double alpha, double beta, double 
       best_d = cd_; best_w = cw_; best_f = cf_; have = 1;                            \
     }                                                                                \
   } while (0)
-
-  int add_best_d_omega_zero = 0;
-  if (isfinite(alpha)) {
-    if ((part & 1) && a <= b) {  // :82-88
-      if (dstar < a) MD_CONSIDER(a, 1.0);
-      else if (dstar > b) MD_CONSIDER(b, 1.0);
-    }
-    if (isfinite(beta)) {
-      if (alpha != 0) {
-        for (int t = 0; t < 2; ++t) {
-          if (!((part >> t) & 1)) continue;
-          double dd;
-          if (t == 0) {
-            if (!(min_diag_B - alpha <= lo)) continue;  // :95-96
-            dd = lo;
-          } else {
-            if (!(isfinite(max_diag_D) && max_diag_D <= max_diag_B)) continue;  // :97-98
-            dd = max_diag_D;
-          }
-          const double q = (-0.5 * beta / alpha) / alpha;  // :103
-          const double p = (dd - gamma) / alpha - q;       // :104
-          if (!isfinite(q) || !isfinite(p)) { add_best_d_omega_zero = 1; continue; }  // :105-110
-          double roots[3];
-          const int nr = md_cubic_real_roots(p, q, roots);
-          const double omega_lower = sqrt(md_pymax(min_diag_B - dd, 0.0) / alpha);        // :118
-          const double omega_upper = md_pymin(sqrt((max_diag_B - dd) / alpha), 1.0);      // :120
-          int add_lower = 0, add_upper = 0;
-          for (int k = 0; k < nr; ++k) {  // :125-131
-            const double w = roots[k];
-            if (w <= omega_lower) add_lower = 1;
-            else if (w >= omega_upper) add_upper = 1;
-            else MD_CONSIDER(dd, w);
-          }
-          if (add_lower) MD_CONSIDER(dd, omega_lower);
-          if (add_upper) MD_CONSIDER(dd, omega_upper);
-        }
-      }
+  if (enabled) {
+    const double q = (-0.5 * beta / alpha) / alpha;  // :103
+    const double p = (dd - gamma) / alpha - q;       // :104
+    if (!isfinite(q) || !isfinite(p)) {              // :105-110
+      *fallback = 1;
     } else {
-      add_best_d_omega_zero = 1;  // :136-139
+      double roots[3];
+      const int nr = md_cubic_real_roots(p, q, roots);
+      const double omega_lower = sqrt(md_pymax(min_diag_B - dd, 0.0) / alpha);        // :118
+      const double omega_upper = md_pymin(sqrt((max_diag_B - dd) / alpha), 1.0);      // :120
+      int add_lower = 0, add_upper = 0;
+      for (int k = 0; k < nr; ++k) {  // :125-131
+        const double w = roots[k];
+        if (w <= omega_lower) add_lower = 1;
+        else if (w >= omega_upper) add_upper = 1;
+        else MD_CONSIDER(dd, w);
+      }
+      if (add_lower) MD_CONSIDER(dd, omega_lower);
+      if (add_upper) MD_CONSIDER(dd, omega_upper);
     }
-  } else {
-    add_best_d_omega_zero = 1;  // :140-143
   }
-  // the fallback is one and the same candidate whoever adds it; a flag raised by the d = lo solve (part bit 0
-  // only) still has to produce it
-  if (add_best_d_omega_zero) {  // :146-148
-    const double dd = md_pymax(md_pymax(lo, min_diag_B), md_pymin(md_pymin(gamma, max_diag_D), max_diag_B));
-    MD_CONSIDER(dd, 0.0);
-  }
-  if ((part & 2) && min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D) MD_CONSIDER(0.0, 0.0);  // :151-152
 #undef MD_CONSIDER
   MdBest r;
   r.d = best_d; r.w = best_w; r.f = best_f; r.have = have;
   return r;
+}
+
+// One candidate (d, omega) as an MdBest
+MD_HD MdBest md_single_candidate(double d, double omega, double alpha, double beta, double gamma) {
+  MdBest r;
+  r.d = d; r.w = omega; r.f = md_difference_frobenius_norm(d, omega, alpha, beta, gamma); r.have = 1;
+  return r;
+}
+
+// The clamped branch of Reimer.py:42-176 assembled from its pieces, in the reference's candidate order:
+//   (a, 1) / (b, 1) :82-88;  roots for d = lo (`from_lo`) :95-96;  roots for d = max_diag_D (`from_max`) :97-98;
+//   the omega = 0 fallback :146-148;  (0, 0) :151-152.
+// `from_lo` / `from_max` are md_candidates_for_d results (have = 0 when that d does not apply), `fallback` the OR of
+// their flags.  The kernels evaluate the two md_candidates_for_d calls in two lanes and call this in one.
+MD_HD MdBest md_assemble_minimal_change(const MdBest& from_lo, const MdBest& from_max, int fallback, double alpha,
+                                        double beta, double gamma, double min_diag_D, double max_diag_D,
+                                        double min_diag_B, double max_diag_B, double min_abs_value_D) {
+  const double lo = md_pymax(min_diag_D, min_abs_value_D);  // :64
+  const double a = md_pymax(lo, min_diag_B - alpha);        // :65
+  const double b = md_pymin(max_diag_D, max_diag_B - alpha);  // :66
+  const double dstar = gamma - alpha;                       // :67
+  MdBest best;
+  best.d = best.w = best.f = 0;
+  best.have = 0;
+  if (isfinite(alpha)) {
+    if (a <= b) {  // :82-88
+      if (dstar < a) best = md_single_candidate(a, 1.0, alpha, beta, gamma);
+      else if (dstar > b) best = md_single_candidate(b, 1.0, alpha, beta, gamma);
+    }
+    if (isfinite(beta)) {
+      best = md_merge_best(best, from_lo);
+      best = md_merge_best(best, from_max);
+    } else {
+      fallback = 1;  // :136-139
+    }
+  } else {
+    fallback = 1;  // :140-143
+  }
+  if (fallback) {  // :146-148
+    const double dd = md_pymax(md_pymax(lo, min_diag_B), md_pymin(md_pymin(gamma, max_diag_D), max_diag_B));
+    best = md_merge_best(best, md_single_candidate(dd, 0.0, alpha, beta, gamma));
+  }
+  if (min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D)  // :151-152
+    best = md_merge_best(best, md_single_candidate(0.0, 0.0, alpha, beta, gamma));
+  return best;
+}
+
+// Which values of d contribute cubic candidates (Reimer.py:89-98): index 0 = lo, 1 = max_diag_D.
+MD_HD bool md_d_candidate(int which, double alpha, double beta, double min_diag_D, double max_diag_D, double min_diag_B,
+                          double max_diag_B, double min_abs_value_D, double* dd) {
+  const double lo = md_pymax(min_diag_D, min_abs_value_D);
+  const bool base = isfinite(alpha) && isfinite(beta) && alpha != 0;
+  if (which == 0) {
+    *dd = lo;
+    return base && (min_diag_B - alpha <= lo);                                 // :95-96
+  }
+  *dd = max_diag_D;
+  return base && isfinite(max_diag_D) && max_diag_D <= max_diag_B;            // :97-98
+}
+
+MD_HD MdBest md_minimal_change_part(int part, double alpha, double beta, double gamma, double min_diag_D,
+                                    double max_diag_D, double min_diag_B, double max_diag_B, double min_abs_value_D) {
+  // kept for the host tests: the subset `part` of the candidate list (bit 0: (a|b, 1) and d = lo; bit 1: the rest)
+  MdBest none;
+  none.d = none.w = none.f = 0;
+  none.have = 0;
+  int fb0 = 0, fb1 = 0;
+  double dd0, dd1;
+  const bool e0 = md_d_candidate(0, alpha, beta, min_diag_D, max_diag_D, min_diag_B, max_diag_B, min_abs_value_D, &dd0);
+  const bool e1 = md_d_candidate(1, alpha, beta, min_diag_D, max_diag_D, min_diag_B, max_diag_B, min_abs_value_D, &dd1);
+  const MdBest c0 = (part & 1) ? md_candidates_for_d(e0, dd0, alpha, beta, gamma, min_diag_B, max_diag_B, &fb0) : none;
+  const MdBest c1 = (part & 2) ? md_candidates_for_d(e1, dd1, alpha, beta, gamma, min_diag_B, max_diag_B, &fb1) : none;
+  if (part == 3)
+    return md_assemble_minimal_change(c0, c1, fb0 | fb1, alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B,
+                                      max_diag_B, min_abs_value_D);
+  // partial lists: the fixed candidates belong to bit 0 ((a|b, 1)) and bit 1 (fallback, (0, 0)) respectively
+  const double lo = md_pymax(min_diag_D, min_abs_value_D);
+  const double a = md_pymax(lo, min_diag_B - alpha);
+  const double b = md_pymin(max_diag_D, max_diag_B - alpha);
+  const double dstar = gamma - alpha;
+  MdBest best = none;
+  int fallback = !isfinite(alpha) || !isfinite(beta);
+  if (part & 1) {
+    if (isfinite(alpha) && a <= b) {
+      if (dstar < a) best = md_single_candidate(a, 1.0, alpha, beta, gamma);
+      else if (dstar > b) best = md_single_candidate(b, 1.0, alpha, beta, gamma);
+    }
+    if (isfinite(alpha) && isfinite(beta)) best = md_merge_best(best, c0);
+    fallback |= fb0;
+  }
+  if (part & 2) {
+    if (isfinite(alpha) && isfinite(beta)) best = md_merge_best(best, c1);
+    fallback |= fb1;
+  }
+  if (fallback) {
+    const double dd = md_pymax(md_pymax(lo, min_diag_B), md_pymin(md_pymin(gamma, max_diag_D), max_diag_B));
+    best = md_merge_best(best, md_single_candidate(dd, 0.0, alpha, beta, gamma));
+  }
+  if ((part & 2) && min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D)
+    best = md_merge_best(best, md_single_candidate(0.0, 0.0, alpha, beta, gamma));
+  return best;
 }
 
 // Reimer.py:68-72: the unclamped branch
