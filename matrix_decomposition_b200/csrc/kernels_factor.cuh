@@ -188,32 +188,54 @@ __device__ __forceinline__ void mdb_cp_async_wait_all() {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal block: columns K = k0 .. k0+kb-1, rows of the block only.  One CTA (NB threads, thread j
-// owns row j of the block), the whole block in shared memory.  Sequential over the columns because
-// the decision for column k needs alpha_k, which contains Lu[k, k0:k]^2 d from this very block:
-//   threads (k, 0..1) : (d, omega) = rule(alpha_k, beta_k, gamma_k)        Reimer.py:479-494 / :42-176
-//                       the rule is ~1300 dependent scalar instructions when the column is clamped (two cubic solves,
-//                       Reimer.py:95-115); the two values of d (lo, max_diag_D) are evaluated by two lanes of the
-//                       warp running the SAME instruction stream (md_candidates_for_d) and merged with the
-//                       reference's key
-//   threads m < k : u[m] = d_m * thresh(omega Lu[k, m])                    Reimer.py:553-560
-//   threads j > k : Lu[j, k] = (r_j - sum_m Lu[j, m] u[m]) / d,  alpha_j, beta_j, rowmax_j updates
-// with r_j = A[j, k] when the whole scaled row k is dropped, else (1 - omega) A[j, k] + omega S0[j, k].
-// Outputs: d, omega, delta, clamped; Ut (for the panel kernel); hdr = (d, omega, drop) of the panel.
+// Diagonal block: columns K = k0 .. k0+kb-1, rows of the block only.  One CTA, the whole block in shared
+// memory, 4 threads per row.  Sequential over the columns because the decision for column k needs alpha_k,
+// which contains Lu[k, k0:k]^2 d from this very block.  The kernel is pure latency, and per column the two
+// expensive things are the rule (~1300 dependent scalar instructions when the column is clamped: two cubic
+// solves, Reimer.py:95-115) and the length-k dot products of the rows below.  They overlap:
+//   phase 1   lanes (k, 0) and (k, 1) : (d, omega) = rule(alpha_k, beta_k, gamma_k)     Reimer.py:479-494 / :42-176
+//             (the candidates of d = lo and d = max_diag_D side by side, one instruction stream, merged with the
+//             reference's key, md_rule.h)  WHILE
+//             rows j > k : G_j = sum_{m < k-1} Lu[j, m] d_m Lu[k, m]   -- the dot product with the UNscaled row k,
+//             which does not need the decision.  (d_m Lu[k, m] sits at the transposed position (m, k) of the tile:
+//             the A entry stored there is dead once column m has been processed.)
+//   barrier
+//   phase 2   x[j, k] = ((1 - omega) A[j, k] + omega (S0[j, k] - G_j)) / d    (= A[j, k] / d when the scaled row k
+//             is dropped), alpha / beta / rowmax updates in column order (Reimer.py:604,684),
+//             threads m < k : Ut[m][k] = d_m thresh(omega Lu[k, m])  (Reimer.py:553-560, for the panel kernel).
+// omega G ignores the reference's thresholding of tiny entries of the scaled row (Reimer.py:558).  A column falls
+// back to the explicit thresholded dot product ("slow", exact w.r.t. the reference inside the block) whenever that
+// could matter -- omega_k * min nonzero |Lu[k, .]| < min_abs_value_L -- or G could overflow (explosive regime,
+// |Lu| > 1e100).  Outputs: d, omega, delta, clamped; Ut; hdr = (d, omega, drop, delta, clamped) of the panel.
 // ------------------------------------------------------------------------------------------------
 // Sblk / Ablk point at element (k0, k0) of the storage that holds S (lower part is read and written) and
 // the permuted original A (upper part is read): the same array W on one GPU, S_loc / A_loc when distributed.
+#define MDB_DIAG_THREADS(NB) (4 * (NB) + 32)
+#define MDB_DIAG_SMEM_DOUBLES(NB) ((NB) * ((NB) + 4) + 9 * (NB))
+
 template <int NB>
-__global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
-                                                       int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
-  // 4 threads per row: thread (j, h) = (tid >> 2, tid & 3) sums the terms m = h (mod 4) of row j's dot product;
-  // the h == 0 thread owns the row's state (alpha, beta, rowmax; mirrored in h == 1 for the two-lane rule).
+__global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
+                                                            int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
+  // Compute warps: thread (j, h) = (tid >> 2, tid & 3), tid < 4 NB, sums the terms m = h (mod 4) of row j's dot
+  // product; lane h == 0 carries the row's state (alpha, beta, rowmax, rowmin) and publishes it in shared memory.
+  // Rule warp (the last one): lanes 0 and 1 evaluate the rule for column k from the published state of row k, so
+  // the rule really runs beside the Gram sums instead of serialising with the lanes of its own warp.
   extern __shared__ double smem_d[];
-  constexpr int LDT = NB + 4;   // 264 j words: the 4 rows of a half warp land in 4 disjoint groups of 8 banks
-  double* T = smem_d;           // T[r * LDT + c] = block element (r, c)
-  double* s_u = T + NB * LDT;   // NB
+  constexpr int LDT = NB + 4;   // 264 words: the 4 rows of a half warp land in 4 disjoint groups of 8 banks
+  constexpr double BIG = 1e100;
+  double* T = smem_d;           // T[r * LDT + c]: c < r: S0 -> Lu;  c >= r: A, then (r, c) <- d_r Lu[c, r]
+  double* s_u = T + NB * LDT;   // NB (slow path)
   double* s_d = s_u + NB;       // NB
-  __shared__ double s_dec[3];   // d, omega, drop of the current column
+  double* s_alpha = s_d + NB;   // per row, published by lane (j, 0) after every column
+  double* s_beta = s_alpha + NB;
+  double* s_rowmax = s_beta + NB;
+  double* s_rowmin = s_rowmax + NB;
+  double* s_gamma = s_rowmin + NB;
+  double* s_mB = s_gamma + NB;
+  double* s_MB = s_mB + NB;
+  __shared__ double s_dec[2][4];  // d, omega, drop, slow of column k (slot k & 1)
+  __shared__ int s_big;
+  __shared__ volatile int s_ready;  // rows 0 .. s_ready have published their state for their own column
 
   const int64_t b = blockIdx.z;
   Sblk += b * F.sW;
@@ -221,126 +243,173 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
   const int64_t vo = b * F.sVec;
   double* Ut = F.Ut + b * F.sUt;
   double* hdr = F.hdr + b * F.sHdr;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool rule_warp = tid >= 4 * NB;
   const int j = tid >> 2, h = tid & 3;
-  const int lane = tid & 31;
-  const bool owner = (h == 0) && (j < kb);
-  const bool tracks = (h < 2) && (j < kb);
+  const bool owner = !rule_warp && (h == 0) && (j < kb);
   const bool exact = F.prm.rule == MD_RULE_EXACT;
   const double mavL = F.prm.min_abs_value_L;
 
   // whole block in flight at once (asynchronous 8-byte copies, coalesced per row):
   // strict lower part from S, diagonal and upper part from A
-  {
+  if (!rule_warp) {
     const int c = tid & (NB - 1);
     if (c < kb)
       for (int r = tid / NB; r < kb; r += 4)
         mdb_cp_async8(&T[r * LDT + c], (c < r) ? &Sblk[r * ldS + c] : &Ablk[r * ldA + c]);
   }
-  double alpha_j = 0, beta_j = 0, rowmax_j = 0, gamma_j = 0, mB = F.prm.min_diag_B, MB = F.prm.max_diag_B;
-  if (tracks) {
+  double alpha_j = 0, beta_j = 0, rowmax_j = 0, rowmin_j = INFINITY;
+  if (owner) {
     alpha_j = F.alpha[vo + k0 + j];
     beta_j = F.beta[vo + k0 + j];
     rowmax_j = F.rowmax[vo + k0 + j];
-    gamma_j = F.gamma[vo + k0 + j];
-    if (F.minB) mB = F.minB[vo + k0 + j];
-    if (F.maxB) MB = F.maxB[vo + k0 + j];
+    s_alpha[j] = alpha_j; s_beta[j] = beta_j; s_rowmax[j] = rowmax_j; s_rowmin[j] = rowmin_j;
+    s_gamma[j] = F.gamma[vo + k0 + j];
+    s_mB[j] = F.minB ? F.minB[vo + k0 + j] : F.prm.min_diag_B;
+    s_MB[j] = F.maxB ? F.maxB[vo + k0 + j] : F.prm.max_diag_B;
   }
+  if (tid == 0) { s_big = 0; s_ready = 0; }
   mdb_cp_async_wait_all();
   __syncthreads();
+  if (owner && rowmax_j > BIG) s_big = 1;
+  __syncthreads();
 
+  const double* Trow = T + (rule_warp ? 0 : j) * LDT;
   for (int k = 0; k < kb; ++k) {
-    // rule: lanes (k, 0) and (k, 1) evaluate the candidates of d = lo and d = max_diag_D side by side
-    MdBest cand;
-    cand.d = cand.w = cand.f = 0;
-    cand.have = 0;
-    int fb = 0;
-    bool uncl = true;
-    double mD = 0;
-    if (tracks && j == k && !exact) {
-      mD = md_effective_min_diag_D(F.prm, gamma_j, mB, MB);
-      uncl = md_unclamped(alpha_j, gamma_j, mD, F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D);
-      if (!uncl) {
-        double dd;
-        const bool en = md_d_candidate(h, alpha_j, beta_j, mD, F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D, &dd);
-        cand = md_candidates_for_d(en, dd, alpha_j, beta_j, gamma_j, mB, MB, &fb);
+    const bool active = !rule_warp && (j > k && j < kb);
+    double G = 0;
+    if (rule_warp) {
+      // ---------------- the rule for column k (lanes 0 and 1: d = lo and d = max_diag_D side by side) ----------------
+      while (s_ready < k) { }  // row k has published alpha_k (it contains column k - 1)
+      __syncwarp();
+      const double al = s_alpha[k], be = s_beta[k], ga = s_gamma[k], mB = s_mB[k], MB = s_MB[k];
+      MdBest cand;
+      cand.d = cand.w = cand.f = 0;
+      cand.have = 0;
+      int fb = 0;
+      bool uncl = true;
+      double mD = 0;
+      if (lane < 2 && !exact) {
+        mD = md_effective_min_diag_D(F.prm, ga, mB, MB);
+        uncl = md_unclamped(al, ga, mD, F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D);
+        if (!uncl) {
+          double dd;
+          const bool en = md_d_candidate(lane, al, be, mD, F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D, &dd);
+          cand = md_candidates_for_d(en, dd, al, be, ga, mB, MB, &fb);
+        }
       }
-    }
-    MdBest other;
-    const int src = (lane & ~3) | 1;
-    other.d = __shfl_sync(0xffffffffu, cand.d, src);
-    other.w = __shfl_sync(0xffffffffu, cand.w, src);
-    other.f = __shfl_sync(0xffffffffu, cand.f, src);
-    other.have = __shfl_sync(0xffffffffu, cand.have, src);
-    const int fb1 = __shfl_sync(0xffffffffu, fb, src);
-    if (owner && j == k) {
-      MdDecision dec;
-      if (exact || uncl) {
-        dec.d = gamma_j - alpha_j; dec.omega = 1; dec.f = 0;
-        dec.clamped = exact ? !(dec.d > 0) : 0;
-      } else {
-        dec = md_decision_from_best(md_assemble_minimal_change(cand, other, fb | fb1, alpha_j, beta_j, gamma_j, mD,
-                                                               F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D));
+      MdBest other;
+      other.d = __shfl_sync(0xffffffffu, cand.d, 1);
+      other.w = __shfl_sync(0xffffffffu, cand.w, 1);
+      other.f = __shfl_sync(0xffffffffu, cand.f, 1);
+      other.have = __shfl_sync(0xffffffffu, cand.have, 1);
+      const int fb1 = __shfl_sync(0xffffffffu, fb, 1);
+      if (lane == 0) {
+        MdDecision dec;
+        if (exact || uncl) {
+          dec.d = ga - al; dec.omega = 1; dec.f = 0;
+          dec.clamped = exact ? !(dec.d > 0) : 0;
+        } else {
+          dec = md_decision_from_best(md_assemble_minimal_change(cand, other, fb | fb1, al, be, ga, mD, F.prm.max_diag_D,
+                                                                 mB, MB, F.prm.min_abs_value_D));
+        }
+        const int64_t K = k0 + k;
+        const double delta = (dec.d - ga) + (dec.omega != 0 ? dec.omega * dec.omega * al : 0.0);  // :541-545
+        F.d[vo + K] = dec.d;
+        F.omega[vo + K] = dec.omega;
+        F.delta[vo + K] = delta;
+        F.clamped[vo + K] = (uint8_t)dec.clamped;
+        if (exact && dec.clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
+        const bool drop = (dec.omega == 0 || dec.omega * s_rowmax[k] < mavL);
+        const bool slow = !drop && k > 0 && (dec.omega * s_rowmin[k] < mavL || s_big != 0);
+        double* sd = s_dec[k & 1];
+        sd[0] = dec.d;
+        sd[1] = dec.omega;
+        sd[2] = drop ? 1.0 : 0.0;
+        sd[3] = slow ? 1.0 : 0.0;
+        s_d[k] = dec.d;
+        hdr[k] = dec.d;
+        hdr[NB + k] = dec.omega;
+        hdr[2 * NB + k] = drop ? 1.0 : 0.0;
+        hdr[3 * NB + k] = delta;
+        hdr[4 * NB + k] = (double)dec.clamped;
       }
-      const int64_t K = k0 + k;
-      const double delta = (dec.d - gamma_j) + (dec.omega != 0 ? dec.omega * dec.omega * alpha_j : 0.0);  // :541-545
-      F.d[vo + K] = dec.d;
-      F.omega[vo + K] = dec.omega;
-      F.delta[vo + K] = delta;
-      F.clamped[vo + K] = (uint8_t)dec.clamped;
-      if (exact && dec.clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
-      const double drop = (dec.omega == 0 || dec.omega * rowmax_j < mavL) ? 1.0 : 0.0;
-      s_dec[0] = dec.d;
-      s_dec[1] = dec.omega;
-      s_dec[2] = drop;
-      s_d[k] = dec.d;
-      hdr[k] = dec.d;
-      hdr[NB + k] = dec.omega;
-      hdr[2 * NB + k] = drop;
-      hdr[3 * NB + k] = delta;
-      hdr[4 * NB + k] = (double)dec.clamped;
+    } else {
+      // ---------------- the Gram dot products G_j = sum_{m < k-1} Lu[j, m] (d_m Lu[k, m]) ----------------
+      double g0 = 0, g1 = 0;
+      if (active) {
+        const double* Tk = T + k;  // (m, k) holds d_m Lu[k, m]
+        int m = h;
+        for (; m + 4 < k - 1; m += 8) {
+          g0 = fma(Trow[m], Tk[m * LDT], g0);
+          g1 = fma(Trow[m + 4], Tk[(m + 4) * LDT], g1);
+        }
+        if (m < k - 1) g0 = fma(Trow[m], Tk[m * LDT], g0);
+      }
+      G = g0 + g1;
+      // every lane takes part in the shuffles (rows of one warp become active at different k)
+      G += __shfl_xor_sync(0xffffffffu, G, 1);
+      G += __shfl_xor_sync(0xffffffffu, G, 2);
     }
     __syncthreads();
-    const double dk = s_dec[0], wk = s_dec[1];
-    const bool drop = s_dec[2] != 0.0;
-    if (tid < k) {
+
+    // ---------------- column k ----------------
+    const double dk = s_dec[k & 1][0], wk = s_dec[k & 1][1];
+    const bool drop = s_dec[k & 1][2] != 0.0, slow = s_dec[k & 1][3] != 0.0;
+    if (tid < k) {  // the scaled, thresholded row k times D: for the panel kernel, and for the slow path
       double lt = wk * T[k * LDT + tid];
       if (wk == 0 || fabs(lt) < mavL) lt = 0;
       const double u = s_d[tid] * lt;
-      s_u[tid] = u;
       Ut[tid * NB + k] = u;
+      if (slow) s_u[tid] = u;
     }
-    __syncthreads();
-    const bool active = (j > k && j < kb);
-    const double* Trow = T + j * LDT;
-    double acc = 0, a = 0, s0k = 0;
+    double a = 0, s0k = 0;
     if (active) {
-      a = T[k * LDT + j];   // read before the shuffles: thread (j, 0) overwrites T[j][k] after them
+      a = T[k * LDT + j];   // A[j, k]; read before thread (j, 0) overwrites it below
       s0k = Trow[k];
-      double a0 = 0, a1 = 0;
-      int m = h;
-      for (; m + 4 < k; m += 8) {
-        a0 += Trow[m] * s_u[m];
-        a1 += Trow[m + 4] * s_u[m + 4];
-      }
-      if (m < k) a0 += Trow[m] * s_u[m];
-      acc = a0 + a1;
+      if (k >= 1) G = fma(Trow[k - 1], T[(k - 1) * LDT + k], G);  // the term m = k - 1, published just before the barrier
     }
-    // every lane takes part in the shuffles (rows of one warp become active at different k)
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (active) {
-      if (h < 2) {
-        double r = a;
-        if (!drop) r = (1.0 - wk) * a + wk * s0k;
-        const double x = (dk != 0) ? (r - acc) / dk : 0.0;
-        if (h == 0) T[j * LDT + k] = x;
-        alpha_j += x * x * dk;
-        beta_j += 2.0 * a * a;
-        rowmax_j = fmax(rowmax_j, fabs(x));
+    double acc = 0;
+    if (slow) {  // uniform over the block
+      __syncthreads();
+      if (active) {
+        double a0 = 0, a1 = 0;
+        int m = h;
+        for (; m + 4 < k; m += 8) {
+          a0 = fma(Trow[m], s_u[m], a0);
+          a1 = fma(Trow[m + 4], s_u[m + 4], a1);
+        }
+        if (m < k) a0 = fma(Trow[m], s_u[m], a0);
+        acc = a0 + a1;
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    }
+    __syncwarp();  // all four lanes of a row have read T[k][j] and T[j][k]
+    if (active && h == 0) {
+      double x = 0;
+      if (dk != 0) {
+        if (drop) x = a / dk;
+        else if (slow) x = (((1.0 - wk) * a + wk * s0k) - acc) / dk;
+        else x = fma(wk, s0k - G, (1.0 - wk) * a) / dk;
+      }
+      T[j * LDT + k] = x;
+      T[k * LDT + j] = x * dk;        // d_k Lu[j, k] at the transposed position
+      alpha_j += x * x * dk;          // Reimer.py:679-684
+      beta_j += 2.0 * a * a;          // Reimer.py:602-604
+      const double ax = fabs(x);
+      rowmax_j = fmax(rowmax_j, ax);
+      if (ax != 0) rowmin_j = fmin(rowmin_j, ax);
+      if (ax > BIG) s_big = 1;
+      if (j == k + 1) {               // the next column's row: hand its state to the rule warp right away
+        s_alpha[j] = alpha_j; s_beta[j] = beta_j; s_rowmax[j] = rowmax_j; s_rowmin[j] = rowmin_j;
+        __threadfence_block();
+        s_ready = k + 1;
       }
     }
-    // no barrier needed here: the next iteration's first barrier orders these writes before any read
+    __syncwarp();  // x[j, k] is visible to the other lanes of the row before they use it in the next Gram sum
+    // no block barrier here: what the next Gram sums read was published before the barrier above; the entries written
+    // just now are first read after the next barrier (the m = k term, s_dec) or through s_ready (the rule warp)
   }
   __syncthreads();
   if (owner) {
@@ -349,22 +418,13 @@ __global__ void __launch_bounds__(4 * NB) k_diag_block(FactorDev F, int64_t k0, 
     F.rowmax[vo + k0 + j] = rowmax_j;
   }
   // strict lower part of the block back to S (unscaled rows Lu)
-  {
+  if (!rule_warp) {
     const int c = tid & (NB - 1);
     for (int r = tid / NB; r < kb; r += 4)
       if (c < r) Sblk[r * ldS + c] = T[r * LDT + c];
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Panel: rows j >= k1 = k0 + NB against the factored diagonal block.  Row-parallel forward
-// substitution X (D Ltilde^T) = R with the mix R = (1 - omega) A + omega S0 applied on load; one
-// thread per row, 8 columns at a time, U broadcast through L1, the row's X staged in shared memory.
-// Epilogue accumulates alpha / beta / rowmax in column order (like Reimer.py:604,684) and writes
-//   W[j, k0:k1] = X (unscaled Lu),  PX[j - p_row0, :] = X,  PY[j - p_row0, :] = -X d   (trailing-update operands).
-// A[j, k] for the mix comes from (Asrc, a_rs, a_cs): element (j, k) at Asrc[j * a_rs + k * a_cs]
-// (single GPU: the upper triangle of W, a_rs = 1, a_cs = ldw; multi GPU: the local copy of A).
-// ------------------------------------------------------------------------------------------------
 #define MDB_PANEL_LDX(R) ((R) + 8)
 #define MDB_PANEL_SMEM_DOUBLES(NB, R) ((NB) * MDB_PANEL_LDX(R) + 4 * (NB) + 2 * (NB) * 8)
 

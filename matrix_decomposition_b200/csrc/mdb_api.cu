@@ -497,7 +497,7 @@ static FactorDev make_dev(mdb_factor* f) {
 static int configure_kernels(mdb_ctx* ctx) {
   static bool done = false;
   if (done) return MDB_OK;
-  const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
+  const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
   const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
   const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
@@ -575,7 +575,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
     MDB_CUDA(ctx, cudaMemsetAsync(f->alpha, 0, (size_t)3 * bn * 8, ctx->stream));  // alpha, beta, rowmax contiguous
     MDB_CUDA(ctx, cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream));
   }
-  const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
+  const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
   const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
   // Two-level blocking.  Panels are NB = 128 columns wide (diagonal block + row-parallel panel kernel); `agg`
   // consecutive panels form an outer block of KB = agg * NB columns whose operands X, Y sit side by side in one
@@ -622,7 +622,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       const int64_t k1 = k0 + kb;
       {
         PhaseTimer t(ctx, 0);
-        k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), 4 * NB, diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
+        k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), MDB_DIAG_THREADS(NB), diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
                                                                                   f->W + k0 * f->ld + k0, f->ld);
         MDB_LAUNCHED(ctx);
       }

@@ -262,9 +262,9 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot, int64_t k
   double* vecs = buf + 5 * NB;
   double* MX = vecs + 3 * rows;  // X part of the message
   FactorDev F = dist_make_dev(s, hdr);
-  const int diag_smem = (NB * (NB + 4) + 2 * NB) * 8;
+  const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
   const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
-  k_diag_block<NB><<<1, 4 * NB, diag_smem, ctx->stream>>>(F, k0, kb, s->S + k0 * s->ld + lc0, s->ld, s->A + k0 * s->ld + lc0,
+  k_diag_block<NB><<<1, MDB_DIAG_THREADS(NB), diag_smem, ctx->stream>>>(F, k0, kb, s->S + k0 * s->ld + lc0, s->ld, s->A + k0 * s->ld + lc0,
                                                        s->ld);
   MDB_LAUNCHED(ctx);
   if (rows > 0) {
