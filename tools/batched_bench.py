@@ -1,6 +1,10 @@
 """BASELINE config 5: many independent 512 x 512 matrix.approximate calls (per GPU: batch = 4096 / N).  Times the
 device-resident batched factorization (matrices generated on the host once, uploaded, factored) and the same
-through the batched C-ABI call with host buffers; reports matrices/s and GFLOP/s (n^3/3 each)."""
+through the batched C-ABI call with host buffers; reports matrices/s and GFLOP/s (n^3/3 each).
+
+Under torchrun (one rank per GPU) every rank factors its own share -- independent units, no data-path
+collective -- and rank 0 reports the whole-job throughput (total matrices / max over ranks of the device time):
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/batched_bench.py 512"""
 import ctypes
 import json
 import os
@@ -18,9 +22,10 @@ from matrix_decomposition_b200 import _native  # noqa: E402
 def main():
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     n = 512
-    ctx = _native.context()
+    rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
+    ctx = _native.context()          # device = LOCAL_RANK under torchrun
     lib = ctx.lib
-    rng = np.random.default_rng(0)
+    rng = np.random.default_rng(rank)
     mu = 1.05 * np.sqrt(2 * n)
     G = rng.standard_normal((batch, n, n))
     As = (G + G.transpose(0, 2, 1)) / 2 + mu * np.eye(n)[None]
@@ -68,8 +73,24 @@ def main():
     out['e2e_s'] = dt
     out['e2e_matrices_per_s'] = batch / dt
     out['n_clamped_mean'] = float(cl.sum(axis=1).mean())
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(ctx.device)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', ctx.device))
+        t = torch.tensor([out['device_s'], out['e2e_s']], dtype=torch.float64, device=torch.device('cuda', ctx.device))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)      # reporting only: the work itself needs no exchange
+        out.update(n_gpus=world, total_matrices=batch * world, device_s_max=float(t[0]), e2e_s_max=float(t[1]),
+                   device_matrices_per_s_total=batch * world / float(t[0]),
+                   e2e_matrices_per_s_total=batch * world / float(t[1]),
+                   device_gflops_total=batch * world * n ** 3 / 3 / float(t[0]) / 1e9)
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     print(json.dumps(out))
-    with open(os.path.join(REPO, 'gpurun_out', 'batched_bench.json'), 'w') as fh:
+    os.makedirs(os.path.join(REPO, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(REPO, 'gpurun_out', 'batched_bench%s.json' % ('_%dgpu' % world if world > 1 else '')), 'w') as fh:
         json.dump(out, fh, indent=1)
 
 
