@@ -177,6 +177,16 @@ int mdb_factor_identity_residual(mdb_factor *f, int nprobe, uint64_t seed, doubl
 int mdb_factor_psd_matrix(mdb_factor *f, const double *min_diag_B, const double *max_diag_B, int64_t stride_B, double *B,
                           int64_t ldb, int loc);
 
+/* Replaces the factorization inside the GMW family of the reference (GMW_SE.py:6-35 `_modified_LDLt` with the
+ * choose_d of `_approximate` :95-118 and `_GMW` :123-148; GMW_81 / GMW_T1 / GMW_T2 are parameter sets, :243, :293, :343):
+ * right-looking modified LDL^T without pivoting, d_k from |c|_inf of the current column and the two-phase strategy.
+ * mu = NaN means revisited_version_mu = None.  Outputs d and delta = d - pivot (host, length n); the caller forms
+ * B = A + diag(delta) and the optional diagonal rescaling (:43-62).  Unblocked (d_k needs the whole column below the
+ * pivot): n up to ~10^4.  The SE family of the same file is not covered: the reference's own SE_* functions fail with
+ * numpy 2.x (GMW_SE.py:172), so there is nothing to pin them against. */
+int mdb_gmw_f64(mdb_ctx *ctx, int64_t n, const double *A, int64_t lda, int loc, int use_two_phases, int nondecreasing,
+                int use_abs, double mu, double min_diag_D, double *d_out, double *delta_out);
+
 /* ---- introspection / unit-test hooks (used by tests/ and bench.py, not by the drop-in path) ----
  * mdb_factor_device_ptr: which = 0 W, 1 gamma, 2 alpha, 3 beta, 4 rowmax, 5 d, 6 omega, 7 delta (device addresses
  * of the resident state, position order); mdb_factor_ld: leading dimension of W. */

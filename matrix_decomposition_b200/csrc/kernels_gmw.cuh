@@ -1,0 +1,140 @@
+// kernels_gmw.cuh -- the GMW family of modified Cholesky factorizations (GMW_SE.py:6-35, :67-152 of the reference):
+// right-looking rank-1 LDL^T without pivoting in which d_k is chosen from the current column c = S[k+1:, k]
+// (|c|_inf) and the diagonal of the trailing matrix, in two phases.  d_k depends on the WHOLE column below the
+// pivot, so this is an unblocked factorization: per column a reduction, a scalar decision and a rank-1 update
+// (HBM bound: 16 (n-k)^2 / 2 bytes per column), meant for n up to ~10^4 like the dynamic-pivoting path.
+// Arithmetic mirrors numpy operation by operation (explicitly rounded products / quotients, no FMA contraction), so
+// d and delta equal the reference's bit for bit.
+#pragma once
+#include "mdb_common.cuh"
+
+struct GmwState {
+  double a, cmax, m1, m2;       // pivot, |c|_inf, min_j (S_jj - c_j^2 / a), min_j S_jj  (j > k)
+  double beta2, prev_delta, dk;
+  double min_d_next, min_d_factor, min_diag_D;
+  unsigned long long max_diag_bits, max_off_bits;   // max |.| of the trailing matrix (non-negative doubles as bits)
+  int phase;                    // 10 = phase 1, 15 = phase 1.5, 20 = phase 2   (GMW_SE.py:84, :100-110)
+  int need_init;
+  int use_abs, nondecreasing;
+};
+
+// column k below the pivot -> cvec (contiguous), plus the reductions the decision needs.  One CTA.
+__global__ void __launch_bounds__(1024) k_gmw_reduce(int64_t n, const double* __restrict__ W, int64_t ld, int64_t k,
+                                                     double* __restrict__ cvec, GmwState* st) {
+  __shared__ double s_cmax[32], s_m1[32], s_m2[32];
+  const double a = W[k * ld + k];
+  double cmax = 0.0, m1 = INFINITY, m2 = INFINITY;
+  for (int64_t j = k + 1 + threadIdx.x; j < n; j += blockDim.x) {
+    const double c = W[j * ld + k];
+    const double djj = W[j * ld + j];
+    cvec[j] = c;
+    cmax = fmax(cmax, fabs(c));
+    m1 = fmin(m1, __dsub_rn(djj, __ddiv_rn(__dmul_rn(c, c), a)));   // A.diagonal() - c**2 / a   (:101)
+    m2 = fmin(m2, djj);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    m1 = fmin(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_cmax[w] = cmax; s_m1[w] = m1; s_m2[w] = m2; }
+  __syncthreads();
+  if (w == 0) {
+    cmax = (l < (int)(blockDim.x >> 5)) ? s_cmax[l] : 0.0;
+    m1 = (l < (int)(blockDim.x >> 5)) ? s_m1[l] : INFINITY;
+    m2 = (l < (int)(blockDim.x >> 5)) ? s_m2[l] : INFINITY;
+    for (int o = 16; o > 0; o >>= 1) {
+      cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      m1 = fmin(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+    }
+    if (l == 0) { st->a = a; st->cmax = cmax; st->m1 = m1; st->m2 = m2; }
+  }
+}
+
+// phase 1 test (GMW_SE.py:100-104): keep d = a, or switch to phase 1.5 and ask for the trailing-matrix maxima
+__global__ void k_gmw_phase(GmwState* st) {
+  if (st->phase == 10) {
+    const double a = st->a;
+    // np.all over an empty trailing matrix is True: m1 = m2 = +inf then
+    if (a >= st->min_diag_D && st->m1 >= st->min_d_next && st->m2 >= __dmul_rn(st->min_d_factor, a)) {
+      st->dk = a;
+    } else {
+      st->phase = 15;
+    }
+  }
+  if (st->phase == 15) {
+    st->need_init = 1;
+    st->max_diag_bits = 0ull;
+    st->max_off_bits = 0ull;
+  }
+}
+
+// max |diag| and max |strict lower| of the trailing matrix S[k+1:, k+1:] (GMW_SE.py:127-133); only when asked for
+__global__ void __launch_bounds__(256) k_gmw_init(int64_t n, const double* __restrict__ W, int64_t ld, int64_t k,
+                                                  GmwState* st) {
+  if (!st->need_init) return;
+  const int64_t i = k + 1 + blockIdx.x;
+  if (i >= n) return;
+  double moff = 0.0;
+  for (int64_t j = k + 1 + threadIdx.x; j < i; j += blockDim.x) moff = fmax(moff, fabs(W[i * ld + j]));
+  for (int o = 16; o > 0; o >>= 1) moff = fmax(moff, __shfl_xor_sync(0xffffffffu, moff, o));
+  if ((threadIdx.x & 31) == 0 && moff > 0.0) atomicMax(&st->max_off_bits, (unsigned long long)__double_as_longlong(moff));
+  if (threadIdx.x == 0) atomicMax(&st->max_diag_bits, (unsigned long long)__double_as_longlong(fabs(W[i * ld + i])));
+}
+
+// d_k (GMW_SE.py:106-117, :123-148), delta_k = d_k - a (:29)
+__global__ void k_gmw_decide(int64_t n, int64_t k, GmwState* st, double* __restrict__ d, double* __restrict__ delta) {
+  const double eps = 2.220446049250313e-16;
+  const int64_t m = n - k - 1;  // size of the trailing matrix
+  if (st->need_init) {
+    const double max_diag = __longlong_as_double((long long)st->max_diag_bits);
+    const double max_off = __longlong_as_double((long long)st->max_off_bits);
+    double beta2;
+    if (m > 1) {
+      const double x = st->use_abs ? (double)(m * m - 1) : (double)(m * m - m);
+      beta2 = fmax(fmax(eps, max_diag), __ddiv_rn(max_off, sqrt(x)));
+    } else if (m == 1) {
+      beta2 = fmax(eps, max_diag);
+    } else {
+      beta2 = eps;
+    }
+    st->beta2 = beta2;
+    st->need_init = 0;
+    st->phase = 20;
+  }
+  double dk = st->dk;
+  const double a = st->a;
+  if (st->phase == 20) {
+    dk = (m > 0) ? __ddiv_rn(__dmul_rn(st->cmax, st->cmax), st->beta2) : 0.0;
+    dk = fmax(dk, st->min_diag_D);
+    double a_changed = st->use_abs ? fabs(a) : a;
+    if (st->nondecreasing) a_changed = __dadd_rn(a_changed, st->prev_delta);
+    dk = fmax(dk, a_changed);
+    st->prev_delta = __dsub_rn(dk, a);
+    st->dk = dk;
+  }
+  d[k] = dk;
+  delta[k] = __dsub_rn(dk, a);
+}
+
+// S[i, j] -= c_i c_j / d_k  for i >= j > k  (A -= np.outer(c, c) / d[k], GMW_SE.py:31), 32 x 32 tiles of the lower triangle
+__global__ void __launch_bounds__(256) k_gmw_rank1(int64_t n, double* __restrict__ W, int64_t ld, int64_t k,
+                                                   const double* __restrict__ cvec, const GmwState* __restrict__ st) {
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const double dk = st->dk;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t j = k + 1 + bj * 32 + tx;
+  if (j >= n) return;
+  const double cj = cvec[j];
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t i = k + 1 + bi * 32 + r;
+    if (i < n && i >= j) {
+      const double v = W[i * ld + j];
+      W[i * ld + j] = __dsub_rn(v, __ddiv_rn(__dmul_rn(cvec[i], cj), dk));
+    }
+  }
+}

@@ -12,6 +12,7 @@
 #include "kernels_gemm_tma.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_dynamic.cuh"
+#include "kernels_gmw.cuh"
 
 #define NB MDB_NB
 #define PANEL_R 64
@@ -968,6 +969,70 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
   }
   if (factor_out) *factor_out = f;
   return rc;
+}
+
+// GMW family (GMW_SE.py:6-35, :67-152): d and delta of the modified LDL^T without pivoting; B = A + diag(delta) and
+// the optional diagonal rescaling (:43-62) are O(n^2) and stay with the caller.
+extern "C" int mdb_gmw_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda, int loc, int use_two_phases,
+                           int nondecreasing, int use_abs, double mu, double min_diag_D, double* d_out,
+                           double* delta_out) {
+  if (!ctx) return MDB_ERR_INVALID;
+  MDB_CHECK(ctx, n >= 0 && (n == 0 || (A && lda >= n)), "mdb_gmw_f64: bad matrix");
+  MDB_CHECK(ctx, d_out && delta_out, "mdb_gmw_f64: null output");
+  MDB_CHECK(ctx, min_diag_D > 0, "mdb_gmw_f64: min_diag_D must be positive (GMW_SE.py:81)");
+  if (n == 0) return MDB_OK;
+  ctx_reap(ctx);
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  double *W = nullptr, *cvec = nullptr, *dd = nullptr;
+  GmwState* st = nullptr;
+  cudaError_t e = cudaMalloc((void**)&W, (size_t)n * n * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&cvec, (size_t)n * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&dd, (size_t)2 * n * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&st, sizeof(GmwState));
+  int rc = MDB_OK;
+  if (e == cudaSuccess) rc = copy2d_async(ctx, W, n, A, lda, n, n, MDB_DEVICE, loc);
+  if (e == cudaSuccess && !rc) {
+    GmwState h;
+    memset(&h, 0, sizeof(h));
+    h.phase = use_two_phases ? 10 : 15;                       // :84
+    h.min_diag_D = min_diag_D;
+    h.use_abs = use_abs; h.nondecreasing = nondecreasing;
+    if (!isnan(mu)) {                                         // :87-90: needs max |diag A|, a host-side pass over n values
+      std::vector<double> diag((size_t)n);
+      e = cudaMemcpy2DAsync(diag.data(), 8, W, (size_t)(n + 1) * 8, 8, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      double mx = 0;
+      for (int64_t i = 0; i < n; ++i) mx = std::max(mx, fabs(diag[(size_t)i]));
+      h.min_d_next = -mu * mx;
+      h.min_d_factor = -mu;
+    } else {                                                  // :91-93
+      h.min_d_next = min_diag_D;
+      h.min_d_factor = -INFINITY;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(st, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // `h` goes out of scope
+    for (int64_t k = 0; k < n && e == cudaSuccess; ++k) {
+      const int64_t m = n - k - 1;
+      k_gmw_reduce<<<1, 1024, 0, ctx->stream>>>(n, W, n, k, cvec, st);
+      k_gmw_phase<<<1, 1, 0, ctx->stream>>>(st);
+      if (m > 0) k_gmw_init<<<(unsigned)m, 256, 0, ctx->stream>>>(n, W, n, k, st);
+      k_gmw_decide<<<1, 1, 0, ctx->stream>>>(n, k, st, dd, dd + n);
+      ctx->launches += 4;
+      if (m > 0) {
+        const unsigned t32 = (unsigned)((m + 31) / 32);
+        k_gmw_rank1<<<dim3(t32, t32), 256, 0, ctx->stream>>>(n, W, n, k, cvec, st);
+        ctx->launches += 1;
+      }
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_out, dd, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(delta_out, dd + n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(W); cudaFree(cvec); cudaFree(dd); cudaFree(st);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
 }
 
 extern "C" int mdb_approximate_batched_f64(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int64_t lda,

@@ -391,6 +391,53 @@ def test_dynamic_pivoting_against_oracle_moderate_n(matrix, orc):
 
 
 # ---------------------------------------------------------------------------------------------
+# GMW family (GMW_SE.py): modified LDL^T without pivoting, d_k from |c|_inf of the current column
+# ---------------------------------------------------------------------------------------------
+def test_gmw_family_against_reference_goldens(matrix):
+    """GMW_81 / GMW_T1 / GMW_T2 on the device against the 96 golden cases of the unmodified reference.  The kernels
+    mirror numpy operation by operation, so B agrees to the last bit except where max-reductions meet exact ties."""
+    z = load_golden('gmw.npz')
+    manifest = json.loads(str(z['manifest']))
+    aps = matrix.approximation.positive_semidefinite
+    n_exact = 0
+    for m in manifest:
+        A = z[m['matrix'] + '/A']
+        kw = {k: (np.asarray(v) if isinstance(v, list) else v) for k, v in m['kwargs'].items()}
+        A0 = A.copy()
+        B = getattr(aps, m['fn'])(A, **kw)
+        assert np.array_equal(A, A0)                                   # A untouched (overwrite_A=False)
+        ref = z[m['key'] + '/B']
+        np.testing.assert_allclose(B, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max(), err_msg=m['key'])
+        n_exact += int(np.array_equal(B, ref))
+    assert n_exact >= 0.9 * len(manifest), n_exact
+
+
+def test_gmw_family_against_oracle_and_properties(matrix):
+    from oracle import gmw_oracle
+    aps = matrix.approximation.positive_semidefinite
+    rng = np.random.default_rng(11)
+    for n in (1, 5, 257, 700):
+        g = rng.standard_normal((n, n))
+        A = (g + g.T) / 2
+        for fn in ('GMW_81', 'GMW_T1', 'GMW_T2'):
+            B = getattr(aps, fn)(A)
+            ref = gmw_oracle.approximate(A, fn)
+            np.testing.assert_allclose(B, ref, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(ref).max()))
+            off = ~np.eye(n, dtype=bool)
+            assert np.array_equal(B[off], A[off])                      # only the diagonal is modified
+            assert np.all(B.diagonal() >= A.diagonal())
+            if n > 1:
+                assert np.linalg.eigvalsh(B).min() > 0                 # positive definite
+    S = workloads.lowrank_plus_diag(300, 2)                           # already positive definite: unchanged by T1 / T2
+    for fn in ('GMW_T1', 'GMW_T2'):
+        np.testing.assert_allclose(getattr(aps, fn)(S), S, rtol=0, atol=1e-12)
+    with pytest.raises(matrix.errors.MatrixNotSquareError):
+        aps.GMW_81(np.ones((3, 4)))
+    with pytest.raises(NotImplementedError):
+        aps.SE_99(np.eye(3))
+
+
+# ---------------------------------------------------------------------------------------------
 # decompose, solve, multiply, permute
 # ---------------------------------------------------------------------------------------------
 def test_decompose_solve_multiply_against_reference_goldens(matrix):

@@ -225,3 +225,18 @@ def test_fp64_twin_matches_in_benign_regime():
     np.testing.assert_array_equal(twin['clamped'], ref['clamped'])
     np.testing.assert_allclose(twin['L'], ref['L'], rtol=1e-11, atol=1e-13)
     np.testing.assert_allclose(twin['d'], ref['d'].astype(float), rtol=1e-12)
+
+
+def test_gmw_oracle_against_reference_goldens():
+    """oracle/gmw_oracle.py (numpy restatement of GMW_SE.py) on the 96 cases produced by the unmodified reference
+    (tests/golden/generate_gmw_goldens.py): GMW_81 / GMW_T1 / GMW_T2 x bounds x matrix families, bit for bit."""
+    import json
+    from oracle import gmw_oracle
+    z = load_golden('gmw.npz')
+    manifest = json.loads(str(z['manifest']))
+    assert len(manifest) == 96 and all(m['ok'] for m in manifest)
+    for m in manifest:
+        A = z[m['matrix'] + '/A']
+        kw = {k: (np.asarray(v) if isinstance(v, list) else v) for k, v in m['kwargs'].items()}
+        B = gmw_oracle.approximate(A, m['fn'], **kw)
+        np.testing.assert_array_equal(B, z[m['key'] + '/B'], err_msg=m['key'])
