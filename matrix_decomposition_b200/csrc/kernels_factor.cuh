@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t
   double* s_gamma = s_rowmin + NB;
   double* s_mB = s_gamma + NB;
   double* s_MB = s_mB + NB;
-  __shared__ double s_dec[2][4];  // d, omega, drop, slow of column k (slot k & 1)
+  __shared__ double s_dec[2][5];  // d, omega, drop, slow, 1 / d of column k (slot k & 1)
   __shared__ int s_big;
   __shared__ volatile int s_ready;  // rows 0 .. s_ready have published their state for their own column
 
@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t
         sd[1] = dec.omega;
         sd[2] = drop ? 1.0 : 0.0;
         sd[3] = slow ? 1.0 : 0.0;
+        sd[4] = (dec.d != 0) ? 1.0 / dec.d : 0.0;   // the division leaves the dependency chain of the rows
         s_d[k] = dec.d;
         hdr[k] = dec.d;
         hdr[NB + k] = dec.omega;
@@ -354,20 +355,20 @@ __global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t
     __syncthreads();
 
     // ---------------- column k ----------------
-    const double dk = s_dec[k & 1][0], wk = s_dec[k & 1][1];
+    const double dk = s_dec[k & 1][0], wk = s_dec[k & 1][1], inv_dk = s_dec[k & 1][4];
     const bool drop = s_dec[k & 1][2] != 0.0, slow = s_dec[k & 1][3] != 0.0;
+    double a = 0, s0k = 0;
+    if (active) {
+      a = T[k * LDT + j];   // A[j, k]; read before thread (j, 0) overwrites it below
+      s0k = Trow[k];
+      if (k >= 1) G = fma(Trow[k - 1], T[(k - 1) * LDT + k], G);  // the term m = k - 1, published just before the barrier
+    }
     if (tid < k) {  // the scaled, thresholded row k times D: for the panel kernel, and for the slow path
       double lt = wk * T[k * LDT + tid];
       if (wk == 0 || fabs(lt) < mavL) lt = 0;
       const double u = s_d[tid] * lt;
       Ut[tid * NB + k] = u;
       if (slow) s_u[tid] = u;
-    }
-    double a = 0, s0k = 0;
-    if (active) {
-      a = T[k * LDT + j];   // A[j, k]; read before thread (j, 0) overwrites it below
-      s0k = Trow[k];
-      if (k >= 1) G = fma(Trow[k - 1], T[(k - 1) * LDT + k], G);  // the term m = k - 1, published just before the barrier
     }
     double acc = 0;
     if (slow) {  // uniform over the block
@@ -387,11 +388,12 @@ __global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t
     }
     __syncwarp();  // all four lanes of a row have read T[k][j] and T[j][k]
     if (active && h == 0) {
+      // x = r * (1 / d_k): the reciprocal comes from the rule warp (<= 1 ulp from r / d_k)
       double x = 0;
       if (dk != 0) {
-        if (drop) x = a / dk;
-        else if (slow) x = (((1.0 - wk) * a + wk * s0k) - acc) / dk;
-        else x = fma(wk, s0k - G, (1.0 - wk) * a) / dk;
+        if (drop) x = a * inv_dk;
+        else if (slow) x = (((1.0 - wk) * a + wk * s0k) - acc) * inv_dk;
+        else x = fma(wk, s0k - G, (1.0 - wk) * a) * inv_dk;
       }
       T[j * LDT + k] = x;
       T[k * LDT + j] = x * dk;        // d_k Lu[j, k] at the transposed position
