@@ -853,7 +853,15 @@ static int one_shot(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int
   if (timing) cudaStreamSynchronize(ctx->stream);
   const double t2 = now();
   bool streamed = false;
-  if (!rc && loc == MDB_HOST && L && batch == 1 && n >= 4096 && ldl >= n) {
+  // Streaming L out needs PINNED host memory: a device -> pageable copy blocks the calling thread until the data is
+  // there, which would stall the launch loop of the factorization behind every row block.
+  bool l_pinned = false;
+  if (!rc && loc == MDB_HOST && L) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, L) == cudaSuccess) l_pinned = (attr.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+  }
+  if (!rc && loc == MDB_HOST && L && l_pinned && batch == 1 && n >= 4096 && ldl >= n) {
     f->out_host = L; f->out_ld = ldl; f->out_stream_type = out_type;  // L leaves the device row block by row block
     streamed = true;
   }

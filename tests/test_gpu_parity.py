@@ -534,7 +534,8 @@ def test_one_shot_streamed_output_equals_resident_factor(matrix, rt):
     p = np.argsort(-A.diagonal()).astype(np.int64)
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
                                        float(np.finfo(float).eps), None, kw['max_diag_B'])
-    L = np.full((n, n), np.nan)
+    L = ctx.pinned_array((n, n))          # streaming needs pinned memory (pageable L takes the one-copy path)
+    L[:] = np.nan
     d, om, de = np.empty(n), np.empty(n), np.empty(n)
     cl = np.zeros(n, dtype=np.uint8)
     h = ctypes.c_void_p()
@@ -543,6 +544,13 @@ def test_one_shot_streamed_output_equals_resident_factor(matrix, rt):
                                       P(d), P(om), P(de), P(cl), _native.HOST, ctypes.byref(h)), 'one-shot')
     resident = _native.Factor(ctx, h).download(n, _native.TYPE_CODES[rt])
     assert np.array_equal(L, resident)
+    Lp = np.full((n, n), np.nan)          # the same call with a pageable L
+    ctx.check(lib.mdb_approximate_f64(ctx.handle, n, P(A), n, P(p), ctypes.byref(bounds), _native.TYPE_CODES[rt], P(Lp), n,
+                                      P(d), P(om), P(de), P(cl), _native.HOST, None), 'one-shot pageable')
+    assert np.array_equal(Lp, resident)
+    Lpin = L
+    L = np.array(Lpin)                     # off the pinned buffer, which is released right away
+    _native.free_pinned(Lpin)
     assert np.all(np.triu(L, 1) == 0)
     # identity: P^T L D L^T P = A o Omega + diag(delta)  on a probe vector
     v = np.random.default_rng(3).standard_normal(n)
