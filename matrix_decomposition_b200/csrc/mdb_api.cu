@@ -124,6 +124,10 @@ extern "C" int mdb_ctx_destroy(mdb_ctx* ctx) {
   if (!ctx) return MDB_OK;
   ctx_reap(ctx);
   cudaSetDevice(ctx->device);
+  for (int i = 0; i < 3; ++i) {
+    if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+    if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -216,9 +220,90 @@ extern "C" int mdb_memcpy(mdb_ctx* ctx, void* dst, const void* src, size_t bytes
   MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MDB_OK;
 }
+// Large copies between PAGEABLE host memory and the device: the driver stages those through a single thread
+// (~10 GB/s).  Here the host side of the staging is done by several threads into / out of three pinned buffers
+// while the DMA of the neighbouring chunks is in flight.  Returns -1 when the plain path should be used.
+static bool host_is_pageable(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+static void parallel_rows_copy(char* dst, size_t dst_pitch, const char* src, size_t src_pitch, size_t row_bytes,
+                               int64_t rows) {
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, std::thread::hardware_concurrency()), rows));
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; ++t)
+    th.emplace_back([=]() {
+      for (int64_t r = rows * t / T; r < rows * (t + 1) / T; ++r) memcpy(dst + r * dst_pitch, src + r * src_pitch, row_bytes);
+    });
+  for (int64_t r = 0; r < rows / T; ++r) memcpy(dst + r * dst_pitch, src + r * src_pitch, row_bytes);
+  for (auto& x : th) x.join();
+}
+
+static int staged_copy2d(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* src, int64_t ld_src, int64_t rows,
+                         int64_t cols, int dst_loc, int src_loc) {
+  static const bool enabled = !(getenv("MDB200_STAGED") && getenv("MDB200_STAGED")[0] == '0');
+  if (!enabled) return -1;
+  const bool h2d = (src_loc == MDB_HOST && dst_loc == MDB_DEVICE), d2h = (src_loc == MDB_DEVICE && dst_loc == MDB_HOST);
+  const size_t row_bytes = (size_t)cols * 8;
+  if (!(h2d || d2h) || (size_t)rows * row_bytes < ((size_t)256 << 20) || row_bytes > ((size_t)64 << 20)) return -1;
+  if (!host_is_pageable(h2d ? src : dst)) return -1;
+  const size_t SB = (size_t)64 << 20;
+  if (!ctx->stage[0]) {
+    for (int i = 0; i < 3; ++i) {
+      if (cudaMallocHost(&ctx->stage[i], SB) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        for (int k = 0; k <= i; ++k) { if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]); ctx->stage[k] = nullptr; }
+        return -1;
+      }
+    }
+    ctx->stage_bytes = SB;
+  }
+  const int64_t R = std::max<int64_t>(1, (int64_t)(SB / row_bytes));   // rows per chunk
+  const int64_t nchunks = (rows + R - 1) / R;
+  if (h2d) {
+    for (int64_t c = 0; c < nchunks; ++c) {
+      const int b = (int)(c % 3);
+      const int64_t r0 = c * R, nr = std::min<int64_t>(R, rows - r0);
+      if (c >= 3) MDB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b]));   // the DMA that read this buffer is done
+      parallel_rows_copy((char*)ctx->stage[b], row_bytes, (const char*)src + (size_t)r0 * ld_src * 8, (size_t)ld_src * 8,
+                         row_bytes, nr);
+      MDB_CUDA(ctx, cudaMemcpy2DAsync((char*)dst + (size_t)r0 * ld_dst * 8, (size_t)ld_dst * 8, ctx->stage[b], row_bytes,
+                                      row_bytes, (size_t)nr, cudaMemcpyHostToDevice, ctx->stream));
+      MDB_CUDA(ctx, cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+    }
+    for (int b = 0; b < 3 && b < nchunks; ++b) MDB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b]));
+  } else {
+    for (int64_t c = 0; c < nchunks + 2; ++c) {
+      if (c < nchunks) {
+        const int b = (int)(c % 3);
+        const int64_t r0 = c * R, nr = std::min<int64_t>(R, rows - r0);
+        MDB_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage[b], row_bytes, (const char*)src + (size_t)r0 * ld_src * 8,
+                                        (size_t)ld_src * 8, row_bytes, (size_t)nr, cudaMemcpyDeviceToHost, ctx->stream));
+        MDB_CUDA(ctx, cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+      }
+      if (c >= 2) {
+        const int64_t cc = c - 2;
+        const int b = (int)(cc % 3);
+        const int64_t r0 = cc * R, nr = std::min<int64_t>(R, rows - r0);
+        MDB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b]));
+        parallel_rows_copy((char*)dst + (size_t)r0 * ld_dst * 8, (size_t)ld_dst * 8, (const char*)ctx->stage[b], row_bytes,
+                           row_bytes, nr);
+      }
+    }
+  }
+  return MDB_OK;
+}
+
 static int copy2d_async(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* src, int64_t ld_src, int64_t rows,
                         int64_t cols, int dst_loc, int src_loc) {
   if (rows <= 0 || cols <= 0) return MDB_OK;
+  {
+    const int r = staged_copy2d(ctx, dst, ld_dst, src, ld_src, rows, cols, dst_loc, src_loc);
+    if (r != -1) return r;
+  }
   MDB_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)ld_dst * 8, src, (size_t)ld_src * 8, (size_t)cols * 8, (size_t)rows,
                                   copy_kind(dst_loc, src_loc), ctx->stream));
   return MDB_OK;

@@ -32,6 +32,9 @@ struct mdb_ctx {
   int64_t launches;
   int profiling;
   double phase_ms[4];
+  void* stage[3];             // pinned staging buffers for large pageable host <-> device copies
+  cudaEvent_t stage_ev[3];
+  size_t stage_bytes;
   std::thread* reaper;        // background release of the previous one-shot call's device buffers (cudaFree of tens
                               // of GB takes 0.2-0.4 s and nothing the caller waits for depends on it)
   int last_input_nonfinite;   // set by mdb_factor_set_matrix: the matrix held an inf / NaN

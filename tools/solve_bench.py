@@ -70,6 +70,11 @@ def main():
     out['solve1024_device_frac_fp64_peak'] = out['solve1024_device_tflops'] / FP64_PEAK_TFLOPS
     ctx.set_profiling(False)
     out['solve1024_residual'] = float(np.max(np.abs(A @ Xk[:, :4] - Bk[:, :4])) / np.max(np.abs(Bk[:, :4])))
+    t = time.perf_counter()
+    L = dec.L                                   # first access: the factor comes home (pageable numpy array)
+    out['L_download_s'] = time.perf_counter() - t
+    out['L_download_gbs'] = 8.0 * n * n / out['L_download_s'] / 1e9
+    del L
     if '--cpu' in sys.argv:
         import scipy.linalg
         p = np.asarray(dec.p)
