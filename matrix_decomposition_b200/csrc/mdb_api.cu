@@ -247,7 +247,8 @@ static int staged_copy2d(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* sr
   if (!enabled) return -1;
   const bool h2d = (src_loc == MDB_HOST && dst_loc == MDB_DEVICE), d2h = (src_loc == MDB_DEVICE && dst_loc == MDB_HOST);
   const size_t row_bytes = (size_t)cols * 8;
-  if (!(h2d || d2h) || (size_t)rows * row_bytes < ((size_t)256 << 20) || row_bytes > ((size_t)64 << 20)) return -1;
+  const size_t total = (size_t)rows * row_bytes;
+  if (!(h2d || d2h) || total < ((size_t)64 << 20) || row_bytes > ((size_t)8 << 20)) return -1;
   if (!host_is_pageable(h2d ? src : dst)) return -1;
   const size_t SB = (size_t)64 << 20;
   if (!ctx->stage[0]) {
@@ -261,7 +262,9 @@ static int staged_copy2d(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* sr
     }
     ctx->stage_bytes = SB;
   }
-  const int64_t R = std::max<int64_t>(1, (int64_t)(SB / row_bytes));   // rows per chunk
+  // chunks of 8 ... 64 MB: at least ~8 of them, so that staging and DMA overlap also for a few hundred MB
+  const size_t chunk_bytes = std::min<size_t>(SB, std::max<size_t>((size_t)8 << 20, total / 8));
+  const int64_t R = std::max<int64_t>(1, (int64_t)(chunk_bytes / row_bytes));   // rows per chunk
   const int64_t nchunks = (rows + R - 1) / R;
   if (h2d) {
     for (int64_t c = 0; c < nchunks; ++c) {
