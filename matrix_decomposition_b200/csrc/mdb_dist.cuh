@@ -234,6 +234,10 @@ extern "C" int mdb_dist_set_bounds(mdb_dist* s, const mdb_bounds* bnd, const int
   return MDB_OK;
 }
 
+__global__ void k_dist_pack(int64_t rows, const double* __restrict__ OX, int64_t ldp, const double* __restrict__ alpha,
+                            const double* __restrict__ beta, const double* __restrict__ rowmax, double* __restrict__ vecs,
+                            double* __restrict__ MX);
+
 static FactorDev dist_make_dev(mdb_dist* s, double* hdr) {
   FactorDev F;
   memset(&F, 0, sizeof(F));
@@ -276,14 +280,28 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot, int64_t k
     k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
                                                                      s->S + lc0, s->ld, PX, PY, ob, s->ldp);
     MDB_LAUNCHED(ctx);
-    MDB_CUDA(ctx, cudaMemcpy2DAsync(MX, (size_t)NB * 8, PX + (k1 - ob) * s->ldp, (size_t)s->ldp * 8, (size_t)NB * 8,
-                                    (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
-    MDB_CUDA(ctx, cudaMemcpyAsync(vecs, s->alpha + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    MDB_CUDA(ctx, cudaMemcpyAsync(vecs + rows, s->beta + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    MDB_CUDA(ctx, cudaMemcpyAsync(vecs + 2 * rows, s->rowmax + k1, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    {  // message = [hdr (already there) | alpha, beta, rowmax of the rows below | X], packed by one kernel
+      const unsigned grid = (unsigned)std::min<int64_t>((rows + 1) / 2, (int64_t)ctx->num_sms * 8);
+      k_dist_pack<<<grid, 256, 0, ctx->stream>>>(rows, PX + (k1 - ob) * s->ldp, s->ldp, s->alpha + k1, s->beta + k1,
+                                                 s->rowmax + k1, vecs, MX);
+      MDB_LAUNCHED(ctx);
+    }
   }
   MDB_CUDA(ctx, cudaGetLastError());
   return MDB_OK;
+}
+
+// owner: operands X (rows x NB inside the outer-block buffer, leading dimension ldp) and the three state slices ->
+// compact message
+__global__ void __launch_bounds__(256) k_dist_pack(int64_t rows, const double* __restrict__ OX, int64_t ldp,
+                                                   const double* __restrict__ alpha, const double* __restrict__ beta,
+                                                   const double* __restrict__ rowmax, double* __restrict__ vecs,
+                                                   double* __restrict__ MX) {
+  const int c = threadIdx.x & (MDB_NB - 1);
+  for (int64_t r = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7); r < rows; r += (int64_t)gridDim.x * 2) {
+    MX[r * MDB_NB + c] = OX[r * ldp + c];
+    if (c == 0) { vecs[r] = alpha[r]; vecs[rows + r] = beta[r]; vecs[2 * rows + r] = rowmax[r]; }
+  }
 }
 
 // header -> replicated d / omega / delta / clamped
@@ -300,15 +318,28 @@ __global__ void k_dist_absorb_hdr(int kb, int64_t k0, const double* __restrict__
 
 // message X (rows x NB, compact) -> operand buffers: OX = X, OY = -X d (the same expression as k_panel, so the
 // owner's and the receivers' operands are identical bit for bit).  HBM bound: 24 * rows * NB bytes.
+// The same kernel takes the alpha / beta / rowmax slices and (its first CTA) the header: one launch per panel on the
+// receiving side.
 __global__ void __launch_bounds__(256) k_dist_absorb_x(int64_t rows, const double* __restrict__ X,
                                                        const double* __restrict__ hdr, double* __restrict__ OX,
-                                                       double* __restrict__ OY, int64_t ldp) {
+                                                       double* __restrict__ OY, int64_t ldp,
+                                                       const double* __restrict__ vecs, double* __restrict__ alpha,
+                                                       double* __restrict__ beta, double* __restrict__ rowmax, int kb,
+                                                       double* __restrict__ d, double* __restrict__ omega,
+                                                       double* __restrict__ delta, uint8_t* __restrict__ clamped) {
   const int c = threadIdx.x & (MDB_NB - 1);
   const double dc = hdr[c];
+  if (blockIdx.x == 0 && threadIdx.x < kb) {  // d / omega / delta / clamped of the panel's columns (pointers at column k0)
+    d[threadIdx.x] = hdr[threadIdx.x];
+    omega[threadIdx.x] = hdr[MDB_NB + threadIdx.x];
+    delta[threadIdx.x] = hdr[3 * MDB_NB + threadIdx.x];
+    clamped[threadIdx.x] = (uint8_t)(hdr[4 * MDB_NB + threadIdx.x] != 0.0);
+  }
   for (int64_t r = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7); r < rows; r += (int64_t)gridDim.x * 2) {
     const double x = X[r * MDB_NB + c];
     OX[r * ldp + c] = x;
     OY[r * ldp + c] = -x * dc;
+    if (c == 0) { alpha[r] = vecs[r]; beta[r] = vecs[rows + r]; rowmax[r] = vecs[2 * rows + r]; }
   }
 }
 
@@ -322,16 +353,16 @@ extern "C" int mdb_dist_absorb_panel(mdb_dist* s, int64_t k, int slot, int64_t k
   if ((k % s->world) == s->rank) return MDB_OK;  // the owner's arrays and operands are already in place
   const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1, ob = k_outer * NB;
   double* buf = s->panel[slot];
-  k_dist_absorb_hdr<<<1, NB, 0, ctx->stream>>>((int)(k1 - k0), k0, buf, s->d, s->omega, s->delta, s->clamped);
-  MDB_LAUNCHED(ctx);
   if (rows > 0) {
     double* vecs = buf + 5 * NB;
-    MDB_CUDA(ctx, cudaMemcpyAsync(s->alpha + k1, vecs, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    MDB_CUDA(ctx, cudaMemcpyAsync(s->beta + k1, vecs + rows, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    MDB_CUDA(ctx, cudaMemcpyAsync(s->rowmax + k1, vecs + 2 * rows, (size_t)rows * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     const int64_t off = (k1 - ob) * s->ldp + (k0 - ob);
     const unsigned grid = (unsigned)std::min<int64_t>((rows + 1) / 2, (int64_t)ctx->num_sms * 8);
-    k_dist_absorb_x<<<grid, 256, 0, ctx->stream>>>(rows, vecs + 3 * rows, buf, s->OPX[oslot] + off, s->OPY[oslot] + off, s->ldp);
+    k_dist_absorb_x<<<grid, 256, 0, ctx->stream>>>(rows, vecs + 3 * rows, buf, s->OPX[oslot] + off, s->OPY[oslot] + off, s->ldp,
+                                                   vecs, s->alpha + k1, s->beta + k1, s->rowmax + k1, (int)(k1 - k0),
+                                                   s->d + k0, s->omega + k0, s->delta + k0, s->clamped + k0);
+    MDB_LAUNCHED(ctx);
+  } else {
+    k_dist_absorb_hdr<<<1, NB, 0, ctx->stream>>>((int)(k1 - k0), k0, buf, s->d, s->omega, s->delta, s->clamped);
     MDB_LAUNCHED(ctx);
   }
   MDB_CUDA(ctx, cudaGetLastError());
