@@ -87,7 +87,7 @@ struct FactorDev {
   const double* maxB;
   int* info;      // first failing pivot + 1 (MDB_RULE_EXACT), 0 = none
   double* Ut;     // NB x NB scratch: Ut[m * NB + k] = d_m * Ltilde[k][m]  (m < k)
-  double* hdr;    // 3 x NB scratch: d, omega, drop flag of the current panel
+  double* hdr;    // 5 x NB scratch: d, omega, drop flag, delta, clamped of the current panel
   // strides between consecutive matrices of a batch (elements)
   int64_t sW, sVec, sUt, sHdr, sPanel;
   MdRuleParams prm;
