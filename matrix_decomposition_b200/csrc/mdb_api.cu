@@ -38,6 +38,8 @@ struct mdb_factor {
   double mavL;
   bool prepared;
   double *Linv, *LinvT, *Ltri, *Utri;
+  // right-hand-side workspaces of solve / multiply (grow-only, so that a solve does not pay cudaMalloc / cudaFree)
+  double* ws[3]; size_t ws_cap[3];
   // streamed output (one-shot calls with a host L): rows of L are finalised and copied out per outer block
   double* out_host; int64_t out_ld; int out_stream_type;
   // persistent triangular sweep (<= 8 right-hand sides): task list, flags, partial sums
@@ -330,6 +332,7 @@ static void factor_release(mdb_factor* f) {
   cudaFree(f->p_dev); cudaFree(f->info); cudaFree(f->Ut); cudaFree(f->hdr); cudaFree(f->PX); cudaFree(f->PY); cudaFree(f->PX2); cudaFree(f->PY2);
   cudaFree(f->Linv); cudaFree(f->LinvT); cudaFree(f->Ltri); cudaFree(f->Utri);
   cudaFree(f->trsv_tasks); cudaFree(f->trsv_sync); cudaFree(f->trsv_partial);
+  for (int i = 0; i < 3; ++i) cudaFree(f->ws[i]);
   delete f;
 }
 
@@ -347,6 +350,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   f->info = nullptr; f->Ut = f->hdr = f->PX = f->PY = f->PX2 = f->PY2 = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
   f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
   f->out_host = nullptr; f->out_ld = 0; f->out_stream_type = MDB_TYPE_LDL;
+  for (int i = 0; i < 3; ++i) { f->ws[i] = nullptr; f->ws_cap[i] = 0; }
   f->trsv_tasks = nullptr; f->trsv_ntasks = 0; f->trsv_sync = nullptr; f->trsv_partial = nullptr; f->trsv_partial_rhs = 0;
   const int64_t nn = std::max<int64_t>(n, 1);
   f->panel_rows = std::max<int64_t>(mdb_round_up(nn, NB), NB);
@@ -1359,20 +1363,35 @@ static int trsv_check(mdb_factor* f) {
   return MDB_OK;
 }
 
+static int ws_get(mdb_factor* f, int i, size_t bytes, double** out) {
+  mdb_ctx* ctx = f->ctx;
+  if (f->ws_cap[i] < bytes) {
+    if (f->ws[i]) cudaFree(f->ws[i]);
+    f->ws[i] = nullptr; f->ws_cap[i] = 0;
+    MDB_CUDA(ctx, cudaMalloc((void**)&f->ws[i], bytes));
+    f->ws_cap[i] = bytes;
+  }
+  *out = f->ws[i];
+  return MDB_OK;
+}
+
+// Bt / Yt / stage are workspaces owned by the factor (not to be freed by the caller)
 static int rhs_in(mdb_factor* f, const double* B, int64_t ldb, int64_t nrhs, int loc, double** Bt, double** Yt,
                   int64_t* ldt_out, double** stage) {
   mdb_ctx* ctx = f->ctx;
   const int64_t n = f->n, ldt = mdb_round_up(n, NB);
   *ldt_out = ldt;
-  MDB_CUDA(ctx, cudaMalloc((void**)Bt, (size_t)nrhs * ldt * 8));
-  MDB_CUDA(ctx, cudaMalloc((void**)Yt, (size_t)nrhs * ldt * 8));
+  int rcw = ws_get(f, 0, (size_t)nrhs * ldt * 8, Bt);
+  if (!rcw) rcw = ws_get(f, 1, (size_t)nrhs * ldt * 8, Yt);
+  if (rcw) return rcw;
   MDB_CUDA(ctx, cudaMemsetAsync(*Bt, 0, (size_t)nrhs * ldt * 8, ctx->stream));
   MDB_CUDA(ctx, cudaMemsetAsync(*Yt, 0, (size_t)nrhs * ldt * 8, ctx->stream));
   const double* src = B;
   int64_t lsrc = ldb;
   *stage = nullptr;
   if (loc == MDB_HOST) {
-    MDB_CUDA(ctx, cudaMalloc((void**)stage, (size_t)n * nrhs * 8));
+    rcw = ws_get(f, 2, (size_t)n * nrhs * 8, stage);
+    if (rcw) return rcw;
     int rc = copy2d_async(ctx, *stage, nrhs, B, ldb, n, nrhs, MDB_DEVICE, MDB_HOST);
     if (rc) return rc;
     src = *stage;
@@ -1435,7 +1454,6 @@ extern "C" int mdb_factor_solve(mdb_factor* f, const double* B, int64_t ldb, int
     if (!rc) rc = rhs_out(f, Bt, ldt, nrhs, X, ldx, loc, stage);
     if (!rc) rc = trsv_check(f);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(Bt); cudaFree(Yt); cudaFree(stage);
     if (rc) return rc;
     MDB_CUDA(ctx, e2);
     return MDB_OK;
@@ -1485,7 +1503,6 @@ extern "C" int mdb_factor_solve(mdb_factor* f, const double* B, int64_t ldb, int
   }
   if (!rc) rc = rhs_out(f, Bt, ldt, nrhs, X, ldx, loc, stage);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(Bt); cudaFree(Yt); cudaFree(stage);
   if (rc) return rc;
   MDB_CUDA(ctx, e);
   return MDB_OK;
@@ -1526,7 +1543,6 @@ extern "C" int mdb_factor_multiply(mdb_factor* f, const double* B, int64_t ldb, 
   }
   if (!rc) rc = rhs_out(f, Xt, ldt, nrhs, X, ldx, loc, stage);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(Xt); cudaFree(Zt); cudaFree(stage);
   if (rc) return rc;
   MDB_CUDA(ctx, e);
   return MDB_OK;
