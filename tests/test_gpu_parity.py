@@ -188,6 +188,39 @@ def test_outer_block_aggregation_matches_oracle(matrix, orc, n, blocking):
     np.testing.assert_allclose(dd.L, rr['L'], rtol=1e-10, atol=1e-12)
 
 
+def test_randomized_configurations_against_oracle(matrix, orc):
+    """Seeded sweep over bound combinations the fixed cases do not hit: scalar / vector / absent B bounds, min_diag_D
+    None / 0 / positive, finite and infinite max_diag_D, all static permutations, sizes across two to four panels.
+    Decisions (permutation, clamped set) must equal the oracle's, the composed matrix must agree to 1e-11."""
+    rng = np.random.default_rng(20261020)
+    perms = ['none', 'decreasing_diagonal_values', 'increasing_diagonal_values', 'decreasing_absolute_diagonal_values',
+             'increasing_absolute_diagonal_values']
+    n_checked = 0
+    for trial in range(24):
+        n = int(rng.choice([130, 200, 260, 390, 515]))
+        shift = float(rng.choice([0.6, 1.0, 1.3]))
+        A = workloads.goe(n, 500 + trial) + shift * np.sqrt(2 * n) * np.eye(n)
+        mu = np.sqrt(2 * n)
+        kw = dict(permutation=perms[trial % len(perms)])
+        mode = trial % 4
+        if mode == 0:      # upper clamps only (benign)
+            kw.update(min_diag_D=0.02 * mu, max_diag_D=0.8 * mu * shift, max_diag_B=2.5 * mu * shift)
+        elif mode == 1:    # vector B bounds, default min_diag_D
+            kw.update(min_diag_B=np.full(n, 0.05 * mu) + rng.random(n), max_diag_B=np.full(n, 3.0 * mu * shift) + rng.random(n))
+        elif mode == 2:    # lower clamp with min_abs_value_D, no upper bounds
+            kw.update(min_diag_D=0.3 * mu, min_abs_value_D=0.3 * mu)
+        else:              # min_diag_D = 0: d may become exactly 0
+            kw.update(min_diag_D=0.0, max_diag_D=1.2 * mu * shift, min_abs_value_D=1e-3)
+        ref = orc.approximate(A, **kw)
+        dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+        np.testing.assert_array_equal(np.asarray(dec.p), ref['p'], err_msg=str(trial))
+        B, B_ref = _composed(dec.L, dec.d), _composed(ref['L'], ref['d'])
+        assert np.linalg.norm(B - B_ref) <= 1e-11 * np.linalg.norm(B_ref), (trial, kw)
+        np.testing.assert_array_equal(dec.clamped, ref['clamped'], err_msg=str(trial))
+        n_checked += 1
+    assert n_checked == 24
+
+
 def test_empty_matrix(matrix):
     dec = matrix.approximation.positive_semidefinite.decomposition(np.zeros((0, 0)), permutation='none')
     assert dec.n == 0 and dec.L.shape == (0, 0)
