@@ -2,9 +2,13 @@
 //
 // Every step evaluates the scalar rule for ALL remaining rows and picks the minimum of the reference's
 // key -- (f, -d, omega, j) or (-d, f, omega, j) -- so alpha must be current for every remaining row at every
-// column.  That rules out the blocked panel scheme; this path is an unblocked right-looking factorization
-// (rank-1 update per column), meant for the sizes at which the reference's O(n^2) rule evaluations are
-// practical at all (n up to ~10^4).  Five small kernels per column, no host round trip.
+// column: the whole column below the pivot has to be computed at every step (no row-local diagonal block as in
+// the static path).  The Schur complement, however, is only updated once per panel of 128 columns: inside a
+// panel column i is read as  S[j, i] + sum_c X[j, c] Y[i, c]  over the panel's earlier columns c (X = unscaled
+// rows, Y = -X D, kept for every row in the operand buffers; O(n * 64) per column instead of the O(n^2) rank-1
+// update), and after the panel the trailing matrix gets the same K = 128 tensor-core update as the static path.
+// Pivot swaps exchange the rows of X and Y together with the rows / columns of W.  Four small kernels per
+// column, no host round trip; n^2 / 2 rule evaluations in total.
 #pragma once
 #include "mdb_common.cuh"
 
@@ -100,10 +104,15 @@ __global__ void __launch_bounds__(256) k_dyn_select2(FactorDev F, int method, in
 // symmetric swap of indices i and j* in both triangles of W: S(a, b) lives at W[max][min], A(a, b) at W[min][max]
 // (Reimer.py:513-518 swaps the rows of L; the Schur complement and the original matrix must follow)
 __global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict__ W, int64_t ld, int64_t i,
-                                                  const DynSel* __restrict__ sel) {
+                                                  const DynSel* __restrict__ sel, double* __restrict__ PX,
+                                                  double* __restrict__ PY, int64_t ldp, int kc) {
   const int64_t js = sel->jstar;
   if (js == i) return;
   const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (m < kc) {  // the pending (not yet applied) panel columns of the two rows follow them
+    double t = PX[i * ldp + m]; PX[i * ldp + m] = PX[js * ldp + m]; PX[js * ldp + m] = t;
+    t = PY[i * ldp + m]; PY[i * ldp + m] = PY[js * ldp + m]; PY[js * ldp + m] = t;
+  }
   if (m >= n || m == i || m == js) return;
   {  // lower triangle: S
     double* a = &W[(i > m ? i : m) * ld + (i > m ? m : i)];
@@ -117,38 +126,41 @@ __global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict_
   }
 }
 
-// column i for every row below: mix, divide, alpha / beta / rowmax; x and y = -x d for the rank-1 update
+// column i for every row below: current Schur complement entry (stored value + the pending updates of this panel),
+// mix, divide, alpha / beta / rowmax; x and y = -x d go into column kc of the operand buffers.  One warp per row
+// would waste lanes for short kc; a thread per row with the row of Y broadcast from shared memory is enough here.
 __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int64_t i, const DynSel* __restrict__ sel,
-                                                    double* __restrict__ xcol, double* __restrict__ ycol) {
+                                                    double* __restrict__ PX, double* __restrict__ PY, int64_t ldp,
+                                                    int kc) {
+  __shared__ double yi[MDB_NB];
+  for (int c = threadIdx.x; c < kc; c += 256) yi[c] = PY[i * ldp + c];   // Y[i, 0:kc]
+  __syncthreads();
   const int64_t j = i + 1 + (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= F.n) return;
   const double d = sel->d, w = sel->omega;
   const bool drop = sel->drop != 0.0;
   const double a = F.W[i * F.ldw + j];
   double r = a;
-  if (!drop) r = (1.0 - w) * a + w * F.W[j * F.ldw + i];
+  if (!drop) {
+    double s = F.W[j * F.ldw + i];
+    const double* xr = PX + j * ldp;
+    double s0 = 0, s1 = 0;
+    int c = 0;
+    for (; c + 1 < kc; c += 2) {
+      s0 = fma(xr[c], yi[c], s0);
+      s1 = fma(xr[c + 1], yi[c + 1], s1);
+    }
+    if (c < kc) s0 = fma(xr[c], yi[c], s0);
+    s += s0 + s1;
+    r = (1.0 - w) * a + w * s;
+  }
   const double x = (d != 0) ? r / d : 0.0;
   F.W[j * F.ldw + i] = x;
   F.alpha[j] += x * x * d;
   F.beta[j] += 2.0 * a * a;
   F.rowmax[j] = fmax(F.rowmax[j], fabs(x));
-  xcol[j] = x;
-  ycol[j] = -x * d;
-}
-
-// S(j, j') += x_j y_j' for j > j' > i
-__global__ void __launch_bounds__(256) k_dyn_rank1(int64_t n, double* __restrict__ W, int64_t ld, int64_t i,
-                                                   const double* __restrict__ xcol, const double* __restrict__ ycol) {
-  const int64_t j0 = i + 1 + (int64_t)blockIdx.y * 32, c0 = i + 1 + (int64_t)blockIdx.x * 32;
-  if (c0 > j0 + 31) return;  // tile above the diagonal
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int64_t c = c0 + tx;
-  if (c >= n) return;
-  const double y = ycol[c];
-  for (int r = ty; r < 32; r += 8) {
-    const int64_t j = j0 + r;
-    if (j < n && j > c) W[j * ld + c] += xcol[j] * y;
-  }
+  PX[j * ldp + kc] = x;
+  PY[j * ldp + kc] = -x * d;
 }
 
 __global__ void k_fill_iota(int64_t n, int64_t* __restrict__ p) {

@@ -1001,7 +1001,7 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
   int rc = mdb_factor_create(ctx, n, 1, &f);
   if (rc) return rc;
   rc = mdb_factor_set_matrix(f, A, lda, nullptr, loc);
-  double *minB = nullptr, *maxB = nullptr, *xcol = nullptr, *ycol = nullptr;
+  double *minB = nullptr, *maxB = nullptr;
   DynCand* cand = nullptr;
   DynSel* sel = nullptr;
   std::vector<int64_t> pfin((size_t)std::max<int64_t>(n, 1));
@@ -1015,8 +1015,6 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
     const int nb_max = (int)((n + 255) / 256);
     cudaError_t e = cudaMalloc((void**)&minB, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&maxB, (size_t)n * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&xcol, (size_t)n * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ycol, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&cand, (size_t)nb_max * sizeof(DynCand));
     if (e == cudaSuccess) e = cudaMalloc((void**)&sel, sizeof(DynSel));
     if (e == cudaSuccess && !f->p_dev) e = cudaMalloc((void**)&f->p_dev, (size_t)n * 8);
@@ -1035,18 +1033,36 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
       F.prm.min_diag_B = -INFINITY; F.prm.max_diag_B = INFINITY;
       f->rule = MDB_RULE_REIMER;
       f->mavL = bnd->min_abs_value_L;
-      for (int64_t i = 0; i < n; ++i) {
-        const int64_t rem = n - i;
-        const int nblk = (int)((rem + 255) / 256);
-        k_dyn_select1<<<nblk, 256, 0, ctx->stream>>>(F, method, i, cand);
-        k_dyn_select2<<<1, 256, 0, ctx->stream>>>(F, method, i, nblk, cand, minB, maxB, f->p_dev, sel);
-        k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, sel);
-        ctx->launches += 3;
-        if (rem > 1) {
-          k_dyn_column<<<(unsigned)((rem - 1 + 255) / 256), 256, 0, ctx->stream>>>(F, i, sel, xcol, ycol);
-          const unsigned t32 = (unsigned)((rem - 1 + 31) / 32);
-          k_dyn_rank1<<<dim3(t32, t32), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, xcol, ycol);
-          ctx->launches += 2;
+      // panels of NB columns: pending updates are applied on the fly inside a panel (k_dyn_column), the trailing
+      // matrix gets one K = NB tensor-core update per panel
+      const int64_t LDP = (int64_t)f->agg * NB;
+      for (int64_t pb = 0; pb < n && !rc; pb += NB) {
+        const int64_t pe = std::min<int64_t>(pb + NB, n);
+        for (int64_t i = pb; i < pe; ++i) {
+          const int64_t rem = n - i;
+          const int kc = (int)(i - pb);
+          const int nblk = (int)((rem + 255) / 256);
+          k_dyn_select1<<<nblk, 256, 0, ctx->stream>>>(F, method, i, cand);
+          k_dyn_select2<<<1, 256, 0, ctx->stream>>>(F, method, i, nblk, cand, minB, maxB, f->p_dev, sel);
+          k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, sel, f->PX, f->PY, LDP, kc);
+          ctx->launches += 3;
+          if (rem > 1) {
+            k_dyn_column<<<(unsigned)((rem - 1 + 255) / 256), 256, 0, ctx->stream>>>(F, i, sel, f->PX, f->PY, LDP, kc);
+            ctx->launches += 1;
+          }
+        }
+        if (pe < n) {
+          GemmArgs g;
+          memset(&g, 0, sizeof(g));
+          const int64_t rows = n - pe;
+          g.A = f->PX + pe * LDP; g.lda = LDP;
+          g.B = f->PY + pe * LDP; g.ldb = LDP;
+          g.C = f->W + pe * f->ld + pe; g.ldc = f->ld;
+          g.M = rows; g.N = rows; g.K = NB;
+          g.row_glob0 = pe; g.col_glob0 = pe; g.b_glob0 = pe; g.b_rows = rows;
+          int r = launch_gemm_tn_tma(ctx, g, rows, rows);
+          if (r == -1) r = launch_gemm_tn<true, true, false>(ctx, g, 1);
+          rc = r;
         }
       }
       cudaError_t e2 = cudaGetLastError();
@@ -1059,7 +1075,7 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
   } else if (!rc) {
     f->state = ST_FACTORED;
   }
-  cudaFree(minB); cudaFree(maxB); cudaFree(xcol); cudaFree(ycol); cudaFree(cand); cudaFree(sel);
+  cudaFree(minB); cudaFree(maxB); cudaFree(cand); cudaFree(sel);
   if (!rc) rc = mdb_factor_get(f, out_type, L, ldl, loc, d, omega, delta, clamped, nullptr);
   if (!rc && p_out)
     for (int64_t i = 0; i < n; ++i) p_out[i] = pfin[(size_t)i];
