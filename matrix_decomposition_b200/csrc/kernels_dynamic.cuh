@@ -66,7 +66,34 @@ __global__ void __launch_bounds__(256) k_dyn_select1(FactorDev F, int method, in
   if (threadIdx.x == 0) cand[blockIdx.x] = c;
 }
 
-// stage 2: best over blocks; swap the position-indexed vectors i <-> j*; record the decision
+// the decision for step i, given the best candidate c: swap the position-indexed vectors i <-> j*, record d / omega /
+// delta / clamped and what the swap and column kernels need.  One thread.
+__device__ __forceinline__ void dyn_commit(const FactorDev& F, int64_t i, const DynCand& c, double* __restrict__ minB,
+                                           double* __restrict__ maxB, int64_t* __restrict__ p, DynSel* __restrict__ sel) {
+  const int64_t js = c.j;
+  if (js != i) {  // Reimer.py:509-512 (p) -- and every per-row quantity kept in position order
+    double t;
+    t = F.gamma[i]; F.gamma[i] = F.gamma[js]; F.gamma[js] = t;
+    t = F.alpha[i]; F.alpha[i] = F.alpha[js]; F.alpha[js] = t;
+    t = F.beta[i]; F.beta[i] = F.beta[js]; F.beta[js] = t;
+    t = F.rowmax[i]; F.rowmax[i] = F.rowmax[js]; F.rowmax[js] = t;
+    t = minB[i]; minB[i] = minB[js]; minB[js] = t;
+    t = maxB[i]; maxB[i] = maxB[js]; maxB[js] = t;
+    const int64_t tp = p[i]; p[i] = p[js]; p[js] = tp;
+  }
+  const double alpha_i = F.alpha[i], gamma_i = F.gamma[i];
+  F.d[i] = c.d;
+  F.omega[i] = c.omega;
+  F.delta[i] = (c.d - gamma_i) + (c.omega != 0 ? c.omega * c.omega * alpha_i : 0.0);  // Reimer.py:541-545
+  F.clamped[i] = (uint8_t)c.clamped;
+  sel->d = c.d;
+  sel->omega = c.omega;
+  sel->drop = (c.omega == 0 || c.omega * F.rowmax[i] < F.prm.min_abs_value_L) ? 1.0 : 0.0;
+  sel->jstar = js;
+}
+
+// stage 2: best over blocks, then dyn_commit.  Only the first column goes through select1 / select2: afterwards
+// k_dyn_column evaluates the rule for the next step itself.
 __global__ void __launch_bounds__(256) k_dyn_select2(FactorDev F, int method, int64_t i, int nblocks,
                                                      const DynCand* __restrict__ cand, double* __restrict__ minB,
                                                      double* __restrict__ maxB, int64_t* __restrict__ p,
@@ -77,28 +104,7 @@ __global__ void __launch_bounds__(256) k_dyn_select2(FactorDev F, int method, in
   for (int b = threadIdx.x; b < nblocks; b += 256)
     if (dyn_better(method, cand[b], c)) c = cand[b];
   c = dyn_block_reduce(method, c, sh);
-  if (threadIdx.x == 0) {
-    const int64_t js = c.j;
-    if (js != i) {  // Reimer.py:509-512 (p) -- and every per-row quantity kept in position order
-      double t;
-      t = F.gamma[i]; F.gamma[i] = F.gamma[js]; F.gamma[js] = t;
-      t = F.alpha[i]; F.alpha[i] = F.alpha[js]; F.alpha[js] = t;
-      t = F.beta[i]; F.beta[i] = F.beta[js]; F.beta[js] = t;
-      t = F.rowmax[i]; F.rowmax[i] = F.rowmax[js]; F.rowmax[js] = t;
-      t = minB[i]; minB[i] = minB[js]; minB[js] = t;
-      t = maxB[i]; maxB[i] = maxB[js]; maxB[js] = t;
-      const int64_t tp = p[i]; p[i] = p[js]; p[js] = tp;
-    }
-    const double alpha_i = F.alpha[i], gamma_i = F.gamma[i];
-    F.d[i] = c.d;
-    F.omega[i] = c.omega;
-    F.delta[i] = (c.d - gamma_i) + (c.omega != 0 ? c.omega * c.omega * alpha_i : 0.0);  // Reimer.py:541-545
-    F.clamped[i] = (uint8_t)c.clamped;
-    sel->d = c.d;
-    sel->omega = c.omega;
-    sel->drop = (c.omega == 0 || c.omega * F.rowmax[i] < F.prm.min_abs_value_L) ? 1.0 : 0.0;
-    sel->jstar = js;
-  }
+  if (threadIdx.x == 0) dyn_commit(F, i, c, minB, maxB, p, sel);
 }
 
 // symmetric swap of indices i and j* in both triangles of W: S(a, b) lives at W[max][min], A(a, b) at W[min][max]
@@ -127,40 +133,74 @@ __global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict_
 }
 
 // column i for every row below: current Schur complement entry (stored value + the pending updates of this panel),
-// mix, divide, alpha / beta / rowmax; x and y = -x d go into column kc of the operand buffers.  One warp per row
-// would waste lanes for short kc; a thread per row with the row of Y broadcast from shared memory is enough here.
-__global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int64_t i, const DynSel* __restrict__ sel,
+// mix, divide, alpha / beta / rowmax; x and y = -x d go into column kc of the operand buffers.  A thread per row with
+// the row of Y broadcast from shared memory.  With its alpha / beta current, every row then evaluates the rule for
+// step i + 1; the block minima are merged by the last block to finish, which commits the decision for step i + 1
+// into sel_next (the two DynSel slots alternate, so no block can still be reading the slot being written).
+__global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, int64_t i, const DynSel* __restrict__ sel,
                                                     double* __restrict__ PX, double* __restrict__ PY, int64_t ldp,
-                                                    int kc) {
+                                                    int kc, DynCand* cand, unsigned* counter,
+                                                    double* __restrict__ minB, double* __restrict__ maxB,
+                                                    int64_t* __restrict__ p, DynSel* __restrict__ sel_next) {
   __shared__ double yi[MDB_NB];
+  __shared__ DynCand sh[256];
+  __shared__ bool s_last;
   for (int c = threadIdx.x; c < kc; c += 256) yi[c] = PY[i * ldp + c];   // Y[i, 0:kc]
   __syncthreads();
   const int64_t j = i + 1 + (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (j >= F.n) return;
-  const double d = sel->d, w = sel->omega;
-  const bool drop = sel->drop != 0.0;
-  const double a = F.W[i * F.ldw + j];
-  double r = a;
-  if (!drop) {
-    double s = F.W[j * F.ldw + i];
-    const double* xr = PX + j * ldp;
-    double s0 = 0, s1 = 0;
-    int c = 0;
-    for (; c + 1 < kc; c += 2) {
-      s0 = fma(xr[c], yi[c], s0);
-      s1 = fma(xr[c + 1], yi[c + 1], s1);
+  DynCand best;
+  best.j = -1; best.d = 0; best.omega = 0; best.f = 0; best.clamped = 0;
+  if (j < F.n) {
+    const double d = sel->d, w = sel->omega;
+    const bool drop = sel->drop != 0.0;
+    const double a = F.W[i * F.ldw + j];
+    double r = a;
+    if (!drop) {
+      double s = F.W[j * F.ldw + i];
+      const double* xr = PX + j * ldp;
+      double s0 = 0, s1 = 0;
+      int c = 0;
+      for (; c + 1 < kc; c += 2) {
+        s0 = fma(xr[c], yi[c], s0);
+        s1 = fma(xr[c + 1], yi[c + 1], s1);
+      }
+      if (c < kc) s0 = fma(xr[c], yi[c], s0);
+      s += s0 + s1;
+      r = (1.0 - w) * a + w * s;
     }
-    if (c < kc) s0 = fma(xr[c], yi[c], s0);
-    s += s0 + s1;
-    r = (1.0 - w) * a + w * s;
+    const double x = (d != 0) ? r / d : 0.0;
+    F.W[j * F.ldw + i] = x;
+    const double al = F.alpha[j] + x * x * d, be = F.beta[j] + 2.0 * a * a;
+    F.alpha[j] = al;
+    F.beta[j] = be;
+    F.rowmax[j] = fmax(F.rowmax[j], fabs(x));
+    PX[j * ldp + kc] = x;
+    PY[j * ldp + kc] = -x * d;
+    const MdDecision dec = md_decide(F.prm, al, be, F.gamma[j], minB[j], maxB[j]);
+    best.d = dec.d; best.omega = dec.omega; best.f = dec.f; best.clamped = dec.clamped; best.j = j;
   }
-  const double x = (d != 0) ? r / d : 0.0;
-  F.W[j * F.ldw + i] = x;
-  F.alpha[j] += x * x * d;
-  F.beta[j] += 2.0 * a * a;
-  F.rowmax[j] = fmax(F.rowmax[j], fabs(x));
-  PX[j * ldp + kc] = x;
-  PY[j * ldp + kc] = -x * d;
+  best = dyn_block_reduce(method, best, sh);
+  if (threadIdx.x == 0) {
+    cand[blockIdx.x] = best;
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  DynCand c;
+  c.j = -1; c.d = 0; c.omega = 0; c.f = 0; c.clamped = 0;
+  for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) {
+    const volatile DynCand* vc = cand + b;   // written by other blocks of this launch
+    DynCand o;
+    o.d = vc->d; o.omega = vc->omega; o.f = vc->f; o.j = vc->j; o.clamped = vc->clamped;
+    if (dyn_better(method, o, c)) c = o;
+  }
+  c = dyn_block_reduce(method, c, sh);
+  if (threadIdx.x == 0) {
+    *counter = 0;
+    dyn_commit(F, i + 1, c, minB, maxB, p, sel_next);
+  }
 }
 
 __global__ void k_fill_iota(int64_t n, int64_t* __restrict__ p) {

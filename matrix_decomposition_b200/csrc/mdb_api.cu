@@ -1016,7 +1016,7 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
     cudaError_t e = cudaMalloc((void**)&minB, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&maxB, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&cand, (size_t)nb_max * sizeof(DynCand));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&sel, sizeof(DynSel));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sel, 2 * sizeof(DynSel) + 16);
     if (e == cudaSuccess && !f->p_dev) e = cudaMalloc((void**)&f->p_dev, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(minB, mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(maxB, Mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -1025,6 +1025,8 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
     if (e != cudaSuccess) rc = mdb_fail(ctx, MDB_ERR_CUDA, "mdb_approximate_dynamic_f64: %s", cudaGetErrorString(e));
     if (!rc) {
       k_fill_iota<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->p_dev);
+      unsigned* counter = (unsigned*)(sel + 2);   // blocks of k_dyn_column that have finished
+      cudaMemsetAsync(counter, 0, sizeof(unsigned), ctx->stream);
       FactorDev F = make_dev(f);
       F.minB = minB; F.maxB = maxB;
       F.prm.rule = MD_RULE_REIMER;
@@ -1041,13 +1043,18 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
         for (int64_t i = pb; i < pe; ++i) {
           const int64_t rem = n - i;
           const int kc = (int)(i - pb);
-          const int nblk = (int)((rem + 255) / 256);
-          k_dyn_select1<<<nblk, 256, 0, ctx->stream>>>(F, method, i, cand);
-          k_dyn_select2<<<1, 256, 0, ctx->stream>>>(F, method, i, nblk, cand, minB, maxB, f->p_dev, sel);
-          k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, sel, f->PX, f->PY, LDP, kc);
-          ctx->launches += 3;
+          DynSel* cur = sel + (i & 1);
+          if (i == 0) {  // later columns are selected by the column kernel of the step before
+            const int nblk = (int)((rem + 255) / 256);
+            k_dyn_select1<<<nblk, 256, 0, ctx->stream>>>(F, method, i, cand);
+            k_dyn_select2<<<1, 256, 0, ctx->stream>>>(F, method, i, nblk, cand, minB, maxB, f->p_dev, cur);
+            ctx->launches += 2;
+          }
+          k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, cur, f->PX, f->PY, LDP, kc);
+          ctx->launches += 1;
           if (rem > 1) {
-            k_dyn_column<<<(unsigned)((rem - 1 + 255) / 256), 256, 0, ctx->stream>>>(F, i, sel, f->PX, f->PY, LDP, kc);
+            k_dyn_column<<<(unsigned)((rem - 1 + 255) / 256), 256, 0, ctx->stream>>>(
+                F, method, i, cur, f->PX, f->PY, LDP, kc, cand, counter, minB, maxB, f->p_dev, sel + ((i + 1) & 1));
             ctx->launches += 1;
           }
         }
