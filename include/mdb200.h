@@ -61,7 +61,8 @@ typedef struct mdb_bounds {
 
 /* ---- context ---- */
 int mdb_version(void);
-/* Creates a context on `device`.  MDB_ERR_NO_DEVICE when CUDA is unavailable (no CPU fallback). */
+/* Creates a context on `device`.  MDB_ERR_NO_DEVICE when CUDA is unavailable (no CPU fallback).  When the call
+ * fails after the context was allocated, *out still receives it so that mdb_last_error() can be read; destroy it. */
 int mdb_ctx_create(int device, mdb_ctx **out);
 int mdb_ctx_destroy(mdb_ctx *ctx);
 /* Use an existing stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the own stream. */

@@ -152,6 +152,9 @@ class Context:
         self.device = int(device)
         if rc != MDB_OK:
             msg = self.lib.mdb_last_error(h).decode() if h else ''
+            if h:
+                self.lib.mdb_ctx_destroy(h)
+                self.handle = None
             raise errors.NativeLibraryError(
                 'no usable CUDA device (mdb_ctx_create(device={}) returned {}{}). This package runs on the GPU only; '
                 'there is no CPU fallback.'.format(device, rc, ': ' + msg if msg else ''))

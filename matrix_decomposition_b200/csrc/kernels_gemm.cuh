@@ -208,12 +208,12 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) k_gemm_tn(GemmArgs g) {
 template <bool LOWER, bool BETA1, bool NEG>
 static int launch_gemm_tn(mdb_ctx* ctx, const GemmArgs& g0, int64_t batch) {
   using namespace gemm;
-  static bool configured = false;
+  static uint64_t configured = 0;
   auto kern = k_gemm_tn<LOWER, BETA1, NEG>;
-  if (!configured) {
+  if (!mdb_device_marked(configured, ctx)) {
     MDB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     MDB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    configured = true;
+    mdb_mark_device(configured, ctx);
   }
   GemmArgs g = g0;
   const int64_t m_tiles = (g.M + BM - 1) / BM - g.m_tile0;

@@ -252,11 +252,11 @@ static int launch_gemm_tn_tma(mdb_ctx* ctx, const GemmArgs& g0, int64_t a_rows, 
   using namespace gemm;
   if (!ctx->use_tma || g0.K % BK != 0 || g0.lda % 2 != 0 || g0.ldb % 2 != 0) return -1;
   if (((uintptr_t)g0.A & 15) || ((uintptr_t)g0.B & 15)) return -1;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (!mdb_device_marked(configured, ctx)) {
     if (cudaFuncSetAttribute(k_gemm_tn_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return -1;
     cudaFuncSetAttribute(k_gemm_tn_tma, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    configured = true;
+    mdb_mark_device(configured, ctx);
   }
   CUtensorMap tmA, tmB;
   if (!mdb_make_operand_map(&tmA, g0.A, a_rows, g0.K, g0.lda, BM)) return -1;

@@ -71,6 +71,7 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
   if (!ctx) return MDB_ERR_INVALID;
   memset(ctx, 0, sizeof(*ctx));
   ctx->device = device;
+  *out = ctx;  // also on failure: the caller reads mdb_last_error() and then destroys the context
   MDB_CUDA(ctx, cudaSetDevice(device));
   {
     int lo_pri = 0, hi_pri = 0;
@@ -114,11 +115,8 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
   if (prop.major < 10) {
     snprintf(ctx->err, sizeof(ctx->err), "device %d is sm_%d%d; libmdb200 is built for sm_100a only", device,
              prop.major, prop.minor);
-    // keep the context so the caller can read the message, but report the failure
-    *out = ctx;
     return MDB_ERR_NO_DEVICE;
   }
-  *out = ctx;
   return MDB_OK;
 }
 
@@ -382,15 +380,20 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   f->gamma = f->vec; f->alpha = f->vec + bn; f->beta = f->vec + 2 * bn; f->rowmax = f->vec + 3 * bn;
   f->d = f->vec + 4 * bn; f->omega = f->vec + 5 * bn; f->delta = f->vec + 6 * bn;
   // zero everything once: the padding columns of W (ld > n) must stay zero for the solve kernels
-  MDB_CUDA(ctx, cudaMemsetAsync(f->W, 0, (size_t)batch * nn * f->ld * 8, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->vec, 0, (size_t)7 * bn * 8, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->clamped, 0, (size_t)bn, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->Ut, 0, (size_t)batch * NB * NB * 8, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->PX, 0, panel_bytes, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->PY, 0, panel_bytes, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->PX2, 0, panel_bytes, ctx->stream));
-  MDB_CUDA(ctx, cudaMemsetAsync(f->PY2, 0, panel_bytes, ctx->stream));
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->W, 0, (size_t)batch * nn * f->ld * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->vec, 0, (size_t)7 * bn * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->clamped, 0, (size_t)bn, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->Ut, 0, (size_t)batch * NB * NB * 8, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->PX, 0, panel_bytes, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->PY, 0, panel_bytes, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->PX2, 0, panel_bytes, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->PY2, 0, panel_bytes, ctx->stream);
+  if (e != cudaSuccess) {
+    snprintf(ctx->err, sizeof(ctx->err), "mdb_factor_create: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    factor_release(f);
+    return MDB_ERR_CUDA;
+  }
   *out = f;
   return MDB_OK;
 }
@@ -436,10 +439,10 @@ static int gather_sym(mdb_ctx* ctx, int64_t n, int64_t batch, const double* A_de
   int C = 1;
   while (C < 8 && (int64_t)C * chunk < n) C *= 2;
   if (!upper_only && ctx->use_cluster_gather && (int64_t)C * chunk >= n && n * C <= 0x7fffffff) {
-    static bool configured = false;
-    if (!configured) {
+    static uint64_t configured = 0;
+    if (!mdb_device_marked(configured, ctx)) {
       MDB_CUDA(ctx, cudaFuncSetAttribute(k_gather_sym_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-      configured = true;
+      mdb_mark_device(configured, ctx);
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -588,15 +591,15 @@ static FactorDev make_dev(mdb_factor* f) {
 }
 
 static int configure_kernels(mdb_ctx* ctx) {
-  static bool done = false;
-  if (done) return MDB_OK;
+  static uint64_t done = 0;
+  if (mdb_device_marked(done, ctx)) return MDB_OK;
   const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
   const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
   const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel<NB, PANEL_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_blocks<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
-  done = true;
+  mdb_mark_device(done, ctx);
   return MDB_OK;
 }
 
@@ -1336,12 +1339,12 @@ static int trsv_prepare(mdb_factor* f, int nrhs) {
     MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_partial, (size_t)T * NC * nrhs * NB * 8));
     f->trsv_partial_rhs = nrhs;
   }
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;
+  if (!mdb_device_marked(configured, ctx)) {
     const int smem = (NB * NB + 2 * 8 * NB) * 8;
     MDB_CUDA(ctx, cudaFuncSetAttribute(k_trsv_persistent<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     MDB_CUDA(ctx, cudaFuncSetAttribute(k_trsv_persistent<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    mdb_mark_device(configured, ctx);
   }
   return MDB_OK;
 }

@@ -66,6 +66,10 @@ static inline int mdb_fail(mdb_ctx* ctx, int code, const char* fmt, const char* 
 
 #define MDB_LAUNCHED(ctx) ((ctx)->launches++)
 
+// cudaFuncSetAttribute is per device: the "already configured" marks of the launchers are bit masks over devices
+static inline bool mdb_device_marked(const uint64_t& mask, const mdb_ctx* ctx) { return (mask >> (ctx->device & 63)) & 1ull; }
+static inline void mdb_mark_device(uint64_t& mask, const mdb_ctx* ctx) { mask |= 1ull << (ctx->device & 63); }
+
 static inline int64_t mdb_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ------------------------------------------------------------------------------------------------
