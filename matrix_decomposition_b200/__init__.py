@@ -24,6 +24,15 @@ from .constants import (  # noqa: E402,F401
 __version__ = '0.1.0'
 
 
+def release_device_memory():
+    """Not in the reference: returns the device buffers that libmdb200 keeps between calls (the working matrix and
+    the upload staging area of the last large factorization, mdb_ctx_trim in include/mdb200.h) to the CUDA driver,
+    e.g. before another library in the same process needs the memory."""
+    from . import _native
+    for ctx in list(_native._contexts.values()):
+        ctx.trim()
+
+
 def __getattr__(name):
     """Deprecated aliases of the reference (matrix/__init__.py:45-55)."""
     deprecated_names = ['decomposition', 'positive_definite_matrix', 'positive_semidefinite_matrix',

@@ -57,6 +57,7 @@ SIGNATURES = {
     'mdb_ctx_create': (_int, [_int, _pp]),
     'mdb_ctx_destroy': (_int, [_vp]),
     'mdb_ctx_set_stream': (_int, [_vp, _vp]),
+    'mdb_ctx_trim': (_int, [_vp]),
     'mdb_ctx_synchronize': (_int, [_vp]),
     'mdb_last_error': (ctypes.c_char_p, [_vp]),
     'mdb_launch_count': (_i64, [_vp]),
@@ -174,6 +175,10 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.mdb_ctx_synchronize(self.handle), 'mdb_ctx_synchronize')
+
+    def trim(self):
+        """Returns the cached working buffers (mdb_ctx_trim) to the driver."""
+        self.check(self.lib.mdb_ctx_trim(self.handle), 'mdb_ctx_trim')
 
     def set_stream(self, cuda_stream):
         self.check(self.lib.mdb_ctx_set_stream(self.handle, ctypes.c_void_p(cuda_stream or 0)), 'mdb_ctx_set_stream')

@@ -23,6 +23,7 @@ struct mdb_factor {
   mdb_ctx* ctx;
   int64_t n, ld, batch;
   double* W;         // batch x n x ld
+  size_t W_cap;      // bytes behind W (for the context's buffer cache)
   double* vec;       // 7 x batch x n: gamma, alpha, beta, rowmax, d, omega, delta
   double *gamma, *alpha, *beta, *rowmax, *d, *omega, *delta;
   uint8_t* clamped;  // batch x n
@@ -59,6 +60,68 @@ static void ctx_reap(mdb_ctx* ctx) {
   }
 }
 
+// ---- device memory ----
+// The two largest buffers of a factorization (the working matrix and the upload staging area, 34 GB each at
+// n = 65536) are kept in the context when they are released and handed out again to the next call that needs the
+// same amount: cudaMalloc + cudaFree of that size cost ~0.1 s per call.  mdb_ctx_trim() gives them back to the driver;
+// any allocation of the library that fails trims the cache and tries once more.  MDB200_CACHE=0 disables the cache.
+static void ctx_trim(mdb_ctx* ctx) {
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->big_ptr[i]) cudaFree(ctx->big_ptr[i]);
+    ctx->big_ptr[i] = nullptr;
+    ctx->big_bytes[i] = 0;
+  }
+}
+
+static cudaError_t dev_malloc(mdb_ctx* ctx, void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation && (ctx->big_ptr[0] || ctx->big_ptr[1])) {
+    cudaGetLastError();
+    ctx_trim(ctx);
+    e = cudaMalloc(p, bytes);
+  }
+  return e;
+}
+
+// *cap receives the size to pass to big_free (the cached buffer may be a little larger than asked for)
+static cudaError_t big_malloc(mdb_ctx* ctx, void** p, size_t bytes, size_t* cap) {
+  for (int i = 0; i < 2; ++i)
+    if (ctx->big_ptr[i] && ctx->big_bytes[i] >= bytes && ctx->big_bytes[i] - bytes <= bytes / 8) {
+      *p = ctx->big_ptr[i];
+      *cap = ctx->big_bytes[i];
+      ctx->big_ptr[i] = nullptr;
+      ctx->big_bytes[i] = 0;
+      return cudaSuccess;
+    }
+  *cap = bytes;
+  return dev_malloc(ctx, p, bytes);
+}
+
+// Caller's thread only (never the reaper), and only after the work that used the buffer has completed.
+static void big_free(mdb_ctx* ctx, void* p, size_t cap) {
+  if (!p) return;
+  if (ctx->use_cache && cap >= ((size_t)256 << 20)) {
+    int slot = !ctx->big_ptr[0] ? 0 : !ctx->big_ptr[1] ? 1 : (ctx->big_bytes[0] <= ctx->big_bytes[1] ? 0 : 1);
+    if (ctx->big_ptr[slot] && ctx->big_bytes[slot] > cap) {  // both slots hold larger buffers: keep those
+      cudaFree(p);
+      return;
+    }
+    if (ctx->big_ptr[slot]) cudaFree(ctx->big_ptr[slot]);
+    ctx->big_ptr[slot] = p;
+    ctx->big_bytes[slot] = cap;
+    return;
+  }
+  cudaFree(p);
+}
+
+extern "C" int mdb_ctx_trim(mdb_ctx* ctx) {
+  if (!ctx) return MDB_ERR_INVALID;
+  ctx_reap(ctx);
+  cudaSetDevice(ctx->device);
+  ctx_trim(ctx);
+  return MDB_OK;
+}
+
 extern "C" int mdb_version(void) { return 100; }
 
 extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
@@ -90,6 +153,8 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
     ctx->use_tma = !(tm && tm[0] == '0');
     const char* tv = getenv("MDB200_TRSV");
     ctx->use_trsv = !(tv && tv[0] == '0');
+    const char* cch = getenv("MDB200_CACHE");
+    ctx->use_cache = !(cch && cch[0] == '0');
     const char* cgv = getenv("MDB200_CLUSTER_GATHER");
     ctx->use_cluster_gather = !(cgv && cgv[0] == '0');
     // outer block width of the factorization: MDB200_AGG = 1, 2, 4, 8 panels (fixed) or unset = by remaining size,
@@ -124,6 +189,7 @@ extern "C" int mdb_ctx_destroy(mdb_ctx* ctx) {
   if (!ctx) return MDB_OK;
   ctx_reap(ctx);
   cudaSetDevice(ctx->device);
+  ctx_trim(ctx);
   for (int i = 0; i < 3; ++i) {
     if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
     if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
@@ -189,7 +255,7 @@ extern "C" int mdb_malloc(mdb_ctx* ctx, size_t bytes, void** dptr) {
   if (!ctx || !dptr) return MDB_ERR_INVALID;
   ctx_reap(ctx);
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
-  MDB_CUDA(ctx, cudaMalloc(dptr, bytes ? bytes : 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, dptr, bytes ? bytes : 8));
   return MDB_OK;
 }
 extern "C" int mdb_free(mdb_ctx* ctx, void* dptr) {
@@ -323,6 +389,14 @@ extern "C" int mdb_memcpy2d(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void*
 // ------------------------------------------------------------------------------------------------
 // factor object
 // ------------------------------------------------------------------------------------------------
+// W goes back to the context's cache: call on the caller's thread, after the factor's work has completed, before
+// factor_release (which may then run on the reaper thread).
+static void factor_detach_W(mdb_factor* f) {
+  big_free(f->ctx, f->W, f->W_cap);
+  f->W = nullptr;
+  f->W_cap = 0;
+}
+
 static void factor_release(mdb_factor* f) {
   if (!f) return;
   cudaSetDevice(f->ctx->device);
@@ -360,8 +434,9 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   }
   const size_t panel_bytes = (size_t)batch * f->panel_rows * f->agg * NB * 8;
   cudaError_t e = cudaSuccess;
-  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8); };
-  A((void**)&f->W, (size_t)batch * nn * f->ld * 8);
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = dev_malloc(ctx, p, bytes ? bytes : 8); };
+  f->W_cap = 0;
+  e = big_malloc(ctx, (void**)&f->W, (size_t)batch * nn * f->ld * 8, &f->W_cap);
   A((void**)&f->vec, (size_t)7 * batch * nn * 8);
   A((void**)&f->clamped, (size_t)batch * nn);
   A((void**)&f->info, (size_t)(batch + 1) * sizeof(int));
@@ -400,7 +475,9 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
 
 extern "C" int mdb_factor_destroy(mdb_factor* f) {
   if (f) {
+    cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
+    factor_detach_W(f);
     factor_release(f);
   }
   return MDB_OK;
@@ -423,7 +500,7 @@ static int factor_set_p(mdb_factor* f, const int64_t* p) {
     }
   }
   f->p_host.assign(p, p + bn);
-  if (!f->p_dev) MDB_CUDA(ctx, cudaMalloc((void**)&f->p_dev, (size_t)std::max<int64_t>(bn, 1) * 8));
+  if (!f->p_dev) MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->p_dev, (size_t)std::max<int64_t>(bn, 1) * 8));
   MDB_CUDA(ctx, cudaMemcpyAsync(f->p_dev, p, (size_t)bn * 8, cudaMemcpyHostToDevice, ctx->stream));
   MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MDB_OK;
@@ -483,10 +560,11 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
   if (n == 0) { f->state = ST_MATRIX; return MDB_OK; }
   const double* A_dev = A;
   double* staging = nullptr;
+  size_t staging_cap = 0;
   int64_t lds = lda;
   int upper_only = 0;
   if (a_loc == MDB_HOST) {
-    MDB_CUDA(ctx, cudaMalloc((void**)&staging, (size_t)f->batch * n * n * 8));
+    MDB_CUDA(ctx, big_malloc(ctx, (void**)&staging, (size_t)f->batch * n * n * 8, &staging_cap));
     if (f->batch == 1 && n >= 4096) {
       // A is symmetric: only its upper triangle crosses PCIe (row blocks [r0, r0 + RB) x columns [r0, n)),
       // the gather mirrors it.  Half the bytes of the full copy.
@@ -502,7 +580,7 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
     } else {
       rc = copy2d_async(ctx, staging, n, A, lda, f->batch * n, n, MDB_DEVICE, MDB_HOST);  // batch stride = n*lda
     }
-    if (rc) { cudaFree(staging); return rc; }
+    if (rc) { cudaStreamSynchronize(ctx->stream); big_free(ctx, staging, staging_cap); return rc; }
     A_dev = staging;
     lds = n;
   }
@@ -513,7 +591,10 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
   int bad = 0;
   cudaError_t ef = cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   if (ef == cudaSuccess) ef = cudaStreamSynchronize(ctx->stream);
-  if (staging) cudaFree(staging);
+  if (staging) {
+    if (ef != cudaSuccess) cudaStreamSynchronize(ctx->stream);
+    big_free(ctx, staging, staging_cap);   // the stream has been synchronised: nothing reads it any more
+  }
   if (rc) return rc;
   MDB_CUDA(ctx, ef);
   ctx->last_input_nonfinite = bad;
@@ -526,7 +607,7 @@ extern "C" int mdb_generate_diag_f2(mdb_ctx* ctx, int64_t n, uint64_t seed, doub
   if (!ctx || !diag_host) return MDB_ERR_INVALID;
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   double* dd = nullptr;
-  MDB_CUDA(ctx, cudaMalloc((void**)&dd, (size_t)std::max<int64_t>(n, 1) * 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&dd, (size_t)std::max<int64_t>(n, 1) * 8));
   if (n > 0) {
     k_generate_f2_diag<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, seed, mu, dd);
     MDB_LAUNCHED(ctx);
@@ -645,8 +726,8 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
           mb[(size_t)(b * n + i)] = bnd->min_diag_B[pi * bnd->stride_B];
           Mb[(size_t)(b * n + i)] = bnd->max_diag_B[pi * bnd->stride_B];
         }
-      MDB_CUDA(ctx, cudaMalloc((void**)&f->minB, (size_t)bn * 8));
-      MDB_CUDA(ctx, cudaMalloc((void**)&f->maxB, (size_t)bn * 8));
+      MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->minB, (size_t)bn * 8));
+      MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->maxB, (size_t)bn * 8));
       MDB_CUDA(ctx, cudaMemcpyAsync(f->minB, mb.data(), (size_t)bn * 8, cudaMemcpyHostToDevice, ctx->stream));
       MDB_CUDA(ctx, cudaMemcpyAsync(f->maxB, Mb.data(), (size_t)bn * 8, cudaMemcpyHostToDevice, ctx->stream));
       MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -892,21 +973,21 @@ extern "C" int mdb_factor_psd_matrix(mdb_factor* f, const double* min_diag_B, co
   const int64_t nb = stride_B != 0 ? n : 1, ldd = (loc == MDB_DEVICE) ? ldb : n;
   cudaError_t e = cudaSuccess;
   if (min_diag_B) {
-    e = cudaMalloc((void**)&mB, (size_t)nb * 8);
+    e = dev_malloc(ctx, (void**)&mB, (size_t)nb * 8);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(mB, 8, min_diag_B, (size_t)std::max<int64_t>(stride_B, 1) * 8, 8, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream);
   }
   if (e == cudaSuccess && max_diag_B) {
-    e = cudaMalloc((void**)&MB, (size_t)nb * 8);
+    e = dev_malloc(ctx, (void**)&MB, (size_t)nb * 8);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(MB, 8, max_diag_B, (size_t)std::max<int64_t>(stride_B, 1) * 8, 8, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream);
   }
   if (e == cudaSuccess && f->p_dev) {
-    e = cudaMalloc((void**)&q, (size_t)n * 8);
+    e = dev_malloc(ctx, (void**)&q, (size_t)n * 8);
     if (e == cudaSuccess) {
       k_invert_permutation<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->p_dev, q);
       MDB_LAUNCHED(ctx);
     }
   }
-  if (e == cudaSuccess && !Bd) e = cudaMalloc((void**)&Bd, (size_t)n * n * 8);
+  if (e == cudaSuccess && !Bd) e = dev_malloc(ctx, (void**)&Bd, (size_t)n * n * 8);
   int rc = MDB_OK;
   if (e == cudaSuccess) {
     dim3 grid((unsigned)n, (unsigned)((n + 1023) / 1024));
@@ -969,6 +1050,7 @@ static int one_shot(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int
     // the results are complete; the tens of GB of device buffers are released in the background
     cudaStreamSynchronize(ctx->stream);
     ctx_reap(ctx);
+    factor_detach_W(f);
     mdb_factor* dead = f;
     ctx->reaper = new (std::nothrow) std::thread([dead]() { factor_release(dead); });
     if (!ctx->reaper) factor_release(dead);
@@ -1016,11 +1098,11 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
       Mb[(size_t)i] = bnd->max_diag_B ? bnd->max_diag_B[i * bnd->stride_B] : INFINITY;
     }
     const int nb_max = (int)((n + 255) / 256);
-    cudaError_t e = cudaMalloc((void**)&minB, (size_t)n * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&maxB, (size_t)n * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&cand, (size_t)nb_max * sizeof(DynCand));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&sel, 2 * sizeof(DynSel) + 16);
-    if (e == cudaSuccess && !f->p_dev) e = cudaMalloc((void**)&f->p_dev, (size_t)n * 8);
+    cudaError_t e = dev_malloc(ctx, (void**)&minB, (size_t)n * 8);
+    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&maxB, (size_t)n * 8);
+    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&cand, (size_t)nb_max * sizeof(DynCand));
+    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&sel, 2 * sizeof(DynSel) + 16);
+    if (e == cudaSuccess && !f->p_dev) e = dev_malloc(ctx, (void**)&f->p_dev, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(minB, mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(maxB, Mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(f->alpha, 0, (size_t)3 * n * 8, ctx->stream);
@@ -1111,10 +1193,10 @@ extern "C" int mdb_gmw_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   double *W = nullptr, *cvec = nullptr, *dd = nullptr;
   GmwState* st = nullptr;
-  cudaError_t e = cudaMalloc((void**)&W, (size_t)n * n * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&cvec, (size_t)n * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&dd, (size_t)2 * n * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&st, sizeof(GmwState));
+  cudaError_t e = dev_malloc(ctx, (void**)&W, (size_t)n * n * 8);
+  if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&cvec, (size_t)n * 8);
+  if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&dd, (size_t)2 * n * 8);
+  if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&st, sizeof(GmwState));
   int rc = MDB_OK;
   if (e == cudaSuccess) rc = copy2d_async(ctx, W, n, A, lda, n, n, MDB_DEVICE, loc);
   if (e == cudaSuccess && !rc) {
@@ -1212,15 +1294,15 @@ extern "C" int mdb_permute_sym_f64(mdb_ctx* ctx, int64_t n, const double* A, int
       if (p[i] < 0 || p[i] >= n || seen[(size_t)p[i]]) return mdb_fail(ctx, MDB_ERR_INVALID, "%s", "p is not a permutation");
       seen[(size_t)p[i]] = 1;
     }
-    e = cudaMalloc((void**)&p_dev, (size_t)n * 8);
+    e = dev_malloc(ctx, (void**)&p_dev, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p_dev, p, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
   }
   const double* src = A;
   double* dst = B;
   int64_t lsrc = lda, ldst = ldb;
   if (e == cudaSuccess && loc == MDB_HOST) {
-    e = cudaMalloc((void**)&A_dev, (size_t)n * n * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&B_dev, (size_t)n * n * 8);
+    e = dev_malloc(ctx, (void**)&A_dev, (size_t)n * n * 8);
+    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&B_dev, (size_t)n * n * 8);
     if (e == cudaSuccess) rc = copy2d_async(ctx, A_dev, n, A, lda, n, n, MDB_DEVICE, MDB_HOST);
     src = A_dev; dst = B_dev; lsrc = n; ldst = n;
   }
@@ -1275,10 +1357,10 @@ static int factor_prepare(mdb_factor* f) {
   const int64_t T = (n + NB - 1) / NB;
   const size_t bytes = (size_t)T * NB * NB * 8;
   if (!f->Linv) {
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->Linv, bytes));
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->LinvT, bytes));
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->Ltri, bytes));
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->Utri, bytes));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->Linv, bytes));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->LinvT, bytes));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->Ltri, bytes));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->Utri, bytes));
   }
   const int64_t t32 = (n + 31) / 32;
   k_symmetrize<<<dim3((unsigned)t32, (unsigned)t32), 256, 0, ctx->stream>>>(n, f->W, f->ld);
@@ -1328,15 +1410,15 @@ static int trsv_prepare(mdb_factor* f, int nrhs) {
       }
     }
     f->trsv_ntasks = (int)tasks.size();
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(int2)));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->trsv_tasks, std::max<size_t>(tasks.size(), 1) * sizeof(int2)));
     MDB_CUDA(ctx, cudaMemcpyAsync(f->trsv_tasks, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `tasks` goes out of scope
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_sync, 2 * sizeof(unsigned int)));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->trsv_sync, 2 * sizeof(unsigned int)));
   }
   if (f->trsv_partial_rhs < nrhs) {
     if (f->trsv_partial) cudaFree(f->trsv_partial);
     f->trsv_partial = nullptr;
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->trsv_partial, (size_t)T * NC * nrhs * NB * 8));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->trsv_partial, (size_t)T * NC * nrhs * NB * 8));
     f->trsv_partial_rhs = nrhs;
   }
   static uint64_t configured = 0;
@@ -1394,7 +1476,7 @@ static int ws_get(mdb_factor* f, int i, size_t bytes, double** out) {
   if (f->ws_cap[i] < bytes) {
     if (f->ws[i]) cudaFree(f->ws[i]);
     f->ws[i] = nullptr; f->ws_cap[i] = 0;
-    MDB_CUDA(ctx, cudaMalloc((void**)&f->ws[i], bytes));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&f->ws[i], bytes));
     f->ws_cap[i] = bytes;
   }
   *out = f->ws[i];
@@ -1589,11 +1671,11 @@ extern "C" int mdb_factor_identity_residual(mdb_factor* f, int nprobe, uint64_t 
   // solve path it finalises the factor (LDL) afterwards and uses mdb_factor_multiply.
   double *v = nullptr, *yb = nullptr, *ya = nullptr, *lhs = nullptr;
   unsigned long long* mx = nullptr;
-  MDB_CUDA(ctx, cudaMalloc((void**)&v, (size_t)nprobe * n * 8));
-  MDB_CUDA(ctx, cudaMalloc((void**)&yb, (size_t)nprobe * n * 8));
-  MDB_CUDA(ctx, cudaMalloc((void**)&ya, (size_t)nprobe * n * 8));
-  MDB_CUDA(ctx, cudaMalloc((void**)&lhs, (size_t)nprobe * n * 8));
-  MDB_CUDA(ctx, cudaMalloc((void**)&mx, 16));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&v, (size_t)nprobe * n * 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&yb, (size_t)nprobe * n * 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&ya, (size_t)nprobe * n * 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&lhs, (size_t)nprobe * n * 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&mx, 16));
   MDB_CUDA(ctx, cudaMemsetAsync(yb, 0, (size_t)nprobe * n * 8, ctx->stream));
   MDB_CUDA(ctx, cudaMemsetAsync(ya, 0, (size_t)nprobe * n * 8, ctx->stream));
   MDB_CUDA(ctx, cudaMemsetAsync(mx, 0, 16, ctx->stream));
@@ -1613,8 +1695,8 @@ extern "C" int mdb_factor_identity_residual(mdb_factor* f, int nprobe, uint64_t 
   double* vcol = nullptr;
   double* lcol = nullptr;
   if (!rc) {
-    cudaError_t e = cudaMalloc((void**)&vcol, (size_t)nprobe * n * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&lcol, (size_t)nprobe * n * 8);
+    cudaError_t e = dev_malloc(ctx, (void**)&vcol, (size_t)nprobe * n * 8);
+    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&lcol, (size_t)nprobe * n * 8);
     if (e != cudaSuccess) rc = mdb_fail(ctx, MDB_ERR_CUDA, "%s", cudaGetErrorString(e));
   }
   if (!rc) {
@@ -1671,9 +1753,9 @@ extern "C" int mdb_debug_gemm_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
   MDB_CHECK(ctx, M > 0 && N > 0 && K > 0 && K % 16 == 0, "mdb_debug_gemm_tn: bad shape");
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   double *dA = nullptr, *dB = nullptr, *dC = nullptr;
-  MDB_CUDA(ctx, cudaMalloc((void**)&dA, (size_t)M * K * 8));
-  MDB_CUDA(ctx, cudaMalloc((void**)&dB, (size_t)N * K * 8));
-  MDB_CUDA(ctx, cudaMalloc((void**)&dC, (size_t)M * N * 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&dA, (size_t)M * K * 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&dB, (size_t)N * K * 8));
+  MDB_CUDA(ctx, dev_malloc(ctx, (void**)&dC, (size_t)M * N * 8));
   int rc = copy2d_async(ctx, dA, K, A, lda, M, K, MDB_DEVICE, MDB_HOST);
   if (!rc) rc = copy2d_async(ctx, dB, K, B, ldb, N, K, MDB_DEVICE, MDB_HOST);
   if (!rc) rc = copy2d_async(ctx, dC, N, C, ldc, M, N, MDB_DEVICE, MDB_HOST);

@@ -77,17 +77,17 @@ extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, dou
   s->pcol_dev = nullptr; s->have_bounds = false;
   s->OPX[0] = s->OPX[1] = s->OPY[0] = s->OPY[1] = nullptr;
   s->ldp = dist_outer_width(ctx, n, 0) * NB;  // the first outer block is the widest
-  cudaError_t e = cudaMalloc((void**)&s->vec, (size_t)7 * n * 8);
+  cudaError_t e = dev_malloc(ctx, (void**)&s->vec, (size_t)7 * n * 8);
   for (int i = 0; i < 2; ++i) {
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->OPX[i], (size_t)n * s->ldp * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->OPY[i], (size_t)n * s->ldp * 8);
+    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->OPX[i], (size_t)n * s->ldp * 8);
+    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->OPY[i], (size_t)n * s->ldp * 8);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->OPX[i], 0, (size_t)n * s->ldp * 8, ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->OPY[i], 0, (size_t)n * s->ldp * 8, ctx->stream);
   }
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->clamped, (size_t)n);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->info, sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->Ut, (size_t)NB * NB * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&s->pcol_dev, (size_t)ld_loc * 8);
+  if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->clamped, (size_t)n);
+  if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->info, sizeof(int));
+  if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->Ut, (size_t)NB * NB * 8);
+  if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->pcol_dev, (size_t)ld_loc * 8);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->vec, 0, (size_t)7 * n * 8, ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->clamped, 0, (size_t)n, ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->info, 0, sizeof(int), ctx->stream);
@@ -147,7 +147,7 @@ extern "C" int mdb_dist_generate_f2(mdb_dist* s, uint64_t seed, double mu, const
   }
   int64_t* prow = nullptr;
   if (p) {
-    MDB_CUDA(ctx, cudaMalloc((void**)&prow, (size_t)n * 8));
+    MDB_CUDA(ctx, dev_malloc(ctx, (void**)&prow, (size_t)n * 8));
     MDB_CUDA(ctx, cudaMemcpyAsync(prow, p, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   MDB_CUDA(ctx, cudaMemcpyAsync(s->pcol_dev, pcol.data(), (size_t)s->ld * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -212,8 +212,8 @@ extern "C" int mdb_dist_set_bounds(mdb_dist* s, const mdb_bounds* bnd, const int
         mb[(size_t)i] = bnd->min_diag_B[pi * bnd->stride_B];
         Mb[(size_t)i] = bnd->max_diag_B[pi * bnd->stride_B];
       }
-      MDB_CUDA(ctx, cudaMalloc((void**)&s->minB, (size_t)n * 8));
-      MDB_CUDA(ctx, cudaMalloc((void**)&s->maxB, (size_t)n * 8));
+      MDB_CUDA(ctx, dev_malloc(ctx, (void**)&s->minB, (size_t)n * 8));
+      MDB_CUDA(ctx, dev_malloc(ctx, (void**)&s->maxB, (size_t)n * 8));
       MDB_CUDA(ctx, cudaMemcpyAsync(s->minB, mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
       MDB_CUDA(ctx, cudaMemcpyAsync(s->maxB, Mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
       MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -162,6 +162,7 @@ class CudaSteps:
         self.n, self.rank, self.world = n, rank, world
         self.device = torch.cuda.current_device() if device is None else device
         self.ctx = _native.context(self.device)
+        self.ctx.trim()     # the slabs below are torch tensors: give cached single-GPU buffers back first
         self.ld = local_cols(n, rank, world)
         dev = torch.device('cuda', self.device)
         self.S = torch.empty((n, self.ld), dtype=torch.float64, device=dev)

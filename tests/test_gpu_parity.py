@@ -747,6 +747,67 @@ def test_device_generator_and_identity_at_scale():
     assert 0.2 * n < cl.sum() < 0.6 * n
 
 
+def test_buffer_cache_reuse_and_trim(matrix):
+    """The context keeps the working matrix / staging buffer of a large call for the next one (mdb_ctx_trim,
+    include/mdb200.h): results must not depend on what the reused buffers held before."""
+    from matrix_decomposition_b200 import _native
+    n = 6100                                    # > 256 MB working matrix, not a multiple of the block size
+    A1, kw = workloads.shifted_goe(n, 31, 1.05)
+    A2, _ = workloads.shifted_goe(n, 32, 0.95)
+    aps = matrix.approximation.positive_semidefinite
+    matrix.release_device_memory()
+    fresh = aps.decomposition(A1, **kw)
+    L_fresh, d_fresh = np.array(fresh.L), np.asarray(fresh.d, dtype=float).copy()
+    del fresh
+    other = aps.decomposition(A2, **kw)         # reuses the buffers, leaves different contents behind
+    _ = other.L
+    del other
+    again = aps.decomposition(A1, **kw)
+    assert np.array_equal(np.asarray(again.d, dtype=float), d_fresh) and np.array_equal(again.L, L_fresh)
+    del again
+    matrix.release_device_memory()
+    _native.context().trim()                    # idempotent
+    once_more = aps.decomposition(A1, **kw)
+    assert np.array_equal(once_more.L, L_fresh)
+
+
+def test_config3_full_size_identity_and_bounds():
+    """BASELINE config 3 (n = 65536, 34 GB, every outer-block width 8 / 4 / 2 / 1 in play): the oracle cannot run
+    here, so the result is checked through the size-independent identity L D L^T = A o Omega + diag(delta)
+    (Reimer.py:947-957) on random probes and through the bounds every d has to respect (Reimer.py:64-67)."""
+    from matrix_decomposition_b200 import _native
+    ctx = _native.context()
+    lib = ctx.lib
+    n = 65536
+    mu = 1.05 * math.sqrt(2 * n)
+    diag = np.empty(n)
+    ctx.check(lib.mdb_generate_diag_f2(ctx.handle, n, 3, mu, _native.ptr(diag)), 'diag')
+    p = np.argsort(-diag).astype(np.int64)
+    f = ctypes.c_void_p()
+    ctx.check(lib.mdb_factor_create(ctx.handle, n, 1, ctypes.byref(f)), 'create')
+    try:
+        ctx.check(lib.mdb_factor_generate_f2(f, 3, mu, _native.ptr(p)), 'gen')
+        kw = workloads.f2_bounds(n)
+        bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
+                                           float(np.finfo(float).eps), None, kw['max_diag_B'])
+        ctx.check(lib.mdb_factor_run(f, ctypes.byref(bounds)), 'run')
+        res = ctypes.c_double()
+        ctx.check(lib.mdb_factor_identity_residual(f, 2, 9, ctypes.byref(res)), 'identity')
+        assert res.value <= 1e-12
+        d, om, de = np.empty(n), np.empty(n), np.empty(n)
+        cl = np.zeros(n, dtype=np.uint8)
+        ctx.check(lib.mdb_factor_get(f, _native.TYPE_LDL, None, 0, _native.HOST, _native.ptr(d), _native.ptr(om),
+                                     _native.ptr(de), _native.ptr(cl), None), 'get')
+    finally:
+        lib.mdb_factor_destroy(f)
+    lo = max(kw['min_diag_D'], kw['min_abs_value_D'])
+    assert np.all(np.isfinite(d)) and d.min() >= lo and d.max() <= kw['max_diag_D']
+    assert np.all((om >= 0) & (om <= 1)) and np.all(np.isfinite(de))
+    cl = cl.astype(bool)
+    assert np.all(om[p][~cl] == 1.0)                  # unclamped <=> the rule stayed in its first branch
+    assert 0.2 * n < cl.sum() < 0.6 * n
+
+
 @pytest.mark.parametrize('n,fixed', [(700, 1), (1500, 4), (1100, 8)])
 def test_distributed_steps_single_rank_equal_single_gpu_path(matrix, orc, n, fixed):
     """The multi-GPU step functions with world = 1 (no collective) reproduce the single-GPU path bit for bit,
