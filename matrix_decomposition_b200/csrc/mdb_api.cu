@@ -1571,6 +1571,46 @@ extern "C" int mdb_factor_solve(mdb_factor* f, const double* B, int64_t ldb, int
   // super block of SB diagonal blocks the updates have K = 128; everything beyond it gets ONE update with
   // K = 128 SB, so the right-hand sides are read and written once per super block.
   const int64_t SB = 4;
+  // Lookahead, as in the factorization: the update of super block S is split into (a) the rows of the next super
+  // block, on the main stream, and (b) everything beyond, on the side stream; the dependent chain of small products
+  // of the next super block then runs while (b) keeps the SMs busy.  Every row block still receives its updates in
+  // the same order (b_0 ... b_{r-2}, a_{r-1}), so the results do not depend on the overlap.
+  const bool overlap = ctx->lookahead;  // the profiling events bracket both sweeps on the main stream, which joins the side stream
+  cudaStream_t main_s = ctx->stream, side_s = overlap ? ctx->side_stream : ctx->stream;
+  auto on_side = [&](auto&& fn) -> int {
+    ctx->stream = side_s;
+    const int r = fn();
+    ctx->stream = main_s;
+    return r;
+  };
+  int64_t si = 0;          // super blocks processed so far (both sweeps): event slots alternate
+  bool side_busy = false;  // a (b) update is in flight on the side stream
+  auto split_update = [&](int64_t rows_a, int64_t rows_b, auto&& upd_a, auto&& upd_b) -> int {
+    // main: (a) after the previous (b) has finished (both touch the rows of the next super block)
+    int r = MDB_OK;
+    if (overlap) {
+      MDB_CUDA(ctx, cudaEventRecord(ctx->ev_panel[si & 1], main_s));  // this super block's solution is complete
+      if (side_busy) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(si - 1) & 1], 0));
+    }
+    if (rows_a > 0) r = upd_a();
+    if (!r && rows_b > 0) {
+      if (overlap) MDB_CUDA(ctx, cudaStreamWaitEvent(side_s, ctx->ev_panel[si & 1], 0));
+      r = on_side(upd_b);
+      if (overlap) {
+        MDB_CUDA(ctx, cudaEventRecord(ctx->ev_upd[si & 1], side_s));
+        side_busy = true;
+      }
+    } else if (overlap) {
+      side_busy = false;
+    }
+    ++si;
+    return r;
+  };
+  auto join_side = [&]() -> int {
+    if (overlap && side_busy) MDB_CUDA(ctx, cudaStreamWaitEvent(main_s, ctx->ev_upd[(si - 1) & 1], 0));
+    side_busy = false;
+    return MDB_OK;
+  };
   // forward sweep  L z = b  (decompositions.py:987 / :1349)
   for (int64_t S0 = 0; S0 < T && !rc; S0 += SB) {
     const int64_t S1 = std::min<int64_t>(S0 + SB, T);
@@ -1581,9 +1621,16 @@ extern "C" int mdb_factor_solve(mdb_factor* f, const double* B, int64_t ldb, int
       if (!rc && j1 < s1)
         rc = product_tn(ctx, nrhs, s1 - j1, NB, Yt + j0, ldt, f->W + j1 * f->ld + j0, f->ld, Bt + j1, ldt, true, true);
     }
-    if (!rc && s1 < n)
-      rc = product_tn(ctx, nrhs, n - s1, (S1 - S0) * NB, Yt + s0, ldt, f->W + s1 * f->ld + s0, f->ld, Bt + s1, ldt, true, true);
+    if (!rc && s1 < n) {
+      const int64_t K = (S1 - S0) * NB;
+      const int64_t s2 = std::min<int64_t>(s1 + SB * NB, n);   // end of the next super block
+      rc = split_update(
+          s2 - s1, n - s2,
+          [&]() { return product_tn(ctx, nrhs, s2 - s1, K, Yt + s0, ldt, f->W + s1 * f->ld + s0, f->ld, Bt + s1, ldt, true, true); },
+          [&]() { return product_tn(ctx, nrhs, n - s2, K, Yt + s0, ldt, f->W + s2 * f->ld + s0, f->ld, Bt + s2, ldt, true, true); });
+    }
   }
+  if (!rc) rc = join_side();
   if (!rc && f->out_type != MDB_TYPE_LL) {  // x / d  (decompositions.py:988)
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)nrhs);
     k_scale_by_d<<<grid, 256, 0, ctx->stream>>>(n, nrhs, Yt, ldt, f->d, 0);
@@ -1599,9 +1646,16 @@ extern "C" int mdb_factor_solve(mdb_factor* f, const double* B, int64_t ldb, int
       if (!rc && j0 > s0)
         rc = product_tn(ctx, nrhs, j0 - s0, NB, Bt + j0, ldt, f->W + s0 * f->ld + j0, f->ld, Yt + s0, ldt, true, true);
     }
-    if (!rc && s0 > 0)
-      rc = product_tn(ctx, nrhs, s0, (S1 - S0) * NB, Bt + s0, ldt, f->W + s0, f->ld, Yt, ldt, true, true);
+    if (!rc && s0 > 0) {
+      const int64_t K = (S1 - S0) * NB;
+      const int64_t sp = s0 > SB * NB ? s0 - SB * NB : 0;      // start of the previous super block
+      rc = split_update(
+          s0 - sp, sp,
+          [&]() { return product_tn(ctx, nrhs, s0 - sp, K, Bt + s0, ldt, f->W + sp * f->ld + s0, f->ld, Yt + sp, ldt, true, true); },
+          [&]() { return product_tn(ctx, nrhs, sp, K, Bt + s0, ldt, f->W + s0, f->ld, Yt, ldt, true, true); });
+    }
   }
+  if (!rc) rc = join_side();
   if (ctx->profiling) {  // device time of the two sweeps -> mdb_ctx_get_phase_ms()[0]
     cudaEventRecord(ctx->ev[1], ctx->stream);
     cudaEventSynchronize(ctx->ev[1]);

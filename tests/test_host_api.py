@@ -188,6 +188,7 @@ def test_constants_and_facade_names():
     for name in ('decompose', 'is_positive_definite', 'is_positive_semidefinite', 'is_invertible', 'solve',
                  'decompositions', 'errors', 'approximation', 'permute'):
         assert hasattr(matrix, name)
+    matrix.release_device_memory()   # no context yet: nothing to do, and no attempt to create one
 
 
 def test_gmw_family_host_side_contract():
