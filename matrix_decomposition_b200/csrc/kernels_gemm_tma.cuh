@@ -26,6 +26,7 @@ struct GemmTmaArgs {
   int cyc_G, cyc_r;
   int64_t b_glob0;
   int variant;   // debugging: 1 = CTA-wide barrier before every refill
+  int mode;      // bit 0: C -= A B^T (instead of +=), bit 1: C is not read (C = A B^T)
   int nbands;
   int band_prefix[MDB_MAX_BANDS + 1];  // tiles before band b (band = 8 M-tiles), tiles ordered (N tile, M tile in band)
 };
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 2)
         const int64_t r = crow0 + mb * 16 + (q >> 1) * 8;
         const int64_t c = ccol0 + nb * 8 + (q & 1) * 4;
         double v = 0.0;
-        if (interior || (r < g.M && c < g.N && (g.row_glob0 + r) > (cg_off + c))) v = C[r * g.ldc + c];
-        acc[mb][nb][q] = v;
+        if (!(g.mode & 2) && (interior || (r < g.M && c < g.N && (g.row_glob0 + r) > (cg_off + c)))) v = C[r * g.ldc + c];
+        acc[mb][nb][q] = (g.mode & 1) ? -v : v;   // C - A B^T = -(-C + A B^T), exactly (rounding is symmetric)
       }
 
   uint32_t a_off[2][2], b_off[4];
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 2)
       for (int q = 0; q < 4; ++q) {
         const int64_t r = crow0 + mb * 16 + (q >> 1) * 8;
         const int64_t c = ccol0 + nb * 8 + (q & 1) * 4;
-        if (interior || (r < g.M && c < g.N && (g.row_glob0 + r) > (cg_off + c))) C[r * g.ldc + c] = acc[mb][nb][q];
+        if (interior || (r < g.M && c < g.N && (g.row_glob0 + r) > (cg_off + c)))
+          C[r * g.ldc + c] = (g.mode & 1) ? -acc[mb][nb][q] : acc[mb][nb][q];
       }
 }
 
@@ -248,7 +250,7 @@ static int64_t mdb_tiles_below(const GemmArgs& g, int64_t limit, int64_t n_tiles
 }
 
 // Returns MDB_OK when launched, -1 when the TMA path does not apply (caller falls back to k_gemm_tn).
-static int launch_gemm_tn_tma(mdb_ctx* ctx, const GemmArgs& g0, int64_t a_rows, int64_t b_rows) {
+static int launch_gemm_tn_tma(mdb_ctx* ctx, const GemmArgs& g0, int64_t a_rows, int64_t b_rows, int mode = 0) {
   using namespace gemm;
   if (!ctx->use_tma || g0.K % BK != 0 || g0.lda % 2 != 0 || g0.ldb % 2 != 0) return -1;
   if (((uintptr_t)g0.A & 15) || ((uintptr_t)g0.B & 15)) return -1;
@@ -267,6 +269,7 @@ static int launch_gemm_tn_tma(mdb_ctx* ctx, const GemmArgs& g0, int64_t a_rows, 
   g.row_glob0 = g0.row_glob0; g.col_glob0 = g0.col_glob0;
   g.m_tile0 = g0.m_tile0; g.n_tile0 = g0.n_tile0;
   g.cyc_G = g0.cyc_G; g.cyc_r = g0.cyc_r; g.b_glob0 = g0.b_glob0;
+  g.mode = mode;
   { const char* v = getenv("MDB200_TMA_VARIANT"); g.variant = v ? atoi(v) : 0; }
   const int64_t n_tiles_total = (g.N + BN - 1) / BN;
   const int64_t nt_limit = g0.n_tiles > 0 ? std::min<int64_t>(g0.n_tile0 + g0.n_tiles, n_tiles_total) : n_tiles_total;

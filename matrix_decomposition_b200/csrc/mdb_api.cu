@@ -1388,6 +1388,13 @@ static int product_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, const doubl
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = (int)K;
+  if (beta1 || !neg) {
+    // TMA-fed tile kernel on the full rectangle: a row origin beyond every column makes each element "below the diagonal"
+    g.row_glob0 = (int64_t)1 << 40; g.b_rows = N;
+    const int r = launch_gemm_tn_tma(ctx, g, M, N, (neg ? 1 : 0) | (beta1 ? 0 : 2));
+    if (r != -1) return r;
+    g.row_glob0 = 0; g.b_rows = 0;
+  }
   if (beta1 && neg) return launch_gemm_tn<false, true, true>(ctx, g, 1);
   if (beta1) return launch_gemm_tn<false, true, false>(ctx, g, 1);
   return launch_gemm_tn<false, false, false>(ctx, g, 1);  // neg without beta is never needed
@@ -1824,9 +1831,7 @@ extern "C" int mdb_debug_gemm_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
       rc = launch_gemm_tn_tma(ctx, g, M, N);
       if (rc == -1) rc = launch_gemm_tn<true, true, false>(ctx, g, 1);
     }
-    else if (beta1 && neg) rc = launch_gemm_tn<false, true, true>(ctx, g, 1);
-    else if (beta1) rc = launch_gemm_tn<false, true, false>(ctx, g, 1);
-    else rc = launch_gemm_tn<false, false, false>(ctx, g, 1);
+    else rc = product_tn(ctx, M, N, K, dA, K, dB, K, dC, N, beta1 != 0, neg != 0);   // the solve / multiply products
   }
   cudaEventRecord(ctx->ev[1], ctx->stream);
   if (!rc) rc = copy2d_async(ctx, C, ldc, dC, N, M, N, MDB_HOST, MDB_DEVICE);
