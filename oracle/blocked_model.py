@@ -149,3 +149,86 @@ def blocked_factor(A, p, rule=RULE_REIMER, min_diag_B=None, max_diag_B=None, min
     de_orig = np.zeros(n)
     de_orig[p] = delta
     return dict(L=L, d=d, omega=om_orig, delta=de_orig, clamped=clamped, p=p, info=info, W=W, alpha=alpha, beta=beta)
+
+
+def dynamic_delayed_factor(A, method, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag_D=None,
+                           min_abs_value_D=None, min_abs_value_L=None, nb=128):
+    """numpy model of csrc/kernels_dynamic.cuh: dynamic pivoting ('maximal_stability' / 'minimal_difference',
+    Reimer.py:497-523) with the Schur-complement updates delayed per panel of nb columns.
+
+    Per column i: rule for every remaining row, arg-min by the reference's key, symmetric swap i <-> j* (rows of the
+    pending operands X, Y included), column i read as  S[j, i] + sum_c X[j, c] Y[i, c]  over the panel's earlier
+    columns, mixed with the original A by omega (the all-dropped shortcut as in the static path), divided by d;
+    alpha / beta / rowmax updated for every row below.  After the panel one product updates the trailing S.
+    Returns dict(L, d, omega, delta, clamped, p) with d / clamped by position, omega / delta by original index."""
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    mavD = float(np.finfo(np.longdouble).eps ** 0.5) if min_abs_value_D is None else max(float(min_abs_value_D),
+                                                                                         float(np.finfo(np.longdouble).eps))
+    eps64 = float(np.finfo(np.float64).eps)
+    mavL = eps64 if min_abs_value_L is None else max(float(min_abs_value_L), eps64)
+    mD = math.nan if min_diag_D is None else float(min_diag_D)
+    MD = math.inf if max_diag_D is None else float(max_diag_D)
+    mB = np.broadcast_to(np.asarray(-math.inf if min_diag_B is None else min_diag_B, dtype=np.float64), (n,)).copy()
+    MB = np.broadcast_to(np.asarray(math.inf if max_diag_B is None else max_diag_B, dtype=np.float64), (n,)).copy()
+    W = A.copy()                   # lower: S / Lu, upper: A (both follow the swaps)
+    p = np.arange(n)
+    gamma = A.diagonal().copy()
+    alpha, beta, rowmax = np.zeros(n), np.zeros(n), np.zeros(n)
+    d, omega, delta = np.zeros(n), np.zeros(n), np.zeros(n)
+    clamped = np.zeros(n, dtype=bool)
+    PX, PY = np.zeros((n, nb)), np.zeros((n, nb))
+
+    def swap_vec(v, i, j):
+        v[i], v[j] = v[j], v[i]
+
+    for pb in range(0, n, nb):
+        pe = min(pb + nb, n)
+        for i in range(pb, pe):
+            kc = i - pb
+            best = None
+            for j in range(i, n):
+                dj, wj, fj, cj = decide(RULE_REIMER, mD, MD, mavD, alpha[j], beta[j], gamma[j], mB[j], MB[j])
+                key = (fj, -dj, wj, j) if method == 'minimal_difference' else (-dj, fj, wj, j)
+                if best is None or key < best[0]:
+                    best = (key, dj, wj, cj, j)
+            _, di, wi, ci, js = best
+            if js != i:
+                for v in (gamma, alpha, beta, rowmax, mB, MB, p):
+                    swap_vec(v, i, js)
+                PX[[i, js], :kc] = PX[[js, i], :kc]
+                PY[[i, js], :kc] = PY[[js, i], :kc]
+                for m in range(n):          # S(a, b) at W[max, min], A(a, b) at W[min, max]
+                    if m == i or m == js:
+                        continue
+                    lo_i, lo_j = (max(i, m), min(i, m)), (max(js, m), min(js, m))
+                    W[lo_i], W[lo_j] = W[lo_j], W[lo_i]
+                    up_i, up_j = (min(i, m), max(i, m)), (min(js, m), max(js, m))
+                    W[up_i], W[up_j] = W[up_j], W[up_i]
+            d[i], omega[i], clamped[i] = di, wi, ci
+            delta[i] = (di - gamma[i]) + (wi * wi * alpha[i] if wi != 0 else 0.0)
+            drop = (wi == 0) or (wi * rowmax[i] < mavL)
+            a = W[i, i + 1:].copy()
+            r = a.copy()
+            if not drop:
+                s = W[i + 1:, i] + PX[i + 1:, :kc] @ PY[i, :kc]
+                r = (1 - wi) * a + wi * s
+            x = r / di if di != 0 else np.zeros_like(r)
+            W[i + 1:, i] = x
+            alpha[i + 1:] += x * x * di
+            beta[i + 1:] += 2 * a * a
+            rowmax[i + 1:] = np.maximum(rowmax[i + 1:], np.abs(x))
+            PX[i + 1:, kc] = x
+            PY[i + 1:, kc] = -x * di
+        if pe < n:
+            upd = PX[pe:, :pe - pb] @ PY[pe:, :pe - pb].T
+            il = np.tril_indices(n - pe, -1)
+            T = W[pe:, pe:]
+            T[il] += upd[il]
+    L = np.tril(W, -1) * omega[:, None]
+    L[np.abs(L) < mavL] = 0
+    L[np.diag_indices(n)] = 1
+    om_orig, de_orig = np.zeros(n), np.zeros(n)
+    om_orig[p] = omega
+    de_orig[p] = delta
+    return dict(L=L, d=d, omega=om_orig, delta=de_orig, clamped=clamped, p=p)
