@@ -1,7 +1,5 @@
 """The blocked right-looking restatement (oracle/blocked_model.py, the numpy twin of the CUDA
 kernels) and the FP64 scalar rule header (csrc/md_rule.h) against the oracle and the goldens."""
-import json
-import math
 
 import numpy as np
 import pytest

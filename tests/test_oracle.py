@@ -1,7 +1,6 @@
 """The CPU oracle (oracle/mdo_oracle.c) against golden vectors produced by the unmodified Python
 reference (tests/golden/generate_goldens.py).  This is what pins the oracle."""
 import json
-import math
 
 import numpy as np
 import pytest

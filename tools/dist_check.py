@@ -1,7 +1,6 @@
 """Multi-GPU bring-up (torchrun, one rank per GPU): the block-cyclic NCCL path against the single-GPU path
 and the oracle at moderate n, then a timing + identity check at a larger n."""
 import json
-import math
 import os
 import sys
 import time
