@@ -250,6 +250,24 @@ int mdb_dist_apply_update(mdb_dist *s, int64_t k_outer, int oslot, int64_t k_fir
  * diagonal, zeros above) and copies the replicated vectors to the host (position order; any may be NULL) */
 int mdb_dist_finalize(mdb_dist *s, double *d, double *omega, double *delta, uint8_t *clamped);
 
+/* ---- EXPERIMENTAL (off by default, not yet run on hardware): panel exchange by peer-memory stores ----
+ * Instead of the NCCL broadcast + mdb_dist_absorb_panel, the owner of a panel stores X, Y = -X D, the alpha / beta /
+ * rowmax slices and d / omega / delta / clamped straight into every peer's buffers over NVLink and raises a flag
+ * (csrc/mdb_peer.cuh).  Every rank provides one zero-filled "symmetric" buffer of mdb_dist_peer_buffer_elems(s)
+ * doubles that is mapped into all ranks (torch.distributed._symmetric_memory); peer_base = host array of `world`
+ * device pointers to those buffers as seen from this process.  Attach before mdb_dist_set_bounds; put a barrier
+ * between mdb_dist_set_bounds and the first panel.
+ *   mdb_dist_push_panel    owner, after mdb_dist_factor_panel on the same stream; outer_index = running index of the
+ *                          panel's outer block (flow control against the double-buffered operand buffers)
+ *   mdb_dist_wait_panel    every rank, on the stream that consumes panel k (replaces waiting for the broadcast)
+ *   mdb_dist_release_outer every rank, on a stream ordered after all its kernels that read the operands of the first
+ *                          `count` outer blocks */
+int64_t mdb_dist_peer_buffer_elems(const mdb_dist *s);
+int mdb_dist_attach_peers(mdb_dist *s, double *const *peer_base);
+int mdb_dist_push_panel(mdb_dist *s, int64_t k, int slot, int64_t k_outer, int oslot, int64_t outer_index);
+int mdb_dist_wait_panel(mdb_dist *s, int64_t k);
+int mdb_dist_release_outer(mdb_dist *s, int64_t count);
+
 #ifdef __cplusplus
 }
 #endif

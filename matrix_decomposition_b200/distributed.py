@@ -66,13 +66,19 @@ def factorize(n, rank, world, steps, comm, main=None, bulk=None, lookahead=True)
     works = {}
     bulk_done = {}
 
-    def issue_factor_and_broadcast(k, k_outer, oslot):
+    exchange = getattr(comm, 'exchange_panel', None)   # PeerComm: one-sided peer stores instead of a broadcast
+    release = getattr(steps, 'release_outer', None) if exchange is not None else None
+
+    def issue_factor_and_broadcast(k, k_outer, oslot, outer_index):
         slot = k % 2
         if owner_of(k, world) == rank:
             steps.factor_panel(k, slot, k_outer, oslot, main)
-        works[k] = comm.broadcast(steps.panel_tensor(slot, k), owner_of(k, world), main)
+        if exchange is not None:
+            works[k] = exchange(steps, k, slot, k_outer, oslot, outer_index, owner_of(k, world), main)
+        else:
+            works[k] = comm.broadcast(steps.panel_tensor(slot, k), owner_of(k, world), main)
 
-    issue_factor_and_broadcast(0, 0, 0)
+    issue_factor_and_broadcast(0, 0, 0, 0)
     kO, oidx = 0, 0
     while kO < T:
         cnt = steps.outer_width(kO)
@@ -83,7 +89,7 @@ def factorize(n, rank, world, steps, comm, main=None, bulk=None, lookahead=True)
             steps.absorb_panel(k, k % 2, kO, oslot, main)
             if k + 1 < kE:                                            # inner updates: stay inside the outer block
                 steps.apply_update(kO, oslot, k, 1, k + 1, k + 2, main)   # next column block first
-                issue_factor_and_broadcast(k + 1, kO, oslot)
+                issue_factor_and_broadcast(k + 1, kO, oslot, oidx)
                 steps.apply_update(kO, oslot, k, 1, k + 2, kE, main)
         if kE < T:
             cntn = steps.outer_width(kE)
@@ -93,15 +99,20 @@ def factorize(n, rank, world, steps, comm, main=None, bulk=None, lookahead=True)
             if lookahead:
                 ready = main.record()                                 # operands of this outer block complete
                 steps.apply_update(kO, oslot, kO, cnt, kE, kE + 1, main)          # next panel's block first
-                issue_factor_and_broadcast(kE, kE, (oidx + 1) % 2)               # overlaps with the bulk update
+                issue_factor_and_broadcast(kE, kE, (oidx + 1) % 2, oidx + 1)     # overlaps with the bulk update
                 steps.apply_update(kO, oslot, kO, cnt, kE + 1, kE + cntn, main)   # rest of the next outer block
                 bulk.wait(ready)
                 steps.apply_update(kO, oslot, kO, cnt, kE + cntn, -1, bulk)       # everything beyond
+                if release is not None:     # nobody on this rank reads this outer block's operands any more
+                    bulk.wait(main.record())
+                    release(oidx + 1, bulk)
                 bulk_done[oidx] = bulk.record()
             else:
                 steps.apply_update(kO, oslot, kO, cnt, kE, -1, main)
+                if release is not None:
+                    release(oidx + 1, main)
                 bulk_done[oidx] = main.record()
-                issue_factor_and_broadcast(kE, kE, (oidx + 1) % 2)
+                issue_factor_and_broadcast(kE, kE, (oidx + 1) % 2, oidx + 1)
         kO, oidx = kE, oidx + 1
     for ev in bulk_done.values():
         main.wait(ev)
@@ -152,6 +163,24 @@ class NcclComm:
         return Handle()
 
 
+class PeerComm:
+    """EXPERIMENTAL (MDB200_P2P=1): no collective at all -- the owner of a panel stores it into every peer's operand
+    buffers over NVLink (mdb_dist_push_panel, csrc/mdb_peer.cuh) and the consumers' streams wait for its arrival flag."""
+
+    def exchange_panel(self, steps, k, slot, k_outer, oslot, outer_index, owner, stream):
+        if owner == steps.rank:
+            steps.push_panel(k, slot, k_outer, oslot, outer_index, stream)
+
+        class Handle:
+            def wait(self, s):
+                steps.wait_panel(k, s)
+        return Handle()
+
+
+def peer_stores_requested():
+    return os.environ.get('MDB200_P2P', '0') == '1'
+
+
 class CudaSteps:
     """Per-rank device state: S_loc / A_loc / panel buffers are torch tensors, the steps are C-ABI calls."""
 
@@ -177,11 +206,64 @@ class CudaSteps:
         self.ctx.check(rc, 'mdb_dist_create')
         self.handle = h
         self.bulk_events = None
+        self._symm = None
 
     def close(self):
         if self.handle:
             self.ctx.lib.mdb_dist_destroy(self.handle)
             self.handle = None
+        self._symm = None
+
+    # ---- experimental peer-store exchange (csrc/mdb_peer.cuh) ----
+    def enable_peer_stores(self):
+        """Allocates this rank's symmetric buffer, maps every rank's buffer into this process
+        (torch.distributed._symmetric_memory) and hands the pointers to the library.  Collective: every rank calls it.
+        Returns False (on every rank) when any rank could not set it up; the NCCL path then stays in place."""
+        import torch
+        import torch.distributed as dist
+        ok, ptrs, keep = 1, None, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            elems = int(self.ctx.lib.mdb_dist_peer_buffer_elems(self.handle))
+            group = dist.group.WORLD
+            try:
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+            except Exception:  # noqa: BLE001  (newer torch versions do not need it)
+                pass
+            t = symm_mem.empty(elems, dtype=torch.float64, device=torch.device('cuda', self.device))
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, group)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or ptrs[self.rank] != t.data_ptr():
+                raise RuntimeError('unexpected symmetric memory handle')
+            keep = (t, hdl)
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            if self.rank == 0:
+                import sys
+                print('[mdb200] peer stores unavailable ({}): staying with the NCCL broadcast'.format(e), file=sys.stderr)
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device('cuda', self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return False
+        torch.cuda.synchronize()
+        arr = (ctypes.c_void_p * self.world)(*ptrs)
+        self.ctx.check(self.ctx.lib.mdb_dist_attach_peers(self.handle, arr), 'mdb_dist_attach_peers')
+        self._symm = keep
+        dist.barrier()
+        return True
+
+    def push_panel(self, k, slot, k_outer, oslot, outer_index, stream):
+        self._on(stream)
+        self.ctx.check(self.ctx.lib.mdb_dist_push_panel(self.handle, k, slot, k_outer, oslot, outer_index), 'mdb_dist_push_panel')
+
+    def wait_panel(self, k, stream):
+        self._on(stream)
+        self.ctx.check(self.ctx.lib.mdb_dist_wait_panel(self.handle, k), 'mdb_dist_wait_panel')
+
+    def release_outer(self, count, stream):
+        self._on(stream)
+        self.ctx.check(self.ctx.lib.mdb_dist_release_outer(self.handle, count), 'mdb_dist_release_outer')
 
     def _on(self, stream):
         self.ctx.set_stream(stream.stream.cuda_stream)
@@ -276,9 +358,12 @@ def approximate_distributed(Ap_or_none, n, bounds_kwargs, p=None, generator=None
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, bounds_kwargs.get('min_diag_D'), bounds_kwargs.get('max_diag_D'),
                                        bounds_kwargs['min_abs_value_D'], bounds_kwargs['min_abs_value_L'],
                                        bounds_kwargs.get('min_diag_B'), bounds_kwargs.get('max_diag_B'))
+    peer = peer_stores_requested() and world > 1 and steps.enable_peer_stores()
     steps.set_bounds(bounds, p, main)
     torch.cuda.synchronize()
-    factorize(n, rank, world, steps, NcclComm(), main, bulk, lookahead=lookahead)
+    if peer:
+        dist.barrier()      # nobody stores into a peer that is still resetting its vectors
+    factorize(n, rank, world, steps, PeerComm() if peer else NcclComm(), main, bulk, lookahead=lookahead)
     torch.cuda.synchronize()
     d, omega, delta, clamped = steps.finalize(main)
     return steps, d, omega, delta, clamped
@@ -356,7 +441,8 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None):
     st = CudaSteps(n, rank, world, device)
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, 0.015 * mu, 0.9 * mu, 0.015 * mu,
                                        float(np.finfo(np.float64).eps), None, 2 * mu)
-    comm = NcclComm()
+    peer = peer_stores_requested() and world > 1 and st.enable_peer_stores()
+    comm = PeerComm() if peer else NcclComm()
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -385,7 +471,8 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None):
     d, omega, delta, clamped = st.finalize(main)
     ident = identity_residual(st, d, omega, delta)
     out = dict(ms_per_step=float(np.mean(times)), gpu_launches=int(launches), identity=ident,
-               n_clamped=int(clamped.sum()))
+               n_clamped=int(clamped.sum()),
+               panel_exchange='peer-memory stores (experimental, MDB200_P2P=1)' if peer else 'NCCL broadcast')
 
     # ---- roofline: one serialised pass (no lookahead, everything on the main stream), events per bulk update ----
     st.generate_f2(seed, mu, p, main)
@@ -434,6 +521,9 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None):
                 t0 = time.perf_counter()
                 st.set_local(host, main)                 # H2D of the slab (+ device copy into the working array)
                 st.set_bounds(bounds, p, main)
+                if peer:
+                    torch.cuda.synchronize()
+                    dist.barrier()
                 factorize(n, rank, world, st, comm, main, bulk, lookahead=True)
                 dv, ov, de, cl = st.finalize(main)       # D2H of d, omega, delta, clamped; L stays distributed on the GPUs
                 torch.cuda.synchronize()
