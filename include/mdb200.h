@@ -250,7 +250,8 @@ int mdb_dist_apply_update(mdb_dist *s, int64_t k_outer, int oslot, int64_t k_fir
  * diagonal, zeros above) and copies the replicated vectors to the host (position order; any may be NULL) */
 int mdb_dist_finalize(mdb_dist *s, double *d, double *omega, double *delta, uint8_t *clamped);
 
-/* ---- EXPERIMENTAL (off by default, not yet run on hardware): panel exchange by peer-memory stores ----
+/* ---- EXPERIMENTAL (off by default; bit-identical results on 2 GPUs, not yet measured at scale): panel exchange by
+ * peer-memory stores ----
  * Instead of the NCCL broadcast + mdb_dist_absorb_panel, the owner of a panel stores X, Y = -X D, the alpha / beta /
  * rowmax slices and d / omega / delta / clamped straight into every peer's buffers over NVLink and raises a flag
  * (csrc/mdb_peer.cuh).  Every rank provides one zero-filled "symmetric" buffer of mdb_dist_peer_buffer_elems(s)

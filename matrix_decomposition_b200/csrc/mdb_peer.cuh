@@ -2,8 +2,9 @@
 // the owner's pack step, instead of a NCCL broadcast followed by an unpack kernel on every receiver.
 // Included at the end of mdb_api.cu, after mdb_dist.cuh.
 //
-// EXPERIMENTAL, off by default (distributed.py enables it with MDB200_P2P=1): written in round 1 without multi-GPU
-// time left to run it; the NCCL path is the verified one.
+// EXPERIMENTAL, off by default (distributed.py enables it with MDB200_P2P=1): one run on 2 B200 at the end of round 1
+// gave results bit-identical to the single-GPU path (tools/dist_check.py); not yet measured at scale, so the NCCL path
+// stays the default.
 //
 // Every rank owns one "symmetric" buffer of mdb_dist_peer_buffer_elems() doubles, mapped into all peers
 // (torch.distributed._symmetric_memory does the mapping; the library only sees the base pointers):

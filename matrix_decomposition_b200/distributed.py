@@ -164,7 +164,7 @@ class NcclComm:
 
 
 class PeerComm:
-    """EXPERIMENTAL (MDB200_P2P=1): no collective at all -- the owner of a panel stores it into every peer's operand
+    """EXPERIMENTAL (MDB200_P2P=1; bit-identical results on 2 GPUs, not yet measured at scale): no collective at all -- the owner of a panel stores it into every peer's operand
     buffers over NVLink (mdb_dist_push_panel, csrc/mdb_peer.cuh) and the consumers' streams wait for its arrival flag."""
 
     def exchange_panel(self, steps, k, slot, k_outer, oslot, outer_index, owner, stream):
