@@ -264,7 +264,7 @@ int mdb_dist_finalize(mdb_dist *s, double *d, double *omega, double *delta, uint
  *   mdb_dist_release_outer every rank, on a stream ordered after all its kernels that read the operands of the first
  *                          `count` outer blocks */
 int64_t mdb_dist_peer_buffer_elems(const mdb_dist *s);
-int mdb_dist_attach_peers(mdb_dist *s, double *const *peer_base);
+int mdb_dist_attach_peers(mdb_dist *s, double *const *peer_base, double *mc_base /* multicast mapping or NULL */);
 int mdb_dist_push_panel(mdb_dist *s, int64_t k, int slot, int64_t k_outer, int oslot, int64_t outer_index);
 int mdb_dist_wait_panel(mdb_dist *s, int64_t k);
 int mdb_dist_release_outer(mdb_dist *s, int64_t count);

@@ -112,7 +112,7 @@ SIGNATURES = {
     'mdb_dist_apply_update': (_int, [_vp, _i64, _int, _i64, _i64, _i64, _i64]),
     'mdb_dist_finalize': (_int, [_vp, _vp, _vp, _vp, _vp]),
     'mdb_dist_peer_buffer_elems': (_i64, [_vp]),
-    'mdb_dist_attach_peers': (_int, [_vp, _vp]),
+    'mdb_dist_attach_peers': (_int, [_vp, _vp, _vp]),
     'mdb_dist_push_panel': (_int, [_vp, _i64, _int, _i64, _int, _i64]),
     'mdb_dist_wait_panel': (_int, [_vp, _i64]),
     'mdb_dist_release_outer': (_int, [_vp, _i64]),

@@ -25,6 +25,7 @@ struct mdb_dist {
   // the caller and mapped into every rank
   bool p2p;
   double* peer_base[16];
+  double* peer_mc;
   unsigned int* push_counter;
   uint32_t epoch;      // factorization counter, tags the arrival / release flags
 };
@@ -83,6 +84,7 @@ extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, dou
   s->pcol_dev = nullptr; s->have_bounds = false;
   s->p2p = false; s->push_counter = nullptr; s->epoch = 0;
   for (int q = 0; q < 16; ++q) s->peer_base[q] = nullptr;
+  s->peer_mc = nullptr;
   s->OPX[0] = s->OPX[1] = s->OPY[0] = s->OPY[1] = nullptr;
   s->ldp = dist_outer_width(ctx, n, 0) * NB;  // the first outer block is the widest
   cudaError_t e = dev_malloc(ctx, (void**)&s->vec, (size_t)7 * n * 8);

@@ -178,7 +178,7 @@ class PeerComm:
 
 
 def peer_stores_requested():
-    return os.environ.get('MDB200_P2P', '0') == '1'
+    return os.environ.get('MDB200_P2P', '0') in ('1', '2')     # 2: through the NVLS multicast mapping when there is one
 
 
 class CudaSteps:
@@ -221,7 +221,7 @@ class CudaSteps:
         Returns False (on every rank) when any rank could not set it up; the NCCL path then stays in place."""
         import torch
         import torch.distributed as dist
-        ok, ptrs, keep = 1, None, None
+        ok, ptrs, keep, mc = 1, None, None, 0
         try:
             import torch.distributed._symmetric_memory as symm_mem
             elems = int(self.ctx.lib.mdb_dist_peer_buffer_elems(self.handle))
@@ -234,6 +234,7 @@ class CudaSteps:
             t.zero_()
             hdl = symm_mem.rendezvous(t, group)
             ptrs = [int(x) for x in hdl.buffer_ptrs]
+            mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if os.environ.get('MDB200_P2P') == '2' else 0
             if len(ptrs) != self.world or ptrs[self.rank] != t.data_ptr():
                 raise RuntimeError('unexpected symmetric memory handle')
             keep = (t, hdl)
@@ -248,7 +249,8 @@ class CudaSteps:
             return False
         torch.cuda.synchronize()
         arr = (ctypes.c_void_p * self.world)(*ptrs)
-        self.ctx.check(self.ctx.lib.mdb_dist_attach_peers(self.handle, arr), 'mdb_dist_attach_peers')
+        self.ctx.check(self.ctx.lib.mdb_dist_attach_peers(self.handle, arr, ctypes.c_void_p(mc or None)), 'mdb_dist_attach_peers')
+        self.peer_multicast = bool(mc)
         self._symm = keep
         dist.barrier()
         return True
@@ -472,7 +474,8 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None):
     ident = identity_residual(st, d, omega, delta)
     out = dict(ms_per_step=float(np.mean(times)), gpu_launches=int(launches), identity=ident,
                n_clamped=int(clamped.sum()),
-               panel_exchange='peer-memory stores (experimental, MDB200_P2P=1)' if peer else 'NCCL broadcast')
+               panel_exchange=('peer-memory stores (experimental, MDB200_P2P), ' +
+                               ('multicast' if getattr(st, 'peer_multicast', False) else 'unicast')) if peer else 'NCCL broadcast')
 
     # ---- roofline: one serialised pass (no lookahead, everything on the main stream), events per bulk update ----
     st.generate_f2(seed, mu, p, main)
