@@ -346,8 +346,8 @@ def run_distributed(args):
                     ms_per_step=ms, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f64',
                     data='synthetic',
                     config=dict(workload='matrix.approximate n=%d float64 (%.0f GB), F2 shifted GOE s=1.05, 1-D block-cyclic '
-                                         'columns (block 128) over %d B200, NCCL panel broadcast with lookahead' %
-                                         (n, 8e-9 * n * n, world), n=n,
+                                         'columns (block 128) over %d B200, panel exchange: %s, lookahead' %
+                                         (n, 8e-9 * n * n, world, out.get('panel_exchange', 'NCCL broadcast')), n=n,
                                 l2='inputs far larger than L2; matrix regenerated between steps',
                                 frac_of_fp64_dmma_peak=value / 1e3 / (FP64_DMMA_PEAK_TFLOPS * world),
                                 identity=out.get('identity'), n_clamped=out.get('n_clamped'),
