@@ -1,16 +1,17 @@
-"""
-This module is deprecated and will be removed in a future release.
-Please use matrix.approximation.positive_semidefinite instead.  (reference: matrix/approximate.py:1-15)
-"""
+"""Deprecated alias module kept for callers of `matrix.approximate` (reference: matrix/approximate.py:1-15): the
+functions live in `approximation.positive_semidefinite`; importing this module warns once."""
+import warnings as _warnings
 
-import warnings
+from .approximation import positive_semidefinite as _psd
 
-warnings.warn("This module is deprecated and will be removed in a future release. Please use "
-              "matrix.approximation.positive_semidefinite instead.", DeprecationWarning, stacklevel=2)
+_warnings.warn('matrix.approximate is deprecated and will be removed in a future release; use '
+               'matrix.approximation.positive_semidefinite instead.', DeprecationWarning, stacklevel=2)
 
-from .approximation.positive_semidefinite import decomposition, APPROXIMATION_ONLY_PERMUTATION_METHODS  # noqa: E402,F401
-from .approximation.positive_semidefinite import positive_semidefinite_matrix as positive_definite_matrix  # noqa: E402
+APPROXIMATION_ONLY_PERMUTATION_METHODS = _psd.APPROXIMATION_ONLY_PERMUTATION_METHODS
+decomposition = _psd.decomposition
+positive_definite_matrix = _psd.positive_semidefinite_matrix     # the old name of today's positive_semidefinite_matrix
 
 
-def positive_semidefinite_matrix(*args, **kargs):
-    return positive_definite_matrix(*args, min_diag_D=0, **kargs)
+def positive_semidefinite_matrix(*args, **kwargs):
+    """ The old `positive_semidefinite_matrix`: D may reach zero (approximate.py:14-15). """
+    return _psd.positive_semidefinite_matrix(*args, min_diag_D=0, **kwargs)

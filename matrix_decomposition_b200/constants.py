@@ -1,38 +1,26 @@
-"""String constants of the public API (same values as the reference's matrix/constants.py:4-35)."""
+"""String constants of the public API.  The names and values are the reference's (matrix/constants.py:4-35): they are
+what callers pass as `return_type=` / `permutation=` and what the save format writes."""
 
-# *** decomposition types (constants.py:3-9) *** #
-
+# decomposition types
 BASE_DECOMPOSITION_TYPE = 'base'
-LDL_DECOMPOSITION_TYPE = 'LDL'
-LDL_DECOMPOSITION_COMPRESSED_TYPE = 'LDL_compressed'
-LL_DECOMPOSITION_TYPE = 'LL'
-
-DECOMPOSITION_TYPES = (LDL_DECOMPOSITION_TYPE, LDL_DECOMPOSITION_COMPRESSED_TYPE, LL_DECOMPOSITION_TYPE)
+DECOMPOSITION_TYPES = ('LDL', 'LDL_compressed', 'LL')
 """ Supported types of decompositions. """
+LDL_DECOMPOSITION_TYPE, LDL_DECOMPOSITION_COMPRESSED_TYPE, LL_DECOMPOSITION_TYPE = DECOMPOSITION_TYPES
 
-# *** permutation methods (constants.py:11-24) *** #
-
+# static permutation methods: by the diagonal values or their absolute values, decreasing or increasing
 NO_PERMUTATION_METHOD = 'none'
-DECREASING_DIAGONAL_VALUES_PERMUTATION_METHOD = 'decreasing_diagonal_values'
-INCREASING_DIAGONAL_VALUES_PERMUTATION_METHOD = 'increasing_diagonal_values'
-DECREASING_ABSOLUTE_DIAGONAL_VALUES_PERMUTATION_METHOD = 'decreasing_absolute_diagonal_values'
-INCREASING_ABSOLUTE_DIAGONAL_VALUES_PERMUTATION_METHOD = 'increasing_absolute_diagonal_values'
-
-DIAGONAL_VALUES_PERMUTATION_METHODS = (
-    DECREASING_DIAGONAL_VALUES_PERMUTATION_METHOD,
-    INCREASING_DIAGONAL_VALUES_PERMUTATION_METHOD,
-    DECREASING_ABSOLUTE_DIAGONAL_VALUES_PERMUTATION_METHOD,
-    INCREASING_ABSOLUTE_DIAGONAL_VALUES_PERMUTATION_METHOD)
+DIAGONAL_VALUES_PERMUTATION_METHODS = tuple(
+    '{}_{}diagonal_values'.format(direction, what) for what in ('', 'absolute_') for direction in ('decreasing', 'increasing'))
+(DECREASING_DIAGONAL_VALUES_PERMUTATION_METHOD, INCREASING_DIAGONAL_VALUES_PERMUTATION_METHOD,
+ DECREASING_ABSOLUTE_DIAGONAL_VALUES_PERMUTATION_METHOD,
+ INCREASING_ABSOLUTE_DIAGONAL_VALUES_PERMUTATION_METHOD) = DIAGONAL_VALUES_PERMUTATION_METHODS
 UNIVERSAL_PERMUTATION_METHODS = (NO_PERMUTATION_METHOD,) + DIAGONAL_VALUES_PERMUTATION_METHODS
 """ Supported permutation methods for dense matrices. """
-
 SPARSE_ONLY_PERMUTATION_METHODS = ()
 """ The sparse (CHOLMOD) backend is out of scope of this package (SURVEY.md section 2). """
 
-# *** save and load (constants.py:29-35) *** #
-
-DECOMPOSITION_ATTRIBUTE_FILENAME = 'attribute_{attribute_name}.{file_extension}'
-DECOMPOSITION_ATTRIBUTE_DENSE_FILE_EXTENSION = 'dense.npz'
-DECOMPOSITION_ATTRIBUTE_SPARSE_FILE_EXTENSION = 'sparse.npz'
-DECOMPOSITION_TYPE_FILENAME = 'type.txt'
+# save / load: a tar file `<name>.dec` holding `type.txt` and one `attribute_<name>.dense.npz` per attribute
 DECOMPOSITION_FILENAME_EXTENSION = 'dec'
+DECOMPOSITION_TYPE_FILENAME = 'type.txt'
+DECOMPOSITION_ATTRIBUTE_FILENAME = 'attribute_{attribute_name}.{file_extension}'
+DECOMPOSITION_ATTRIBUTE_DENSE_FILE_EXTENSION, DECOMPOSITION_ATTRIBUTE_SPARSE_FILE_EXTENSION = 'dense.npz', 'sparse.npz'

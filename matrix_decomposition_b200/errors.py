@@ -1,12 +1,14 @@
 """Exception hierarchy of the public API.
 
-Same class names, constructor arguments, attributes and messages as the reference's
-matrix/errors.py:8-176, so that `except matrix.errors.X` clauses keep working.
+The class names, constructor arguments and attributes are those of the reference (matrix/errors.py:8-176), so that
+`except matrix.errors.X` clauses and code that reads `.matrix`, `.decomposition`, `.filename`,
+`.problematic_leading_principal_submatrix_index` ... keep working.  Here every class only declares the text of its
+message; the two bases below fill it in.
 """
 
 
 class BaseError(Exception):
-    """ Base exception of this package (errors.py:8-16). """
+    """ Root of all exceptions of this package. """
 
     def __init__(self, message):
         self.message = message
@@ -16,92 +18,100 @@ class BaseError(Exception):
         return self.message
 
 
-# *** matrix exceptions (errors.py:21-76) *** #
+class _AboutMatrix(BaseError):
+    text = 'Error with matrix with shape {shape}'
 
-class MatrixError(BaseError):
     def __init__(self, matrix, message=None):
         self.matrix = matrix
-        if message is None:
-            message = 'Error with matrix with shape {}'.format(self.matrix.shape)
-        super().__init__(message)
+        super().__init__(message if message is not None else self.text.format(shape=getattr(matrix, 'shape', None)))
+
+
+class _AboutDecomposition(BaseError):
+    text = 'Error with decomposition {dec}'
+
+    def __init__(self, decomposition, message=None):
+        self.decomposition = decomposition
+        super().__init__(message if message is not None else self.text.format(dec=decomposition))
+
+
+# ---- something is wrong with a matrix argument (errors.py:21-76) ----
+
+class MatrixError(_AboutMatrix):
+    pass
 
 
 class MatrixNotSquareError(MatrixError):
-    def __init__(self, matrix):
-        super().__init__(matrix, message='Matrix with shape {} is not a square matrix.'.format(matrix.shape))
+    text = 'Matrix with shape {shape} is not a square matrix.'
 
 
 class MatrixNotFiniteError(MatrixError):
-    def __init__(self, matrix):
-        super().__init__(matrix, message='Matrix with shape {} has not finite entries.'.format(matrix.shape))
+    text = 'Matrix with shape {shape} has not finite entries.'
 
 
 class MatrixSingularError(MatrixError):
-    def __init__(self, matrix):
-        super().__init__(matrix, message='Matrix with shape {} is singular.'.format(matrix.shape))
+    text = 'Matrix with shape {shape} is singular.'
 
 
 class MatrixNotHermitianError(MatrixError):
+    text = 'Matrix with shape {shape} is not Hermitian.'
+
     def __init__(self, matrix, i=None, j=None):
-        message = 'Matrix with shape {} is not Hermitian.'.format(matrix.shape)
+        where = ''
         if i is not None and j is not None:
-            if i != j:
-                message += (' Its value at index ({i}, {j}) is {A_i_j} and its value at index ({j}, {i}) is {A_j_i}.'
-                            ).format(i=i, j=j, A_i_j=matrix[i, j], A_j_i=matrix[j, i])
+            if i == j:
+                where = ' Its {}-th diagonal value {} is complex.'.format(i, matrix[i, i])
             else:
-                message += ' Its {i}-th diagonal value {A_i_i} is complex.'.format(i=i, A_i_i=matrix[i, i])
-        super().__init__(matrix, message=message)
+                where = ' Its value at index ({0}, {1}) is {2} and its value at index ({1}, {0}) is {3}.'.format(
+                    i, j, matrix[i, j], matrix[j, i])
+        super().__init__(matrix, self.text.format(shape=matrix.shape) + where)
 
 
 class MatrixComplexDiagonalValueError(MatrixNotHermitianError):
     def __init__(self, matrix, i=None):
-        super().__init__(matrix, i=i, j=i)
+        super().__init__(matrix, i, i)
 
 
-# *** decomposition exceptions (errors.py:81-122) *** #
+# ---- something is wrong with a decomposition object or file (errors.py:81-122) ----
 
-class DecompositionError(BaseError):
-    def __init__(self, decomposition, message=None):
-        self.decomposition = decomposition
-        if message is None:
-            message = 'Error with decomposition {}'.format(self.decomposition)
-        super().__init__(message)
+class DecompositionError(_AboutDecomposition):
+    pass
 
 
 class DecompositionNotFiniteError(DecompositionError):
-    def __init__(self, decomposition):
-        super().__init__(decomposition, 'Decomposition {} has non-finite entries.'.format(decomposition))
+    text = 'Decomposition {dec} has non-finite entries.'
 
 
 class DecompositionSingularError(DecompositionError):
-    def __init__(self, decomposition):
-        super().__init__(decomposition, 'Decomposition {} represents a singular matrix.'.format(decomposition))
+    text = 'Decomposition {dec} represents a singular matrix.'
 
 
 class DecompositionInvalidFile(DecompositionError, OSError):
-    def __init__(self, filename):
+    text = 'File {filename} is not a valid decomposition file.'
+
+    def __init__(self, filename, **details):
         self.filename = filename
-        DecompositionError.__init__(self, None, 'File {} is not a valid decomposition file.'.format(filename))
+        DecompositionError.__init__(self, None, self.text.format(filename=filename, **details))
 
 
 class DecompositionInvalidDecompositionTypeFile(DecompositionInvalidFile):
+    text = 'File {filename} contains a decomposition of type {found} but type {needed} is needed.'
+
     def __init__(self, filename, type_file, type_needed):
-        self.filename = filename
-        DecompositionError.__init__(
-            self, None, 'File {} contains a decomposition of type {} but type {} is needed.'.format(
-                filename, type_file, type_needed))
+        super().__init__(filename, found=type_file, needed=type_needed)
 
 
-# *** decomposition not calculable (errors.py:127-157) *** #
+# ---- a decomposition cannot be computed or converted (errors.py:127-157) ----
 
 class NoDecompositionPossibleError(BaseError):
     def __init__(self, base, desired_type):
-        self.desired_type = desired_type
-        self.base = base
+        self.base, self.desired_type = base, desired_type
         super().__init__('Base {} can not be converted to type {}.'.format(base, desired_type))
 
 
 class NoDecompositionPossibleWithProblematicSubdecompositionError(NoDecompositionPossibleError):
+    """ Raised by `decompose` for a matrix that is not positive definite: the index of the first leading principal
+    submatrix that fails, and (when available) the decomposition computed up to there. """
+
     def __init__(self, base, desired_type, problematic_leading_principal_submatrix_index, subdecomposition=None):
         super().__init__(base, desired_type)
         self.problematic_leading_principal_submatrix_index = problematic_leading_principal_submatrix_index
@@ -110,16 +120,14 @@ class NoDecompositionPossibleWithProblematicSubdecompositionError(NoDecompositio
 
 
 class NoDecompositionPossibleTooManyEntriesError(NoDecompositionPossibleError):
-    def __init__(self, matrix, desired_type):
-        super().__init__(matrix, desired_type)
+    pass
 
 
 class NoDecompositionConversionImplementedError(NoDecompositionPossibleError):
-    def __init__(self, decomposition, desired_type):
-        super().__init__(decomposition, desired_type)
+    pass
 
 
-# *** this package only *** #
+# ---- this package only ----
 
 class NativeLibraryError(BaseError):
     """ libmdb200.so is missing or a CUDA call failed.  There is no CPU fallback. """
