@@ -11,6 +11,8 @@ explosive regime d / L individually are decided by rounding noise in the referen
 import ctypes
 import json
 import math
+import os
+import sys
 
 import numpy as np
 import pytest
@@ -19,6 +21,8 @@ import workloads
 from conftest import load_golden, ld_join
 
 pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOL = 1e-10
 TOL_B = 1e-12
@@ -846,3 +850,28 @@ def test_distributed_steps_single_rank_equal_single_gpu_path(matrix, orc, n, fix
     assert np.array_equal(clamped, dec.clamped)
     assert np.array_equal(d, np.asarray(dec.d, dtype=float))
     assert np.array_equal(L, dec.L)
+
+
+@pytest.mark.parametrize('p2p', ['0', '1'])
+def test_two_gpu_block_cyclic_equals_single_gpu(p2p, tmp_path):
+    """Needs two GPUs (skipped on a single-GPU box; run with `gpurun --gpus 2`): tools/dist_check.py under torchrun --
+    the 1-D block-cyclic factorization with the NCCL panel broadcast (p2p = 0) and with the experimental peer-memory
+    stores (p2p = 1) must reproduce the single-GPU factor bit for bit (outer blocks of 1, 2 and 4 panels, with and
+    without lookahead) and satisfy the identity at a size with many outer blocks."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    env = dict(os.environ, MDB200_P2P=p2p, DIST_N='4096')
+    env.pop('MDB200_DEVICE', None)
+    port = 29600 + int(p2p)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', str(port),
+                        os.path.join(REPO, 'tools', 'dist_check.py')], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.load(open(os.path.join(REPO, 'gpurun_out', 'dist_check_2gpu.json')))
+    cases = [v for k, v in out.items() if k.startswith('n')]
+    assert len(cases) == 6 and all(c['bitwise_equal_single_gpu'] and c['identity'] <= 1e-12 for c in cases)
+    big = out['bench_n4096_gpus2']
+    assert big['identity'] <= 1e-12
+    assert ('peer-memory' in big['panel_exchange']) == (p2p == '1')
