@@ -249,8 +249,48 @@ int mdb_dist_apply_update(mdb_dist *s, int64_t k_outer, int oslot, int64_t k_fir
 /* finalises the local columns in place (S_loc then holds the local columns of L: scaled, thresholded, unit
  * diagonal, zeros above) and copies the replicated vectors to the host (position order; any may be NULL) */
 int mdb_dist_finalize(mdb_dist *s, double *d, double *omega, double *delta, uint8_t *clamped);
+/* device-side status word of the current factorization: 0 fine; > 0 first non-positive pivot + 1 (MDB_RULE_EXACT);
+ * <= -1001 a bounded wait of the peer-store exchange ran out.  mdb_dist_finalize returns MDB_ERR_NOT_POSITIVE_DEFINITE
+ * / MDB_ERR_STATE accordingly (results are still copied out, for diagnosis); callers exchange the word between the
+ * ranks, because only the rank that timed out sees a protocol error (distributed.py all-reduces it). */
+int mdb_dist_info(mdb_dist *s, int *info_out);
 
-/* ---- EXPERIMENTAL (off by default; bit-identical results on 2 GPUs, not yet measured at scale): panel exchange by
+/* ---- consumers of the distributed factor (config 4): the result must reach dec.solve (decompositions.py:983-991,
+ * :738-766) and the decomposition object (Reimer.py:810-812).  csrc/mdb_dist_solve.cuh. ----
+ * (1) gather, for sizes whose factor fits one GPU: mdb_dist_place_columns writes the column blocks of rank
+ * `src_rank`'s finalised slab (n x ld_slab on THIS device: the rank's own S_loc or a copy received from a peer) to
+ * their global positions in a full n x ld_dst matrix; mdb_factor_upload_device wraps a device-resident L (copied)
+ * in a factor object for mdb_factor_solve / multiply / get (d, p on the host as in mdb_factor_upload). */
+int mdb_dist_place_columns(mdb_ctx *ctx, int64_t n, int src_rank, int world, const double *slab, int64_t ld_slab,
+                           double *dst, int64_t ld_dst);
+int mdb_factor_upload_device(mdb_ctx *ctx, int64_t n, int type, const double *L_dev, int64_t ldl, const double *d,
+                             const int64_t *p, mdb_factor **out);
+/* (2) distributed solve on the slabs where they are (after mdb_dist_finalize).  Right-hand sides: r = n x k doubles
+ * row-major on the device, k in {1, 2, 4, 8}, already permuted (b[p]), replicated on every rank; the solution
+ * replaces them (still in position order).  Rows are processed in windows of 1024; the caller provides the buffers
+ * and the two kinds of small collectives (sum all-reduce over the ranks; with one rank: nothing):
+ *   once per factor   band (mdb_dist_solve_band_elems doubles): mdb_dist_solve_fill_band -> all-reduce(band) ->
+ *                     mdb_dist_solve_invert_band(band, tinv)      (tinv: mdb_dist_solve_tinv_elems doubles)
+ *   forward sweep     t = 0 (n x k);  for w = 0 .. windows-1:  all-reduce(t[1024 w k : 1024 (w+1) k]) ->
+ *                     mdb_dist_solve_fwd_window(w)
+ *   mdb_dist_solve_scale                                          (y / d)
+ *   backward sweep    for w = windows-1 .. 0:  mdb_dist_solve_bwd_colsum(w, r, xchg, partial) -> all-reduce(xchg,
+ *                     1024 k doubles) -> mdb_dist_solve_bwd_window(w)
+ * partial: scratch of mdb_dist_solve_partial_elems doubles.  All calls are asynchronous on the ctx stream. */
+int64_t mdb_dist_solve_band_elems(const mdb_dist *s);
+int64_t mdb_dist_solve_tinv_elems(const mdb_dist *s);
+int64_t mdb_dist_solve_partial_elems(const mdb_dist *s);
+int64_t mdb_dist_solve_windows(const mdb_dist *s);
+int mdb_dist_solve_fill_band(mdb_dist *s, double *band);
+int mdb_dist_solve_invert_band(mdb_dist *s, const double *band, double *tinv);
+int mdb_dist_solve_fwd_window(mdb_dist *s, int64_t w, const double *band, const double *tinv, double *r, double *t,
+                              int k);
+int mdb_dist_solve_scale(mdb_dist *s, double *r, int k);
+int mdb_dist_solve_bwd_colsum(mdb_dist *s, int64_t w, const double *r, double *xchg, double *partial, int k);
+int mdb_dist_solve_bwd_window(mdb_dist *s, int64_t w, const double *band, const double *tinv, double *r,
+                              const double *xchg, int k);
+
+/* ---- optional (MDB200_P2P=1 in distributed.py; bit-identical to the NCCL path): panel exchange by unicast
  * peer-memory stores ----
  * Instead of the NCCL broadcast + mdb_dist_absorb_panel, the owner of a panel stores X, Y = -X D, the alpha / beta /
  * rowmax slices and d / omega / delta / clamped straight into every peer's buffers over NVLink and raises a flag
@@ -264,7 +304,7 @@ int mdb_dist_finalize(mdb_dist *s, double *d, double *omega, double *delta, uint
  *   mdb_dist_release_outer every rank, on a stream ordered after all its kernels that read the operands of the first
  *                          `count` outer blocks */
 int64_t mdb_dist_peer_buffer_elems(const mdb_dist *s);
-int mdb_dist_attach_peers(mdb_dist *s, double *const *peer_base, double *mc_base /* multicast mapping or NULL */);
+int mdb_dist_attach_peers(mdb_dist *s, double *const *peer_base);
 int mdb_dist_push_panel(mdb_dist *s, int64_t k, int slot, int64_t k_outer, int oslot, int64_t outer_index);
 int mdb_dist_wait_panel(mdb_dist *s, int64_t k);
 int mdb_dist_release_outer(mdb_dist *s, int64_t count);

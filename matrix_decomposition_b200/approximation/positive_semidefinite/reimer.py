@@ -26,69 +26,85 @@ APPROXIMATION_ONLY_PERMUTATION_METHODS = (MINIMAL_DIFFERENCE_PERMUTATION_METHOD,
 RESULT_DTYPE = np.longdouble
 
 
-def _check_float_scalar_or_vector(f, n, f_name, default_value, minus_inf_okay=False, plus_inf_okay=False):
-    """R.py:291-322"""
-    if f is not None:
-        try:
-            f = np.asarray(f)
-        except TypeError as original_error:
-            error = ValueError(f'{f_name} must a scalar value or a vector but it is {f}.')
-            logger.error(error)
-            raise error from original_error
-        if not (f.ndim == 0 or (f.ndim == 1 and f.shape[0] == n)):
-            error = ValueError(f'{f_name} must be a scalar or a vector with the same '
-                               f'dimension as A but its shape is {f.shape}.')
-            logger.error(error)
-            raise error
-        if not (np.all(np.isreal(f))):
-            error = ValueError(f'{f_name} must be real valued but it is {f}.')
-            logger.error(error)
-            raise error
-        ok = np.isfinite(f)
-        if plus_inf_okay:
-            ok = np.logical_or(ok, f == math.inf)
-        if minus_inf_okay:
-            ok = np.logical_or(ok, f == -math.inf)
-        if not np.all(ok):
-            error = ValueError(f'{f_name} must be finite'
-                               + (' or minus infinity' if minus_inf_okay else '')
-                               + (' or plus infinity' if plus_inf_okay else '')
-                               + f' but it is {f}.')
-            logger.error(error)
-            raise error
-    else:
-        f = np.asarray(default_value)
-    return f
+def _reject(message, cause=None):
+    """Logs and raises the ValueError every argument check of R.py:291-457 ends in."""
+    error = ValueError(message)
+    logger.error(error)
+    if cause is not None:
+        raise error from cause
+    raise error
 
 
-def _check_float_scalar(f, f_name, default_value=None, lower_bound=None, upper_bound=None,
-                        minus_inf_okay=False, plus_inf_okay=False):
-    """R.py:324-354"""
-    if f is not None:
-        try:
-            f = float(f)
-        except TypeError as original_error:
-            error = ValueError(f'{f_name} must a float value but it is {f}.')
-            logger.error(error)
-            raise error from original_error
-        if not (math.isfinite(f) or (minus_inf_okay and f == -math.inf) or (plus_inf_okay and f == math.inf)):
-            error = ValueError(f'{f_name} must be finite'
-                               + (' or minus infinity' if minus_inf_okay else '')
-                               + (' or plus infinity' if plus_inf_okay else '')
-                               + f' but it is {f}.')
-            logger.error(error)
-            raise error
-        if lower_bound is not None and f < lower_bound:
-            error = ValueError(f'{f_name} must be greater or equal to {lower_bound} but it is {f}.')
-            logger.error(error)
-            raise error
-        if upper_bound is not None and f > upper_bound:
-            error = ValueError(f'{f_name} must be less or equal to {upper_bound} but it is {f}.')
-            logger.error(error)
-            raise error
-    else:
-        f = default_value
-    return f
+def _infinity_policy(allow_minus, allow_plus):
+    """(predicate on an ndarray, description) for the values a bound may take besides finite ones."""
+    extras = [(-math.inf, 'minus infinity')] * allow_minus + [(math.inf, 'plus infinity')] * allow_plus
+
+    def admissible(values):
+        mask = np.isfinite(values)
+        for special, _ in extras:
+            mask = mask | (values == special)
+        return mask
+    return admissible, ''.join(' or ' + text for _, text in extras)
+
+
+def _diag_bound(value, n, name, default, allow_minus=False, allow_plus=False):
+    """A bound on diag(B): None -> default, else a real scalar or an n-vector (contract of R.py:291-322)."""
+    if value is None:
+        return np.asarray(default)
+    try:
+        arr = np.asarray(value)
+    except TypeError as cause:
+        _reject(f'{name}: expected a scalar or a vector, got {value!r}.', cause)
+    if arr.shape not in ((), (n,)):
+        _reject(f'{name}: expected a scalar or a vector of length {n} (the dimension of A), got shape {arr.shape}.')
+    if not np.all(np.isreal(arr)):
+        _reject(f'{name}: expected real values, got {arr}.')
+    admissible, extra_text = _infinity_policy(allow_minus, allow_plus)
+    if not np.all(admissible(arr)):
+        _reject(f'{name}: every value has to be finite{extra_text}, got {arr}.')
+    return arr
+
+
+def _scalar_bound(value, name, default=None, at_least=None, at_most=None, allow_plus=False):
+    """A scalar option: None -> default, else a float inside [at_least, at_most] (contract of R.py:324-354)."""
+    if value is None:
+        return default
+    try:
+        x = float(value)
+    except TypeError as cause:
+        _reject(f'{name}: expected a float, got {value!r}.', cause)
+    if not (math.isfinite(x) or (allow_plus and x == math.inf)):
+        _reject(f'{name}: has to be finite{" or plus infinity" if allow_plus else ""}, got {x}.')
+    if at_least is not None and x < at_least:
+        _reject(f'{name}: has to be >= {at_least}, got {x}.')
+    if at_most is not None and x > at_most:
+        _reject(f'{name}: has to be <= {at_most}, got {x}.')
+    return x
+
+
+_DYNAMIC_CODES = {MINIMAL_DIFFERENCE_PERMUTATION_METHOD: 1, MAXIMAL_STABILITY_PERMUTATION_METHOD: 2}
+
+
+def _resolve_permutation(A, n, permutation, min_diag_D):
+    """-> (p or None, dynamic code).  Strings name a static method (resolved on the host exactly like
+    permute.permutation_vector) or one of the two dynamic pivoting rules (resolved on the device, starting from the
+    identity, R.py:443); anything else must be a length-n vector (R.py:414-457).  None = 'maximal_stability'."""
+    if permutation is None:
+        permutation = MAXIMAL_STABILITY_PERMUTATION_METHOD
+    if not isinstance(permutation, str):
+        p = np.asanyarray(permutation)
+        if p.shape != (n,):
+            _reject(f'permutation: a vector must have one entry per row of A ({n}), got shape {p.shape}.')
+        return p, 0
+    method = permutation.lower()
+    if method in _DYNAMIC_CODES:
+        if method == MINIMAL_DIFFERENCE_PERMUTATION_METHOD and min_diag_D is not None and min_diag_D <= 0:
+            _reject(f"permutation '{method}' needs min_diag_D > 0 (R.py:437-441).")
+        return None, _DYNAMIC_CODES[method]
+    if method not in constants.UNIVERSAL_PERMUTATION_METHODS:
+        known = constants.UNIVERSAL_PERMUTATION_METHODS + APPROXIMATION_ONLY_PERMUTATION_METHODS
+        _reject(f"permutation '{method}' is not one of {known}.")
+    return permute.permutation_vector(A, permutation_method=method), 0
 
 
 def _prepare(A, min_diag_B, max_diag_B, min_diag_D, max_diag_D, min_abs_value_D, min_abs_value_L, permutation):
@@ -103,53 +119,23 @@ def _prepare(A, min_diag_B, max_diag_B, min_diag_D, max_diag_D, min_abs_value_D,
             raise errors.MatrixComplexDiagonalValueError(A, i=np.where(~np.isreal(gamma))[0][0])
         raise ValueError('complex matrices are outside the dense real (float64) path of this package.')
 
-    min_diag_B = _check_float_scalar_or_vector(min_diag_B, n, 'min_diag_B', -math.inf, minus_inf_okay=True)
-    max_diag_B = _check_float_scalar_or_vector(max_diag_B, n, 'max_diag_B', math.inf, plus_inf_okay=True)
-    min_diag_D = _check_float_scalar(min_diag_D, 'min_diag_D', default_value=None, lower_bound=0)
-    max_diag_D = _check_float_scalar(max_diag_D, 'max_diag_D', default_value=math.inf, plus_inf_okay=True)
-    if not (max(np.max(min_diag_B), min_diag_D if min_diag_D is not None else 0)
-            <= min(np.min(max_diag_B), max_diag_D)):  # R.py:368-373
-        error = ValueError(('The values of min_diag_B and min_diag_D must be lower or equal '
-                            'to the values of max_diag_B and max_diag_D.'))
-        logger.error(error)
-        raise error
+    min_diag_B = _diag_bound(min_diag_B, n, 'min_diag_B', -math.inf, allow_minus=True)
+    max_diag_B = _diag_bound(max_diag_B, n, 'max_diag_B', math.inf, allow_plus=True)
+    min_diag_D = _scalar_bound(min_diag_D, 'min_diag_D', at_least=0)
+    max_diag_D = _scalar_bound(max_diag_D, 'max_diag_D', default=math.inf, allow_plus=True)
+    lowest_allowed = max(np.max(min_diag_B), 0 if min_diag_D is None else min_diag_D)
+    highest_allowed = min(np.min(max_diag_B), max_diag_D)
+    if not lowest_allowed <= highest_allowed:  # R.py:368-373
+        _reject(f'the lower bounds (min_diag_B, min_diag_D: {lowest_allowed}) exceed the upper bounds '
+                f'(max_diag_B, max_diag_D: {highest_allowed}).')
 
-    d_eps = np.finfo(np.longdouble).eps  # R.py:396-408
-    min_abs_value_D = _check_float_scalar(min_abs_value_D, 'min_abs_value_D', default_value=d_eps**0.5, lower_bound=0)
-    min_abs_value_D = max(min_abs_value_D, d_eps)
-    L_eps = np.finfo(np.float64).eps
-    min_abs_value_L = _check_float_scalar(min_abs_value_L, 'min_abs_value_L', default_value=L_eps,
-                                          lower_bound=0, upper_bound=1)
-    min_abs_value_L = max(min_abs_value_L, L_eps)
+    # floors of R.py:396-408: |d| >= eps(float128), thresholding of L at >= eps(float64)
+    eps_D = np.finfo(np.longdouble).eps   # stays a longdouble so that its square root rounds like the reference's
+    eps_L = float(np.finfo(np.float64).eps)
+    min_abs_value_D = max(_scalar_bound(min_abs_value_D, 'min_abs_value_D', default=eps_D ** 0.5, at_least=0), eps_D)
+    min_abs_value_L = max(_scalar_bound(min_abs_value_L, 'min_abs_value_L', default=eps_L, at_least=0, at_most=1), eps_L)
 
-    dynamic = 0
-    if permutation is None:  # R.py:415-416
-        permutation = MAXIMAL_STABILITY_PERMUTATION_METHOD
-    if isinstance(permutation, str):
-        permutation_method = permutation.lower()
-        supported = constants.UNIVERSAL_PERMUTATION_METHODS + APPROXIMATION_ONLY_PERMUTATION_METHODS
-        if permutation_method not in supported:
-            error = ValueError(f'Permutation method {permutation_method} is unknown. Only the '
-                               f'following methods are supported {supported}.')
-            logger.error(error)
-            raise error
-        if permutation_method in APPROXIMATION_ONLY_PERMUTATION_METHODS:
-            if (permutation_method == MINIMAL_DIFFERENCE_PERMUTATION_METHOD
-                    and min_diag_D is not None and min_diag_D <= 0):  # R.py:437-441
-                raise ValueError(f'The permutation method {MINIMAL_DIFFERENCE_PERMUTATION_METHOD} is '
-                                 f'only available if min_diag_D is greater zero.')
-            # dynamic pivoting starts from the identity (R.py:443) and is resolved on the device
-            p = None
-            dynamic = 1 if permutation_method == MINIMAL_DIFFERENCE_PERMUTATION_METHOD else 2
-        else:
-            p = permute.permutation_vector(A, permutation_method=permutation_method)
-    else:
-        p = np.asanyarray(permutation)
-        if p.ndim != 1 or p.shape[0] != n:
-            error = ValueError(f'Permutation vector must have same length as the dimensions of '
-                               f'A. Its shape is {p.shape} and the shape of A is {A.shape}.')
-            logger.error(error)
-            raise error
+    p, dynamic = _resolve_permutation(A, n, permutation, min_diag_D)
     return (A, n, p, dynamic, min_diag_B, max_diag_B, min_diag_D, max_diag_D, float(min_abs_value_D),
             float(min_abs_value_L))
 
@@ -206,12 +192,8 @@ def decomposition(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag
     'minimal_difference' run as an unblocked right-looking factorization with a device-wide arg-min per
     column (mdb_approximate_dynamic_f64); they need n^2/2 rule evaluations and are meant for n up to ~10^4.
     """
-    supported_return_types = constants.DECOMPOSITION_TYPES
-    if return_type is not None and return_type not in supported_return_types:
-        error = ValueError(f'Unkown return type {return_type}. Only values in '
-                           f'{supported_return_types} are supported.')
-        logger.error(error)
-        raise error
+    if return_type is not None and return_type not in constants.DECOMPOSITION_TYPES:
+        _reject(f'return_type {return_type!r} is not one of {constants.DECOMPOSITION_TYPES}.')
     type_str = constants.LDL_DECOMPOSITION_TYPE if return_type is None else return_type
     # the factor stays in HBM: dec.L / dec.LD download it on first access, solve / multiply never need to
     _, d64, p, omega, delta, clamped, factor = _run(
@@ -237,6 +219,110 @@ def decomposition(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag
     dec.delta = delta.astype(RESULT_DTYPE)
     dec.clamped = clamped
     return dec
+
+
+def shard_for_rank(batch, rank=None, world=None):
+    """Slice of a batch of independent matrices that rank `rank` of `world` processes factors (contiguous shares,
+    sizes differ by at most one).  Defaults: RANK / WORLD_SIZE of the launcher (torchrun), else the whole batch.
+    Independent units: no data-path collective (BASELINE config 5)."""
+    import os
+    rank = int(os.environ.get('RANK', '0')) if rank is None else int(rank)
+    world = int(os.environ.get('WORLD_SIZE', '1')) if world is None else int(world)
+    if not 0 <= rank < world:
+        raise ValueError(f'rank {rank} is not in [0, {world}).')
+    base, extra = divmod(int(batch), world)
+    begin = rank * base + min(rank, extra)
+    return slice(begin, begin + base + (1 if rank < extra else 0))
+
+
+class BatchedDecompositions:
+    """Result of `decomposition_batched`: a read-only sequence of `batch` LDL decompositions that share their storage
+    (L: batch x n x n, d / omega / delta: batch x n in float64, p: batch x n, clamped: batch x n bool).
+    `result[b]` builds the reference's `LDL_Decomposition` for matrix b with `.omega`, `.delta`, `.clamped` attached
+    exactly as `decomposition` does (R.py:810-812); the arrays themselves are available for bulk use."""
+
+    def __init__(self, L, d, p, omega, delta, clamped):
+        self.L, self.d, self.p, self.omega, self.delta, self.clamped = L, d, p, omega, delta, clamped
+
+    def __len__(self):
+        return self.d.shape[0]
+
+    def __getitem__(self, b):
+        if isinstance(b, slice):
+            return [self[i] for i in range(*b.indices(len(self)))]
+        b = range(len(self))[b]
+        dec = decompositions.LDL_Decomposition(self.L[b], self.d[b].astype(RESULT_DTYPE), p=self.p[b])
+        dec.omega = self.omega[b].astype(RESULT_DTYPE)
+        dec.delta = self.delta[b].astype(RESULT_DTYPE)
+        dec.clamped = self.clamped[b]
+        return dec
+
+    def __iter__(self):
+        return (self[b] for b in range(len(self)))
+
+
+def decomposition_batched(As, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag_D=None,
+                          min_abs_value_D=None, min_abs_value_L=None, permutation=None):
+    """
+    `decomposition(A, ...)` for a stack of independent matrices of one size in ONE device pass: `As` has shape
+    (batch, n, n) (or is a sequence of n x n matrices); the options mean what they mean for `decomposition`
+    (R.py:712-816) and apply to every matrix (a vector `min_diag_B` / `max_diag_B` is indexed by the original row
+    index of each matrix).  Returns a `BatchedDecompositions`; element b equals `decomposition(As[b], ...,
+    return_type='LDL')`.  This is the many-small-matrix regime (BASELINE config 5: 4096 matrices of 512 x 512):
+    the batch rides on the grid's z dimension of every kernel (mdb_approximate_batched_f64) instead of 12 launches
+    per matrix.  A process factors what it is given on its own GPU (LOCAL_RANK); shard a larger job over the ranks
+    of a torchrun launch with `As[shard_for_rank(len(As))]` -- independent units, no collective.
+
+    Static permutation methods and explicit vectors (one length-n vector for all matrices, or batch x n) run
+    batched; the two dynamic pivoting rules need a device-wide arg-min per column and fall back to one
+    `decomposition` call per matrix.
+    """
+    As = np.asarray(As)
+    if As.ndim != 3 or As.shape[1] != As.shape[2]:
+        raise errors.MatrixNotSquareError(As)
+    batch, n = As.shape[0], As.shape[1]
+    explicit = permutation is not None and not isinstance(permutation, str)
+    if explicit:
+        P_all = np.asanyarray(permutation)
+        if P_all.shape not in ((n,), (batch, n)):
+            _reject(f'permutation: expected one vector of length {n} or an array of shape {(batch, n)}, '
+                    f'got shape {P_all.shape}.')
+        P_all = np.broadcast_to(P_all, (batch, n))
+    common = dict(min_diag_B=min_diag_B, max_diag_B=max_diag_B, min_diag_D=min_diag_D, max_diag_D=max_diag_D,
+                  min_abs_value_D=min_abs_value_D, min_abs_value_L=min_abs_value_L)
+    if batch == 0:
+        z = np.zeros((0, n))
+        return BatchedDecompositions(np.zeros((0, n, n)), z, np.zeros((0, n), dtype=np.int64), z, z, np.zeros((0, n), dtype=bool))
+    # the shared options are validated once, against the first matrix (R.py:273-457)
+    first = _prepare(As[0], permutation=P_all[0] if explicit else permutation, **common)
+    _, _, _, dynamic, mB, MB, mD, MD, mavD, mavL = first
+    if dynamic:
+        decs = [decomposition(As[b], permutation=permutation, **common) for b in range(batch)]
+        return BatchedDecompositions(np.stack([x.L for x in decs]), np.stack([np.asarray(x.d, dtype=np.float64) for x in decs]),
+                                     np.stack([np.asarray(x.p, dtype=np.int64) for x in decs]),
+                                     np.stack([np.asarray(x.omega, dtype=np.float64) for x in decs]),
+                                     np.stack([np.asarray(x.delta, dtype=np.float64) for x in decs]),
+                                     np.stack([x.clamped for x in decs]))
+    if np.issubdtype(As.dtype, np.complexfloating):
+        raise ValueError('complex matrices are outside the dense real (float64) path of this package.')
+    A64 = np.ascontiguousarray(As, dtype=np.float64)
+    if explicit:
+        ps = np.ascontiguousarray(P_all, dtype=np.int64)
+    else:
+        method = (permutation or MAXIMAL_STABILITY_PERMUTATION_METHOD).lower()
+        ps = np.stack([np.asarray(permute.permutation_vector(A64[b], permutation_method=method), dtype=np.int64)
+                       for b in range(batch)])
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, mD, MD, mavD, mavL, mB, MB)
+    L = np.empty((batch, n, n), dtype=np.float64)
+    d, omega, delta = (np.empty((batch, n), dtype=np.float64) for _ in range(3))
+    clamped = np.zeros((batch, n), dtype=np.uint8)
+    ctx = _native.context()
+    P = _native.ptr
+    rc = ctx.lib.mdb_approximate_batched_f64(ctx.handle, batch, n, P(A64), n, P(ps), ctypes.byref(bounds), P(L), n, P(d),
+                                             P(omega), P(delta), P(clamped), _native.HOST)
+    ctx.check(rc, 'mdb_approximate_batched_f64')
+    del keep
+    return BatchedDecompositions(L, d, ps, omega, delta, clamped.astype(bool))
 
 
 def positive_semidefinite_matrix(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag_D=None,

@@ -551,6 +551,7 @@ static int gather_sym(mdb_ctx* ctx, int64_t n, int64_t batch, const double* A_de
 extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda, const int64_t* p, int a_loc) {
   if (!f) return MDB_ERR_INVALID;
   mdb_ctx* ctx = f->ctx;
+  ctx->last_input_nonfinite = 0;   // describes THIS call from here on, also when it returns early
   MDB_CHECK(ctx, A || f->n == 0, "mdb_factor_set_matrix: A is null");
   MDB_CHECK(ctx, lda >= f->n, "mdb_factor_set_matrix: lda < n");
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1847,3 +1848,4 @@ extern "C" int mdb_debug_gemm_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
 
 #include "mdb_dist.cuh"
 #include "mdb_peer.cuh"
+#include "mdb_dist_solve.cuh"

@@ -25,7 +25,6 @@ struct mdb_dist {
   // the caller and mapped into every rank
   bool p2p;
   double* peer_base[16];
-  double* peer_mc;
   unsigned int* push_counter;
   uint32_t epoch;      // factorization counter, tags the arrival / release flags
 };
@@ -84,7 +83,6 @@ extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, dou
   s->pcol_dev = nullptr; s->have_bounds = false;
   s->p2p = false; s->push_counter = nullptr; s->epoch = 0;
   for (int q = 0; q < 16; ++q) s->peer_base[q] = nullptr;
-  s->peer_mc = nullptr;
   s->OPX[0] = s->OPX[1] = s->OPY[0] = s->OPY[1] = nullptr;
   s->ldp = dist_outer_width(ctx, n, 0) * NB;  // the first outer block is the widest
   cudaError_t e = dev_malloc(ctx, (void**)&s->vec, (size_t)7 * n * 8);
@@ -431,6 +429,19 @@ extern "C" int mdb_dist_apply_update(mdb_dist* s, int64_t k_outer, int oslot, in
   return launch_gemm_tn<true, true, false>(ctx, g, 1);
 }
 
+static int dist_info_status(mdb_dist* s, int info) {
+  if (info == 0) return MDB_OK;
+  mdb_ctx* ctx = s->ctx;
+  if (info > 0) {
+    snprintf(ctx->err, sizeof(ctx->err), "distributed factorization: pivot %d is not positive", info - 1);
+    return MDB_ERR_NOT_POSITIVE_DEFINITE;
+  }
+  snprintf(ctx->err, sizeof(ctx->err),
+           "distributed factorization: panel exchange protocol error %d (a bounded wait on a peer ran out; the factor "
+           "is not valid)", info);
+  return MDB_ERR_STATE;
+}
+
 extern "C" int mdb_dist_finalize(mdb_dist* s, double* d, double* omega, double* delta, uint8_t* clamped) {
   if (!s) return MDB_ERR_INVALID;
   mdb_ctx* ctx = s->ctx;
@@ -445,6 +456,21 @@ extern "C" int mdb_dist_finalize(mdb_dist* s, double* d, double* omega, double* 
   if (omega) MDB_CUDA(ctx, cudaMemcpyAsync(omega, s->omega, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (delta) MDB_CUDA(ctx, cudaMemcpyAsync(delta, s->delta, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (clamped) MDB_CUDA(ctx, cudaMemcpyAsync(clamped, s->clamped, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  int info = 0;
+  MDB_CUDA(ctx, cudaMemcpyAsync(&info, s->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return dist_info_status(s, info);
+}
+
+// The device-side status word of the current factorization: 0 = fine, > 0 = first non-positive pivot + 1
+// (MDB_RULE_EXACT), <= -1001 = a bounded wait of the peer-store exchange ran out (mdb_peer.cuh).  The factor of a
+// run with info != 0 must not be used; mdb_dist_finalize returns the matching error status.  Every rank should
+// exchange the value (distributed.py all-reduces it) because only the rank that timed out sees a protocol error.
+extern "C" int mdb_dist_info(mdb_dist* s, int* info_out) {
+  if (!s || !info_out) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = s->ctx;
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  MDB_CUDA(ctx, cudaMemcpyAsync(info_out, s->info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MDB_OK;
 }

@@ -52,7 +52,6 @@ extern "C" int64_t mdb_dist_peer_buffer_elems(const mdb_dist* s) { return s ? pe
 
 struct PeerPtrs {
   double* base[MDB_PEER_MAX];  // symmetric buffer of every rank as mapped into this process (base[rank] = own)
-  double* mc;                  // multicast mapping of the same buffers (a store lands on every rank), or null
   int world, rank;
 };
 
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(256) k_dist_push(int64_t rows, const double* _
   if (blockIdx.x == 0 && threadIdx.x < kb) {  // d / omega / delta / clamped of the panel's columns
     const double dv = hdr[threadIdx.x], ov = hdr[MDB_NB + threadIdx.x], ev = hdr[3 * MDB_NB + threadIdx.x];
     const uint8_t cv = (uint8_t)(hdr[4 * MDB_NB + threadIdx.x] != 0.0);
-    for (int q = 0; q < P.world; ++q) {   // 4 x 128 values per panel: unicast in both modes (byte stores included)
+    for (int q = 0; q < P.world; ++q) {   // 4 x 128 values per panel
       if (q == P.rank) continue;
       double* v = P.base[q] + off_vec;
       v[4 * n + k0 + threadIdx.x] = dv;
@@ -106,27 +105,17 @@ __global__ void __launch_bounds__(256) k_dist_push(int64_t rows, const double* _
   for (int64_t r = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7); r < rows; r += (int64_t)gridDim.x * 2) {
     const double x = OX[r * ldp + c];
     const double y = -x * dc;
-    if (P.mc) {  // one store, replicated by the switch to every rank (the owner's own copy receives the same value)
-      P.mc[off_x + r * ldp + c] = x;
-      P.mc[off_y + r * ldp + c] = y;
-    } else {
-      for (int q = 0; q < P.world; ++q) {
-        if (q == P.rank) continue;
-        P.base[q][off_x + r * ldp + c] = x;
-        P.base[q][off_y + r * ldp + c] = y;
-      }
+    for (int q = 0; q < P.world; ++q) {
+      if (q == P.rank) continue;
+      P.base[q][off_x + r * ldp + c] = x;
+      P.base[q][off_y + r * ldp + c] = y;
     }
     if (c == 0) {
       const double a = alpha[r], b = beta[r], m = rowmax[r];
-      if (P.mc) {
-        double* v = P.mc + off_alpha + r;
+      for (int q = 0; q < P.world; ++q) {
+        if (q == P.rank) continue;
+        double* v = P.base[q] + off_alpha + r;   // alpha at vec + n, beta at vec + 2 n, rowmax at vec + 3 n
         v[0] = a; v[n] = b; v[2 * n] = m;
-      } else {
-        for (int q = 0; q < P.world; ++q) {
-          if (q == P.rank) continue;
-          double* v = P.base[q] + off_alpha + r;   // alpha at vec + n, beta at vec + 2 n, rowmax at vec + 3 n
-          v[0] = a; v[n] = b; v[2 * n] = m;
-        }
       }
     }
   }
@@ -159,16 +148,15 @@ static PeerPtrs peer_ptrs(const mdb_dist* s) {
   memset(&P, 0, sizeof(P));
   P.world = s->world; P.rank = s->rank;
   for (int q = 0; q < s->world; ++q) P.base[q] = s->peer_base[q];
-  P.mc = s->peer_mc;
   return P;
 }
 
 // peer_base: host array of `world` device pointers, the symmetric buffer of every rank as mapped into this process
 // (peer_base[rank] = this rank's own).  The buffers must be zero-filled and all ranks must have attached before the
 // first mdb_dist_set_bounds.  From here on the operand buffers and the state vectors live in the symmetric buffer.
-// mc_base (may be null): multicast mapping of the same buffers (NVLS); the bulk of a panel then leaves the owner once
-// instead of once per peer.  Untested so far.
-extern "C" int mdb_dist_attach_peers(mdb_dist* s, double* const* peer_base, double* mc_base) {
+// Stores are unicast (one copy per peer on the owner's egress links).  An NVLS multicast variant would have to use
+// multimem.st with its own fence (plain stores to a multicast address are undefined); it is not implemented.
+extern "C" int mdb_dist_attach_peers(mdb_dist* s, double* const* peer_base) {
   if (!s || !peer_base) return MDB_ERR_INVALID;
   mdb_ctx* ctx = s->ctx;
   MDB_CHECK(ctx, s->world <= MDB_PEER_MAX, "mdb_dist_attach_peers: more ranks than MDB_PEER_MAX");
@@ -190,7 +178,6 @@ extern "C" int mdb_dist_attach_peers(mdb_dist* s, double* const* peer_base, doub
   s->gamma = s->vec; s->alpha = s->vec + n; s->beta = s->vec + 2 * n; s->rowmax = s->vec + 3 * n;
   s->d = s->vec + 4 * n; s->omega = s->vec + 5 * n; s->delta = s->vec + 6 * n;
   for (int q = 0; q < s->world; ++q) s->peer_base[q] = peer_base[q];
-  s->peer_mc = mc_base;
   if (!s->push_counter) {
     MDB_CUDA(ctx, dev_malloc(ctx, (void**)&s->push_counter, sizeof(unsigned int)));
     MDB_CUDA(ctx, cudaMemsetAsync(s->push_counter, 0, sizeof(unsigned int), ctx->stream));

@@ -164,8 +164,9 @@ class NcclComm:
 
 
 class PeerComm:
-    """EXPERIMENTAL (MDB200_P2P=1; bit-identical results on 2 GPUs, not yet measured at scale): no collective at all -- the owner of a panel stores it into every peer's operand
-    buffers over NVLink (mdb_dist_push_panel, csrc/mdb_peer.cuh) and the consumers' streams wait for its arrival flag."""
+    """MDB200_P2P=1: no collective at all -- the owner of a panel stores it into every peer's operand buffers over
+    NVLink (unicast stores, mdb_dist_push_panel, csrc/mdb_peer.cuh) and the consumers' streams wait for its arrival
+    flag.  Bit-identical to the NCCL path and to one GPU."""
 
     def exchange_panel(self, steps, k, slot, k_outer, oslot, outer_index, owner, stream):
         if owner == steps.rank:
@@ -178,7 +179,7 @@ class PeerComm:
 
 
 def peer_stores_requested():
-    return os.environ.get('MDB200_P2P', '0') in ('1', '2')     # 2: through the NVLS multicast mapping when there is one
+    return os.environ.get('MDB200_P2P', '0') == '1'
 
 
 class CudaSteps:
@@ -209,10 +210,23 @@ class CudaSteps:
         self._symm = None
 
     def close(self):
+        if self._symm is not None:
+            # peers may still have stores in flight into this rank's symmetric buffer (e.g. the release counter written
+            # from a peer's bulk stream): nobody unmaps before everybody has drained its streams
+            import torch
+            import torch.distributed as dist
+            torch.cuda.synchronize()
+            dist.barrier()
         if self.handle:
             self.ctx.lib.mdb_dist_destroy(self.handle)
             self.handle = None
         self._symm = None
+
+    def info(self):
+        """The device-side status word of the current factorization (mdb_dist_info)."""
+        v = ctypes.c_int(0)
+        self.ctx.check(self.ctx.lib.mdb_dist_info(self.handle, ctypes.byref(v)), 'mdb_dist_info')
+        return int(v.value)
 
     # ---- experimental peer-store exchange (csrc/mdb_peer.cuh) ----
     def enable_peer_stores(self):
@@ -221,7 +235,7 @@ class CudaSteps:
         Returns False (on every rank) when any rank could not set it up; the NCCL path then stays in place."""
         import torch
         import torch.distributed as dist
-        ok, ptrs, keep, mc = 1, None, None, 0
+        ok, ptrs, keep = 1, None, None
         try:
             import torch.distributed._symmetric_memory as symm_mem
             elems = int(self.ctx.lib.mdb_dist_peer_buffer_elems(self.handle))
@@ -234,7 +248,6 @@ class CudaSteps:
             t.zero_()
             hdl = symm_mem.rendezvous(t, group)
             ptrs = [int(x) for x in hdl.buffer_ptrs]
-            mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if os.environ.get('MDB200_P2P') == '2' else 0
             if len(ptrs) != self.world or ptrs[self.rank] != t.data_ptr():
                 raise RuntimeError('unexpected symmetric memory handle')
             keep = (t, hdl)
@@ -249,8 +262,7 @@ class CudaSteps:
             return False
         torch.cuda.synchronize()
         arr = (ctypes.c_void_p * self.world)(*ptrs)
-        self.ctx.check(self.ctx.lib.mdb_dist_attach_peers(self.handle, arr, ctypes.c_void_p(mc or None)), 'mdb_dist_attach_peers')
-        self.peer_multicast = bool(mc)
+        self.ctx.check(self.ctx.lib.mdb_dist_attach_peers(self.handle, arr), 'mdb_dist_attach_peers')
         self._symm = keep
         dist.barrier()
         return True
@@ -320,14 +332,37 @@ class CudaSteps:
         self.ctx.check(self.ctx.lib.mdb_dist_set_local(self.handle, self._native.ptr(A_loc_host), self.ld, self._native.HOST),
                        'mdb_dist_set_local')
 
-    def finalize(self, stream):
+    def finalize(self, stream, collective=True):
+        """Finalises the local columns and returns the replicated vectors.  Raises on EVERY rank when any rank's
+        device-side status word is non-zero (a protocol time-out of the peer-store exchange is only seen by the
+        rank that waited): the word is all-reduced (min and max) before the local status is looked at."""
         self._on(stream)
         n = self.n
         d, omega, delta = np.empty(n), np.empty(n), np.empty(n)
         clamped = np.zeros(n, dtype=np.uint8)
         P = self._native.ptr
-        self.ctx.check(self.ctx.lib.mdb_dist_finalize(self.handle, P(d), P(omega), P(delta), P(clamped)), 'mdb_dist_finalize')
+        rc = self.ctx.lib.mdb_dist_finalize(self.handle, P(d), P(omega), P(delta), P(clamped))
+        if collective and self.world > 1:
+            check_status_all_ranks(self.info(), self.device)
+        self.ctx.check(rc, 'mdb_dist_finalize')
         return d, omega, delta, clamped.astype(bool)
+
+
+def check_status_all_ranks(info, device=None):
+    """All-reduces a rank-local status word; raises the same NativeLibraryError on every rank when any is non-zero."""
+    import torch
+    import torch.distributed as dist
+    from . import errors
+    dev = torch.device('cuda', device) if (device is not None and dist.get_backend() == 'nccl') else torch.device('cpu')
+    t = torch.tensor([info, -info], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    hi, lo = int(t[0].item()), -int(t[1].item())
+    if hi == 0 and lo == 0:
+        return
+    if lo < 0:
+        raise errors.NativeLibraryError('distributed factorization: panel exchange protocol error {} on some rank (a bounded '
+                                        'wait on a peer ran out); the factor is not valid'.format(lo))
+    raise errors.NativeLibraryError('distributed factorization: pivot {} is not positive'.format(hi - 1))
 
 
 def _streams(device):
@@ -367,31 +402,223 @@ def approximate_distributed(Ap_or_none, n, bounds_kwargs, p=None, generator=None
         dist.barrier()      # nobody stores into a peer that is still resetting its vectors
     factorize(n, rank, world, steps, PeerComm() if peer else NcclComm(), main, bulk, lookahead=lookahead)
     torch.cuda.synchronize()
+    if peer:
+        dist.barrier()      # every rank's one-sided stores (release counters included) have landed before anyone goes on
     d, omega, delta, clamped = steps.finalize(main)
     return steps, d, omega, delta, clamped
 
 
-def identity_residual(steps, d, omega, delta, nprobe=2, seed=5):
-    """Oracle-free check at any n (Reimer.py:947-957): L D L^T v == (A o Omega + diag(gamma + delta)) v in
-    position order, with L and A as local column slabs and one all-reduce per side.  Test / bench helper
-    (plain torch products on the slabs), not part of the factorization path."""
+class DistributedFactor:
+    """The result of `approximate_distributed` as something a caller can USE:
+    L stays block-cyclic on the GPUs, `solve` runs there (decompositions.py:983-991), `gather` turns it into the
+    reference's LDL_Decomposition on one rank when it fits (Reimer.py:810-812).
+
+    `d`, `p` are replicated numpy arrays (position order / position -> original index); `omega`, `delta` are in
+    POSITION order as approximate_distributed returns them.  Collective methods must be called by every rank."""
+
+    SOLVE_WINDOW = 8 * NB
+
+    def __init__(self, steps, d, p, omega=None, delta=None, clamped=None):
+        self.steps, self.n = steps, steps.n
+        self.d = np.asarray(d, dtype=np.float64)
+        self.p = np.arange(self.n, dtype=np.int64) if p is None else np.asarray(p, dtype=np.int64)
+        self.omega, self.delta, self.clamped = omega, delta, clamped
+        self._solve_ws = None
+        self._stream = None
+
+    def close(self):
+        self._solve_ws = None
+        self.steps.close()
+
+    def _main(self):
+        import torch
+        if self._stream is None:
+            self._stream = TorchStream(torch.cuda.Stream(device=self.steps.device, priority=-1))
+        return self._stream
+
+    @staticmethod
+    def _all_reduce(t, world):
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t)
+
+    # ---- gather (collective) ----
+    def gather(self, dst=0):
+        """The whole factor on rank `dst` as an LDL_Decomposition (with the factor resident on its GPU; `.L`
+        downloads it), None on the other ranks.  Needs n^2 * 8 bytes plus one slab of free memory on that GPU."""
+        import torch
+        import torch.distributed as dist
+        from . import decompositions
+        st = self.steps
+        n, world, rank = self.n, st.world, st.rank
+        main = self._main()
+        lib, ctx = st.ctx.lib, st.ctx
+        dec = None
+        with torch.cuda.stream(main.stream):
+            st._on(main)
+            full = torch.zeros((n, n), dtype=torch.float64, device=st.S.device) if rank == dst else None
+            for r in range(world):
+                ld_r = local_cols(n, r, world)
+                if rank == dst:
+                    slab = st.S if r == rank else torch.empty((n, ld_r), dtype=torch.float64, device=st.S.device)
+                    if r != rank:
+                        dist.recv(slab, src=r)
+                    ctx.check(lib.mdb_dist_place_columns(ctx.handle, n, r, world, ctypes.c_void_p(slab.data_ptr()), ld_r,
+                                                         ctypes.c_void_p(full.data_ptr()), n), 'mdb_dist_place_columns')
+                    torch.cuda.current_stream().synchronize()
+                    del slab
+                elif rank == r:
+                    dist.send(st.S, dst=dst)
+            if rank == dst:
+                h = ctypes.c_void_p()
+                P = st._native.ptr
+                d64 = np.ascontiguousarray(self.d)
+                p64 = np.ascontiguousarray(self.p)
+                ctx.check(lib.mdb_factor_upload_device(ctx.handle, n, st._native.TYPE_LDL, ctypes.c_void_p(full.data_ptr()), n,
+                                                       P(d64), P(p64), ctypes.byref(h)), 'mdb_factor_upload_device')
+                del full
+                dec = decompositions.LDL_Decomposition(None, self.d.astype(np.longdouble), p=self.p)
+                dec._attach_lazy_matrix(st._native.Factor(ctx, h), n, np.ones(n))
+                if self.omega is not None:      # original index order like R.py:538,545
+                    for name in ('omega', 'delta'):
+                        v = np.empty(n, dtype=np.longdouble)
+                        v[self.p] = getattr(self, name)
+                        setattr(dec, name, v)
+                    dec.clamped = self.clamped
+        return dec
+
+    # ---- distributed solve (collective) ----
+    def _prepare_solve(self):
+        import torch
+        if self._solve_ws is not None:
+            return self._solve_ws
+        st = self.steps
+        lib, ctx, h = st.ctx.lib, st.ctx, st.handle
+        dev = st.S.device
+        main = self._main()
+        ws = dict(windows=int(lib.mdb_dist_solve_windows(h)))
+        with torch.cuda.stream(main.stream):
+            st._on(main)
+            ws['band'] = torch.empty(int(lib.mdb_dist_solve_band_elems(h)), dtype=torch.float64, device=dev)
+            ws['tinv'] = torch.empty(int(lib.mdb_dist_solve_tinv_elems(h)), dtype=torch.float64, device=dev)
+            ws['partial'] = torch.empty(int(lib.mdb_dist_solve_partial_elems(h)), dtype=torch.float64, device=dev)
+            ctx.check(lib.mdb_dist_solve_fill_band(h, ctypes.c_void_p(ws['band'].data_ptr())), 'mdb_dist_solve_fill_band')
+            self._all_reduce(ws['band'], st.world)     # disjoint supports: the sum is exact
+            ctx.check(lib.mdb_dist_solve_invert_band(h, ctypes.c_void_p(ws['band'].data_ptr()),
+                                                     ctypes.c_void_p(ws['tinv'].data_ptr())), 'mdb_dist_solve_invert_band')
+        self._solve_ws = ws
+        return ws
+
+    def solve(self, b):
+        """x with A x = b for the factorized (approximated) matrix, b of shape (n,) or (n, k), the same on every rank;
+        returns x on every rank.  Same contract as DecompositionBase.solve (decompositions.py:738-766)."""
+        import torch
+        from . import errors
+        st = self.steps
+        n, world = self.n, st.world
+        b = np.asarray(b)
+        B = np.ascontiguousarray(b.reshape(n, -1), dtype=np.float64)
+        if np.any(np.abs(self.d) < np.finfo(np.longdouble).resolution):       # decompositions.py:949-951
+            raise errors.DecompositionSingularError(self)
+        ws = self._prepare_solve()
+        lib, ctx, h = st.ctx.lib, st.ctx, st.handle
+        dev = st.S.device
+        main = self._main()
+        WD = self.SOLVE_WINDOW
+        X = np.empty_like(B)
+        q = np.empty(n, dtype=np.int64)
+        q[self.p] = np.arange(n)
+        vp = ctypes.c_void_p
+        with torch.cuda.stream(main.stream):
+            st._on(main)
+            for c0 in range(0, B.shape[1], 8):
+                kc = min(8, B.shape[1] - c0)
+                k = 1 if kc == 1 else 2 if kc == 2 else 4 if kc <= 4 else 8
+                chunk = np.zeros((n, k))
+                chunk[:, :kc] = B[self.p, c0:c0 + kc]                      # b[p]
+                r = torch.from_numpy(chunk).to(dev)
+                t = torch.zeros((n, k), dtype=torch.float64, device=dev)
+                xchg = torch.empty((WD, k), dtype=torch.float64, device=dev)
+                for w in range(ws['windows']):
+                    self._all_reduce(t[w * WD:min((w + 1) * WD, n)], world)
+                    ctx.check(lib.mdb_dist_solve_fwd_window(h, w, vp(ws['band'].data_ptr()), vp(ws['tinv'].data_ptr()),
+                                                            vp(r.data_ptr()), vp(t.data_ptr()), k), 'mdb_dist_solve_fwd_window')
+                ctx.check(lib.mdb_dist_solve_scale(h, vp(r.data_ptr()), k), 'mdb_dist_solve_scale')
+                for w in range(ws['windows'] - 1, -1, -1):
+                    ctx.check(lib.mdb_dist_solve_bwd_colsum(h, w, vp(r.data_ptr()), vp(xchg.data_ptr()),
+                                                            vp(ws['partial'].data_ptr()), k), 'mdb_dist_solve_bwd_colsum')
+                    self._all_reduce(xchg, world)
+                    ctx.check(lib.mdb_dist_solve_bwd_window(h, w, vp(ws['band'].data_ptr()), vp(ws['tinv'].data_ptr()),
+                                                            vp(r.data_ptr()), vp(xchg.data_ptr()), k), 'mdb_dist_solve_bwd_window')
+                X[:, c0:c0 + kc] = r.cpu().numpy()[q, :kc]                 # x[p^-1]
+        return X.reshape(b.shape)
+
+
+def decomposition_distributed(A, n=None, generator=None, lookahead=True, **bounds_kwargs):
+    """`approximation.positive_semidefinite.decomposition` over all ranks of the default process group, for matrices
+    that need more than one GPU (BASELINE config 4): returns a DistributedFactor (solve on the slabs, gather when it
+    fits).  `A`: the host matrix, the same on every rank (or None with generator = (seed, mu) for family F2);
+    static permutation methods / explicit vectors only (dynamic pivoting would need an arg-min all-reduce per column:
+    replicas only)."""
+    from . import permute
+    from .approximation.positive_semidefinite import reimer
+    permutation = bounds_kwargs.pop('permutation', 'decreasing_diagonal_values')
+    if A is not None:
+        A = np.asarray(A)
+        n = A.shape[0]
+        prepared = reimer._prepare(A, bounds_kwargs.get('min_diag_B'), bounds_kwargs.get('max_diag_B'),
+                                   bounds_kwargs.get('min_diag_D'), bounds_kwargs.get('max_diag_D'),
+                                   bounds_kwargs.get('min_abs_value_D'), bounds_kwargs.get('min_abs_value_L'), permutation)
+        _, _, p, dynamic, mB, MB, mD, MD, mavD, mavL = prepared
+        if dynamic:
+            raise ValueError('the dynamic pivoting methods are not available for the distributed factorization; pass a '
+                             'static permutation method or a permutation vector.')
+        p = np.asarray(p, dtype=np.int64)
+        Ap = np.ascontiguousarray(A[p[:, None], p[None, :]], dtype=np.float64)
+        kw = dict(min_diag_D=mD, max_diag_D=MD, min_abs_value_D=mavD, min_abs_value_L=mavL,
+                  min_diag_B=None if np.all(np.isneginf(mB)) else mB, max_diag_B=None if np.all(np.isposinf(MB)) else MB)
+    else:
+        from . import _native
+        seed, mu = generator
+        ctx = _native.context()
+        diag = np.empty(n)
+        ctx.check(ctx.lib.mdb_generate_diag_f2(ctx.handle, n, seed, mu, _native.ptr(diag)), 'mdb_generate_diag_f2')
+        p = np.asarray(permute.permutation_vector(_DiagOnly(diag), permutation) if isinstance(permutation, str)
+                       else permutation, dtype=np.int64)
+        Ap = None
+        kw = dict(bounds_kwargs)
+        kw.setdefault('min_abs_value_D', float(np.finfo(np.longdouble).eps) ** 0.5)
+        kw.setdefault('min_abs_value_L', float(np.finfo(np.float64).eps))
+    steps, d, omega, delta, clamped = approximate_distributed(Ap, n, kw, p=p, generator=generator, lookahead=lookahead)
+    return DistributedFactor(steps, d, p, omega, delta, clamped)
+
+
+class _DiagOnly:
+    """Just enough of a matrix for permute.permutation_vector: shape and diagonal()."""
+
+    def __init__(self, diag):
+        self._diag = diag
+        self.shape = (len(diag), len(diag))
+
+    def diagonal(self):
+        return self._diag
+
+
+def _apply_composed_from_A(steps, omega, delta, V):
+    """(A o Omega + diag(gamma + delta)) V and A V in position order from the local column slabs of the ORIGINAL
+    matrix (steps.A), one all-reduce each -- the right-hand side of Reimer.py:947-957.  Test / bench helper (plain
+    torch products on the slabs), not part of the factorization or solve path."""
     import torch
     import torch.distributed as dist
     n, ld, rank, world = steps.n, steps.ld, steps.rank, steps.world
     dev = steps.S.device
-    g = torch.Generator(device='cpu')
-    g.manual_seed(seed)
-    V = torch.rand((n, nprobe), generator=g, dtype=torch.float64).to(dev) * 2 - 1
+    nprobe = V.shape[1]
     lc = torch.arange(ld, device=dev)
     gc = ((lc // NB) * world + rank) * NB + lc % NB
     valid = gc < n
     gcv = gc.clamp(max=n - 1)
-    d_t = torch.as_tensor(d, device=dev)
     w_t = torch.as_tensor(omega, device=dev)
     de_t = torch.as_tensor(delta, device=dev)
-    L = steps.S                                   # local columns of L after finalize
-    z = (L.T @ V) * (d_t[gcv] * valid)[:, None]   # d_k (L[:, k] . v) for local k
-    lhs = L @ z
     # (A o Omega)[i, k] = A[i, k] * omega[max(i, k)], diagonal replaced by gamma + delta
     rows = torch.arange(n, device=dev)
     rhs = torch.zeros((n, nprobe), dtype=torch.float64, device=dev)
@@ -408,10 +635,43 @@ def identity_residual(steps, d, omega, delta, nprobe=2, seed=5):
         rhs += M @ V[g_blk] * 1.0
         av += (Ablk * valid[c0:c1][None, :]) @ V[g_blk]
         del W, Om, M
-    dist.all_reduce(lhs)
-    dist.all_reduce(rhs)
-    dist.all_reduce(av)
+    if world > 1:
+        dist.all_reduce(rhs)
+        dist.all_reduce(av)
+    return rhs, av, gcv, valid
+
+
+def identity_residual(steps, d, omega, delta, nprobe=2, seed=5):
+    """Oracle-free check at any n (Reimer.py:947-957): L D L^T v == (A o Omega + diag(gamma + delta)) v in
+    position order, with L and A as local column slabs and one all-reduce per side.  Test / bench helper
+    (plain torch products on the slabs), not part of the factorization path."""
+    import torch
+    import torch.distributed as dist
+    n = steps.n
+    dev = steps.S.device
+    g = torch.Generator(device='cpu')
+    g.manual_seed(seed)
+    V = torch.rand((n, nprobe), generator=g, dtype=torch.float64).to(dev) * 2 - 1
+    rhs, av, gcv, valid = _apply_composed_from_A(steps, omega, delta, V)
+    d_t = torch.as_tensor(d, device=dev)
+    L = steps.S                                   # local columns of L after finalize
+    z = (L.T @ V) * (d_t[gcv] * valid)[:, None]   # d_k (L[:, k] . v) for local k
+    lhs = L @ z
+    if steps.world > 1:
+        dist.all_reduce(lhs)
     return float((lhs - rhs).abs().max() / av.abs().max())
+
+
+def solve_residual(factor, b_pos, x_pos):
+    """|| (A o Omega + diag(gamma + delta)) x - b ||_max / || b ||_max in position order: the distributed solve checked
+    against the ORIGINAL matrix slabs through the identity B = A o Omega + diag(delta) (Reimer.py:947-957), so it
+    does not use L at all.  Test / bench helper."""
+    import torch
+    dev = factor.steps.S.device
+    X = torch.as_tensor(np.ascontiguousarray(x_pos.reshape(factor.n, -1)), device=dev)
+    Bx, _, _, _ = _apply_composed_from_A(factor.steps, factor.omega, factor.delta, X)
+    B = torch.as_tensor(np.ascontiguousarray(b_pos.reshape(factor.n, -1)), device=dev)
+    return float((Bx - B).abs().max() / B.abs().max())
 
 
 def _mem_available_bytes():
@@ -424,7 +684,7 @@ def _mem_available_bytes():
     return 0
 
 
-def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None):
+def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None, peak_hbm_gbs=None):
     """bench.py's N > 1 leg: family F2 generated on the devices, timed with CUDA events, max over ranks.
     Adds a serialised profiling pass (roofline of the bulk update kernel on this rank's share) and an
     end-to-end leg in which every rank starts from its own column slab in pinned HOST memory."""
@@ -472,10 +732,33 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None):
             launches += ctx.launch_count() - l0
     d, omega, delta, clamped = st.finalize(main)
     ident = identity_residual(st, d, omega, delta)
+    # ---- the consumer of the distributed factor: solve on the slabs (1 right-hand side), checked against the
+    #      original matrix through B = A o Omega + diag(delta) ----
+    dsolve = None
+    try:
+        import time as _time
+        hbm = peak_hbm_gbs or 6547.5
+        fac = DistributedFactor(st, d, np.arange(n, dtype=np.int64), omega, delta, clamped)   # position order in and out
+        b = np.random.default_rng(1).standard_normal(n)
+        x = fac.solve(b)                       # builds the replicated band (once per factor)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = _time.perf_counter()
+        x = fac.solve(b)
+        torch.cuda.synchronize()
+        sec = max_over_ranks(_time.perf_counter() - t0)
+        gbs = 8.0 * n * n / sec / 1e9
+        dsolve = dict(n=n, nrhs=1, seconds=sec, algorithmic_bytes=8.0 * n * n, achieved=gbs, peak=hbm * world, unit='GB/s',
+                      frac=gbs / (hbm * world), residual_vs_original_matrix=solve_residual(fac, b, x),
+                      note='host-timed (max over ranks), b and x as numpy arrays; L streamed once per sweep from the '
+                           'block-cyclic slabs, one 1024-row window = one small all-reduce per sweep')
+        fac._solve_ws = None
+        del fac
+    except Exception as e:  # noqa: BLE001
+        dsolve = dict(error='%s: %s' % (type(e).__name__, e))
     out = dict(ms_per_step=float(np.mean(times)), gpu_launches=int(launches), identity=ident,
-               n_clamped=int(clamped.sum()),
-               panel_exchange=('peer-memory stores (experimental, MDB200_P2P), ' +
-                               ('multicast' if getattr(st, 'peer_multicast', False) else 'unicast')) if peer else 'NCCL broadcast')
+               n_clamped=int(clamped.sum()), dist_solve=dsolve,
+               panel_exchange='peer-memory stores (MDB200_P2P=1, unicast)' if peer else 'NCCL broadcast')
 
     # ---- roofline: one serialised pass (no lookahead, everything on the main stream), events per bulk update ----
     st.generate_f2(seed, mu, p, main)

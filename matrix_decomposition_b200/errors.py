@@ -127,6 +127,21 @@ class NoDecompositionConversionImplementedError(NoDecompositionPossibleError):
     pass
 
 
+# ---- iterative helpers (errors.py:162-176; raised by nothing on the dense path, kept for `except` clauses) ----
+
+class TooManyIterationsError(BaseError):
+    """ An iterative calculation gave up.  `iteration` / `result` exist only when they were passed. """
+
+    def __init__(self, message=None, iteration=None, result=None):
+        if message is None:
+            message = ('No solution found in maximal number of iterations.' if iteration is None
+                       else 'No solution found in {} iterations.'.format(iteration))
+        super().__init__(message)
+        for name, value in (('iteration', iteration), ('result', result)):
+            if value is not None:
+                setattr(self, name, value)
+
+
 # ---- this package only ----
 
 class NativeLibraryError(BaseError):

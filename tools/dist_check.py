@@ -35,6 +35,12 @@ def main():
             steps, d, omega, delta, clamped = md.approximate_distributed(Ap, n, bk, p=p, lookahead=la)
             ident = md.identity_residual(steps, d, omega, delta)
             Lloc = steps.S.cpu().numpy()
+            # the consumers of the distributed factor: solve on the slabs, gather to rank 0 (collective calls)
+            fac = md.DistributedFactor(steps, d, p, omega, delta, clamped)
+            b = np.random.default_rng(n).standard_normal((n, 3))
+            x = fac.solve(b)
+            x1 = fac.solve(b[:, 0])
+            gathered = fac.gather(0)
             if rank == 0:
                 dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
                 ok = np.array_equal(clamped, dec.clamped) and np.array_equal(d, np.asarray(dec.d, dtype=float))
@@ -42,7 +48,15 @@ def main():
                     g0 = (lb * world) * md.NB
                     w = min(md.NB, n - g0)
                     ok = ok and np.array_equal(Lloc[:, lb * md.NB: lb * md.NB + w], dec.L[:, g0:g0 + w])
-                out[f'n{n}_agg{fixed}_lookahead{int(la)}'] = dict(bitwise_equal_single_gpu=bool(ok), identity=ident)
+                x_ref = dec.solve(b)
+                out[f'n{n}_agg{fixed}_lookahead{int(la)}'] = dict(
+                    bitwise_equal_single_gpu=bool(ok), identity=ident,
+                    gather_bitwise_equal=bool(np.array_equal(gathered.L, dec.L)
+                                              and np.array_equal(np.asarray(gathered.omega, dtype=float), np.asarray(dec.omega, dtype=float))),
+                    gathered_solve_equal=bool(np.array_equal(gathered.solve(b), x_ref)),
+                    dist_solve_rel_err=float(np.max(np.abs(x - x_ref)) / np.max(np.abs(x_ref))),
+                    dist_solve_1rhs_rel_err=float(np.max(np.abs(x1 - x_ref[:, 0])) / np.max(np.abs(x_ref[:, 0]))))
+                del gathered
             steps.close()
             del steps
     _native.context(local).set_blocking()
