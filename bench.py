@@ -156,7 +156,7 @@ def parity_against_oracle(ref, n=CPU_SAMPLE_N):
     L_gpu = dec.L
     out['max_abs_dL'] = float(np.max(np.abs(L_gpu - ref['L']) / np.maximum(1.0, np.abs(ref['L']))))
     del L_gpu
-    B_ref = matrix.LDL_Decomposition(ref['L'], d_ref, p=ref['p']).composed_matrix
+    B_ref = matrix.decompositions.LDL_Decomposition(ref['L'], d_ref, p=ref['p']).composed_matrix
     out['relB'] = float(np.linalg.norm(B_gpu - B_ref) / np.linalg.norm(B_ref))
     out['tolerances'] = dict(max_rel_d=1e-10, max_abs_dL=1e-10, relB=1e-12)
     out['ok'] = bool(out['p_equal'] and out['clamped_equal'] and out['max_rel_d'] <= 1e-10 and out['max_abs_dL'] <= 1e-10
@@ -604,7 +604,7 @@ def parity_distributed(ref_path, rank, world, device):
         L = g.L
         out['max_abs_dL'] = float(np.max(np.abs(L - ref['L']) / np.maximum(1.0, np.abs(ref['L']))))
         B = g.composed_matrix
-        B_ref = matrix.LDL_Decomposition(ref['L'], d_ref, p=ref['p']).composed_matrix
+        B_ref = matrix.decompositions.LDL_Decomposition(ref['L'], d_ref, p=ref['p']).composed_matrix
         out['relB'] = float(np.linalg.norm(B - B_ref) / np.linalg.norm(B_ref))
         del B, B_ref
         one = matrix.approximation.positive_semidefinite.decomposition(A, **kw)     # single-GPU path on GPU 0

@@ -189,53 +189,121 @@ __device__ __forceinline__ void mdb_cp_async_wait_all() {
 
 // ------------------------------------------------------------------------------------------------
 // Diagonal block: columns K = k0 .. k0+kb-1, rows of the block only.  One CTA, the whole block in shared
-// memory, 4 threads per row.  Sequential over the columns because the decision for column k needs alpha_k,
-// which contains Lu[k, k0:k]^2 d from this very block.  The kernel is pure latency, and per column the two
-// expensive things are the rule (~1300 dependent scalar instructions when the column is clamped: two cubic
-// solves, Reimer.py:95-115) and the length-k dot products of the rows below.  They overlap:
-//   phase 1   lanes (k, 0) and (k, 1) : (d, omega) = rule(alpha_k, beta_k, gamma_k)     Reimer.py:479-494 / :42-176
-//             (the candidates of d = lo and d = max_diag_D side by side, one instruction stream, merged with the
-//             reference's key, md_rule.h)  WHILE
-//             rows j > k : G_j = sum_{m < k-1} Lu[j, m] d_m Lu[k, m]   -- the dot product with the UNscaled row k,
-//             which does not need the decision.  (d_m Lu[k, m] sits at the transposed position (m, k) of the tile:
-//             the A entry stored there is dead once column m has been processed.)
+// memory.  Sequential over the columns because the decision for column k needs alpha_k, which contains
+// Lu[k, k0:k]^2 d from this very block: the kernel is one dependency chain, and everything is arranged to keep the
+// per-column part of it short (round 2: 1750 -> ~X cycles per column).
+//
+// Threads: 16 compute warps, thread (j, h) = (tid >> 2, tid & 3): the four lanes of a row share its dot products,
+// lanes h = 0 and 1 both carry the row's state (alpha, beta, rowmax, rowmin) redundantly -- identical arithmetic --
+// so that the row itself can decide its column without a hand-over: the unclamped test, MD_RULE_EXACT and the upper
+// clamp (md_upper_clamp_shortcut) are a few comparisons in lane h = 0; a column that needs the two cubic solves
+// (Reimer.py:95-115) evaluates the candidates of d = lo and d = max_diag_D side by side in lanes h = 0 / 1
+// (mdb_rule_full_pair, one instruction stream, merged with the reference's key).  Warp 16 is a helper (below).
+// Per column k, compute warps only (named barrier, the helper does not take part):
+//   phase A   rows j > k : G_j = sum_{sb0 <= m < k-1} Lu[j, m] d_m Lu[k, m]   -- the dot product with the UNscaled row
+//             k (d_m Lu[k, m] sits at the transposed position (m, k) of the tile: the A entry stored there is dead
+//             once column m has been processed).  Does not need the decision for column k.
 //   barrier
-//   phase 2   x[j, k] = ((1 - omega) A[j, k] + omega (S0[j, k] - G_j)) / d    (= A[j, k] / d when the scaled row k
-//             is dropped), alpha / beta / rowmax updates in column order (Reimer.py:604,684),
-//             threads m < k : Ut[m][k] = d_m thresh(omega Lu[k, m])  (Reimer.py:553-560, for the panel kernel).
+//   phase B   x[j, k] = ((1 - omega) A[j, k] + omega (S'[j, k] - G_j)) / d    (= A[j, k] / d when the scaled row k
+//             is dropped), alpha / beta / rowmax updates in column order (Reimer.py:604,684); row k + 1 then decides
+//             column k + 1 at once (d, omega, 1 / d, flags into the double-buffered s_dec).
+// Two-level inside the block: sub-blocks of SB = 32 columns.  The dot products only run over the columns of the
+// current sub-block (sb0 = its first column): when a sub-block is complete, its contribution
+// S'[j, c] -= sum_{m in sub-block} Lu[j, m] d_m Lu[c, m]  to every later column c of the block is applied at once on
+// the FP64 tensor cores (mma.m16n8k4 from shared memory).
 // omega G ignores the reference's thresholding of tiny entries of the scaled row (Reimer.py:558).  A column falls
-// back to the explicit thresholded dot product ("slow", exact w.r.t. the reference inside the block) whenever that
-// could matter -- omega_k * min nonzero |Lu[k, .]| < min_abs_value_L -- or G could overflow (explosive regime,
-// |Lu| > 1e100).  Outputs: d, omega, delta, clamped; Ut; hdr = (d, omega, drop, delta, clamped) of the panel.
+// back to the explicit thresholded dot product over ALL earlier columns of the block and the block-entry value of S
+// (re-read from global memory, which this kernel only overwrites at its end) -- "slow", exact w.r.t. the reference
+// inside the block -- whenever that could matter: omega_k * min nonzero |Lu[k, .]| < min_abs_value_L, or the
+// products could overflow (explosive regime, |Lu| > 1e100; from then on S' is not used any more).
+// Helper warp: trails the column loop (polls s_progress) and forms, row by row, the inverse of the scaled unit
+// triangle Ltilde[c][m] = thresh(omega_c Lu[c, m]) of each sub-block; the panel kernel k_panel_gemm multiplies by
+// these 32 x 32 inverses instead of substituting column by column.  Vinv[4096] = 1 tells it not to (an entry of an
+// inverse above 1e8 or not finite, |Lu| > 1e100 anywhere, or a zero d): it then substitutes.
+// Outputs: d, omega, delta, clamped; Ut[m][k] = d_m thresh(omega_k Lu[k, m]) (Reimer.py:553-560); hdr = (d, omega,
+// drop, delta, clamped) of the panel; Vinv.
 // ------------------------------------------------------------------------------------------------
 // Sblk / Ablk point at element (k0, k0) of the storage that holds S (lower part is read and written) and
 // the permuted original A (upper part is read): the same array W on one GPU, S_loc / A_loc when distributed.
 #define MDB_DIAG_THREADS(NB) (4 * (NB) + 32)
-#define MDB_DIAG_SMEM_DOUBLES(NB) ((NB) * ((NB) + 4) + 9 * (NB))
+#define MDB_DIAG_SMEM_DOUBLES(NB) ((NB) * ((NB) + 4) + 3 * (NB) + 8 + 32 * 33 + 32)
+#define MDB_DIAG_SB 32
+
+// S'[j, c] -= sum_{m0 <= m < m0 + SB} T[j][m] T[m][c]  for c0 <= c < j < kb (c0 = m0 + SB), tiles of 16 x 8 dealt
+// round-robin to the 16 compute warps.  mma.m16n8k4: a0 = A[g][t4], a1 = A[g+8][t4], b0 = B[t4][g],
+// c = C[g | g+8][2 t4 | 2 t4 + 1].
+template <int NB>
+__device__ __forceinline__ void mdb_diag_subblock_update(double* __restrict__ T, int m0, int kb, int warp, int lane) {
+  constexpr int LDT = NB + 4;
+  constexpr int SB = MDB_DIAG_SB;
+  const int c0 = m0 + SB;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int n_rt = (kb - c0 + 15) >> 4, n_ct_all = (kb - c0 + 7) >> 3;
+  int t = 0;
+  for (int ri = 0; ri < n_rt; ++ri) {
+    const int r0 = c0 + 16 * ri;
+    const int n_ct = (2 * ri + 2 < n_ct_all) ? 2 * ri + 2 : n_ct_all;   // tiles that reach below the diagonal
+    for (int ci = 0; ci < n_ct; ++ci, ++t) {
+      if ((t & 15) != warp) continue;
+      const int cc0 = c0 + 8 * ci;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      const double* Ap0 = T + (r0 + g) * LDT + m0 + t4;
+      const double* Ap1 = Ap0 + 8 * LDT;
+      const double* Bp = T + (m0 + t4) * LDT + cc0 + g;
+#pragma unroll
+      for (int kk = 0; kk < SB; kk += 4) {
+        const double a0 = Ap0[kk], a1 = Ap1[kk], b0 = Bp[kk * LDT];
+        asm volatile(
+            "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+            : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3])
+            : "d"(a0), "d"(a1), "d"(b0));
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = r0 + g + ((e & 2) ? 8 : 0), col = cc0 + 2 * t4 + (e & 1);
+        if (row < kb && col < row) T[row * LDT + col] -= acc[e];
+      }
+    }
+  }
+}
+
+// The clamped branch with both cubic solves (Reimer.py:89-135), lanes h = 0 / 1 of one row group: lane h evaluates the
+// candidates of d = lo (h = 0) or d = max_diag_D (h = 1), the pair exchanges them and both lanes assemble the same
+// decision.  Kept out of line: it is ~1300 instructions and the column loop calls it rarely.
+__device__ __noinline__ MdDecision mdb_rule_full_pair(MdRuleParams prm, int h, unsigned pairmask, double al, double be,
+                                                      double ga, double mD, double mB, double MB) {
+  double dd;
+  int fb = 0;
+  const bool en = md_d_candidate(h, al, be, mD, prm.max_diag_D, mB, MB, prm.min_abs_value_D, &dd);
+  const MdBest mine = md_candidates_for_d(en, dd, al, be, ga, mB, MB, &fb);
+  MdBest other;
+  other.d = __shfl_xor_sync(pairmask, mine.d, 1);
+  other.w = __shfl_xor_sync(pairmask, mine.w, 1);
+  other.f = __shfl_xor_sync(pairmask, mine.f, 1);
+  other.have = __shfl_xor_sync(pairmask, mine.have, 1);
+  const int fb_other = __shfl_xor_sync(pairmask, fb, 1);
+  const MdBest from_lo = (h == 0) ? mine : other, from_max = (h == 0) ? other : mine;
+  return md_decision_from_best(md_assemble_minimal_change(from_lo, from_max, fb | fb_other, al, be, ga, mD, prm.max_diag_D,
+                                                          mB, MB, prm.min_abs_value_D));
+}
 
 template <int NB>
 __global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
                                                             int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
-  // Compute warps: thread (j, h) = (tid >> 2, tid & 3), tid < 4 NB, sums the terms m = h (mod 4) of row j's dot
-  // product; lane h == 0 carries the row's state (alpha, beta, rowmax, rowmin) and publishes it in shared memory.
-  // Rule warp (the last one): lanes 0 and 1 evaluate the rule for column k from the published state of row k, so
-  // the rule really runs beside the Gram sums instead of serialising with the lanes of its own warp.
   extern __shared__ double smem_d[];
   constexpr int LDT = NB + 4;   // 264 words: the 4 rows of a half warp land in 4 disjoint groups of 8 banks
+  constexpr int SB = MDB_DIAG_SB;
+  constexpr int NCOMPUTE = 4 * NB;
   constexpr double BIG = 1e100;
-  double* T = smem_d;           // T[r * LDT + c]: c < r: S0 -> Lu;  c >= r: A, then (r, c) <- d_r Lu[c, r]
+  double* T = smem_d;           // T[r * LDT + c]: c < r: S0 -> S' -> Lu;  c >= r: A, then (r, c) <- d_r Lu[c, r]
   double* s_u = T + NB * LDT;   // NB (slow path)
-  double* s_d = s_u + NB;       // NB
-  double* s_alpha = s_d + NB;   // per row, published by lane (j, 0) after every column
-  double* s_beta = s_alpha + NB;
-  double* s_rowmax = s_beta + NB;
-  double* s_rowmin = s_rowmax + NB;
-  double* s_gamma = s_rowmin + NB;
-  double* s_mB = s_gamma + NB;
-  double* s_MB = s_mB + NB;
-  __shared__ double s_dec[2][5];  // d, omega, drop, slow, 1 / d of column k (slot k & 1)
-  __shared__ int s_big;
-  __shared__ volatile int s_ready;  // rows 0 .. s_ready have published their state for their own column
+  double* s_d = s_u + NB;       // NB: d of the finished columns
+  double* s_w = s_d + NB;       // NB: omega of the finished columns
+  double* s_dec = s_w + NB;     // 2 x 4: d, omega, 1 / d, flags (1 = drop, 2 = slow) of column k in slot k & 1
+  double* s_inv = s_dec + 8;    // 32 x 33: inverse of the current sub-block's scaled unit triangle (helper warp)
+  double* s_lt = s_inv + 32 * 33;  // 32: the scaled, thresholded row the helper is working on
+  __shared__ int s_bigf[2], s_unsafe;   // s_bigf[k & 1]: some |Lu| > 1e100 seen up to phase B of a column of that parity
+  __shared__ volatile int s_progress;  // columns whose decision and row are final (the helper polls it)
 
   const int64_t b = blockIdx.z;
   Sblk += b * F.sW;
@@ -243,136 +311,181 @@ __global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t
   const int64_t vo = b * F.sVec;
   double* Ut = F.Ut + b * F.sUt;
   double* hdr = F.hdr + b * F.sHdr;
+  double* Vout = F.Vinv + b * F.sV;
   const int tid = threadIdx.x, lane = tid & 31;
-  const bool rule_warp = tid >= 4 * NB;
+  const bool helper = tid >= NCOMPUTE;
   const int j = tid >> 2, h = tid & 3;
-  const bool owner = !rule_warp && (h == 0) && (j < kb);
+  const bool keeper = !helper && (h < 2) && (j < kb);   // lanes that carry the row's state
   const bool exact = F.prm.rule == MD_RULE_EXACT;
   const double mavL = F.prm.min_abs_value_L;
+  const unsigned pairmask = 0x3u << (lane & 28);
+#define MDB_DIAG_BAR() asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory")
 
   // whole block in flight at once (asynchronous 8-byte copies, coalesced per row):
   // strict lower part from S, diagonal and upper part from A
-  if (!rule_warp) {
+  if (!helper) {
     const int c = tid & (NB - 1);
     if (c < kb)
       for (int r = tid / NB; r < kb; r += 4)
         mdb_cp_async8(&T[r * LDT + c], (c < r) ? &Sblk[r * ldS + c] : &Ablk[r * ldA + c]);
   }
-  double alpha_j = 0, beta_j = 0, rowmax_j = 0, rowmin_j = INFINITY;
-  if (owner) {
+  double alpha_j = 0, beta_j = 0, rowmax_j = 0, rowmin_j = INFINITY, gamma_j = 0, mB_j = 0, MB_j = 0;
+  if (keeper) {
     alpha_j = F.alpha[vo + k0 + j];
     beta_j = F.beta[vo + k0 + j];
     rowmax_j = F.rowmax[vo + k0 + j];
-    s_alpha[j] = alpha_j; s_beta[j] = beta_j; s_rowmax[j] = rowmax_j; s_rowmin[j] = rowmin_j;
-    s_gamma[j] = F.gamma[vo + k0 + j];
-    s_mB[j] = F.minB ? F.minB[vo + k0 + j] : F.prm.min_diag_B;
-    s_MB[j] = F.maxB ? F.maxB[vo + k0 + j] : F.prm.max_diag_B;
+    gamma_j = F.gamma[vo + k0 + j];
+    mB_j = F.minB ? F.minB[vo + k0 + j] : F.prm.min_diag_B;
+    MB_j = F.maxB ? F.maxB[vo + k0 + j] : F.prm.max_diag_B;
   }
-  if (tid == 0) { s_big = 0; s_ready = 0; }
+  if (tid == 0) { s_bigf[0] = s_bigf[1] = 0; s_unsafe = 0; s_progress = 0; }
   mdb_cp_async_wait_all();
   __syncthreads();
-  if (owner && rowmax_j > BIG) s_big = 1;
+  if (keeper && h == 0 && rowmax_j > BIG) s_bigf[0] = s_bigf[1] = 1;
   __syncthreads();
 
-  const double* Trow = T + (rule_warp ? 0 : j) * LDT;
-  for (int k = 0; k < kb; ++k) {
-    const bool active = !rule_warp && (j > k && j < kb);
-    double G = 0;
-    if (rule_warp) {
-      // ---------------- the rule for column k (lanes 0 and 1: d = lo and d = max_diag_D side by side) ----------------
-      while (s_ready < k) { }  // row k has published alpha_k (it contains column k - 1)
+  if (helper) {
+    // ---------------- inverses of the scaled unit triangles, one row per finished column ----------------
+    double vmax = 0;
+    for (int k = 0; k < kb; ++k) {
+      const int kk = k & (SB - 1), sb0 = k - kk;
+      while (s_progress <= k) __nanosleep(40);
+      __threadfence_block();
+      const double wk = s_w[k];
+      double lt = 0;
+      if (lane < kk) {
+        lt = wk * T[k * LDT + sb0 + lane];
+        if (wk == 0 || fabs(lt) < mavL) lt = 0;
+      }
+      s_lt[lane] = lt;
       __syncwarp();
-      const double al = s_alpha[k], be = s_beta[k], ga = s_gamma[k], mB = s_mB[k], MB = s_MB[k];
-      MdBest cand;
-      cand.d = cand.w = cand.f = 0;
-      cand.have = 0;
-      int fb = 0;
-      bool uncl = true;
-      double mD = 0;
-      if (lane < 2 && !exact) {
-        mD = md_effective_min_diag_D(F.prm, ga, mB, MB);
-        uncl = md_unclamped(al, ga, mD, F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D);
-        if (!uncl) {
-          double dd;
-          const bool en = md_d_candidate(lane, al, be, mD, F.prm.max_diag_D, mB, MB, F.prm.min_abs_value_D, &dd);
-          cand = md_candidates_for_d(en, dd, al, be, ga, mB, MB, &fb);
+      double x = (lane == kk) ? 1.0 : 0.0;
+      if (lane < kk) {
+        double a0 = 0, a1 = 0;
+        int m = lane;
+        for (; m + 1 < kk; m += 2) {
+          a0 = fma(s_lt[m], s_inv[m * 33 + lane], a0);
+          a1 = fma(s_lt[m + 1], s_inv[(m + 1) * 33 + lane], a1);
         }
+        if (m < kk) a0 = fma(s_lt[m], s_inv[m * 33 + lane], a0);
+        x = -(a0 + a1);
       }
-      MdBest other;
-      other.d = __shfl_sync(0xffffffffu, cand.d, 1);
-      other.w = __shfl_sync(0xffffffffu, cand.w, 1);
-      other.f = __shfl_sync(0xffffffffu, cand.f, 1);
-      other.have = __shfl_sync(0xffffffffu, cand.have, 1);
-      const int fb1 = __shfl_sync(0xffffffffu, fb, 1);
-      if (lane == 0) {
-        MdDecision dec;
-        if (exact || uncl) {
-          dec.d = ga - al; dec.omega = 1; dec.f = 0;
-          dec.clamped = exact ? !(dec.d > 0) : 0;
-        } else {
-          dec = md_decision_from_best(md_assemble_minimal_change(cand, other, fb | fb1, al, be, ga, mD, F.prm.max_diag_D,
-                                                                 mB, MB, F.prm.min_abs_value_D));
-        }
-        const int64_t K = k0 + k;
-        const double delta = (dec.d - ga) + (dec.omega != 0 ? dec.omega * dec.omega * al : 0.0);  // :541-545
-        F.d[vo + K] = dec.d;
-        F.omega[vo + K] = dec.omega;
-        F.delta[vo + K] = delta;
-        F.clamped[vo + K] = (uint8_t)dec.clamped;
-        if (exact && dec.clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
-        const bool drop = (dec.omega == 0 || dec.omega * s_rowmax[k] < mavL);
-        const bool slow = !drop && k > 0 && (dec.omega * s_rowmin[k] < mavL || s_big != 0);
-        double* sd = s_dec[k & 1];
-        sd[0] = dec.d;
-        sd[1] = dec.omega;
-        sd[2] = drop ? 1.0 : 0.0;
-        sd[3] = slow ? 1.0 : 0.0;
-        sd[4] = (dec.d != 0) ? 1.0 / dec.d : 0.0;   // the division leaves the dependency chain of the rows
-        s_d[k] = dec.d;
-        hdr[k] = dec.d;
-        hdr[NB + k] = dec.omega;
-        hdr[2 * NB + k] = drop ? 1.0 : 0.0;
-        hdr[3 * NB + k] = delta;
-        hdr[4 * NB + k] = (double)dec.clamped;
+      s_inv[kk * 33 + lane] = x;
+      if (!(fabs(x) <= 1e8)) vmax = INFINITY;   // also catches NaN
+      __syncwarp();
+      if (kk == SB - 1 || k == kb - 1) {
+        double* V = Vout + (sb0 / SB) * (SB * SB);
+        for (int r = 0; r < SB; ++r) V[r * SB + lane] = (r <= kk) ? s_inv[r * 33 + lane] : ((r == lane) ? 1.0 : 0.0);
+        __syncwarp();
       }
-    } else {
-      // ---------------- the Gram dot products G_j = sum_{m < k-1} Lu[j, m] (d_m Lu[k, m]) ----------------
-      double g0 = 0, g1 = 0;
-      if (active) {
-        const double* Tk = T + k;  // (m, k) holds d_m Lu[k, m]
-        int m = h;
-        for (; m + 4 < k - 1; m += 8) {
-          g0 = fma(Trow[m], Tk[m * LDT], g0);
-          g1 = fma(Trow[m + 4], Tk[(m + 4) * LDT], g1);
-        }
-        if (m < k - 1) g0 = fma(Trow[m], Tk[m * LDT], g0);
-      }
-      G = g0 + g1;
-      // every lane takes part in the shuffles (rows of one warp become active at different k)
-      G += __shfl_xor_sync(0xffffffffu, G, 1);
-      G += __shfl_xor_sync(0xffffffffu, G, 2);
     }
+    const unsigned bad = __ballot_sync(0xffffffffu, vmax != 0.0);
     __syncthreads();
+    if (lane == 0) Vout[4 * SB * SB] = (bad != 0 || s_bigf[0] != 0 || s_bigf[1] != 0 || s_unsafe != 0) ? 1.0 : 0.0;
+    return;
+  }
 
-    // ---------------- column k ----------------
-    const double dk = s_dec[k & 1][0], wk = s_dec[k & 1][1], inv_dk = s_dec[k & 1][4];
-    const bool drop = s_dec[k & 1][2] != 0.0, slow = s_dec[k & 1][3] != 0.0;
-    double a = 0, s0k = 0;
-    if (active) {
-      a = T[k * LDT + j];   // A[j, k]; read before thread (j, 0) overwrites it below
-      s0k = Trow[k];
-      if (k >= 1) G = fma(Trow[k - 1], T[(k - 1) * LDT + k], G);  // the term m = k - 1, published just before the barrier
+  // decision of column kc by the two keeper lanes of row kc (their state is complete); lane h == 0 publishes it
+  auto decide = [&](int kc, bool big) {
+    double d, w;
+    int clamped;
+    if (exact) {
+      d = gamma_j - alpha_j; w = 1.0;
+      clamped = !(d > 0);
+    } else {
+      const double mD = md_effective_min_diag_D(F.prm, gamma_j, mB_j, MB_j);
+      MdBest quick;
+      if (md_unclamped(alpha_j, gamma_j, mD, F.prm.max_diag_D, mB_j, MB_j, F.prm.min_abs_value_D)) {
+        d = gamma_j - alpha_j; w = 1.0; clamped = 0;
+      } else if (md_upper_clamp_shortcut(alpha_j, beta_j, gamma_j, mD, F.prm.max_diag_D, mB_j, MB_j, F.prm.min_abs_value_D,
+                                         &quick)) {
+        d = quick.d; w = quick.w; clamped = 1;
+      } else {
+        const MdDecision dec = mdb_rule_full_pair(F.prm, h, pairmask, alpha_j, beta_j, gamma_j, mD, mB_j, MB_j);
+        d = dec.d; w = dec.omega; clamped = 1;
+      }
     }
-    if (tid < k) {  // the scaled, thresholded row k times D: for the panel kernel, and for the slow path
-      double lt = wk * T[k * LDT + tid];
-      if (wk == 0 || fabs(lt) < mavL) lt = 0;
-      const double u = s_d[tid] * lt;
-      Ut[tid * NB + k] = u;
-      if (slow) s_u[tid] = u;
+    if (h == 0) {
+      const bool drop = (w == 0 || w * rowmax_j < mavL);
+      const bool slow = !drop && kc > 0 && (w * rowmin_j < mavL || big);
+      double* sd = s_dec + 4 * (kc & 1);
+      sd[0] = d;
+      sd[1] = w;
+      sd[2] = (d != 0) ? 1.0 / d : 0.0;
+      sd[3] = (drop ? 1.0 : 0.0) + (slow ? 2.0 : 0.0);
+      s_d[kc] = d;
+      s_w[kc] = w;
+      if (d == 0) s_unsafe = 1;
+      // (global results after the shared ones: nothing on the chip waits for them)
+      const int64_t K = k0 + kc;
+      F.d[vo + K] = d;
+      F.omega[vo + K] = w;
+      const double delta = (d - gamma_j) + (w != 0 ? w * w * alpha_j : 0.0);  // :541-545
+      F.delta[vo + K] = delta;
+      F.clamped[vo + K] = (uint8_t)clamped;
+      if (exact && clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
+      hdr[kc] = d;
+      hdr[NB + kc] = w;
+      hdr[2 * NB + kc] = drop ? 1.0 : 0.0;
+      hdr[3 * NB + kc] = delta;
+      hdr[4 * NB + kc] = (double)clamped;
+    }
+  };
+
+  bool big = s_bigf[0] != 0;   // sticky; refreshed after every column barrier from the flag of the previous column's parity
+  if (keeper && j == 0) decide(0, big);
+  const double* Trow = T + j * LDT;
+  for (int k = 0; k < kb; ++k) {
+    const int kk = k & (SB - 1), sb0 = k - kk;
+    if (kk == 0 && k > 0) {
+      MDB_DIAG_BAR();   // every x of the finished sub-block is in shared memory
+      mdb_diag_subblock_update<NB>(T, sb0 - SB, kb, tid >> 5, lane);
+      // (made visible to the readers of column k by the column barrier below; the Gram sum of a sub-block's first
+      // column is empty)
+    }
+    const bool active = (j > k && j < kb);
+    // ---------------- phase A: G_j = sum_{sb0 <= m < k-1} Lu[j, m] (d_m Lu[k, m]), lane h takes m = sb0 + h + 4 i ----------------
+    double a = 0, g0 = 0, g1 = 0;
+    if (active) {
+      a = T[k * LDT + j];   // A[j, k]; lane (j, 0) overwrites it in phase B
+      const double* Tr = Trow + sb0 + h;
+      const double* Tk = T + (sb0 + h) * LDT + k;   // (m, k) holds d_m Lu[k, m]
+      const int lim = kk - 1 - h;                   // terms 4 i < lim
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        if (4 * i < lim) g0 = fma(Tr[4 * i], Tk[4 * i * LDT], g0);
+        if (4 * i + 4 < lim) g1 = fma(Tr[4 * i + 4], Tk[(4 * i + 4) * LDT], g1);
+      }
+    }
+    double G = g0 + g1;
+    // every lane takes part in the shuffles (rows of one warp become active at different k)
+    G += __shfl_xor_sync(0xffffffffu, G, 1);
+    G += __shfl_xor_sync(0xffffffffu, G, 2);
+    MDB_DIAG_BAR();
+    if (tid == 0) s_progress = k + 1;
+
+    // ---------------- phase B: column k ----------------
+    const double2 dec01 = *reinterpret_cast<const double2*>(s_dec + 4 * (k & 1));
+    const double2 dec23 = *reinterpret_cast<const double2*>(s_dec + 4 * (k & 1) + 2);
+    const double dk = dec01.x, wk = dec01.y, inv_dk = dec23.x;
+    const int flags = (int)dec23.y;
+    const bool drop = (flags & 1) != 0, slow = (flags & 2) != 0;
+    big = big || (s_bigf[(k + 1) & 1] != 0);   // written in phase B of column k - 1, complete since the barrier: the same
+                                               // value in every thread (the flag of this column's parity is being written now)
+    double s0k = 0;
+    if (active) {
+      s0k = Trow[k];        // S'[j, k]: the block-entry value minus the finished sub-blocks
+      if (kk >= 1) G = fma(Trow[k - 1], T[(k - 1) * LDT + k], G);  // the term m = k - 1, published just before the barrier
     }
     double acc = 0;
     if (slow) {  // uniform over the block
-      __syncthreads();
+      if (tid < k) {  // the scaled, thresholded row k times D
+        double lt = wk * T[k * LDT + tid];
+        if (wk == 0 || fabs(lt) < mavL) lt = 0;
+        s_u[tid] = s_d[tid] * lt;
+      }
+      if (active) s0k = Sblk[j * ldS + k];   // the block-entry value of S (global memory is still untouched)
+      MDB_DIAG_BAR();
       if (active) {
         double a0 = 0, a1 = 0;
         int m = h;
@@ -386,209 +499,243 @@ __global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     }
-    __syncwarp();  // all four lanes of a row have read T[k][j] and T[j][k]
-    if (active && h == 0) {
-      // x = r * (1 / d_k): the reciprocal comes from the rule warp (<= 1 ulp from r / d_k)
+    __syncwarp();  // all four lanes of a row have read T[k][j] and T[j][k] before lane (j, 0) overwrites them
+    if (active && h < 2) {
+      // x = r * (1 / d_k): the reciprocal comes with the decision (<= 1 ulp from r / d_k)
       double x = 0;
       if (dk != 0) {
         if (drop) x = a * inv_dk;
         else if (slow) x = (((1.0 - wk) * a + wk * s0k) - acc) * inv_dk;
         else x = fma(wk, s0k - G, (1.0 - wk) * a) * inv_dk;
       }
-      T[j * LDT + k] = x;
-      T[k * LDT + j] = x * dk;        // d_k Lu[j, k] at the transposed position
+      if (h == 0) {
+        T[j * LDT + k] = x;
+        T[k * LDT + j] = x * dk;      // d_k Lu[j, k] at the transposed position
+      }
       alpha_j += x * x * dk;          // Reimer.py:679-684
       beta_j += 2.0 * a * a;          // Reimer.py:602-604
       const double ax = fabs(x);
       rowmax_j = fmax(rowmax_j, ax);
       if (ax != 0) rowmin_j = fmin(rowmin_j, ax);
-      if (ax > BIG) s_big = 1;
-      if (j == k + 1) {               // the next column's row: hand its state to the rule warp right away
-        s_alpha[j] = alpha_j; s_beta[j] = beta_j; s_rowmax[j] = rowmax_j; s_rowmin[j] = rowmin_j;
-        __threadfence_block();
-        s_ready = k + 1;
-      }
+      if (ax > BIG && h == 0) s_bigf[k & 1] = 1;
+      if (j == k + 1) decide(k + 1, big || rowmax_j > BIG);   // the next column's row: its state is complete now
     }
     __syncwarp();  // x[j, k] is visible to the other lanes of the row before they use it in the next Gram sum
     // no block barrier here: what the next Gram sums read was published before the barrier above; the entries written
-    // just now are first read after the next barrier (the m = k term, s_dec) or through s_ready (the rule warp)
+    // just now are first read after the next barrier
   }
   __syncthreads();
-  if (owner) {
+  if (keeper && h == 0) {
     F.alpha[vo + k0 + j] = alpha_j;
     F.beta[vo + k0 + j] = beta_j;
     F.rowmax[vo + k0 + j] = rowmax_j;
   }
-  // strict lower part of the block back to S (unscaled rows Lu)
-  if (!rule_warp) {
+  {
     const int c = tid & (NB - 1);
+    // strict lower part of the block back to S (unscaled rows Lu)
     for (int r = tid / NB; r < kb; r += 4)
       if (c < r) Sblk[r * ldS + c] = T[r * LDT + c];
+    // Ut[m][k] = d_m thresh(omega_k Lu[k, m]) for m < k: the scaled, thresholded rows times D (Reimer.py:553-560),
+    // written row by row (coalesced over k)
+    if (c < kb) {
+      const double wk = s_w[c];
+      for (int m = tid / NB; m < c; m += 4) {
+        double lt = wk * T[c * LDT + m];
+        if (wk == 0 || fabs(lt) < mavL) lt = 0;
+        Ut[m * NB + c] = s_d[m] * lt;
+      }
+    }
   }
+#undef MDB_DIAG_BAR
 }
 
-#define MDB_PANEL_LDX(R) ((R) + 8)
-#define MDB_PANEL_SMEM_DOUBLES(NB, R) ((NB) * MDB_PANEL_LDX(R) + 4 * (NB) + 2 * (NB) * 8)
+// ------------------------------------------------------------------------------------------------
+// Panel: rows j below the diagonal block, columns of the panel.  Per row, X (D Ltilde^T) = R with
+// R[j, c] = (1 - omega_c) A[j, c] + omega_c S0[j, c]  (A[j, c] when the scaled row c is dropped; the mix identity of
+// DESIGN.md 2), i.e. forward substitution over the 128 columns -- done four columns-blocks of 32 at a time as matrix
+// products on the FP64 tensor cores:
+//     Z_s = R_s - X_{<s} U[<s, s]          (U[m][c] = d_m Ltilde[c][m] = Ut, written by k_diag_block)
+//     X_s = (Z_s Ltilde_ss^-T) D_s^-1      (the 32 x 32 inverses Vinv, formed by k_diag_block's helper warp)
+// A CTA owns 64 rows, a warp 16 of them (one m16 tile; 4 n8 tiles = 4 independent accumulator chains per step).
+// R / Z / X live in one shared tile (row-major), the A entries of the mix are staged TRANSPOSED so that both source
+// layouts (column-major inside W on one GPU, row-major in A_loc when distributed) load coalesced and the warp-per-row
+// passes read them without bank conflicts.  Ut and Vinv (160 KB for all CTAs together) are read straight from global
+// memory: L1 / L2 hits.  alpha / beta / rowmax: one pass per row with lanes over the columns and a fixed butterfly
+// (deterministic).  When Vinv[4096] != 0 (explosive regime, zero d) the rows substitute column by column instead.
+// HBM traffic: reads 2 x rows x 128 doubles (S0, A), writes 3 x (Lu, X, Y).
+// ------------------------------------------------------------------------------------------------
+#define MDB_PANEL_RT 64
+#define MDB_PANEL_THREADS 128
+#define MDB_PANEL_LDX(NB) ((NB) + 4)
+#define MDB_PANEL_LDA (MDB_PANEL_RT + 1)
+#define MDB_PANEL_SMEM_DOUBLES(NB) (MDB_PANEL_RT * MDB_PANEL_LDX(NB) + (NB) * MDB_PANEL_LDA + 4 * (NB))
 
-template <int NB, int R>
-__global__ void __launch_bounds__(R) k_panel(FactorDev F, int64_t k0, int64_t row_begin, int64_t n_rows,
-                                             const double* __restrict__ Asrc, int64_t a_rs, int64_t a_cs,
-                                             double* __restrict__ Wcol, int64_t w_ld,
-                                             double* __restrict__ PX, double* __restrict__ PY, int64_t p_row0,
-                                             int64_t p_ld) {
+__device__ __forceinline__ void mdb_dmma(double (&c)[4], double a0, double a1, double b0) {
+  asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+               : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+               : "d"(a0), "d"(a1), "d"(b0));
+}
+
+template <int NB>
+__global__ void __launch_bounds__(MDB_PANEL_THREADS) k_panel_gemm(FactorDev F, int64_t k0, int64_t row_begin,
+                                                                 int64_t n_rows, const double* __restrict__ Asrc,
+                                                                 int64_t a_rs, int64_t a_cs, double* __restrict__ Wcol,
+                                                                 int64_t w_ld, double* __restrict__ PX,
+                                                                 double* __restrict__ PY, int64_t p_row0, int64_t p_ld) {
   // Wcol: pointer such that S0[j, k0 + c] lives at Wcol[j * w_ld + c]  (j = global row)
   // PX / PY: row (j - p_row0) of the operand buffers, leading dimension p_ld (>= NB: the buffers hold the
   // panels of one outer block side by side so that the bulk trailing update contracts over all of them)
   extern __shared__ double smem_d[];
-  constexpr int LDX = MDB_PANEL_LDX(R);  // 72: the DMMA fragment loads below then take the minimal two wavefronts
-  double* xs = smem_d;          // xs[c * LDX + r]
-  double* s_d = xs + NB * LDX;  // NB
-  double* s_w = s_d + NB;       // NB
-  double* s_drop = s_w + NB;    // NB
-  double* s_inv = s_drop + NB;  // NB: 1 / d (0 where d == 0): x = r * (1 / d), <= 1 ulp from r / d, one division per column
-  double* us = s_inv + NB;      // 2 x (NB x 8): double-buffered 8-column slices of U (L1 is too small to hold U
-                                // next to the X tiles, so U is staged through shared memory with cp.async)
+  constexpr int RT = MDB_PANEL_RT, LDX = MDB_PANEL_LDX(NB), LDA = MDB_PANEL_LDA, SB = 32;
+  double* xs = smem_d;             // xs[r * LDX + c]: S0 -> R -> Z -> X
+  double* as_t = xs + RT * LDX;    // as_t[c * LDA + r]: A[j, k0 + c]
+  double* s_d = as_t + NB * LDA;   // NB
+  double* s_w = s_d + NB;          // NB
+  double* s_drop = s_w + NB;       // NB
+  double* s_inv = s_drop + NB;     // NB: 1 / d (0 where d == 0)
 
   const int64_t b = blockIdx.z;
   const int64_t vo = b * F.sVec;
-  const double* Ut = F.Ut + b * F.sUt;
+  const double* __restrict__ U = F.Ut + b * F.sUt;
+  const double* __restrict__ V = F.Vinv + b * F.sV;
   const double* hdr = F.hdr + b * F.sHdr;
   Asrc += b * F.sW;
   Wcol += b * F.sW;
   PX += b * F.sPanel;
   PY += b * F.sPanel;
-  const int tid = threadIdx.x;
-  const int64_t jbase = row_begin + (int64_t)blockIdx.x * R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t jbase = row_begin + (int64_t)blockIdx.x * RT;
   const int64_t jend = row_begin + n_rows;
-  const int64_t j = jbase + tid;
-  const bool valid = j < jend;
+  const int nrow = (int)((jend - jbase < RT) ? jend - jbase : RT);
 
-  // slice sb = columns [8 sb, 8 sb + 8) of U, rows m < 8 sb + 8 (rows m >= column hold stale data and are not used)
-  auto load_slice = [&](int sb, int buf) {
-    const int c0 = sb * 8;
-    const int chunks = (c0 + 8) * 4;  // 16-byte chunks
-    for (int idx = tid; idx < chunks; idx += R) {
-      const int m = idx >> 2, q = idx & 3;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(us + buf * (NB * 8) + m * 8 + q * 2);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Ut + m * NB + c0 + q * 2));
-    }
-  };
-
-  for (int c = tid; c < NB; c += R) {
+  for (int c = tid; c < NB; c += MDB_PANEL_THREADS) {
     const double dc = hdr[c];
     s_d[c] = dc;
     s_inv[c] = (dc != 0) ? 1.0 / dc : 0.0;
     s_w[c] = hdr[NB + c];
     s_drop[c] = hdr[2 * NB + c];
   }
-  load_slice(0, 0);
-  // S0 tile, transposed into shared memory: coalesced row segments, all rows in flight at once
-  for (int rr = 0; rr < R; ++rr) {
-    const int64_t jj = jbase + rr;
-    if (jj < jend)
-      for (int c = tid; c < NB; c += R) mdb_cp_async8(&xs[c * LDX + rr], &Wcol[jj * w_ld + c]);
+  {  // S0 rows: 16-byte chunks, coalesced
+    const int q = tid & 63;
+    for (int rr = tid >> 6; rr < nrow; rr += 2) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + rr * LDX + 2 * q);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Wcol + (jbase + rr) * w_ld + 2 * q));
+    }
+  }
+  if (a_rs == 1) {  // A is column-major in (j, c): consecutive threads take consecutive rows
+    const int jr = tid & 63;
+    if (jr < nrow)
+      for (int c = tid >> 6; c < NB; c += 2) mdb_cp_async8(&as_t[c * LDA + jr], Asrc + (jbase + jr) + (k0 + c) * a_cs);
+  } else {          // row-major: consecutive threads take consecutive columns
+    for (int jr = 0; jr < nrow; ++jr) mdb_cp_async8(&as_t[tid * LDA + jr], Asrc + (jbase + jr) * a_rs + (k0 + tid) * a_cs);
   }
   mdb_cp_async_wait_all();
   __syncthreads();
+  const bool unsafe = V[4 * SB * SB] != 0.0;
 
-  double alpha_j = 0, beta_j = 0, rowmax_j = 0;
-  if (valid) {
-    alpha_j = F.alpha[vo + j];
-    beta_j = F.beta[vo + j];
-    rowmax_j = F.rowmax[vo + j];
-    // mix with the original A column entries; beta in column order
-    const double* Aj = Asrc + j * a_rs + k0 * a_cs;
-    for (int cb = 0; cb < NB; cb += 32) {
-      double av[32];
+  // ---- R = mix(A, S0), beta += sum_c 2 A^2: the warp's own 16 rows, lanes over the columns ----
+  const int r0 = 16 * warp;
+  for (int rr = r0; rr < r0 + 16 && rr < nrow; ++rr) {
+    double bsum = 0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) av[i] = Aj[(int64_t)(cb + i) * a_cs];  // 32 independent loads in flight
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int c = cb + i;
-        const double a = av[i];
-        const double w = s_w[c];
-        double r = a;
-        if (s_drop[c] == 0.0) r = (1.0 - w) * a + w * xs[c * LDX + tid];
-        xs[c * LDX + tid] = r;
-        beta_j += 2.0 * a * a;
-      }
+    for (int e = 0; e < 4; ++e) {
+      const int c = lane + 32 * e;
+      const double a = as_t[c * LDA + rr];
+      const double w = s_w[c];
+      double r = a;
+      if (s_drop[c] == 0.0) r = (1.0 - w) * a + w * xs[rr * LDX + c];
+      xs[rr * LDX + c] = r;
+      bsum += 2.0 * a * a;
     }
-  }
-  // forward substitution, 8 columns at a time; the next U slice streams in while this one is used
-  for (int sb = 0; sb < NB / 8; ++sb) {
-    const int c0 = sb * 8;
-    if (sb + 1 < NB / 8) load_slice(sb + 1, (sb + 1) & 1);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    {
-      // acc = R - X U on the FP64 tensor cores: each warp owns its 32 rows (two 16 x 8 tiles), K = c0.
-      // mma.m16n8k4: a0 = A[g][t4], a1 = A[g+8][t4], b0 = B[t4][g], c = C[g | g+8][2 t4 | 2 t4 + 1].
-      const double* U = us + (sb & 1) * (NB * 8);
-      const int lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-      const int rb = (tid & ~31);  // first row of this warp inside the CTA tile
-      if (jbase + rb < jend && c0 > 0) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const int r0 = rb + 16 * mt + g;
-          double cfrag[4];
-          cfrag[0] = xs[(c0 + 2 * t4) * LDX + r0];
-          cfrag[1] = xs[(c0 + 2 * t4 + 1) * LDX + r0];
-          cfrag[2] = xs[(c0 + 2 * t4) * LDX + r0 + 8];
-          cfrag[3] = xs[(c0 + 2 * t4 + 1) * LDX + r0 + 8];
+    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    if (lane == 0) F.beta[vo + jbase + rr] += bsum;   // Reimer.py:602-604
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, t4 = lane & 3;
+  if (!unsafe) {
+    double* X0 = xs + (r0 + g) * LDX;   // rows r0 + g and r0 + g + 8 of the tile
+    double* X1 = X0 + 8 * LDX;
+#pragma unroll
+    for (int s = 0; s < NB / SB; ++s) {
+      const int cs = SB * s;
+      double acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = cs + 8 * nt + 2 * t4;
+        acc[nt][0] = X0[col]; acc[nt][1] = X0[col + 1]; acc[nt][2] = X1[col]; acc[nt][3] = X1[col + 1];
+      }
+      // Z_s = R_s - X_{<s} U[<s, s]
 #pragma unroll 4
-          for (int k = 0; k < c0; k += 4) {
-            const double a0 = xs[(k + t4) * LDX + r0];
-            const double a1 = xs[(k + t4) * LDX + r0 + 8];
-            const double b0 = -U[(k + t4) * 8 + g];
-            asm volatile(
-                "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
-                : "+d"(cfrag[0]), "+d"(cfrag[1]), "+d"(cfrag[2]), "+d"(cfrag[3])
-                : "d"(a0), "d"(a1), "d"(b0));
-          }
-          xs[(c0 + 2 * t4) * LDX + r0] = cfrag[0];
-          xs[(c0 + 2 * t4 + 1) * LDX + r0] = cfrag[1];
-          xs[(c0 + 2 * t4) * LDX + r0 + 8] = cfrag[2];
-          xs[(c0 + 2 * t4 + 1) * LDX + r0 + 8] = cfrag[3];
-        }
+      for (int kq = 0; kq < cs; kq += 4) {
+        const double a0 = -X0[kq + t4], a1 = -X1[kq + t4];
+        const double* Up = U + (kq + t4) * NB + cs + g;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mdb_dmma(acc[nt], a0, a1, __ldg(Up + 8 * nt));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = cs + 8 * nt + 2 * t4;
+        X0[col] = acc[nt][0]; X0[col + 1] = acc[nt][1]; X1[col] = acc[nt][2]; X1[col + 1] = acc[nt][3];
       }
       __syncwarp();
-      if (valid) {
-        // the 8 x 8 triangle of the slice, one thread per row
-        double acc[8];
+      // W_s = Z_s Ltilde_ss^-T  (B[m][c] = inverse[c][m], zero for m > c: tile nt only needs m < 8 nt + 8)
+      double w2[4][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = xs[(c0 + i) * LDX + tid];
+      for (int nt = 0; nt < 4; ++nt) w2[nt][0] = w2[nt][1] = w2[nt][2] = w2[nt][3] = 0.0;
+      const double* Vs = V + s * SB * SB;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = c0 + i;
-          const double dk = s_d[c];
-          const double x = (dk != 0) ? acc[i] * s_inv[c] : 0.0;
-          xs[c * LDX + tid] = x;
-          alpha_j += x * x * dk;          // Reimer.py:679-684
-          rowmax_j = fmax(rowmax_j, fabs(x));
+      for (int kq = 0; kq < SB; kq += 4) {
+        const double a0 = X0[cs + kq + t4], a1 = X1[cs + kq + t4];
 #pragma unroll
-          for (int i2 = i + 1; i2 < 8; ++i2) acc[i2] -= x * U[c * 8 + i2];
-        }
+        for (int nt = 0; nt < 4; ++nt)
+          if (kq < 8 * nt + 8) mdb_dmma(w2[nt], a0, a1, __ldg(Vs + (8 * nt + g) * SB + kq + t4));
+      }
+      __syncwarp();  // every lane has read Z before X replaces it
+      // X_s = W_s D_s^-1
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = cs + 8 * nt + 2 * t4;
+        const double i0 = s_inv[col], i1 = s_inv[col + 1];
+        X0[col] = w2[nt][0] * i0; X0[col + 1] = w2[nt][1] * i1; X1[col] = w2[nt][2] * i0; X1[col + 1] = w2[nt][3] * i1;
       }
       __syncwarp();
     }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
+  } else if (lane < 16 && r0 + lane < nrow) {
+    // column-by-column substitution, one lane per row (explosive regime / zero d: rare, small matrices)
+    double* Xr = xs + (r0 + lane) * LDX;
+    for (int c = 0; c < NB; ++c) {
+      double acc = Xr[c];
+      for (int m = 0; m < c; ++m) acc = fma(-Xr[m], __ldg(U + m * NB + c), acc);
+      Xr[c] = (s_d[c] != 0) ? acc * s_inv[c] : 0.0;
+    }
   }
-  if (valid) {
-    F.alpha[vo + j] = alpha_j;
-    F.beta[vo + j] = beta_j;
-    F.rowmax[vo + j] = rowmax_j;
-  }
-  // write back (coalesced rows): Lu into W, X and Y = -X d into the compact panel buffers
-  for (int rr = 0; rr < R; ++rr) {
+  __syncwarp();
+
+  // ---- alpha, rowmax, and the results: Lu into W, X and Y = -X d into the operand buffers (coalesced rows) ----
+  for (int rr = r0; rr < r0 + 16 && rr < nrow; ++rr) {
     const int64_t jj = jbase + rr;
-    if (jj < jend) {
-      const int64_t pr = jj - p_row0;
-      for (int c = tid; c < NB; c += R) {
-        const double x = xs[c * LDX + rr];
-        Wcol[jj * w_ld + c] = x;
-        PX[pr * p_ld + c] = x;
-        PY[pr * p_ld + c] = -x * s_d[c];
-      }
+    const int64_t pr = jj - p_row0;
+    double asum = 0, mx = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = lane + 32 * e;
+      const double x = xs[rr * LDX + c], dc = s_d[c];
+      asum += x * x * dc;          // Reimer.py:679-684
+      mx = fmax(mx, fabs(x));
+      Wcol[jj * w_ld + c] = x;
+      PX[pr * p_ld + c] = x;
+      PY[pr * p_ld + c] = -x * dc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      asum += __shfl_xor_sync(0xffffffffu, asum, o);
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) {
+      F.alpha[vo + jj] += asum;
+      F.rowmax[vo + jj] = fmax(F.rowmax[vo + jj], mx);
     }
   }
 }

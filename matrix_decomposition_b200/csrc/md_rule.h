@@ -290,6 +290,36 @@ MD_HD MdBest md_minimal_change_part(int part, double alpha, double beta, double 
   return best;
 }
 
+// Upper clamp without the two cubic solves.  When the unclamped value d* = gamma - alpha lies ABOVE the admissible
+// interval [a, b] and b is max_diag_D itself, the candidate (b, 1) of Reimer.py:87-88 wins the minimisation of
+// :156-160 whatever the cubic roots are, so they need not be computed:
+//   every other candidate of the list is (dd, omega) with dd in {lo, max_diag_D} and omega in [0, 1] (the roots are
+//   clipped to [omega_lower, omega_upper], omega_lower <= 1 whenever dd = lo is admitted (:95) and = 0 for
+//   dd = max_diag_D because min_diag_B <= max_diag_D);  for those, with alpha > 0,
+//       g = dd + omega^2 alpha - gamma <= dd + alpha - gamma <= b + alpha - gamma = -(d* - b) < 0,
+//   hence f = g^2 + (omega - 1)^2 beta >= (b + alpha - gamma)^2 = f(b, 1), with equality only for dd = b and omega
+//   within rounding of 1 -- the same point.  For dd = lo < b the gap is (d* - lo)^2 - (d* - b)^2 > 0; the shortcut
+//   asks for lo == b or a gap far above any rounding of the reference's float128 evaluation.  It does not apply when
+//   the omega = 0 fallback (:136-148) or the (0, 0) candidate (:151-152) are in play, or when a > b.
+// Returns true and fills (d, omega, f) exactly as md_single_candidate(b, 1) would.  This covers every clamp of the
+// benign regime (family F2 with s > 1: "all clamps hit the upper bound") at the cost of a few comparisons.
+MD_HD bool md_upper_clamp_shortcut(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
+                                   double min_diag_B, double max_diag_B, double min_abs_value_D, MdBest* out) {
+  const double lo = md_pymax(min_diag_D, min_abs_value_D);
+  const double a = md_pymax(lo, min_diag_B - alpha);
+  const double b = md_pymin(max_diag_D, max_diag_B - alpha);
+  const double dstar = gamma - alpha;
+  if (!(isfinite(alpha) && isfinite(beta) && isfinite(gamma) && alpha > 0 && beta >= 0)) return false;
+  if (!(a <= b && dstar > b && b == max_diag_D)) return false;
+  if (!(lo == b || (b - lo) > 1e-9 * (fabs(alpha) + fabs(gamma) + fabs(b)))) return false;
+  if (min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D) return false;   // (0, 0) is a candidate
+  // the fallback candidate appears when p or q of either cubic is not finite (:105-110)
+  const double q = (-0.5 * beta / alpha) / alpha;
+  if (!isfinite(q) || !isfinite((lo - gamma) / alpha - q) || !isfinite((max_diag_D - gamma) / alpha - q)) return false;
+  *out = md_single_candidate(b, 1.0, alpha, beta, gamma);
+  return true;
+}
+
 // Reimer.py:68-72: the unclamped branch
 MD_HD bool md_unclamped(double alpha, double gamma, double min_diag_D, double max_diag_D, double min_diag_B,
                         double max_diag_B, double min_abs_value_D) {
@@ -312,6 +342,21 @@ MD_HD MdDecision md_decision_from_best(const MdBest& m) {
 MD_HD MdDecision md_minimal_change(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
                                    double min_diag_B, double max_diag_B, double min_abs_value_D) {
   if (md_unclamped(alpha, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, min_abs_value_D)) {  // :68-72
+    MdDecision r;
+    r.d = gamma - alpha; r.omega = 1; r.f = 0; r.clamped = 0;
+    return r;
+  }
+  MdBest quick;
+  if (md_upper_clamp_shortcut(alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, min_abs_value_D, &quick))
+    return md_decision_from_best(quick);
+  return md_decision_from_best(
+      md_minimal_change_part(3, alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, min_abs_value_D));
+}
+
+// The same without the shortcut (the reference's full candidate list): kept for the tests that prove the shortcut.
+MD_HD MdDecision md_minimal_change_full(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
+                                        double min_diag_B, double max_diag_B, double min_abs_value_D) {
+  if (md_unclamped(alpha, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, min_abs_value_D)) {
     MdDecision r;
     r.d = gamma - alpha; r.omega = 1; r.f = 0; r.clamped = 0;
     return r;

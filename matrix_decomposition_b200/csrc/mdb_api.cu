@@ -15,7 +15,7 @@
 #include "kernels_gmw.cuh"
 
 #define NB MDB_NB
-#define PANEL_R 64
+#define PANEL_R MDB_PANEL_RT
 
 enum { ST_EMPTY = 0, ST_MATRIX = 1, ST_FACTORED = 2, ST_FINAL = 3 };
 
@@ -30,7 +30,8 @@ struct mdb_factor {
   double *minB, *maxB;
   int64_t* p_dev;    // batch x n (null = identity)
   int* info;         // batch
-  double *Ut, *hdr;  // batch x NB*NB, batch x 3*NB
+  double *Ut, *hdr;  // batch x NB*NB, batch x 5*NB
+  double* Vinv;      // batch x MDB_VINV_DOUBLES
   double *PX, *PY;   // batch x panel_rows x (agg * NB): operands of one outer block
   double *PX2, *PY2; // second pair for lookahead
   int64_t panel_rows;
@@ -401,7 +402,7 @@ static void factor_release(mdb_factor* f) {
   if (!f) return;
   cudaSetDevice(f->ctx->device);
   cudaFree(f->W); cudaFree(f->vec); cudaFree(f->clamped); cudaFree(f->minB); cudaFree(f->maxB);
-  cudaFree(f->p_dev); cudaFree(f->info); cudaFree(f->Ut); cudaFree(f->hdr); cudaFree(f->PX); cudaFree(f->PY); cudaFree(f->PX2); cudaFree(f->PY2);
+  cudaFree(f->p_dev); cudaFree(f->info); cudaFree(f->Ut); cudaFree(f->hdr); cudaFree(f->Vinv); cudaFree(f->PX); cudaFree(f->PY); cudaFree(f->PX2); cudaFree(f->PY2);
   cudaFree(f->Linv); cudaFree(f->LinvT); cudaFree(f->Ltri); cudaFree(f->Utri);
   cudaFree(f->trsv_tasks); cudaFree(f->trsv_sync); cudaFree(f->trsv_partial);
   for (int i = 0; i < 3; ++i) cudaFree(f->ws[i]);
@@ -419,7 +420,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   f->ctx = ctx; f->n = n; f->batch = batch;
   f->ld = std::max<int64_t>(mdb_round_up(n, NB), NB);
   f->W = nullptr; f->vec = nullptr; f->clamped = nullptr; f->minB = f->maxB = nullptr; f->p_dev = nullptr;
-  f->info = nullptr; f->Ut = f->hdr = f->PX = f->PY = f->PX2 = f->PY2 = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
+  f->info = nullptr; f->Vinv = nullptr; f->Ut = f->hdr = f->PX = f->PY = f->PX2 = f->PY2 = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
   f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
   f->out_host = nullptr; f->out_ld = 0; f->out_stream_type = MDB_TYPE_LDL;
   for (int i = 0; i < 3; ++i) { f->ws[i] = nullptr; f->ws_cap[i] = 0; }
@@ -442,6 +443,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   A((void**)&f->info, (size_t)(batch + 1) * sizeof(int));
   A((void**)&f->Ut, (size_t)batch * NB * NB * 8);
   A((void**)&f->hdr, (size_t)batch * 5 * NB * 8);
+  A((void**)&f->Vinv, (size_t)batch * MDB_VINV_DOUBLES * 8);
   A((void**)&f->PX, panel_bytes);
   A((void**)&f->PY, panel_bytes);
   A((void**)&f->PX2, panel_bytes);
@@ -667,8 +669,8 @@ static FactorDev make_dev(mdb_factor* f) {
   F.n = f->n; F.ldw = f->ld; F.W = f->W;
   F.gamma = f->gamma; F.alpha = f->alpha; F.beta = f->beta; F.rowmax = f->rowmax;
   F.d = f->d; F.omega = f->omega; F.delta = f->delta; F.clamped = f->clamped;
-  F.minB = f->minB; F.maxB = f->maxB; F.info = f->info; F.Ut = f->Ut; F.hdr = f->hdr;
-  F.sW = f->n * f->ld; F.sVec = f->n; F.sUt = NB * NB; F.sHdr = 5 * NB; F.sPanel = f->panel_rows * f->agg * NB;
+  F.minB = f->minB; F.maxB = f->maxB; F.info = f->info; F.Ut = f->Ut; F.hdr = f->hdr; F.Vinv = f->Vinv;
+  F.sW = f->n * f->ld; F.sVec = f->n; F.sUt = NB * NB; F.sHdr = 5 * NB; F.sV = MDB_VINV_DOUBLES; F.sPanel = f->panel_rows * f->agg * NB;
   return F;
 }
 
@@ -676,10 +678,10 @@ static int configure_kernels(mdb_ctx* ctx) {
   static uint64_t done = 0;
   if (mdb_device_marked(done, ctx)) return MDB_OK;
   const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
-  const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
+  const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB) * 8;
   const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
-  MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel<NB, PANEL_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
+  MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel_gemm<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_blocks<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
   mdb_mark_device(done, ctx);
   return MDB_OK;
@@ -754,7 +756,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
     MDB_CUDA(ctx, cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream));
   }
   const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
-  const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
+  const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB) * 8;
   // Two-level blocking.  Panels are NB = 128 columns wide (diagonal block + row-parallel panel kernel); `agg`
   // consecutive panels form an outer block of KB = agg * NB columns whose operands X, Y sit side by side in one
   // (rows x KB) buffer.  After panel j only the remaining columns of its outer block are updated (K = 128,
@@ -809,7 +811,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       {
         PhaseTimer t(ctx, 1);
         dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, (unsigned)batch);
-        k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, main_s>>>(F, k0, k1, rows, f->W, 1, f->ld, f->W + k0, f->ld,
+        k_panel_gemm<NB><<<grid, MDB_PANEL_THREADS, panel_smem, main_s>>>(F, k0, k1, rows, f->W, 1, f->ld, f->W + k0, f->ld,
                                                                     PX + (k0 - ob), PY + (k0 - ob), ob, LDP);
         MDB_LAUNCHED(ctx);
       }

@@ -13,6 +13,7 @@
 #include "md_rule.h"
 
 #define MDB_NB 128  // panel width = distribution block = K of the trailing update
+#define MDB_VINV_DOUBLES (4 * 32 * 32 + 8)
 
 struct mdb_ctx {
   int device;
@@ -95,7 +96,9 @@ struct FactorDev {
   int* info;      // first failing pivot + 1 (MDB_RULE_EXACT), 0 = none
   double* Ut;     // NB x NB scratch: Ut[m * NB + k] = d_m * Ltilde[k][m]  (m < k)
   double* hdr;    // 5 x NB scratch: d, omega, drop flag, delta, clamped of the current panel
+  double* Vinv;   // MDB_VINV_DOUBLES scratch: inverses of the four 32 x 32 scaled unit triangles of the diagonal block
+                  // (row-major, [sub-block][c][m]) + [4096] = 1.0 when the panel must not use them
   // strides between consecutive matrices of a batch (elements)
-  int64_t sW, sVec, sUt, sHdr, sPanel;
+  int64_t sW, sVec, sUt, sHdr, sPanel, sV;
   MdRuleParams prm;
 };

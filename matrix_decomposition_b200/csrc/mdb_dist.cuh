@@ -18,6 +18,7 @@ struct mdb_dist {
   double *minB, *maxB;
   int* info;
   double* Ut;
+  double* Vinv;
   int64_t* pcol_dev;   // scratch for the generator
   MdRuleParams prm;
   bool have_bounds;
@@ -79,7 +80,7 @@ extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, dou
   s->nblk_glob = (n + NB - 1) / NB;
   s->nblk_loc = dist_local_blocks(n, rank, world);
   s->S = S_loc; s->A = A_loc; s->panel[0] = panel0; s->panel[1] = panel1;
-  s->vec = nullptr; s->clamped = nullptr; s->minB = s->maxB = nullptr; s->info = nullptr; s->Ut = nullptr;
+  s->vec = nullptr; s->clamped = nullptr; s->minB = s->maxB = nullptr; s->info = nullptr; s->Ut = nullptr; s->Vinv = nullptr;
   s->pcol_dev = nullptr; s->have_bounds = false;
   s->p2p = false; s->push_counter = nullptr; s->epoch = 0;
   for (int q = 0; q < 16; ++q) s->peer_base[q] = nullptr;
@@ -95,6 +96,7 @@ extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, dou
   if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->clamped, (size_t)n);
   if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->info, sizeof(int));
   if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->Ut, (size_t)NB * NB * 8);
+  if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->Vinv, (size_t)MDB_VINV_DOUBLES * 8);
   if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&s->pcol_dev, (size_t)ld_loc * 8);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->vec, 0, (size_t)7 * n * 8, ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->clamped, 0, (size_t)n, ctx->stream);
@@ -119,7 +121,7 @@ extern "C" int mdb_dist_destroy(mdb_dist* s) {
     cudaFree(s->vec); cudaFree(s->clamped);
     for (int i = 0; i < 2; ++i) { cudaFree(s->OPX[i]); cudaFree(s->OPY[i]); }
   }
-  cudaFree(s->minB); cudaFree(s->maxB); cudaFree(s->info); cudaFree(s->Ut);
+  cudaFree(s->minB); cudaFree(s->maxB); cudaFree(s->info); cudaFree(s->Ut); cudaFree(s->Vinv);
   cudaFree(s->pcol_dev); cudaFree(s->push_counter);
   delete s;
   return MDB_OK;
@@ -256,7 +258,7 @@ static FactorDev dist_make_dev(mdb_dist* s, double* hdr) {
   F.n = s->n; F.ldw = s->ld; F.W = s->S;
   F.gamma = s->gamma; F.alpha = s->alpha; F.beta = s->beta; F.rowmax = s->rowmax;
   F.d = s->d; F.omega = s->omega; F.delta = s->delta; F.clamped = s->clamped;
-  F.minB = s->minB; F.maxB = s->maxB; F.info = s->info; F.Ut = s->Ut; F.hdr = hdr;
+  F.minB = s->minB; F.maxB = s->maxB; F.info = s->info; F.Ut = s->Ut; F.hdr = hdr; F.Vinv = s->Vinv;
   F.prm = s->prm;
   return F;
 }
@@ -279,7 +281,7 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot, int64_t k
   double* MX = vecs + 3 * rows;  // X part of the message
   FactorDev F = dist_make_dev(s, hdr);
   const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
-  const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB, PANEL_R) * 8;
+  const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB) * 8;
   k_diag_block<NB><<<1, MDB_DIAG_THREADS(NB), diag_smem, ctx->stream>>>(F, k0, kb, s->S + k0 * s->ld + lc0, s->ld, s->A + k0 * s->ld + lc0,
                                                        s->ld);
   MDB_LAUNCHED(ctx);
@@ -289,7 +291,7 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot, int64_t k
     // The owner's operands go straight into the outer-block buffers; X is then copied into the message.
     double* PX = s->OPX[oslot] + (k0 - ob);
     double* PY = s->OPY[oslot] + (k0 - ob);
-    k_panel<NB, PANEL_R><<<grid, PANEL_R, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
+    k_panel_gemm<NB><<<grid, MDB_PANEL_THREADS, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
                                                                      s->S + lc0, s->ld, PX, PY, ob, s->ldp);
     MDB_LAUNCHED(ctx);
     if (!s->p2p) {  // message = [hdr (already there) | alpha, beta, rowmax of the rows below | X], packed by one kernel

@@ -122,33 +122,32 @@ extern "C" int mdb_dist_solve_fill_band(mdb_dist* s, double* band) {
 }
 
 // Inverse of the unit lower triangular 128 x 128 diagonal block J (rows / columns past n: identity).  One CTA per
-// block, thread c computes column c of the inverse by forward substitution; T staged in shared memory.
+// block, thread c computes column c of the inverse by forward substitution.  The inverse lives in shared memory
+// ([128][129] doubles); T is read from the band in global memory (every thread walks the same row i at the same
+// time, so the loads are L1-friendly).
 __global__ void __launch_bounds__(MDB_NB) k_dsolve_invert(int64_t n, const double* __restrict__ band,
                                                           double* __restrict__ tinv, double* __restrict__ tinvT) {
   extern __shared__ double smem_d[];
   constexpr int LDS = MDB_NB + 1;
-  double* T = smem_d;               // T[i * LDS + m]
-  double* X = T + MDB_NB * LDS;     // X[i * LDS + c]: column c of the inverse, owned by thread c
+  double* X = smem_d;               // X[i * LDS + c]: column c of the inverse, owned by thread c
   const int64_t J = blockIdx.x, g0 = J * MDB_NB;
   const int c = threadIdx.x;
   const int cw = (int)(g0 % MDB_DSOLVE_WD);   // first column of the block inside its window
   for (int i = 0; i < MDB_NB; ++i) {
     const int64_t g = g0 + i;
-    T[i * LDS + c] = (g < n && c < i) ? band[g * MDB_DSOLVE_WD + cw + c] : 0.0;
-  }
-  __syncthreads();
-  for (int i = 0; i < MDB_NB; ++i) {
+    const double* Trow = band + g * MDB_DSOLVE_WD + cw;   // T[i][m] = Trow[m] for m < i (valid when g < n)
     double x;
     if (i < c) x = 0.0;
     else if (i == c) x = 1.0;
+    else if (g >= n) x = 0.0;
     else {
       double a0 = 0, a1 = 0;
       int m = c;
       for (; m + 1 < i; m += 2) {
-        a0 = fma(T[i * LDS + m], X[m * LDS + c], a0);
-        a1 = fma(T[i * LDS + m + 1], X[(m + 1) * LDS + c], a1);
+        a0 = fma(Trow[m], X[m * LDS + c], a0);
+        a1 = fma(Trow[m + 1], X[(m + 1) * LDS + c], a1);
       }
-      if (m < i) a0 = fma(T[i * LDS + m], X[m * LDS + c], a0);
+      if (m < i) a0 = fma(Trow[m], X[m * LDS + c], a0);
       x = -(a0 + a1);
     }
     X[i * LDS + c] = x;
@@ -167,7 +166,7 @@ extern "C" int mdb_dist_solve_invert_band(mdb_dist* s, const double* band, doubl
   mdb_ctx* ctx = s->ctx;
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   static uint64_t configured = 0;
-  const int smem = 2 * NB * (NB + 1) * 8;
+  const int smem = NB * (NB + 1) * 8;
   if (!mdb_device_marked(configured, ctx)) {
     MDB_CUDA(ctx, cudaFuncSetAttribute(k_dsolve_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     mdb_mark_device(configured, ctx);

@@ -11,6 +11,20 @@ int mdh_minimal_change(double alpha, double beta, double gamma, double min_diag_
   out3[0] = r.d; out3[1] = r.omega; out3[2] = r.f;
   return r.clamped;
 }
+// the full candidate list (no upper-clamp shortcut)
+int mdh_minimal_change_full(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D, double min_diag_B,
+                            double max_diag_B, double mav, double* out3) {
+  MdDecision r = md_minimal_change_full(alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav);
+  out3[0] = r.d; out3[1] = r.omega; out3[2] = r.f;
+  return r.clamped;
+}
+int mdh_upper_clamp_shortcut(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D, double min_diag_B,
+                             double max_diag_B, double mav, double* out3) {
+  MdBest b;
+  const bool hit = md_upper_clamp_shortcut(alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav, &b);
+  if (hit) { out3[0] = b.d; out3[1] = b.w; out3[2] = b.f; }
+  return hit ? 1 : 0;
+}
 // the two-thread evaluation of the kernels: both halves of the candidate list, merged
 int mdh_minimal_change_split(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
                              double min_diag_B, double max_diag_B, double mav, double* out3) {

@@ -30,6 +30,50 @@ def test_fp64_rule_against_reference_vectors():
     assert n_far <= 4
 
 
+def test_upper_clamp_shortcut_equals_full_candidate_list():
+    """md_upper_clamp_shortcut (csrc/md_rule.h) skips the two cubic solves when d* lies above [a, b] and b is
+    max_diag_D.  Wherever it fires it must return what the reference's full candidate list returns: checked on the
+    reference's golden _minimal_change vectors and on 20000 random upper-clamp situations (benign and huge alpha)."""
+    import ctypes
+    shim = bm.rule_shim()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    z = load_golden('scalar_rule.npz')
+    want = ld_join(z, 'mc_out').astype(np.float64)
+    quick, full = np.zeros(3), np.zeros(3)
+    n_hit = 0
+    for row, w in zip(z['mc_in'], want):
+        args = [float(v) for v in row]
+        if shim.mdh_upper_clamp_shortcut(*args, P(quick)):
+            n_hit += 1
+            assert shim.mdh_minimal_change_full(*args, P(full)) == 1
+            assert quick[0] == full[0] and abs(quick[1] - full[1]) <= 1e-15 and abs(quick[2] - full[2]) <= 1e-15 * abs(full[2])
+            assert abs(quick[0] - w[0]) <= 1e-15 * abs(w[0]) and abs(quick[1] - w[1]) <= 1e-12   # the reference itself
+    rng = np.random.default_rng(0)
+    n_rand = 0
+    for _ in range(20000):
+        scale = 10.0 ** rng.uniform(-3, 6)
+        max_diag_D = scale * rng.uniform(0.5, 2.0)
+        min_diag_D = max_diag_D * rng.choice([0.0, 1e-3, 0.2, 0.999, 1.0])
+        alpha = scale * 10.0 ** rng.uniform(-6, 3)
+        gamma = alpha + max_diag_D * (1 + 10.0 ** rng.uniform(-8, 2))        # d* above max_diag_D
+        beta = scale ** 2 * 10.0 ** rng.uniform(-4, 6) * rng.choice([0.0, 1.0, 1.0])
+        max_diag_B = rng.choice([np.inf, max_diag_D + alpha * rng.uniform(1.0, 3.0), max_diag_D + alpha])
+        min_diag_B = rng.choice([-np.inf, 0.0, min_diag_D * 0.5])
+        mav = rng.choice([3.3e-10, scale * 1e-3])
+        args = [alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav]
+        if not shim.mdh_upper_clamp_shortcut(*args, P(quick)):
+            continue
+        n_rand += 1
+        assert shim.mdh_minimal_change_full(*args, P(full)) == 1
+        assert quick[0] == full[0], args
+        # the full FP64 list may return a cubic root a hair below 1 whose f ties with f(b, 1) in double precision (the
+        # u + v form of roots.py is only good to ~1e-12 when alpha << |d* - b|; the true root lies above 1 and is
+        # clipped to omega = 1): the shortcut's omega = 1 is the exact answer, the difference is far below 1e-10
+        assert abs(quick[1] - full[1]) <= 1e-9, (args, quick, full)
+        assert abs(quick[2] - full[2]) <= 1e-12 * abs(full[2]), (args, quick, full)
+    assert n_hit >= 20 and n_rand >= 10000, (n_hit, n_rand)
+
+
 def test_fp64_cubic_against_reference_vectors():
     z = load_golden('scalar_rule.npz')
     want = ld_join(z, 'cubic_out').astype(np.float64)
