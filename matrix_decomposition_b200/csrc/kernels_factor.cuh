@@ -190,120 +190,425 @@ __device__ __forceinline__ void mdb_cp_async_wait_all() {
 // ------------------------------------------------------------------------------------------------
 // Diagonal block: columns K = k0 .. k0+kb-1, rows of the block only.  One CTA, the whole block in shared
 // memory.  Sequential over the columns because the decision for column k needs alpha_k, which contains
-// Lu[k, k0:k]^2 d from this very block: the kernel is one dependency chain, and everything is arranged to keep the
-// per-column part of it short (round 2: 1750 -> ~X cycles per column).
+// Lu[k, k0:k]^2 d from this very block: the kernel is ONE dependency chain
+//     decision k  ->  x[k+1, k]  ->  alpha_{k+1}  ->  decision k+1,
+// and only row k + 1 is on it.  Everything is arranged so that a column costs that chain and nothing else
+// (round 1: one CTA-wide barrier per column, ~2200 cycles per column; now one warp carries the chain through
+// register shuffles, ~250 cycles per column, and every other row trails it on a progress counter).
 //
-// Threads: 16 compute warps, thread (j, h) = (tid >> 2, tid & 3): the four lanes of a row share its dot products,
-// lanes h = 0 and 1 both carry the row's state (alpha, beta, rowmax, rowmin) redundantly -- identical arithmetic --
-// so that the row itself can decide its column without a hand-over: the unclamped test, MD_RULE_EXACT and the upper
-// clamp (md_upper_clamp_shortcut) are a few comparisons in lane h = 0; a column that needs the two cubic solves
-// (Reimer.py:95-115) evaluates the candidates of d = lo and d = max_diag_D side by side in lanes h = 0 / 1
-// (mdb_rule_full_pair, one instruction stream, merged with the reference's key).  Warp 16 is a helper (below).
-// Per column k, compute warps only (named barrier, the helper does not take part):
-//   phase A   rows j > k : G_j = sum_{sb0 <= m < k-1} Lu[j, m] d_m Lu[k, m]   -- the dot product with the UNscaled row
-//             k (d_m Lu[k, m] sits at the transposed position (m, k) of the tile: the A entry stored there is dead
-//             once column m has been processed).  Does not need the decision for column k.
-//   barrier
-//   phase B   x[j, k] = ((1 - omega) A[j, k] + omega (S'[j, k] - G_j)) / d    (= A[j, k] / d when the scaled row k
-//             is dropped), alpha / beta / rowmax updates in column order (Reimer.py:604,684); row k + 1 then decides
-//             column k + 1 at once (d, omega, 1 / d, flags into the double-buffered s_dec).
-// Two-level inside the block: sub-blocks of SB = 32 columns.  The dot products only run over the columns of the
-// current sub-block (sb0 = its first column): when a sub-block is complete, its contribution
-// S'[j, c] -= sum_{m in sub-block} Lu[j, m] d_m Lu[c, m]  to every later column c of the block is applied at once on
-// the FP64 tensor cores (mma.m16n8k4 from shared memory).
-// omega G ignores the reference's thresholding of tiny entries of the scaled row (Reimer.py:558).  A column falls
-// back to the explicit thresholded dot product over ALL earlier columns of the block and the block-entry value of S
+// Two-level inside the block: sub-blocks of SB = 32 columns.  Roles per sub-block (first column sb0):
+//   chain warp (warp 0), lane = row sb0 + lane: owns the 32 x 32 triangle.  Per column k the lane of row k holds
+//     the decision (d, omega, 1 / d, flags) in registers; one shuffle broadcasts it; every lane j > k forms
+//         x[j, k] = ((1 - omega) A[j, k] + omega S''[j, k]) / d        (= A[j, k] / d when the scaled row k is dropped)
+//     where S''[j, c], c = k .. sb0 + 31, is the row's part of the Schur complement kept up to date in REGISTERS
+//     (right-looking inside the sub-block: after column k, S''[j, c] -= x[j, k] d_k x[c, k]; the register file is
+//     rotated by one column per step so that the loop body has static indices), updates alpha / beta / rowmax /
+//     rowmin in column order (Reimer.py:604,684), and every lane evaluates the cheap part of the rule on its own row
+//     -- the unclamped test, MD_RULE_EXACT and the division-free upper-clamp shortcut (md_upper_clamp_shortcut_cheap) --
+//     so that lane k + 1 has the next decision a few dependent instructions after alpha_{k+1}.  A column that needs
+//     the cubic solves (Reimer.py:95-115) calls md_decide in that one lane (rare in the benign regime).
+//   trailing warps (warps 1..3), one thread per row below the sub-block: the same column step, decision read from
+//     shared memory once s_progress says column k is published (they never hold the chain up).
+//   helper warp (warp 5): trails as well and forms, row by row, the inverse of the scaled unit triangle
+//     Ltilde[c][m] = thresh(omega_c Lu[c, m]) of each sub-block; the panel kernel k_panel_gemm multiplies by these
+//     32 x 32 inverses instead of substituting column by column.  Vinv[4096] = 1 tells it not to (an entry of an inverse
+//     above 1e8 or not finite, |Lu| > 1e100 anywhere, or a zero d): it then substitutes.
+//   When a sub-block is complete (named barrier of the 7 compute warps), its contribution
+//     S'[j, c] -= sum_{m in sub-block} Lu[j, m] d_m Lu[c, m]  to every later column c of the block is applied at once on
+//     the FP64 tensor cores (mma.m16n8k4 from shared memory; d_m Lu[c, m] sits at the transposed tile position (m, c),
+//     where the A entry is dead once row c has passed column m).
+// omega S'' ignores the reference's thresholding of tiny entries of the scaled row (Reimer.py:558).  A row falls back
+// to the explicit thresholded dot product over ALL earlier columns of the block and the block-entry value of S
 // (re-read from global memory, which this kernel only overwrites at its end) -- "slow", exact w.r.t. the reference
-// inside the block -- whenever that could matter: omega_k * min nonzero |Lu[k, .]| < min_abs_value_L, or the
-// products could overflow (explosive regime, |Lu| > 1e100; from then on S' is not used any more).
-// Helper warp: trails the column loop (polls s_progress) and forms, row by row, the inverse of the scaled unit
-// triangle Ltilde[c][m] = thresh(omega_c Lu[c, m]) of each sub-block; the panel kernel k_panel_gemm multiplies by
-// these 32 x 32 inverses instead of substituting column by column.  Vinv[4096] = 1 tells it not to (an entry of an
-// inverse above 1e8 or not finite, |Lu| > 1e100 anywhere, or a zero d): it then substitutes.
+// inside the block -- whenever that could matter: omega_k * min nonzero |Lu[k, .]| < min_abs_value_L, or the products
+// could overflow (|Lu| > 1e100 in row k or in the row itself: both are properties of the two rows involved, so the
+// choice does not depend on how far the trailing warps lag).
 // Outputs: d, omega, delta, clamped; Ut[m][k] = d_m thresh(omega_k Lu[k, m]) (Reimer.py:553-560); hdr = (d, omega,
 // drop, delta, clamped) of the panel; Vinv.
 // ------------------------------------------------------------------------------------------------
 // Sblk / Ablk point at element (k0, k0) of the storage that holds S (lower part is read and written) and
 // the permuted original A (upper part is read): the same array W on one GPU, S_loc / A_loc when distributed.
-#define MDB_DIAG_THREADS(NB) (4 * (NB) + 32)
-#define MDB_DIAG_SMEM_DOUBLES(NB) ((NB) * ((NB) + 4) + 3 * (NB) + 8 + 32 * 33 + 32)
+#define MDB_DIAG_WARPS 8
+#define MDB_DIAG_THREADS(NB) (32 * MDB_DIAG_WARPS)
 #define MDB_DIAG_SB 32
+#define MDB_DIAG_YLD 36
+#define MDB_DIAG_HELPER_WARP 4
 
-// S'[j, c] -= sum_{m0 <= m < m0 + SB} T[j][m] T[m][c]  for c0 <= c < j < kb (c0 = m0 + SB), tiles of 16 x 8 dealt
-// round-robin to the 16 compute warps.  mma.m16n8k4: a0 = A[g][t4], a1 = A[g+8][t4], b0 = B[t4][g],
-// c = C[g | g+8][2 t4 | 2 t4 + 1].
+// shared-memory layout of k_diag_block (offsets in doubles from the dynamic shared base)
+template <int NB>
+struct DiagLayout {
+  static constexpr int LDT = NB + 4;            // 264 words: the DMMA fragment loads of the sub-block update are conflict-free
+  static constexpr int T = 0;                   // T[r * LDT + c]: c < r: S0 -> S' -> Lu;  c >= r: A, then (r, c) <- d_r Lu[c, r]
+  static constexpr int YT = T + NB * LDT;       // 33 x YLD: Yt[kk * YLD + c + ((kk + 1) & 1)] = d_k x[c, k] of the chain rows c
+  static constexpr int DEC = YT + 33 * MDB_DIAG_YLD;  // 4 per column: d, omega, 1 / d, flags (1 = drop, 2 = slow, 4 = clamped)
+  static constexpr int ALPHA = DEC + 4 * NB;    // row state, by row of the block
+  static constexpr int BETA = ALPHA + NB;
+  static constexpr int ROWMAX = BETA + NB;
+  static constexpr int ROWMIN = ROWMAX + NB;
+  static constexpr int GAMMA = ROWMIN + NB;
+  static constexpr int MINB = GAMMA + NB;
+  static constexpr int MAXB = MINB + NB;
+  static constexpr int INV = MAXB + NB;         // 32 x 33: inverse of the current sub-block's scaled unit triangle (helper warp)
+  static constexpr int LT = INV + 32 * 33;      // 36 (16-byte aligned): the scaled, thresholded row the helper is working on
+  static constexpr int FLAGS = LT + 36;         // int progress: columns whose x of the chain rows and whose decision are published
+  static constexpr int TOTAL = FLAGS + 2;
+  static_assert((YT % 2) == 0 && (DEC % 2) == 0 && (LT % 2) == 0, "16-byte alignment of the vector accesses");
+};
+#define MDB_DIAG_SMEM_DOUBLES(NB) (DiagLayout<NB>::TOTAL)
+
+// Shared-memory accesses of the column loop by 32-bit shared address (one base register, immediate offsets: the
+// compiler otherwise re-derives the shared window base inside the loop).  asm volatile keeps their program order.
+__device__ __forceinline__ double mdb_lds(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ double2 mdb_lds2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ double mdb_lds1(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ void mdb_sts(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+template <int OFF>
+__device__ __forceinline__ void mdb_sts2(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0+%3], {%1, %2};" ::"r"(a), "d"(x), "d"(y), "n"(OFF) : "memory");
+}
+__device__ __forceinline__ int mdb_lds_flag(uint32_t a) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mdb_sts_flag(uint32_t a, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// S'[j, c] -= sum_{m0 <= m < m0 + SB} T[j][m] T[m][c]  for c0 <= c < j < kb (c0 = m0 + SB): items of 16 x 16 (one A
+// fragment stream, two independent accumulator chains) dealt round-robin to the warps.  mma.m16n8k4: a0 = A[g][t4],
+// a1 = A[g+8][t4], b0 = B[t4][g], c = C[g | g+8][2 t4 | 2 t4 + 1].
 template <int NB>
 __device__ __forceinline__ void mdb_diag_subblock_update(double* __restrict__ T, int m0, int kb, int warp, int lane) {
   constexpr int LDT = NB + 4;
   constexpr int SB = MDB_DIAG_SB;
   const int c0 = m0 + SB;
   const int g = lane >> 2, t4 = lane & 3;
-  const int n_rt = (kb - c0 + 15) >> 4, n_ct_all = (kb - c0 + 7) >> 3;
-  int t = 0;
+  const int n_rt = (kb - c0 + 15) >> 4;
+  int t = 0, next = warp;
   for (int ri = 0; ri < n_rt; ++ri) {
-    const int r0 = c0 + 16 * ri;
-    const int n_ct = (2 * ri + 2 < n_ct_all) ? 2 * ri + 2 : n_ct_all;   // tiles that reach below the diagonal
-    for (int ci = 0; ci < n_ct; ++ci, ++t) {
-      if ((t & 15) != warp) continue;
-      const int cc0 = c0 + 8 * ci;
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int cj = 0; cj <= ri; ++cj, ++t) {
+      if (t != next) continue;
+      next += MDB_DIAG_WARPS;
+      const int r0 = c0 + 16 * ri, cc0 = c0 + 16 * cj;
+      double acc0[4] = {0.0, 0.0, 0.0, 0.0}, acc1[4] = {0.0, 0.0, 0.0, 0.0};
       const double* Ap0 = T + (r0 + g) * LDT + m0 + t4;
       const double* Ap1 = Ap0 + 8 * LDT;
       const double* Bp = T + (m0 + t4) * LDT + cc0 + g;
 #pragma unroll
       for (int kk = 0; kk < SB; kk += 4) {
-        const double a0 = Ap0[kk], a1 = Ap1[kk], b0 = Bp[kk * LDT];
+        const double a0 = Ap0[kk], a1 = Ap1[kk], b0 = Bp[kk * LDT], b1 = Bp[kk * LDT + 8];
         asm volatile(
             "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
-            : "+d"(acc[0]), "+d"(acc[1]), "+d"(acc[2]), "+d"(acc[3])
+            : "+d"(acc0[0]), "+d"(acc0[1]), "+d"(acc0[2]), "+d"(acc0[3])
             : "d"(a0), "d"(a1), "d"(b0));
+        asm volatile(
+            "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+            : "+d"(acc1[0]), "+d"(acc1[1]), "+d"(acc1[2]), "+d"(acc1[3])
+            : "d"(a0), "d"(a1), "d"(b1));
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int row = r0 + g + ((e & 2) ? 8 : 0), col = cc0 + 2 * t4 + (e & 1);
-        if (row < kb && col < row) T[row * LDT + col] -= acc[e];
+        if (row < kb && col < row) T[row * LDT + col] -= acc0[e];
+        if (row < kb && col + 8 < row) T[row * LDT + col + 8] -= acc1[e];
       }
     }
   }
 }
 
-// The clamped branch with both cubic solves (Reimer.py:89-135), lanes h = 0 / 1 of one row group: lane h evaluates the
-// candidates of d = lo (h = 0) or d = max_diag_D (h = 1), the pair exchanges them and both lanes assemble the same
-// decision.  Kept out of line: it is ~1300 instructions and the column loop calls it rarely.
-__device__ __noinline__ MdDecision mdb_rule_full_pair(MdRuleParams prm, int h, unsigned pairmask, double al, double be,
-                                                      double ga, double mD, double mB, double MB) {
-  double dd;
-  int fb = 0;
-  const bool en = md_d_candidate(h, al, be, mD, prm.max_diag_D, mB, MB, prm.min_abs_value_D, &dd);
-  const MdBest mine = md_candidates_for_d(en, dd, al, be, ga, mB, MB, &fb);
-  MdBest other;
-  other.d = __shfl_xor_sync(pairmask, mine.d, 1);
-  other.w = __shfl_xor_sync(pairmask, mine.w, 1);
-  other.f = __shfl_xor_sync(pairmask, mine.f, 1);
-  other.have = __shfl_xor_sync(pairmask, mine.have, 1);
-  const int fb_other = __shfl_xor_sync(pairmask, fb, 1);
-  const MdBest from_lo = (h == 0) ? mine : other, from_max = (h == 0) ? other : mine;
-  return md_decision_from_best(md_assemble_minimal_change(from_lo, from_max, fb | fb_other, al, be, ga, mD, prm.max_diag_D,
-                                                          mB, MB, prm.min_abs_value_D));
+// x[j, k] of a "slow" column: the reference's own form, Reimer.py:553-560 and :586-600 inside the block,
+//   x = ((1 - w) A[j, k] + w S0[j, k] - sum_{m < k} Lu[j, m] d_m thresh(w Lu[k, m])) / d_k
+__device__ __noinline__ double mdb_diag_slow_x(const double* __restrict__ T, int ldt, const double* __restrict__ dec, int j,
+                                               int k, double w, double inv, double a, double s0k, double mavL) {
+  const double* Tj = T + j * ldt;
+  const double* Tk = T + k * ldt;
+  double a0 = 0, a1 = 0;
+  int m = 0;
+  for (; m + 1 < k; m += 2) {
+    double l0 = w * Tk[m], l1 = w * Tk[m + 1];
+    if (w == 0 || fabs(l0) < mavL) l0 = 0;
+    if (w == 0 || fabs(l1) < mavL) l1 = 0;
+    a0 = fma(Tj[m], dec[4 * m] * l0, a0);
+    a1 = fma(Tj[m + 1], dec[4 * m + 4] * l1, a1);
+  }
+  if (m < k) {
+    double l0 = w * Tk[m];
+    if (w == 0 || fabs(l0) < mavL) l0 = 0;
+    a0 = fma(Tj[m], dec[4 * m] * l0, a0);
+  }
+  return (((1.0 - w) * a + w * s0k) - (a0 + a1)) * inv;
 }
 
-template <int NB>
-__global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
-                                                            int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
-  extern __shared__ double smem_d[];
-  constexpr int LDT = NB + 4;   // 264 words: the 4 rows of a half warp land in 4 disjoint groups of 8 banks
-  constexpr int SB = MDB_DIAG_SB;
-  constexpr int NCOMPUTE = 4 * NB;
+// 1 / d for the chain: MUFU.RCP64H and the Newton steps of __drcp_rn without its special-case branch, so that the
+// compiler can interleave it with the register update.  Only valid for 1e-280 <= |d| <= 1e280 (the caller redoes
+// everything else with __drcp_rn).
+__device__ __forceinline__ double mdb_rcp_normal(double d) {
+  double x0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(d));
+  double e = fma(-d, x0, 1.0);
+  e = fma(e, e, e);
+  const double x1 = fma(x0, e, x0);
+  const double e2 = fma(-d, x1, 1.0);
+  return fma(x1, e2, x1);
+}
+
+__device__ __forceinline__ void mdb_fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+
+// What the chain keeps out of its loop body (one lane, rare): x of a column that is dropped, slow or has d = 0 ...
+__device__ __noinline__ double mdb_diag_special_x(const double* __restrict__ T, int ldt, const double* __restrict__ dec, int j,
+                                                  int k, double dk, double wk, double inv, int flags, bool row_big, double a,
+                                                  double r0, const double* __restrict__ Sblk, int64_t ldS, double mavL) {
+  if (dk == 0) return 0.0;
+  if (flags & 1) return a * inv;   // the scaled row k is dropped: column k of L is A[:, k] / d
+  if (k > 0 && ((flags & 2) || row_big)) return mdb_diag_slow_x(T, ldt, dec, j, k, wk, inv, a, Sblk[j * ldS + k], mavL);
+  return fma(wk, r0, (1.0 - wk) * a) * inv;
+}
+
+// ... and a decision that is not one of the cheap cases (or whose d is outside the range of mdb_rcp_normal):
+// out = (d, omega, 1 / d), returns the flags
+__device__ __noinline__ int mdb_diag_special_decision(MdRuleParams prm, bool rare, double nd, int ncl, int kc, double al,
+                                                      double be, double ga, double mB, double MB, double rowmax,
+                                                      double rowmin, double* __restrict__ out) {
+  double nw = 1.0;
+  if (rare) {
+    const MdDecision dd = md_decide(prm, al, be, ga, mB, MB);
+    nd = dd.d; nw = dd.omega; ncl = dd.clamped;
+  }
+  const double ninv = (nd != 0) ? __drcp_rn(nd) : 0.0;
+  const double mavL = prm.min_abs_value_L;
+  const bool drop = (nw == 0 || nw * rowmax < mavL);
+  const bool slow = !drop && kc > 0 && (nw * rowmin < mavL || rowmax > 1e100);
+  out[0] = nd; out[1] = nw; out[2] = ninv;
+  return (drop ? 1 : 0) | (slow ? 2 : 0) | (ncl ? 4 : 0);
+}
+
+// The columns of one sub-block for one row (thread): CHAIN = the rows of the sub-block itself (one warp, decisions made
+// here), otherwise a row below it.  The body of the column loop is what the whole factorization of small matrices
+// waits for.
+template <int NB, bool EXACT, bool CHAIN>
+__device__ __forceinline__ void mdb_diag_columns(const FactorDev& F, double* __restrict__ sm, int sb0, int kb, int j, int lane,
+                                                 const double* __restrict__ Sblk, int64_t ldS) {
+  using L = DiagLayout<NB>;
+  constexpr int LDT = L::LDT, SB = MDB_DIAG_SB, YLD = MDB_DIAG_YLD;
   constexpr double BIG = 1e100;
-  double* T = smem_d;           // T[r * LDT + c]: c < r: S0 -> S' -> Lu;  c >= r: A, then (r, c) <- d_r Lu[c, r]
-  double* s_u = T + NB * LDT;   // NB (slow path)
-  double* s_d = s_u + NB;       // NB: d of the finished columns
-  double* s_w = s_d + NB;       // NB: omega of the finished columns
-  double* s_dec = s_w + NB;     // 2 x 4: d, omega, 1 / d, flags (1 = drop, 2 = slow) of column k in slot k & 1
-  double* s_inv = s_dec + 8;    // 32 x 33: inverse of the current sub-block's scaled unit triangle (helper warp)
-  double* s_lt = s_inv + 32 * 33;  // 32: the scaled, thresholded row the helper is working on
-  __shared__ int s_bigf[2], s_unsafe;   // s_bigf[k & 1]: some |Lu| > 1e100 seen up to phase B of a column of that parity
-  __shared__ volatile int s_progress;  // columns whose decision and row are final (the helper polls it)
+  const unsigned FULL = 0xffffffffu;
+  const bool valid = j < kb;
+  const double mavL = F.prm.min_abs_value_L;
+  const bool track_min = mavL > 0;   // rowmin only matters for the threshold test
+  double* T = sm + L::T;
+  double* dec = sm + L::DEC;
+  const int jr = valid ? j : 0;   // rows beyond the block only go through the motions
+  const double* Trow = T + jr * LDT;
+
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
+  uint32_t a_col = sbase + 8u * (uint32_t)(L::T + sb0 * LDT + jr);   // &T[k][j]: A[j, k], then d_k Lu[j, k]
+  uint32_t a_x = sbase + 8u * (uint32_t)(L::T + jr * LDT + sb0);     // &T[j][k]: Lu[j, k]
+  uint32_t a_dec = sbase + 8u * (uint32_t)(L::DEC + 4 * sb0);        // decision of column k
+  uint32_t a_yst = sbase + 8u * (uint32_t)(L::YT + lane);            // row kk of Yt, this lane's slot (before the parity shift)
+  uint32_t a_yld = sbase + 8u * (uint32_t)(L::YT + 1);               // row kk of Yt from column kk + 1 on (before the parity shift)
+  const uint32_t a_prog = sbase + 8u * (uint32_t)L::FLAGS;
+
+  double r[SB];   // r[i] = S''[j, k + i] at the top of column step k (rotated by one per step)
+#pragma unroll
+  for (int c = 0; c < SB; c += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(Trow + sb0 + c);
+    r[c] = v.x; r[c + 1] = v.y;
+  }
+  double alpha = sm[L::ALPHA + jr], beta = sm[L::BETA + jr], rowmax = sm[L::ROWMAX + jr], rowmin = sm[L::ROWMIN + jr];
+  double gamma = 0, mB = 0, MB = 0;
+  const double MD = F.prm.max_diag_D;
+  MdRowConst rc;
+  rc.lo = 0; rc.alpha_hi = 0; rc.ok = 0;
+  bool d_in_range = false;   // lo and max_diag_D inside the range of mdb_rcp_normal: then so is every cheap d
+  double dec_d = 0, dec_w = 0, dec_inv = 0;
+  int dec_fl = 0;
+  if (CHAIN) {
+    gamma = sm[L::GAMMA + jr]; mB = sm[L::MINB + jr]; MB = sm[L::MAXB + jr];
+    if (!EXACT) {
+      rc = md_row_const(gamma, md_effective_min_diag_D(F.prm, gamma, mB, MB), MD, mB, F.prm.min_abs_value_D);
+      d_in_range = rc.lo >= 1e-280 && MD <= 1e280;
+    }
+  }
+
+  // The decision of this lane's own row from its state: the cheap cases -- the unclamped test (Reimer.py:68-72),
+  // MD_RULE_EXACT, the division-free upper clamp -- are arithmetic only and evaluated by every lane after every column
+  // (only the lane of the next column uses the result); everything else goes through mdb_diag_special_decision in
+  // that one lane.  a_d = shared address of the column's decision record.
+  auto decide = [&](int kc, bool mine, uint32_t a_d) {
+    const double dstar = gamma - alpha;
+    double nd = dstar;
+    int ncl;
+    bool rule_rare = false, special;
+    if (EXACT) {
+      ncl = !(dstar > 0);
+      special = !(fabs(nd) >= 1e-280 && fabs(nd) <= 1e280);
+    } else {
+      const double a_lim = md_pymax(rc.lo, mB - alpha), t2 = MB - alpha, b_lim = md_pymin(MD, t2);
+      const bool uncl = a_lim <= dstar && dstar <= b_lim;   // then lo <= d <= max_diag_D
+      const bool sc = md_upper_clamp_shortcut_row(rc, alpha, beta, dstar, a_lim, t2, MD);
+      nd = uncl ? dstar : MD;
+      ncl = !uncl;
+      rule_rare = !(uncl || sc);
+      special = rule_rare || !d_in_range;
+    }
+    double ninv = mdb_rcp_normal(nd);
+    const bool drop = rowmax < mavL;   // omega = 1 in every cheap case
+    const bool slow = !drop && kc > 0 && ((track_min && rowmin < mavL) || rowmax > BIG);
+    int fl = (drop ? 1 : 0) | (slow ? 2 : 0) | (ncl ? 4 : 0);
+    double nw = 1.0;
+    if (mine) {
+      if (special) {
+        double o[3];
+        fl = mdb_diag_special_decision(F.prm, rule_rare, nd, ncl, kc, alpha, beta, gamma, mB, MB, rowmax, rowmin, o);
+        nd = o[0]; nw = o[1]; ninv = o[2];
+      }
+      dec_d = nd; dec_w = nw; dec_inv = ninv; dec_fl = fl;
+      mdb_sts2<0>(a_d, nd, nw);
+      mdb_sts2<16>(a_d, ninv, (double)fl);
+    }
+  };
+
+  if (CHAIN) decide(sb0, lane == 0 && valid, a_dec);
+  const int kend = (kb - sb0 < SB) ? kb - sb0 : SB;
+  for (int kk = 0; kk < kend; ++kk) {
+    const int k = sb0 + kk;
+    double dk, wk, inv;
+    int flags;
+    if (CHAIN) {
+      dk = __shfl_sync(FULL, dec_d, kk);
+      wk = __shfl_sync(FULL, dec_w, kk);
+      inv = __shfl_sync(FULL, dec_inv, kk);
+      flags = __shfl_sync(FULL, dec_fl, kk);
+    } else {
+      while (mdb_lds_flag(a_prog) <= k) __nanosleep(20);
+      mdb_fence_cta();
+      const double2 d01 = mdb_lds2<0>(a_dec), d23 = mdb_lds2<16>(a_dec);
+      dk = d01.x; wk = d01.y; inv = d23.x; flags = (int)d23.y;
+    }
+    const bool active = valid && j > k;
+    const double a = mdb_lds(a_col);   // A[j, k] (rows j > k)
+    // the reciprocal comes with the decision (<= 1 ulp from r / d_k)
+    double x = fma(wk, r[0], (1.0 - wk) * a) * inv;
+    if (active && ((flags & 3) != 0 || dk == 0 || rowmax > BIG))
+      x = mdb_diag_special_x(T, LDT, dec, j, k, dk, wk, inv, flags, rowmax > BIG, a, r[0], Sblk, ldS, mavL);
+    if (!active) x = 0.0;
+    const double y = x * dk;
+    if (active) {
+      mdb_sts(a_x, x);
+      mdb_sts(a_col, y);                // d_k Lu[j, k] at the transposed position
+      alpha = fma(x, y, alpha);         // Reimer.py:679-684
+      beta = fma(2.0 * a, a, beta);     // Reimer.py:602-604
+      const double ax = fabs(x);
+      rowmax = fmax(rowmax, ax);
+      if (track_min && ax != 0) rowmin = fmin(rowmin, ax);
+    }
+    const uint32_t par8 = 8u * (uint32_t)((kk + 1) & 1);
+    if (CHAIN) {
+      mdb_sts(a_yst + par8, y);
+      __syncwarp();
+    }
+    // S''[j, c] -= x[j, k] (d_k x[c, k]) for the remaining columns c of the sub-block, registers rotated by one
+    {
+      const uint32_t ay = a_yld + par8;
+      const double nx = -x;
+#define MDB_ROT2(I)                                   \
+  {                                                   \
+    const double2 yy = mdb_lds2<8 * (I)>(ay);         \
+    r[I] = fma(nx, yy.x, r[(I) + 1]);                 \
+    r[(I) + 1] = fma(nx, yy.y, r[(I) + 2]);           \
+  }
+      MDB_ROT2(0) MDB_ROT2(2) MDB_ROT2(4) MDB_ROT2(6) MDB_ROT2(8) MDB_ROT2(10) MDB_ROT2(12) MDB_ROT2(14)
+      MDB_ROT2(16) MDB_ROT2(18) MDB_ROT2(20) MDB_ROT2(22) MDB_ROT2(24) MDB_ROT2(26) MDB_ROT2(28)
+#undef MDB_ROT2
+      r[SB - 2] = fma(nx, mdb_lds1<8 * (SB - 2)>(ay), r[SB - 1]);
+    }
+    if (CHAIN) {
+      decide(k + 1, lane == kk + 1 && valid, a_dec + 32u);   // the next column's row: its state is complete now
+      __syncwarp();
+      mdb_fence_cta();
+      if (lane == 0) mdb_sts_flag(a_prog, k + 1);
+    }
+    a_col += 8u * LDT; a_x += 8u; a_dec += 32u; a_yst += 8u * YLD; a_yld += 8u * (YLD + 1);
+  }
+  if (valid) {
+    sm[L::ALPHA + j] = alpha; sm[L::BETA + j] = beta; sm[L::ROWMAX + j] = rowmax; sm[L::ROWMIN + j] = rowmin;
+  }
+}
+
+// Helper warp, one sub-block: trails the chain and forms, row by row, the inverse of the scaled unit triangle
+// Ltilde[c][m] = thresh(omega_c Lu[c, m]):  row kk of the inverse = -(ltilde row kk) x (rows < kk of the inverse).
+// Returns true when an entry is above 1e8 or not finite.
+template <int NB>
+__device__ __forceinline__ bool mdb_diag_inverse_rows(double* __restrict__ sm, int sb0, int kb, int lane, double mavL,
+                                                      double* __restrict__ Vout) {
+  using L = DiagLayout<NB>;
+  constexpr int LDT = L::LDT, SB = MDB_DIAG_SB;
+  double* T = sm + L::T;
+  const double* dec = sm + L::DEC;
+  double* s_inv = sm + L::INV;
+  double* s_lt = sm + L::LT;
+  const uint32_t a_prog = (uint32_t)__cvta_generic_to_shared(sm) + 8u * (uint32_t)L::FLAGS;
+  bool bad = false;
+  for (int r = 0; r < SB; ++r) s_inv[r * 33 + lane] = 0.0;   // rows beyond the current one count as zero below
+  if (lane < 4) s_lt[32 + lane] = 0.0;
+  __syncwarp();
+  const int kend = (kb - sb0 < SB) ? kb - sb0 : SB;
+  double* V = Vout + (sb0 / SB) * (SB * SB);
+  for (int kk = 0; kk < kend; ++kk) {
+    const int k = sb0 + kk;
+    while (mdb_lds_flag(a_prog) <= k) __nanosleep(40);
+    mdb_fence_cta();
+    const double wk = dec[4 * k + 1];
+    double lt = 0;
+    if (lane < kk) {
+      lt = wk * T[k * LDT + sb0 + lane];
+      if (wk == 0 || fabs(lt) < mavL) lt = 0;
+    }
+    s_lt[lane] = lt;
+    __syncwarp();
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int m = 0; m < kk; m += 4) {   // (lt and the rows of the inverse are zero from kk on)
+      const double2 l01 = *reinterpret_cast<const double2*>(s_lt + m), l23 = *reinterpret_cast<const double2*>(s_lt + m + 2);
+      a0 = fma(l01.x, s_inv[m * 33 + lane], a0);
+      a1 = fma(l01.y, s_inv[(m + 1) * 33 + lane], a1);
+      a2 = fma(l23.x, s_inv[(m + 2) * 33 + lane], a2);
+      a3 = fma(l23.y, s_inv[(m + 3) * 33 + lane], a3);
+    }
+    const double x = (lane < kk) ? -((a0 + a1) + (a2 + a3)) : ((lane == kk) ? 1.0 : 0.0);
+    s_inv[kk * 33 + lane] = x;
+    V[kk * SB + lane] = x;
+    bad = bad || !(fabs(x) <= 1e8);   // also catches NaN
+    __syncwarp();
+  }
+  for (int r = kend; r < SB; ++r) V[r * SB + lane] = (r == lane) ? 1.0 : 0.0;
+  return bad;
+}
+
+template <int NB, bool EXACT>
+__global__ void __launch_bounds__(32 * MDB_DIAG_WARPS, 1) k_diag_block(FactorDev F, int64_t k0, int kb, double* __restrict__ Sblk,
+                                                                      int64_t ldS, const double* __restrict__ Ablk, int64_t ldA) {
+  extern __shared__ double smem_d[];
+  using L = DiagLayout<NB>;
+  constexpr int LDT = L::LDT;
+  constexpr int SB = MDB_DIAG_SB;
+  constexpr int NT = 32 * MDB_DIAG_WARPS;
+  static_assert(NB == 4 * SB, "three trailing warps cover the rows below the first sub-block");
+  double* sm = smem_d;
+  double* T = sm + L::T;
+  double* dec = sm + L::DEC;
 
   const int64_t b = blockIdx.z;
   Sblk += b * F.sW;
@@ -312,241 +617,119 @@ __global__ void __launch_bounds__(4 * NB + 32) k_diag_block(FactorDev F, int64_t
   double* Ut = F.Ut + b * F.sUt;
   double* hdr = F.hdr + b * F.sHdr;
   double* Vout = F.Vinv + b * F.sV;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const bool helper = tid >= NCOMPUTE;
-  const int j = tid >> 2, h = tid & 3;
-  const bool keeper = !helper && (h < 2) && (j < kb);   // lanes that carry the row's state
-  const bool exact = F.prm.rule == MD_RULE_EXACT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double mavL = F.prm.min_abs_value_L;
-  const unsigned pairmask = 0x3u << (lane & 28);
-#define MDB_DIAG_BAR() asm volatile("bar.sync 1, %0;" ::"n"(NCOMPUTE) : "memory")
+  const bool vec_ok = ((ldS & 1) == 0) && ((reinterpret_cast<uintptr_t>(Sblk) & 15) == 0);
 
-  // whole block in flight at once (asynchronous 8-byte copies, coalesced per row):
-  // strict lower part from S, diagonal and upper part from A
-  if (!helper) {
+  // whole block in flight at once (asynchronous copies, coalesced per row): strict lower part from S, diagonal and
+  // upper part from A (one array on a single GPU: 16-byte copies)
+  if (Sblk == Ablk && vec_ok) {
+    const int c2 = 2 * (tid & (NB / 2 - 1));
+    if (c2 < kb)   // (a pair that straddles kb copies one element of padding: the rows of W are padded to 128)
+      for (int r = tid / (NB / 2); r < kb; r += NT / (NB / 2)) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&T[r * LDT + c2]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(&Sblk[r * ldS + c2]));
+      }
+  } else {
     const int c = tid & (NB - 1);
     if (c < kb)
-      for (int r = tid / NB; r < kb; r += 4)
+      for (int r = tid / NB; r < kb; r += NT / NB)
         mdb_cp_async8(&T[r * LDT + c], (c < r) ? &Sblk[r * ldS + c] : &Ablk[r * ldA + c]);
   }
-  double alpha_j = 0, beta_j = 0, rowmax_j = 0, rowmin_j = INFINITY, gamma_j = 0, mB_j = 0, MB_j = 0;
-  if (keeper) {
-    alpha_j = F.alpha[vo + k0 + j];
-    beta_j = F.beta[vo + k0 + j];
-    rowmax_j = F.rowmax[vo + k0 + j];
-    gamma_j = F.gamma[vo + k0 + j];
-    mB_j = F.minB ? F.minB[vo + k0 + j] : F.prm.min_diag_B;
-    MB_j = F.maxB ? F.maxB[vo + k0 + j] : F.prm.max_diag_B;
+  if (tid < NB) {
+    const bool in = tid < kb;
+    sm[L::ALPHA + tid] = in ? F.alpha[vo + k0 + tid] : 0.0;
+    sm[L::BETA + tid] = in ? F.beta[vo + k0 + tid] : 0.0;
+    sm[L::ROWMAX + tid] = in ? F.rowmax[vo + k0 + tid] : 0.0;
+    sm[L::ROWMIN + tid] = INFINITY;
+    sm[L::GAMMA + tid] = in ? F.gamma[vo + k0 + tid] : 0.0;
+    sm[L::MINB + tid] = (in && F.minB) ? F.minB[vo + k0 + tid] : F.prm.min_diag_B;
+    sm[L::MAXB + tid] = (in && F.maxB) ? F.maxB[vo + k0 + tid] : F.prm.max_diag_B;
   }
-  if (tid == 0) { s_bigf[0] = s_bigf[1] = 0; s_unsafe = 0; s_progress = 0; }
+  if (tid == NT - 1) *reinterpret_cast<volatile int*>(sm + L::FLAGS) = 0;
   mdb_cp_async_wait_all();
   __syncthreads();
-  if (keeper && h == 0 && rowmax_j > BIG) s_bigf[0] = s_bigf[1] = 1;
-  __syncthreads();
 
-  if (helper) {
-    // ---------------- inverses of the scaled unit triangles, one row per finished column ----------------
-    double vmax = 0;
-    for (int k = 0; k < kb; ++k) {
-      const int kk = k & (SB - 1), sb0 = k - kk;
-      while (s_progress <= k) __nanosleep(40);
-      __threadfence_block();
-      const double wk = s_w[k];
-      double lt = 0;
-      if (lane < kk) {
-        lt = wk * T[k * LDT + sb0 + lane];
-        if (wk == 0 || fabs(lt) < mavL) lt = 0;
-      }
-      s_lt[lane] = lt;
-      __syncwarp();
-      double x = (lane == kk) ? 1.0 : 0.0;
-      if (lane < kk) {
-        double a0 = 0, a1 = 0;
-        int m = lane;
-        for (; m + 1 < kk; m += 2) {
-          a0 = fma(s_lt[m], s_inv[m * 33 + lane], a0);
-          a1 = fma(s_lt[m + 1], s_inv[(m + 1) * 33 + lane], a1);
-        }
-        if (m < kk) a0 = fma(s_lt[m], s_inv[m * 33 + lane], a0);
-        x = -(a0 + a1);
-      }
-      s_inv[kk * 33 + lane] = x;
-      if (!(fabs(x) <= 1e8)) vmax = INFINITY;   // also catches NaN
-      __syncwarp();
-      if (kk == SB - 1 || k == kb - 1) {
-        double* V = Vout + (sb0 / SB) * (SB * SB);
-        for (int r = 0; r < SB; ++r) V[r * SB + lane] = (r <= kk) ? s_inv[r * 33 + lane] : ((r == lane) ? 1.0 : 0.0);
-        __syncwarp();
-      }
+  bool inv_bad = false;
+  for (int sb0 = 0; sb0 < kb; sb0 += SB) {
+    if (warp == 0) {
+      mdb_diag_columns<NB, EXACT, true>(F, sm, sb0, kb, sb0 + lane, lane, Sblk, ldS);
+    } else if (warp <= 3) {
+      if (sb0 + SB * warp < kb) mdb_diag_columns<NB, EXACT, false>(F, sm, sb0, kb, sb0 + SB * warp + lane, lane, Sblk, ldS);
+    } else if (warp == MDB_DIAG_HELPER_WARP) {
+      inv_bad = mdb_diag_inverse_rows<NB>(sm, sb0, kb, lane, mavL, Vout) || inv_bad;
     }
-    const unsigned bad = __ballot_sync(0xffffffffu, vmax != 0.0);
-    __syncthreads();
-    if (lane == 0) Vout[4 * SB * SB] = (bad != 0 || s_bigf[0] != 0 || s_bigf[1] != 0 || s_unsafe != 0) ? 1.0 : 0.0;
-    return;
+    __syncthreads();   // every x of the finished sub-block is in shared memory
+    if (sb0 + SB < kb) {
+      mdb_diag_subblock_update<NB>(T, sb0, kb, warp, lane);
+      __syncthreads();
+    }
   }
-
-  // decision of column kc by the two keeper lanes of row kc (their state is complete); lane h == 0 publishes it
-  auto decide = [&](int kc, bool big) {
-    double d, w;
-    int clamped;
-    if (exact) {
-      d = gamma_j - alpha_j; w = 1.0;
-      clamped = !(d > 0);
-    } else {
-      const double mD = md_effective_min_diag_D(F.prm, gamma_j, mB_j, MB_j);
-      MdBest quick;
-      if (md_unclamped(alpha_j, gamma_j, mD, F.prm.max_diag_D, mB_j, MB_j, F.prm.min_abs_value_D)) {
-        d = gamma_j - alpha_j; w = 1.0; clamped = 0;
-      } else if (md_upper_clamp_shortcut(alpha_j, beta_j, gamma_j, mD, F.prm.max_diag_D, mB_j, MB_j, F.prm.min_abs_value_D,
-                                         &quick)) {
-        d = quick.d; w = quick.w; clamped = 1;
-      } else {
-        const MdDecision dec = mdb_rule_full_pair(F.prm, h, pairmask, alpha_j, beta_j, gamma_j, mD, mB_j, MB_j);
-        d = dec.d; w = dec.omega; clamped = 1;
-      }
-    }
-    if (h == 0) {
-      const bool drop = (w == 0 || w * rowmax_j < mavL);
-      const bool slow = !drop && kc > 0 && (w * rowmin_j < mavL || big);
-      double* sd = s_dec + 4 * (kc & 1);
-      sd[0] = d;
-      sd[1] = w;
-      sd[2] = (d != 0) ? 1.0 / d : 0.0;
-      sd[3] = (drop ? 1.0 : 0.0) + (slow ? 2.0 : 0.0);
-      s_d[kc] = d;
-      s_w[kc] = w;
-      if (d == 0) s_unsafe = 1;
-      // (global results after the shared ones: nothing on the chip waits for them)
-      const int64_t K = k0 + kc;
-      F.d[vo + K] = d;
-      F.omega[vo + K] = w;
-      const double delta = (d - gamma_j) + (w != 0 ? w * w * alpha_j : 0.0);  // :541-545
-      F.delta[vo + K] = delta;
-      F.clamped[vo + K] = (uint8_t)clamped;
-      if (exact && clamped && F.info[b] == 0) F.info[b] = (int)(K + 1);
-      hdr[kc] = d;
-      hdr[NB + kc] = w;
-      hdr[2 * NB + kc] = drop ? 1.0 : 0.0;
-      hdr[3 * NB + kc] = delta;
-      hdr[4 * NB + kc] = (double)clamped;
-    }
-  };
-
-  bool big = s_bigf[0] != 0;   // sticky; refreshed after every column barrier from the flag of the previous column's parity
-  if (keeper && j == 0) decide(0, big);
-  const double* Trow = T + j * LDT;
-  for (int k = 0; k < kb; ++k) {
-    const int kk = k & (SB - 1), sb0 = k - kk;
-    if (kk == 0 && k > 0) {
-      MDB_DIAG_BAR();   // every x of the finished sub-block is in shared memory
-      mdb_diag_subblock_update<NB>(T, sb0 - SB, kb, tid >> 5, lane);
-      // (made visible to the readers of column k by the column barrier below; the Gram sum of a sub-block's first
-      // column is empty)
-    }
-    const bool active = (j > k && j < kb);
-    // ---------------- phase A: G_j = sum_{sb0 <= m < k-1} Lu[j, m] (d_m Lu[k, m]), lane h takes m = sb0 + h + 4 i ----------------
-    double a = 0, g0 = 0, g1 = 0;
-    if (active) {
-      a = T[k * LDT + j];   // A[j, k]; lane (j, 0) overwrites it in phase B
-      const double* Tr = Trow + sb0 + h;
-      const double* Tk = T + (sb0 + h) * LDT + k;   // (m, k) holds d_m Lu[k, m]
-      const int lim = kk - 1 - h;                   // terms 4 i < lim
+  if (warp == MDB_DIAG_HELPER_WARP) {
+    // the panel kernel must substitute instead of multiplying by the inverses: an entry of an inverse above 1e8 or
+    // not finite, |Lu| > 1e100 in a row of the block (the row maxima are complete now), a zero d
+    bool bad = inv_bad;
+    for (int c = lane; c < kb; c += 32) bad = bad || sm[L::ROWMAX + c] > 1e100 || dec[4 * c] == 0;
+    const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0) Vout[4 * SB * SB] = anybad ? 1.0 : 0.0;
+  }
+  // results of the block: the row state, the decisions (kept in shared memory while the chain ran: nothing on the chip
+  // waits for the global copies), the unscaled rows, Ut
+  if (tid < kb) {
+    const int64_t K = k0 + tid;
+    const double alpha_k = sm[L::ALPHA + tid];   // alpha of row k is final when column k is decided
+    F.alpha[vo + K] = alpha_k;
+    F.beta[vo + K] = sm[L::BETA + tid];
+    F.rowmax[vo + K] = sm[L::ROWMAX + tid];
+    const double dk = dec[4 * tid], wk = dec[4 * tid + 1];
+    const int fl = (int)dec[4 * tid + 3];
+    const double delta = (dk - sm[L::GAMMA + tid]) + (wk != 0 ? wk * wk * alpha_k : 0.0);  // Reimer.py:541-545
+    F.d[vo + K] = dk;
+    F.omega[vo + K] = wk;
+    F.delta[vo + K] = delta;
+    F.clamped[vo + K] = (uint8_t)((fl >> 2) & 1);
+    hdr[tid] = dk;
+    hdr[NB + tid] = wk;
+    hdr[2 * NB + tid] = (fl & 1) ? 1.0 : 0.0;
+    hdr[3 * NB + tid] = delta;
+    hdr[4 * NB + tid] = (double)((fl >> 2) & 1);
+  }
+  if (EXACT && warp == 1) {   // first pivot that is not positive, like LAPACK's info
+    int first = NB;
+    for (int c = lane; c < kb; c += 32)
+      if (((int)dec[4 * c + 3]) & 4) { first = c; break; }
 #pragma unroll
-      for (int i = 0; i < 8; i += 2) {
-        if (4 * i < lim) g0 = fma(Tr[4 * i], Tk[4 * i * LDT], g0);
-        if (4 * i + 4 < lim) g1 = fma(Tr[4 * i + 4], Tk[(4 * i + 4) * LDT], g1);
-      }
-    }
-    double G = g0 + g1;
-    // every lane takes part in the shuffles (rows of one warp become active at different k)
-    G += __shfl_xor_sync(0xffffffffu, G, 1);
-    G += __shfl_xor_sync(0xffffffffu, G, 2);
-    MDB_DIAG_BAR();
-    if (tid == 0) s_progress = k + 1;
-
-    // ---------------- phase B: column k ----------------
-    const double2 dec01 = *reinterpret_cast<const double2*>(s_dec + 4 * (k & 1));
-    const double2 dec23 = *reinterpret_cast<const double2*>(s_dec + 4 * (k & 1) + 2);
-    const double dk = dec01.x, wk = dec01.y, inv_dk = dec23.x;
-    const int flags = (int)dec23.y;
-    const bool drop = (flags & 1) != 0, slow = (flags & 2) != 0;
-    big = big || (s_bigf[(k + 1) & 1] != 0);   // written in phase B of column k - 1, complete since the barrier: the same
-                                               // value in every thread (the flag of this column's parity is being written now)
-    double s0k = 0;
-    if (active) {
-      s0k = Trow[k];        // S'[j, k]: the block-entry value minus the finished sub-blocks
-      if (kk >= 1) G = fma(Trow[k - 1], T[(k - 1) * LDT + k], G);  // the term m = k - 1, published just before the barrier
-    }
-    double acc = 0;
-    if (slow) {  // uniform over the block
-      if (tid < k) {  // the scaled, thresholded row k times D
-        double lt = wk * T[k * LDT + tid];
-        if (wk == 0 || fabs(lt) < mavL) lt = 0;
-        s_u[tid] = s_d[tid] * lt;
-      }
-      if (active) s0k = Sblk[j * ldS + k];   // the block-entry value of S (global memory is still untouched)
-      MDB_DIAG_BAR();
-      if (active) {
-        double a0 = 0, a1 = 0;
-        int m = h;
-        for (; m + 4 < k; m += 8) {
-          a0 = fma(Trow[m], s_u[m], a0);
-          a1 = fma(Trow[m + 4], s_u[m + 4], a1);
-        }
-        if (m < k) a0 = fma(Trow[m], s_u[m], a0);
-        acc = a0 + a1;
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    }
-    __syncwarp();  // all four lanes of a row have read T[k][j] and T[j][k] before lane (j, 0) overwrites them
-    if (active && h < 2) {
-      // x = r * (1 / d_k): the reciprocal comes with the decision (<= 1 ulp from r / d_k)
-      double x = 0;
-      if (dk != 0) {
-        if (drop) x = a * inv_dk;
-        else if (slow) x = (((1.0 - wk) * a + wk * s0k) - acc) * inv_dk;
-        else x = fma(wk, s0k - G, (1.0 - wk) * a) * inv_dk;
-      }
-      if (h == 0) {
-        T[j * LDT + k] = x;
-        T[k * LDT + j] = x * dk;      // d_k Lu[j, k] at the transposed position
-      }
-      alpha_j += x * x * dk;          // Reimer.py:679-684
-      beta_j += 2.0 * a * a;          // Reimer.py:602-604
-      const double ax = fabs(x);
-      rowmax_j = fmax(rowmax_j, ax);
-      if (ax != 0) rowmin_j = fmin(rowmin_j, ax);
-      if (ax > BIG && h == 0) s_bigf[k & 1] = 1;
-      if (j == k + 1) decide(k + 1, big || rowmax_j > BIG);   // the next column's row: its state is complete now
-    }
-    __syncwarp();  // x[j, k] is visible to the other lanes of the row before they use it in the next Gram sum
-    // no block barrier here: what the next Gram sums read was published before the barrier above; the entries written
-    // just now are first read after the next barrier
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if (lane == 0 && first < NB && F.info[b] == 0) F.info[b] = (int)(k0 + first + 1);
   }
-  __syncthreads();
-  if (keeper && h == 0) {
-    F.alpha[vo + k0 + j] = alpha_j;
-    F.beta[vo + k0 + j] = beta_j;
-    F.rowmax[vo + k0 + j] = rowmax_j;
+  // strict lower part of the block back to S (unscaled rows Lu)
+  if (vec_ok) {
+    const int c2 = 2 * (tid & (NB / 2 - 1));
+#pragma unroll 4
+    for (int r = tid / (NB / 2); r < kb; r += NT / (NB / 2)) {
+      if (c2 + 1 < r) *reinterpret_cast<double2*>(&Sblk[r * ldS + c2]) = *reinterpret_cast<const double2*>(&T[r * LDT + c2]);
+      else if (c2 < r) Sblk[r * ldS + c2] = T[r * LDT + c2];
+    }
+  } else {
+    const int c = tid & (NB - 1);
+#pragma unroll 4
+    for (int r = tid / NB; r < kb; r += NT / NB)
+      if (c < r) Sblk[r * ldS + c] = T[r * LDT + c];
   }
   {
-    const int c = tid & (NB - 1);
-    // strict lower part of the block back to S (unscaled rows Lu)
-    for (int r = tid / NB; r < kb; r += 4)
-      if (c < r) Sblk[r * ldS + c] = T[r * LDT + c];
     // Ut[m][k] = d_m thresh(omega_k Lu[k, m]) for m < k: the scaled, thresholded rows times D (Reimer.py:553-560),
     // written row by row (coalesced over k)
+    const int c = tid & (NB - 1);
     if (c < kb) {
-      const double wk = s_w[c];
-      for (int m = tid / NB; m < c; m += 4) {
+      const double wk = dec[4 * c + 1];
+#pragma unroll 4
+      for (int m = tid / NB; m < c; m += NT / NB) {
         double lt = wk * T[c * LDT + m];
         if (wk == 0 || fabs(lt) < mavL) lt = 0;
-        Ut[m * NB + c] = s_d[m] * lt;
+        Ut[m * NB + c] = dec[4 * m] * lt;
       }
     }
   }
-#undef MDB_DIAG_BAR
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -320,6 +320,59 @@ MD_HD bool md_upper_clamp_shortcut(double alpha, double beta, double gamma, doub
   return true;
 }
 
+// The same test without its three divisions, for the dependency chain of the diagonal-block kernel: a SUFFICIENT
+// condition (true only where md_upper_clamp_shortcut is true; the result is then (b, 1) with b = max_diag_D).  The
+// divisions of the full test only detect a non-finite p or q of the cubics; with alpha in [1e-100, 1e100] and beta,
+// |gamma|, lo, max_diag_D <= 1e100 they are finite: |q| <= 0.5e100 / 1e-200, |(dd - gamma) / alpha| <= 2e100 / 1e-100.
+// Columns that fail this cheap test go through md_decide (which tries the full shortcut first).
+MD_HD bool md_upper_clamp_shortcut_cheap(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
+                                         double min_diag_B, double max_diag_B, double min_abs_value_D) {
+  const double lo = md_pymax(min_diag_D, min_abs_value_D);
+  const double a = md_pymax(lo, min_diag_B - alpha);
+  const double b = md_pymin(max_diag_D, max_diag_B - alpha);
+  const double dstar = gamma - alpha;
+  const double R = 1e100;
+  const bool range = alpha >= 1e-100 && alpha <= R && beta >= 0 && beta <= R && fabs(gamma) <= R && fabs(lo) <= R &&
+                     fabs(max_diag_D) <= R;
+  const bool geom = a <= b && dstar > b && b == max_diag_D;
+  const bool gap = lo == b || (b - lo) > 1e-9 * (fabs(alpha) + fabs(gamma) + fabs(b));
+  const bool zero_cand = min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D;
+  return range && geom && gap && !zero_cand;
+}
+
+// The cheap test once more, with everything that does not depend on alpha / beta folded into per-row constants (the
+// diagonal-block kernel evaluates it after every column on its dependency chain): a SUFFICIENT condition for
+// md_upper_clamp_shortcut_cheap, hence for md_upper_clamp_shortcut.  The gap test (b - lo) > 1e-9 (|alpha| + |gamma| + |b|)
+// with b = max_diag_D becomes alpha <= alpha_hi with a factor 2 of margin, so rounding cannot make it fire where the
+// original does not.
+struct MdRowConst {
+  double lo;        // max(min_diag_D, min_abs_value_D), Reimer.py:64
+  double alpha_hi;  // the shortcut needs 1e-100 <= alpha <= alpha_hi
+  int ok;           // the alpha-independent conditions hold
+};
+
+MD_HD MdRowConst md_row_const(double gamma, double min_diag_D, double max_diag_D, double min_diag_B,
+                              double min_abs_value_D) {
+  MdRowConst c;
+  const double R = 1e100;
+  c.lo = md_pymax(min_diag_D, min_abs_value_D);
+  const bool zero_cand = min_diag_D == 0 && min_diag_B <= 0 && 2 * gamma <= min_abs_value_D;
+  c.ok = (fabs(gamma) <= R && fabs(c.lo) <= R && fabs(max_diag_D) <= R && !zero_cand) ? 1 : 0;
+  c.alpha_hi = R;
+  if (c.lo != max_diag_D) {
+    const double t = 0.5 * ((max_diag_D - c.lo) / 1e-9) - fabs(gamma) - fabs(max_diag_D);
+    c.alpha_hi = (t < R) ? t : R;   // NaN -> stays NaN -> every comparison below is false
+  }
+  return c;
+}
+
+// t2 = max_diag_B - alpha and a_lim = max(lo, min_diag_B - alpha) are passed in because the caller needs them anyway
+MD_HD bool md_upper_clamp_shortcut_row(const MdRowConst& c, double alpha, double beta, double dstar, double a_lim,
+                                       double t2, double max_diag_D) {
+  return c.ok && alpha >= 1e-100 && alpha <= c.alpha_hi && beta >= 0 && beta <= 1e100 && t2 >= max_diag_D && a_lim <= max_diag_D &&
+         dstar > max_diag_D;
+}
+
 // Reimer.py:68-72: the unclamped branch
 MD_HD bool md_unclamped(double alpha, double gamma, double min_diag_D, double max_diag_D, double min_diag_B,
                         double max_diag_B, double min_abs_value_D) {

@@ -680,7 +680,8 @@ static int configure_kernels(mdb_ctx* ctx) {
   const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
   const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB) * 8;
   const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
-  MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+  MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+  MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel_gemm<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_blocks<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
   mdb_mark_device(done, ctx);
@@ -802,8 +803,9 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       const int64_t k1 = k0 + kb;
       {
         PhaseTimer t(ctx, 0);
-        k_diag_block<NB><<<dim3(1, 1, (unsigned)batch), MDB_DIAG_THREADS(NB), diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
-                                                                                  f->W + k0 * f->ld + k0, f->ld);
+        auto kdiag = (bnd->rule == MDB_RULE_EXACT) ? k_diag_block<NB, true> : k_diag_block<NB, false>;
+        kdiag<<<dim3(1, 1, (unsigned)batch), MDB_DIAG_THREADS(NB), diag_smem, main_s>>>(F, k0, kb, f->W + k0 * f->ld + k0, f->ld,
+                                                                                        f->W + k0 * f->ld + k0, f->ld);
         MDB_LAUNCHED(ctx);
       }
       if (k1 >= n) break;

@@ -282,8 +282,8 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot, int64_t k
   FactorDev F = dist_make_dev(s, hdr);
   const int diag_smem = MDB_DIAG_SMEM_DOUBLES(NB) * 8;
   const int panel_smem = MDB_PANEL_SMEM_DOUBLES(NB) * 8;
-  k_diag_block<NB><<<1, MDB_DIAG_THREADS(NB), diag_smem, ctx->stream>>>(F, k0, kb, s->S + k0 * s->ld + lc0, s->ld, s->A + k0 * s->ld + lc0,
-                                                       s->ld);
+  auto kdiag = (F.prm.rule == MD_RULE_EXACT) ? k_diag_block<NB, true> : k_diag_block<NB, false>;
+  kdiag<<<1, MDB_DIAG_THREADS(NB), diag_smem, ctx->stream>>>(F, k0, kb, s->S + k0 * s->ld + lc0, s->ld, s->A + k0 * s->ld + lc0, s->ld);
   MDB_LAUNCHED(ctx);
   if (rows > 0) {
     dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, 1);

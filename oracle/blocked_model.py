@@ -56,6 +56,10 @@ def rule_shim():
         s.mdh_minimal_change_full.restype = ctypes.c_int
         s.mdh_upper_clamp_shortcut.argtypes = [dbl] * 8 + [vp]
         s.mdh_upper_clamp_shortcut.restype = ctypes.c_int
+        s.mdh_upper_clamp_shortcut_cheap.argtypes = [dbl] * 8
+        s.mdh_upper_clamp_shortcut_cheap.restype = ctypes.c_int
+        s.mdh_upper_clamp_shortcut_row.argtypes = [dbl] * 8
+        s.mdh_upper_clamp_shortcut_row.restype = ctypes.c_int
         s.mdh_decide.argtypes = [ctypes.c_int] + [dbl] * 8 + [vp]
         s.mdh_decide.restype = ctypes.c_int
         _shim = s

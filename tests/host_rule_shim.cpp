@@ -25,6 +25,18 @@ int mdh_upper_clamp_shortcut(double alpha, double beta, double gamma, double min
   if (hit) { out3[0] = b.d; out3[1] = b.w; out3[2] = b.f; }
   return hit ? 1 : 0;
 }
+// the division-free sufficient condition used on the dependency chain of k_diag_block
+int mdh_upper_clamp_shortcut_cheap(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
+                                   double min_diag_B, double max_diag_B, double mav) {
+  return md_upper_clamp_shortcut_cheap(alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav) ? 1 : 0;
+}
+// ... and its per-row precomputed form (what the chain of k_diag_block evaluates after every column)
+int mdh_upper_clamp_shortcut_row(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
+                                 double min_diag_B, double max_diag_B, double mav) {
+  const MdRowConst c = md_row_const(gamma, min_diag_D, max_diag_D, min_diag_B, mav);
+  const double a_lim = md_pymax(c.lo, min_diag_B - alpha);
+  return md_upper_clamp_shortcut_row(c, alpha, beta, gamma - alpha, a_lim, max_diag_B - alpha, max_diag_D) ? 1 : 0;
+}
 // the two-thread evaluation of the kernels: both halves of the candidate list, merged
 int mdh_minimal_change_split(double alpha, double beta, double gamma, double min_diag_D, double max_diag_D,
                              double min_diag_B, double max_diag_B, double mav, double* out3) {

@@ -49,7 +49,7 @@ def test_upper_clamp_shortcut_equals_full_candidate_list():
             assert quick[0] == full[0] and abs(quick[1] - full[1]) <= 1e-15 and abs(quick[2] - full[2]) <= 1e-15 * abs(full[2])
             assert abs(quick[0] - w[0]) <= 1e-15 * abs(w[0]) and abs(quick[1] - w[1]) <= 1e-12   # the reference itself
     rng = np.random.default_rng(0)
-    n_rand = 0
+    n_rand = n_cheap = n_row = 0
     for _ in range(20000):
         scale = 10.0 ** rng.uniform(-3, 6)
         max_diag_D = scale * rng.uniform(0.5, 2.0)
@@ -61,7 +61,14 @@ def test_upper_clamp_shortcut_equals_full_candidate_list():
         min_diag_B = rng.choice([-np.inf, 0.0, min_diag_D * 0.5])
         mav = rng.choice([3.3e-10, scale * 1e-3])
         args = [alpha, beta, gamma, min_diag_D, max_diag_D, min_diag_B, max_diag_B, mav]
-        if not shim.mdh_upper_clamp_shortcut(*args, P(quick)):
+        hit = shim.mdh_upper_clamp_shortcut(*args, P(quick))
+        cheap = shim.mdh_upper_clamp_shortcut_cheap(*args)
+        assert hit or not cheap, args        # the division-free test of the kernel's chain is a sufficient condition
+        n_cheap += int(cheap)
+        row = shim.mdh_upper_clamp_shortcut_row(*args)
+        assert cheap or not row, args      # ... and so is its per-row precomputed form
+        n_row += int(row)
+        if not hit:
             continue
         n_rand += 1
         assert shim.mdh_minimal_change_full(*args, P(full)) == 1
@@ -72,6 +79,20 @@ def test_upper_clamp_shortcut_equals_full_candidate_list():
         assert abs(quick[1] - full[1]) <= 1e-9, (args, quick, full)
         assert abs(quick[2] - full[2]) <= 1e-12 * abs(full[2]), (args, quick, full)
     assert n_hit >= 20 and n_rand >= 10000, (n_hit, n_rand)
+    assert n_cheap >= 0.95 * n_rand, (n_cheap, n_rand)     # ... that covers the benign regime
+    assert n_row >= 0.95 * n_rand, (n_row, n_rand)
+    # outside its range window the cheap test must stay silent (the full shortcut decides there)
+    for alpha in (1e-120, 1e120, np.inf, np.nan):
+        assert not shim.mdh_upper_clamp_shortcut_cheap(alpha, 1.0, alpha + 10.0, 0.1, 2.0, -np.inf, np.inf, 3.3e-10)
+    assert not shim.mdh_upper_clamp_shortcut_cheap(1.0, np.inf, 11.0, 0.1, 2.0, -np.inf, np.inf, 3.3e-10)
+    assert shim.mdh_upper_clamp_shortcut_cheap(1.0, 1.0, 11.0, 0.1, 2.0, -np.inf, np.inf, 3.3e-10)
+    assert shim.mdh_upper_clamp_shortcut_row(1.0, 1.0, 11.0, 0.1, 2.0, -np.inf, np.inf, 3.3e-10)
+    for alpha in (1e-120, 1e120, np.inf, np.nan):
+        assert not shim.mdh_upper_clamp_shortcut_row(alpha, 1.0, alpha + 10.0, 0.1, 2.0, -np.inf, np.inf, 3.3e-10)
+    # a gap between lo and max_diag_D at rounding level: the row form must not fire where the cheap form does not
+    for g in (1e-9, 1e-8, 1e-7):
+        args = (1.0, 1.0, 11.0, 2.0 * (1 - g), 2.0, -np.inf, np.inf, 3.3e-10)
+        assert shim.mdh_upper_clamp_shortcut_cheap(*args) or not shim.mdh_upper_clamp_shortcut_row(*args)
 
 
 def test_fp64_cubic_against_reference_vectors():

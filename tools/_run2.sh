@@ -1,9 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 300 python tools/chain_profile.py 8192 > gpurun_out/r2_chain2.log 2>&1
-timeout 300 python tools/chain_profile.py 16384 >> gpurun_out/r2_chain2.log 2>&1
-cat gpurun_out/r2_chain2.log
-timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest.log
-tail -15 gpurun_out/r2_pytest.log
-timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; echo "bench rc=$?"
-tail -5 gpurun_out/r2_bench_n1.err
+timeout 600 ncu --set full --clock-control none --import-source on --warp-sampling-interval 0 -k regex:'k_diag_block' --launch-skip 20 --launch-count 1 -o gpurun_out/r2_diag4 -f python tools/chain_profile.py 8192 --quick > gpurun_out/r2_diag4.log 2>&1; echo "ncu rc=$?"
