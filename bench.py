@@ -446,7 +446,7 @@ def run_single(args):
                                 'MEASURED_PEAKS.json has no FP64 entry',
                     launches=st['bulk_launches'], avg_launch_ms=phases['trailing'] / max(st['bulk_launches'], 1),
                     algorithmic_flop_per_launch='K * rows * (rows - 1), rows = n - end of the outer block, K = its width '
-                                                '(1024 / 512 / 256 / 128 while >= 32768 / 16384 / 8192 / 0 rows remain)',
+                                                '(1024 / 512 / 256 / 128 while >= 32768 / 8192 / 4096 / 0 rows remain)',
                     algorithmic_flop_total=st['bulk_flop'], share_of_n3_over_3=st['bulk_flop'] / (n ** 3 / 3),
                     inner_update=dict(flop=st['inner_flop'], launches=st['inner_launches'], ms=phases['inner'],
                                       tflops=(st['inner_flop'] / (phases['inner'] * 1e-3) / 1e12 if phases['inner'] > 0 else None)),

@@ -204,7 +204,7 @@ class Context:
     def set_profiling(self, on):
         self.check(self.lib.mdb_ctx_set_profiling(self.handle, int(bool(on))), 'mdb_ctx_set_profiling')
 
-    def set_blocking(self, fixed=0, t2=8192, t4=16384, t8=32768):
+    def set_blocking(self, fixed=0, t2=4096, t4=8192, t8=32768):
         """Outer-block width of the factorization (see mdb_ctx_set_blocking in include/mdb200.h)."""
         self.check(self.lib.mdb_ctx_set_blocking(self.handle, int(fixed), int(t2), int(t4), int(t8)), 'mdb_ctx_set_blocking')
 

@@ -739,19 +739,23 @@ __global__ void __launch_bounds__(32 * MDB_DIAG_WARPS, 1) k_diag_block(FactorDev
 // products on the FP64 tensor cores:
 //     Z_s = R_s - X_{<s} U[<s, s]          (U[m][c] = d_m Ltilde[c][m] = Ut, written by k_diag_block)
 //     X_s = (Z_s Ltilde_ss^-T) D_s^-1      (the 32 x 32 inverses Vinv, formed by k_diag_block's helper warp)
-// A CTA owns 64 rows, a warp 16 of them (one m16 tile; 4 n8 tiles = 4 independent accumulator chains per step).
-// R / Z / X live in one shared tile (row-major), the A entries of the mix are staged TRANSPOSED so that both source
-// layouts (column-major inside W on one GPU, row-major in A_loc when distributed) load coalesced and the warp-per-row
-// passes read them without bank conflicts.  Ut and Vinv (160 KB for all CTAs together) are read straight from global
-// memory: L1 / L2 hits.  alpha / beta / rowmax: one pass per row with lanes over the columns and a fixed butterfly
-// (deterministic).  When Vinv[4096] != 0 (explosive regime, zero d) the rows substitute column by column instead.
+// A CTA owns 64 rows, a warp 16 of them (one m16 tile; 4 n8 tiles = 4 independent accumulator chains per step), and
+// everything a warp does after the one CTA-wide barrier is private to its rows.  What the tensor-core loops read is
+// in shared memory: the R / Z / X tile (row-major), the six 32 x 32 blocks of Ut above the diagonal blocks and the four
+// inverses (row pitch 36 doubles: conflict-free fragment loads) -- staged by cp.async while the A entries of the mix
+// travel from global memory into registers (64 independent loads per thread, issued first).  The A entries are
+// addressed through (a_rs, a_cs): column-major inside W on one GPU (lanes take 16 consecutive rows of two columns),
+// row-major in A_loc when distributed (lanes take consecutive columns of one row).  alpha / beta / rowmax of the rows
+// are read at the start and written once at the end; the row sums use a fixed butterfly (deterministic).
+// When Vinv[4096] != 0 (explosive regime, zero d) the rows substitute column by column instead.
 // HBM traffic: reads 2 x rows x 128 doubles (S0, A), writes 3 x (Lu, X, Y).
 // ------------------------------------------------------------------------------------------------
 #define MDB_PANEL_RT 64
 #define MDB_PANEL_THREADS 128
 #define MDB_PANEL_LDX(NB) ((NB) + 4)
-#define MDB_PANEL_LDA (MDB_PANEL_RT + 1)
-#define MDB_PANEL_SMEM_DOUBLES(NB) (MDB_PANEL_RT * MDB_PANEL_LDX(NB) + (NB) * MDB_PANEL_LDA + 4 * (NB))
+#define MDB_PANEL_LDB 36
+#define MDB_PANEL_U_ROWS(NB) (3 * (NB) / 2)   // 32 + 64 + 96 rows of Ut above the diagonal blocks of column blocks 1, 2, 3
+#define MDB_PANEL_SMEM_DOUBLES(NB) (MDB_PANEL_RT * MDB_PANEL_LDX(NB) + (MDB_PANEL_U_ROWS(NB) + (NB)) * MDB_PANEL_LDB + 6 * (NB) + 3 * MDB_PANEL_RT)
 
 __device__ __forceinline__ void mdb_dmma(double (&c)[4], double a0, double a1, double b0) {
   asm volatile("mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
@@ -759,7 +763,33 @@ __device__ __forceinline__ void mdb_dmma(double (&c)[4], double a0, double a1, d
                : "d"(a0), "d"(a1), "d"(b0));
 }
 
-template <int NB>
+__device__ __forceinline__ void mdb_cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+
+// Reduction of 16 per-lane values (one per row of a warp's strip) over the 32 lanes: lanes 2 R and 2 R + 1 end up with
+// the total of value R.  Lanes are paired with strides 16, 8, 4, 2, 1 -- the tree of the xor butterfly, hence the same
+// bits -- but every step halves the number of values a lane carries: 16 + 1 shuffles instead of 16 x 5.
+template <bool MAX>
+__device__ __forceinline__ double mdb_reduce16(double (&v)[16], int lane) {
+#pragma unroll
+  for (int st = 0; st < 4; ++st) {
+    const int o = 16 >> st, n = 8 >> st;
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const double send = up ? v[i] : v[i + n];
+      const double keep = up ? v[i + n] : v[i];
+      const double recv = __shfl_xor_sync(0xffffffffu, send, o);
+      v[i] = MAX ? fmax(keep, recv) : keep + recv;
+    }
+  }
+  const double recv = __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return MAX ? fmax(v[0], recv) : v[0] + recv;
+}
+
+template <int NB, bool A_ROW_MAJOR>
 __global__ void __launch_bounds__(MDB_PANEL_THREADS) k_panel_gemm(FactorDev F, int64_t k0, int64_t row_begin,
                                                                  int64_t n_rows, const double* __restrict__ Asrc,
                                                                  int64_t a_rs, int64_t a_cs, double* __restrict__ Wcol,
@@ -769,13 +799,19 @@ __global__ void __launch_bounds__(MDB_PANEL_THREADS) k_panel_gemm(FactorDev F, i
   // PX / PY: row (j - p_row0) of the operand buffers, leading dimension p_ld (>= NB: the buffers hold the
   // panels of one outer block side by side so that the bulk trailing update contracts over all of them)
   extern __shared__ double smem_d[];
-  constexpr int RT = MDB_PANEL_RT, LDX = MDB_PANEL_LDX(NB), LDA = MDB_PANEL_LDA, SB = 32;
-  double* xs = smem_d;             // xs[r * LDX + c]: S0 -> R -> Z -> X
-  double* as_t = xs + RT * LDX;    // as_t[c * LDA + r]: A[j, k0 + c]
-  double* s_d = as_t + NB * LDA;   // NB
-  double* s_w = s_d + NB;          // NB
-  double* s_drop = s_w + NB;       // NB
-  double* s_inv = s_drop + NB;     // NB: 1 / d (0 where d == 0)
+  constexpr int RT = MDB_PANEL_RT, LDX = MDB_PANEL_LDX(NB), LDB = MDB_PANEL_LDB, SB = 32;
+  static_assert(NB == 4 * SB, "four column blocks of 32");
+  double* xs = smem_d;                           // xs[r * LDX + c]: S0 -> R -> Z -> X
+  double* us = xs + RT * LDX;                    // column block s = 1, 2, 3: rows m < 32 s of Ut[m][32 s ..], stacked
+  double* vs = us + MDB_PANEL_U_ROWS(NB) * LDB;  // vs[(32 s + c) * LDB + m] = inverse_s[c][m]
+  double* s_d = vs + NB * LDB;                   // NB
+  double* s_w = s_d + NB;                        // NB
+  double* s_drop = s_w + NB;                     // NB
+  double* s_inv = s_drop + NB;                   // NB: 1 / d (0 where d == 0)
+  double2* s_mix = reinterpret_cast<double2*>(s_inv + NB);   // NB pairs (1 - omega_c, omega_c); (1, 0) for a dropped column
+  double* s_alpha = s_inv + 3 * NB;              // RT: alpha of the rows at entry
+  double* s_rowmax = s_alpha + RT;               // RT: rowmax at entry
+  double* s_beta = s_rowmax + RT;                // RT: beta at entry, then the new beta
 
   const int64_t b = blockIdx.z;
   const int64_t vo = b * F.sVec;
@@ -790,49 +826,119 @@ __global__ void __launch_bounds__(MDB_PANEL_THREADS) k_panel_gemm(FactorDev F, i
   const int64_t jbase = row_begin + (int64_t)blockIdx.x * RT;
   const int64_t jend = row_begin + n_rows;
   const int nrow = (int)((jend - jbase < RT) ? jend - jbase : RT);
+  const int r0 = 16 * warp;          // the warp's rows of the tile
+  const int64_t jw = jbase + r0;     // ... and of the matrix
 
+  // ---- A entries of the warp's own 16 rows: 64 loads per lane, all in flight before anything waits ----
+  // (A_ROW_MAJOR: a_cs == 1, A[j, k0 + c] = Asrc[j * a_rs + k0 + c]; otherwise a_rs == 1, Asrc[j + (k0 + c) * a_cs])
+  double areg[64];
+  if (!A_ROW_MAJOR) {  // column-major in (j, c): lane (cc, r) = (lane >> 4, lane & 15) takes columns 2 i + cc of row r
+    const int r = lane & 15, cc = lane >> 4;
+    const bool ok = r0 + r < nrow;
+    const double* ap = Asrc + (jw + r) + (k0 + cc) * a_cs;
+    const int64_t step = 2 * a_cs;
+#pragma unroll
+    for (int i = 0; i < 64; ++i, ap += step) areg[i] = ok ? __ldg(ap) : 0.0;
+  } else {          // row-major: lanes take columns lane + 32 e of row rr
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      const bool ok = r0 + rr < nrow;
+      const double* ap = Asrc + (jw + rr) * a_rs + (k0 + lane);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) areg[4 * rr + e] = ok ? __ldg(ap + 32 * e) : 0.0;
+    }
+  }
+  // row state at entry (written back once at the end)
+  if (tid < RT) {
+    const bool ok = tid < nrow;
+    s_alpha[tid] = ok ? F.alpha[vo + jbase + tid] : 0.0;
+    s_rowmax[tid] = ok ? F.rowmax[vo + jbase + tid] : 0.0;
+    s_beta[tid] = ok ? F.beta[vo + jbase + tid] : 0.0;
+  }
+
+  // ---- staged by cp.async: S0 rows, the blocks of Ut and the inverses, the panel header ----
+  {
+    const int q = tid & 63;
+    for (int rr = tid >> 6; rr < nrow; rr += 2) mdb_cp_async16(xs + rr * LDX + 2 * q, Wcol + (jbase + rr) * w_ld + 2 * q);
+    const int q16 = tid & 15;   // 16-byte chunk of a 32-column block row
+    for (int row = tid >> 4; row < MDB_PANEL_U_ROWS(NB); row += MDB_PANEL_THREADS / 16) {
+      // stacked row -> (column block s, m): rows [0, 32) -> s = 1, [32, 96) -> s = 2, [96, 192) -> s = 3
+      const int s = (row < 32) ? 1 : ((row < 96) ? 2 : 3);
+      const int m = row - ((s == 1) ? 0 : ((s == 2) ? 32 : 96));
+      mdb_cp_async16(us + row * LDB + 2 * q16, U + m * NB + SB * s + 2 * q16);
+    }
+    for (int row = tid >> 4; row < NB; row += MDB_PANEL_THREADS / 16)
+      mdb_cp_async16(vs + row * LDB + 2 * q16, V + row * SB + 2 * q16);
+  }
+  int dropped = 0;
   for (int c = tid; c < NB; c += MDB_PANEL_THREADS) {
     const double dc = hdr[c];
     s_d[c] = dc;
     s_inv[c] = (dc != 0) ? 1.0 / dc : 0.0;
-    s_w[c] = hdr[NB + c];
-    s_drop[c] = hdr[2 * NB + c];
+    const double wc = hdr[NB + c], dropc = hdr[2 * NB + c];
+    s_w[c] = wc;
+    s_drop[c] = dropc;
+    s_mix[c] = (dropc == 0.0) ? make_double2(1.0 - wc, wc) : make_double2(1.0, 0.0);
+    dropped |= (dropc != 0.0);
   }
-  {  // S0 rows: 16-byte chunks, coalesced
-    const int q = tid & 63;
-    for (int rr = tid >> 6; rr < nrow; rr += 2) {
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + rr * LDX + 2 * q);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(Wcol + (jbase + rr) * w_ld + 2 * q));
-    }
-  }
-  if (a_rs == 1) {  // A is column-major in (j, c): consecutive threads take consecutive rows
-    const int jr = tid & 63;
-    if (jr < nrow)
-      for (int c = tid >> 6; c < NB; c += 2) mdb_cp_async8(&as_t[c * LDA + jr], Asrc + (jbase + jr) + (k0 + c) * a_cs);
-  } else {          // row-major: consecutive threads take consecutive columns
-    for (int jr = 0; jr < nrow; ++jr) mdb_cp_async8(&as_t[tid * LDA + jr], Asrc + (jbase + jr) * a_rs + (k0 + tid) * a_cs);
-  }
-  mdb_cp_async_wait_all();
-  __syncthreads();
   const bool unsafe = V[4 * SB * SB] != 0.0;
+  mdb_cp_async_wait_all();
+  const int any_drop = __syncthreads_or(dropped);
+  if (any_drop) {
+    // a dropped column takes A[j, c] alone: its S0 entries (possibly not finite) must not enter the mix as 0 x S0
+    for (int c = lane; c < NB; c += 32)
+      if (s_drop[c] != 0.0)
+        for (int rr = 0; rr < 16; ++rr) xs[(r0 + rr) * LDX + c] = 0.0;
+    __syncwarp();
+  }
 
-  // ---- R = mix(A, S0), beta += sum_c 2 A^2: the warp's own 16 rows, lanes over the columns ----
-  const int r0 = 16 * warp;
-  for (int rr = r0; rr < r0 + 16 && rr < nrow; ++rr) {
-    double bsum = 0;
+  // ---- R = (1 - omega_c) A + omega_c S0, beta += sum_c 2 A^2 (Reimer.py:602-604) ----
+  // (the partial sums of both branches are combined in the same order -- columns c = l + 32 e summed over e, then the
+  // butterfly tree over l with strides 16, 8, 4, 2, 1 -- so that one GPU and the distributed path produce the same bits)
+  if (!A_ROW_MAJOR) {
+    const int r = lane & 15, cc = lane >> 4;
+    double* xr = xs + (r0 + r) * LDX + cc;
+    const double2* mx2 = s_mix + cc;
+    double p[16];
+#pragma unroll
+    for (int li = 0; li < 16; ++li) p[li] = 0.0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int c = lane + 32 * e;
-      const double a = as_t[c * LDA + rr];
-      const double w = s_w[c];
-      double r = a;
-      if (s_drop[c] == 0.0) r = (1.0 - w) * a + w * xs[rr * LDX + c];
-      xs[rr * LDX + c] = r;
-      bsum += 2.0 * a * a;
+#pragma unroll
+      for (int li = 0; li < 16; ++li) {
+        const int i = 16 * e + li;   // column c = 2 i + cc = l + 32 e with l = 2 li + cc
+        const double a = areg[i];
+        const double2 m = mx2[2 * i];
+        xr[2 * i] = fma(m.y, xr[2 * i], m.x * a);
+        p[li] = fma(2.0 * a, a, p[li]);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-    if (lane == 0) F.beta[vo + jbase + rr] += bsum;   // Reimer.py:602-604
+    for (int h = 8; h >= 1; h >>= 1) {
+#pragma unroll
+      for (int li = 0; li < h; ++li) p[li] += p[li + h];   // l <-> l + 2 h: strides 16, 8, 4, 2
+    }
+    const double bsum = p[0] + __shfl_xor_sync(0xffffffffu, p[0], 16);   // l <-> l ^ 1: the lane of the other parity
+    if (cc == 0) s_beta[r0 + r] += bsum;
+  } else {
+    double2 m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = s_mix[lane + 32 * e];
+    double p[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) {
+      double* xr = xs + (r0 + rr) * LDX + lane;
+      double bs = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double a = areg[4 * rr + e];
+        xr[32 * e] = fma(m[e].y, xr[32 * e], m[e].x * a);
+        bs = fma(2.0 * a, a, bs);
+      }
+      p[rr] = bs;
+    }
+    const double bsum = mdb_reduce16<false>(p, lane);   // lanes 2 R and 2 R + 1: row R
+    if ((lane & 1) == 0) s_beta[r0 + (lane >> 1)] += bsum;
   }
   __syncwarp();
 
@@ -840,40 +946,43 @@ __global__ void __launch_bounds__(MDB_PANEL_THREADS) k_panel_gemm(FactorDev F, i
   if (!unsafe) {
     double* X0 = xs + (r0 + g) * LDX;   // rows r0 + g and r0 + g + 8 of the tile
     double* X1 = X0 + 8 * LDX;
-#pragma unroll
-    for (int s = 0; s < NB / SB; ++s) {
+#pragma unroll 1
+    for (int s = 0; s < NB / SB; ++s) {   // (rolled: the body is executed four times from the instruction cache)
       const int cs = SB * s;
       double acc[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int col = cs + 8 * nt + 2 * t4;
-        acc[nt][0] = X0[col]; acc[nt][1] = X0[col + 1]; acc[nt][2] = X1[col]; acc[nt][3] = X1[col + 1];
+        const double2 v0 = *reinterpret_cast<const double2*>(X0 + col), v1 = *reinterpret_cast<const double2*>(X1 + col);
+        acc[nt][0] = v0.x; acc[nt][1] = v0.y; acc[nt][2] = v1.x; acc[nt][3] = v1.y;
       }
       // Z_s = R_s - X_{<s} U[<s, s]
-#pragma unroll 4
+      const double* Ub = us + (16 * s * (s - 1)) * LDB + g;   // stacked rows start at 0, 32, 96
+#pragma unroll 2
       for (int kq = 0; kq < cs; kq += 4) {
         const double a0 = -X0[kq + t4], a1 = -X1[kq + t4];
-        const double* Up = U + (kq + t4) * NB + cs + g;
+        const double* Up = Ub + (kq + t4) * LDB;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mdb_dmma(acc[nt], a0, a1, __ldg(Up + 8 * nt));
+        for (int nt = 0; nt < 4; ++nt) mdb_dmma(acc[nt], a0, a1, Up[8 * nt]);
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int col = cs + 8 * nt + 2 * t4;
-        X0[col] = acc[nt][0]; X0[col + 1] = acc[nt][1]; X1[col] = acc[nt][2]; X1[col + 1] = acc[nt][3];
+        *reinterpret_cast<double2*>(X0 + col) = make_double2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<double2*>(X1 + col) = make_double2(acc[nt][2], acc[nt][3]);
       }
       __syncwarp();
       // W_s = Z_s Ltilde_ss^-T  (B[m][c] = inverse[c][m], zero for m > c: tile nt only needs m < 8 nt + 8)
       double w2[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) w2[nt][0] = w2[nt][1] = w2[nt][2] = w2[nt][3] = 0.0;
-      const double* Vs = V + s * SB * SB;
+      const double* Vs = vs + (cs + g) * LDB + t4;
 #pragma unroll
       for (int kq = 0; kq < SB; kq += 4) {
         const double a0 = X0[cs + kq + t4], a1 = X1[cs + kq + t4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
-          if (kq < 8 * nt + 8) mdb_dmma(w2[nt], a0, a1, __ldg(Vs + (8 * nt + g) * SB + kq + t4));
+          if (kq < 8 * nt + 8) mdb_dmma(w2[nt], a0, a1, Vs[(8 * nt) * LDB + kq]);
       }
       __syncwarp();  // every lane has read Z before X replaces it
       // X_s = W_s D_s^-1
@@ -881,7 +990,8 @@ __global__ void __launch_bounds__(MDB_PANEL_THREADS) k_panel_gemm(FactorDev F, i
       for (int nt = 0; nt < 4; ++nt) {
         const int col = cs + 8 * nt + 2 * t4;
         const double i0 = s_inv[col], i1 = s_inv[col + 1];
-        X0[col] = w2[nt][0] * i0; X0[col + 1] = w2[nt][1] * i1; X1[col] = w2[nt][2] * i0; X1[col + 1] = w2[nt][3] * i1;
+        *reinterpret_cast<double2*>(X0 + col) = make_double2(w2[nt][0] * i0, w2[nt][1] * i1);
+        *reinterpret_cast<double2*>(X1 + col) = make_double2(w2[nt][2] * i0, w2[nt][3] * i1);
       }
       __syncwarp();
     }
@@ -896,29 +1006,63 @@ __global__ void __launch_bounds__(MDB_PANEL_THREADS) k_panel_gemm(FactorDev F, i
   }
   __syncwarp();
 
-  // ---- alpha, rowmax, and the results: Lu into W, X and Y = -X d into the operand buffers (coalesced rows) ----
-  for (int rr = r0; rr < r0 + 16 && rr < nrow; ++rr) {
-    const int64_t jj = jbase + rr;
-    const int64_t pr = jj - p_row0;
-    double asum = 0, mx = 0;
+  // ---- alpha, rowmax, and the results: Lu into W, X and Y = -X d into the operand buffers (16-byte stores) ----
+  // Four rows per (rolled) iteration; their sums are reduced over the lanes with strides 16, 8 (halving the number of
+  // values per lane) and then 4, 2, 1: lane (b4, b3, 0, 0, 0) ends up with row 2 b4 + b3 of the group.
+  {
+    const double2 d01 = *reinterpret_cast<const double2*>(s_d + 2 * lane), d23 = *reinterpret_cast<const double2*>(s_d + 64 + 2 * lane);
+    const double* xp = xs + r0 * LDX + 2 * lane;
+    double* wp = Wcol + jw * w_ld + 2 * lane;
+    double* pxp = PX + (jw - p_row0) * p_ld + 2 * lane;
+    double* pyp = PY + (jw - p_row0) * p_ld + 2 * lane;
+    const int row_in_grp = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+#pragma unroll 1
+    for (int grp = 0; grp < 4; ++grp) {
+      double as4[4], mx4[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = lane + 32 * e;
-      const double x = xs[rr * LDX + c], dc = s_d[c];
-      asum += x * x * dc;          // Reimer.py:679-684
-      mx = fmax(mx, fabs(x));
-      Wcol[jj * w_ld + c] = x;
-      PX[pr * p_ld + c] = x;
-      PY[pr * p_ld + c] = -x * dc;
-    }
+      for (int q = 0; q < 4; ++q, xp += LDX, wp += w_ld, pxp += p_ld, pyp += p_ld) {
+        as4[q] = 0.0; mx4[q] = 0.0;
+        if (r0 + 4 * grp + q < nrow) {   // (uniform)
+          const double2 x01 = *reinterpret_cast<const double2*>(xp), x23 = *reinterpret_cast<const double2*>(xp + 64);
+          *reinterpret_cast<double2*>(wp) = x01;
+          *reinterpret_cast<double2*>(wp + 64) = x23;
+          *reinterpret_cast<double2*>(pxp) = x01;
+          *reinterpret_cast<double2*>(pxp + 64) = x23;
+          *reinterpret_cast<double2*>(pyp) = make_double2(-x01.x * d01.x, -x01.y * d01.y);
+          *reinterpret_cast<double2*>(pyp + 64) = make_double2(-x23.x * d23.x, -x23.y * d23.y);
+          double a = x01.x * x01.x * d01.x;          // Reimer.py:679-684
+          a = fma(x01.y * x01.y, d01.y, a);
+          a = fma(x23.x * x23.x, d23.x, a);
+          a = fma(x23.y * x23.y, d23.y, a);
+          as4[q] = a;
+          mx4[q] = fmax(fmax(fabs(x01.x), fabs(x01.y)), fmax(fabs(x23.x), fabs(x23.y)));
+        }
+      }
+      {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      asum += __shfl_xor_sync(0xffffffffu, asum, o);
-      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    if (lane == 0) {
-      F.alpha[vo + jj] += asum;
-      F.rowmax[vo + jj] = fmax(F.rowmax[vo + jj], mx);
+        for (int i = 0; i < 2; ++i) {
+          const double sa = up16 ? as4[i] : as4[i + 2], ka = up16 ? as4[i + 2] : as4[i];
+          const double sm = up16 ? mx4[i] : mx4[i + 2], km = up16 ? mx4[i + 2] : mx4[i];
+          as4[i] = ka + __shfl_xor_sync(0xffffffffu, sa, 16);
+          mx4[i] = fmax(km, __shfl_xor_sync(0xffffffffu, sm, 16));
+        }
+        const double sa = up8 ? as4[0] : as4[1], ka = up8 ? as4[1] : as4[0];
+        const double sm = up8 ? mx4[0] : mx4[1], km = up8 ? mx4[1] : mx4[0];
+        double a = ka + __shfl_xor_sync(0xffffffffu, sa, 8);
+        double m = fmax(km, __shfl_xor_sync(0xffffffffu, sm, 8));
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        }
+        const int R = r0 + 4 * grp + row_in_grp;
+        if ((lane & 7) == 0 && R < nrow) {
+          F.alpha[vo + jbase + R] = s_alpha[R] + a;
+          F.beta[vo + jbase + R] = s_beta[R];
+          F.rowmax[vo + jbase + R] = fmax(s_rowmax[R], m);
+        }
+      }
     }
   }
 }

@@ -163,7 +163,7 @@ extern "C" int mdb_ctx_create(int device, mdb_ctx** out) {
     const char* ag = getenv("MDB200_AGG");
     ctx->agg_fixed = ag ? atoi(ag) : 0;
     if (ctx->agg_fixed != 1 && ctx->agg_fixed != 2 && ctx->agg_fixed != 4 && ctx->agg_fixed != 8) ctx->agg_fixed = 0;
-    ctx->agg_thresh[0] = 8192; ctx->agg_thresh[1] = 16384; ctx->agg_thresh[2] = 32768;
+    ctx->agg_thresh[0] = 4096; ctx->agg_thresh[1] = 8192; ctx->agg_thresh[2] = 32768;
     const char* at = getenv("MDB200_AGG_THRESH");
     if (at) {
       long long a = 0, b = 0, c = 0;
@@ -682,7 +682,8 @@ static int configure_kernels(mdb_ctx* ctx) {
   const int prep_smem = (NB * (NB + 1) / 2 + NB * (NB + 1)) * 8;
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_diag_block<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
-  MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel_gemm<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
+  MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel_gemm<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
+  MDB_CUDA(ctx, cudaFuncSetAttribute(k_panel_gemm<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_smem));
   MDB_CUDA(ctx, cudaFuncSetAttribute(k_prepare_blocks<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, prep_smem));
   mdb_mark_device(done, ctx);
   return MDB_OK;
@@ -813,7 +814,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       {
         PhaseTimer t(ctx, 1);
         dim3 grid((unsigned)((rows + PANEL_R - 1) / PANEL_R), 1, (unsigned)batch);
-        k_panel_gemm<NB><<<grid, MDB_PANEL_THREADS, panel_smem, main_s>>>(F, k0, k1, rows, f->W, 1, f->ld, f->W + k0, f->ld,
+        k_panel_gemm<NB, false><<<grid, MDB_PANEL_THREADS, panel_smem, main_s>>>(F, k0, k1, rows, f->W, 1, f->ld, f->W + k0, f->ld,
                                                                     PX + (k0 - ob), PY + (k0 - ob), ob, LDP);
         MDB_LAUNCHED(ctx);
       }

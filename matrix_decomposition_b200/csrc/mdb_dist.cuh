@@ -291,7 +291,7 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot, int64_t k
     // The owner's operands go straight into the outer-block buffers; X is then copied into the message.
     double* PX = s->OPX[oslot] + (k0 - ob);
     double* PY = s->OPY[oslot] + (k0 - ob);
-    k_panel_gemm<NB><<<grid, MDB_PANEL_THREADS, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
+    k_panel_gemm<NB, true><<<grid, MDB_PANEL_THREADS, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
                                                                      s->S + lc0, s->ld, PX, PY, ob, s->ldp);
     MDB_LAUNCHED(ctx);
     if (!s->p2p) {  // message = [hdr (already there) | alpha, beta, rowmax of the rows below | X], packed by one kernel

@@ -1,7 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "known_answer or reference_test_grid_n10_static or families or sizes_around or explosive or batched_many or decompose_solve_multiply or outer_block" > gpurun_out/r2_pytest_quick.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_quick.log
-tail -25 gpurun_out/r2_pytest_quick.log
-timeout 300 python tools/chain_profile.py 8192 > gpurun_out/r2_chain4.log 2>&1
-timeout 300 python tools/chain_profile.py 16384 >> gpurun_out/r2_chain4.log 2>&1
-cat gpurun_out/r2_chain4.log
+timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest.log
+tail -15 gpurun_out/r2_pytest.log
+timeout 900 python bench.py --steps 2 --warmup 3 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; echo "bench rc=$?"
+tail -5 gpurun_out/r2_bench_n1.err
