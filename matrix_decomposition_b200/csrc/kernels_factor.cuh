@@ -109,6 +109,93 @@ __global__ void __launch_bounds__(256) k_gather_sym_cluster(int64_t n, const dou
   cluster.sync();  // nobody leaves while its shared memory may still be read
 }
 
+// ------------------------------------------------------------------------------------------------
+// The permutation of large matrices (n > 8192, one matrix) in TWO passes of "gather rows, transpose":
+//     pass 1:  B[c, i] = A[p[i], c]            pass 2:  W[i, j] = B[p[j], i]  ( = A[p[i], p[j]] )
+// A random p turns any one-pass formulation into 8-byte accesses on one side -- gathers inside the source row or
+// scattered writes -- and those are what the memory system cannot do: measured at n = 65536 (tools/permute_bench.py),
+// 8-byte gathers from L2 85 ms, scattered 8-byte writes 169 ms (partial sectors on ECC memory), the source row staged in
+// the distributed shared memory of a cluster 61 ms (random ld.shared::cluster: ~0.17 accesses per clock and SM), the same
+// with persistent clusters 99 ms.  A transposing tile kernel only ever touches 512-byte pieces of rows: tile (I, C) of
+// 64 x 64 loads the 64 rows map[i] at the contiguous columns C (16-byte loads, 8 in flight per thread), turns it in
+// shared memory and writes 64 contiguous pieces of the rows c of the destination.  Two such passes move 32 n^2 bytes
+// instead of the algorithmic 16 n^2; pass 2 uses the symmetry of the result -- tile (I, J) and its mirror image come
+// from one read -- so it reads only half of B: 28 n^2 bytes in total, all of them full sectors.
+// The finite check of the input (dense/util.py:15-21) rides on pass 1, gamma[i] = W[i, i] on the diagonal tiles of pass 2.
+// ------------------------------------------------------------------------------------------------
+#define MDB_TT 64            // tile edge
+#define MDB_TT_PITCH 65      // odd pitch: the transposed reads are conflict-free
+#define MDB_TT_THREADS 256
+
+__global__ void __launch_bounds__(MDB_TT_THREADS) k_gather_rows_transpose(int64_t n, const double* __restrict__ src, int64_t lds,
+                                                                         const int64_t* __restrict__ map,
+                                                                         double* __restrict__ dst, int64_t ldd, int symmetric,
+                                                                         double* __restrict__ gamma, int* __restrict__ nonfinite) {
+  // dst[c, i] = src[map[i], c] for i in tile blockIdx.x, c in tile blockIdx.y;  symmetric: only tiles with
+  // blockIdx.y >= blockIdx.x, which also write dst[i, c] = dst[c, i]
+  __shared__ double tile[MDB_TT * MDB_TT_PITCH];
+  const int ti = blockIdx.x, tc = blockIdx.y;
+  if (symmetric && tc < ti) return;
+  const int64_t i0 = (int64_t)ti * MDB_TT, c0 = (int64_t)tc * MDB_TT;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool bad = false;
+  {  // rows map[i0 + r], r = warp + 8 k: 64 contiguous doubles each, two per lane
+    const bool vec = ((lds & 1) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (c0 + MDB_TT <= n);
+    double2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = warp + 8 * k;
+      v[k] = make_double2(0.0, 0.0);
+      if (i0 + r < n) {
+        const int64_t row = map ? map[i0 + r] : i0 + r;
+        const double* sp = src + row * lds + c0 + 2 * lane;
+        if (vec) {
+          v[k] = *reinterpret_cast<const double2*>(sp);
+        } else {
+          if (c0 + 2 * lane < n) v[k].x = sp[0];
+          if (c0 + 2 * lane + 1 < n) v[k].y = sp[1];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = warp + 8 * k;
+      tile[r * MDB_TT_PITCH + 2 * lane] = v[k].x;
+      tile[r * MDB_TT_PITCH + 2 * lane + 1] = v[k].y;
+      bad |= !(isfinite(v[k].x) && isfinite(v[k].y));
+    }
+  }
+  __syncthreads();
+  // dst rows c0 + cc, cc = warp + 8 k: columns i0 + lane, i0 + lane + 32 (the tile read down its columns)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int cc = warp + 8 * k;
+    if (c0 + cc < n) {
+      double* dp = dst + (c0 + cc) * ldd + i0;
+      const double a = tile[lane * MDB_TT_PITCH + cc], b = tile[(lane + 32) * MDB_TT_PITCH + cc];
+      if (i0 + lane < n) dp[lane] = a;
+      if (i0 + lane + 32 < n) dp[lane + 32] = b;
+      if (gamma && ti == tc) {
+        if (lane == cc) gamma[c0 + cc] = a;
+        if (lane + 32 == cc) gamma[c0 + cc] = b;
+      }
+    }
+  }
+  if (symmetric && tc != ti) {
+    // the mirror image: dst rows i0 + r, columns c0 .. c0 + 63 (the tile read along its rows)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = warp + 8 * k;
+      if (i0 + r < n) {
+        double* dp = dst + (i0 + r) * ldd + c0;
+        if (c0 + lane < n) dp[lane] = tile[r * MDB_TT_PITCH + lane];
+        if (c0 + lane + 32 < n) dp[lane + 32] = tile[r * MDB_TT_PITCH + lane + 32];
+      }
+    }
+  }
+  if (bad && nonfinite) *nonfinite = 1;
+}
+
 // lower triangle <- transpose of the upper triangle (the host upload sends only the upper triangle of a symmetric A)
 __global__ void __launch_bounds__(256) k_mirror_upper_to_lower(int64_t n, double* __restrict__ A, int64_t lda) {
   __shared__ double tile[32][33];

@@ -67,7 +67,7 @@ static void ctx_reap(mdb_ctx* ctx) {
 // same amount: cudaMalloc + cudaFree of that size cost ~0.1 s per call.  mdb_ctx_trim() gives them back to the driver;
 // any allocation of the library that fails trims the cache and tries once more.  MDB200_CACHE=0 disables the cache.
 static void ctx_trim(mdb_ctx* ctx) {
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     if (ctx->big_ptr[i]) cudaFree(ctx->big_ptr[i]);
     ctx->big_ptr[i] = nullptr;
     ctx->big_bytes[i] = 0;
@@ -76,7 +76,7 @@ static void ctx_trim(mdb_ctx* ctx) {
 
 static cudaError_t dev_malloc(mdb_ctx* ctx, void** p, size_t bytes) {
   cudaError_t e = cudaMalloc(p, bytes);
-  if (e == cudaErrorMemoryAllocation && (ctx->big_ptr[0] || ctx->big_ptr[1])) {
+  if (e == cudaErrorMemoryAllocation && (ctx->big_ptr[0] || ctx->big_ptr[1] || ctx->big_ptr[2])) {
     cudaGetLastError();
     ctx_trim(ctx);
     e = cudaMalloc(p, bytes);
@@ -86,7 +86,7 @@ static cudaError_t dev_malloc(mdb_ctx* ctx, void** p, size_t bytes) {
 
 // *cap receives the size to pass to big_free (the cached buffer may be a little larger than asked for)
 static cudaError_t big_malloc(mdb_ctx* ctx, void** p, size_t bytes, size_t* cap) {
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 3; ++i)
     if (ctx->big_ptr[i] && ctx->big_bytes[i] >= bytes && ctx->big_bytes[i] - bytes <= bytes / 8) {
       *p = ctx->big_ptr[i];
       *cap = ctx->big_bytes[i];
@@ -102,8 +102,12 @@ static cudaError_t big_malloc(mdb_ctx* ctx, void** p, size_t bytes, size_t* cap)
 static void big_free(mdb_ctx* ctx, void* p, size_t cap) {
   if (!p) return;
   if (ctx->use_cache && cap >= ((size_t)256 << 20)) {
-    int slot = !ctx->big_ptr[0] ? 0 : !ctx->big_ptr[1] ? 1 : (ctx->big_bytes[0] <= ctx->big_bytes[1] ? 0 : 1);
-    if (ctx->big_ptr[slot] && ctx->big_bytes[slot] > cap) {  // both slots hold larger buffers: keep those
+    int slot = 0;   // a free slot, else the smallest buffer
+    for (int i = 0; i < 3; ++i) {
+      if (!ctx->big_ptr[i]) { slot = i; break; }
+      if (ctx->big_bytes[i] < ctx->big_bytes[slot]) slot = i;
+    }
+    if (ctx->big_ptr[slot] && ctx->big_bytes[slot] > cap) {  // every slot holds a larger buffer: keep those
       cudaFree(p);
       return;
     }
@@ -510,8 +514,29 @@ static int factor_set_p(mdb_factor* f, const int64_t* p) {
 
 static int gather_sym(mdb_ctx* ctx, int64_t n, int64_t batch, const double* A_dev, int64_t lda, int64_t sA,
                       const int64_t* p_dev, double* W, int64_t ldw, int64_t sW, double* gamma, int* nonfinite = nullptr,
-                      int upper_only = 0) {
+                      int upper_only = 0, int known_symmetric = 0) {
+  // known_symmetric: A[i, j] == A[j, i] bit for bit (the mirrored upload of mdb_factor_set_matrix); the second pass of
+  // the large-matrix path then reads only half of its input.  permute.symmetric (dense/permute.py:26) is defined for any
+  // square matrix and never sets it.
   if (n == 0) return MDB_OK;
+  // large single matrices: two passes of "gather rows, transpose" through a temporary n x n buffer (k_gather_rows_transpose)
+  if (!upper_only && ctx->use_cluster_gather && batch == 1 && n > 8192) {
+    double* B = nullptr;
+    size_t cap = 0;
+    if (big_malloc(ctx, (void**)&B, (size_t)n * n * 8, &cap) == cudaSuccess) {
+      const unsigned t = (unsigned)((n + MDB_TT - 1) / MDB_TT);
+      k_gather_rows_transpose<<<dim3(t, t), MDB_TT_THREADS, 0, ctx->stream>>>(n, A_dev, lda, p_dev, B, n, 0, nullptr, nonfinite);
+      k_gather_rows_transpose<<<dim3(t, t), MDB_TT_THREADS, 0, ctx->stream>>>(n, B, n, p_dev, W, ldw, known_symmetric, gamma, nullptr);
+      MDB_LAUNCHED(ctx);
+      MDB_LAUNCHED(ctx);
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // B goes back to the cache only when nothing reads it
+      big_free(ctx, B, cap);
+      MDB_CUDA(ctx, e);
+      return MDB_OK;
+    }
+    cudaGetLastError();   // no room for the temporary: one pass with the source row in distributed shared memory
+  }
   // cluster kernel: source row staged in (distributed) shared memory, row read once
   const int shift = (n <= 8 * 8192) ? 13 : 14;  // chunk of 8192 doubles (64 KB) or 16384 (128 KB)
   const int64_t chunk = (int64_t)1 << shift;
@@ -565,7 +590,7 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
   double* staging = nullptr;
   size_t staging_cap = 0;
   int64_t lds = lda;
-  int upper_only = 0;
+  int upper_only = 0, mirrored = 0;
   if (a_loc == MDB_HOST) {
     MDB_CUDA(ctx, big_malloc(ctx, (void**)&staging, (size_t)f->batch * n * n * 8, &staging_cap));
     if (f->batch == 1 && n >= 4096) {
@@ -579,6 +604,7 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
         const unsigned t32 = (unsigned)((n + 31) / 32);
         k_mirror_upper_to_lower<<<dim3(t32, t32), 256, 0, ctx->stream>>>(n, staging, n);
         MDB_LAUNCHED(ctx);
+        mirrored = 1;
       }
     } else {
       rc = copy2d_async(ctx, staging, n, A, lda, f->batch * n, n, MDB_DEVICE, MDB_HOST);  // batch stride = n*lda
@@ -590,7 +616,7 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
   // the finite check of the input rides on the gather: flag = the int after the per-matrix info entries
   int* flag = f->info + f->batch;
   MDB_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
-  rc = gather_sym(ctx, n, f->batch, A_dev, lds, n * lds, f->p_dev, f->W, f->ld, n * f->ld, f->gamma, flag, upper_only);
+  rc = gather_sym(ctx, n, f->batch, A_dev, lds, n * lds, f->p_dev, f->W, f->ld, n * f->ld, f->gamma, flag, upper_only, mirrored);
   int bad = 0;
   cudaError_t ef = cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   if (ef == cudaSuccess) ef = cudaStreamSynchronize(ctx->stream);

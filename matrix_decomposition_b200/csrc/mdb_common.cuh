@@ -38,8 +38,8 @@ struct mdb_ctx {
   size_t stage_bytes;
   std::thread* reaper;        // background release of the previous one-shot call's device buffers (cudaFree of tens
                               // of GB takes 0.2-0.4 s and nothing the caller waits for depends on it)
-  void* big_ptr[2];           // released working matrix / staging buffers kept for the next call (mdb_ctx_trim)
-  size_t big_bytes[2];
+  void* big_ptr[3];           // released working matrix / staging / permutation buffers kept for the next call (mdb_ctx_trim)
+  size_t big_bytes[3];
   int use_cache;
   int last_input_nonfinite;   // set by mdb_factor_set_matrix: the matrix held an inf / NaN
   double gemm_flop[2];        // algorithmic flop of the bulk / inner trailing updates of the last mdb_factor_run

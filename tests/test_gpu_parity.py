@@ -705,6 +705,14 @@ def test_permute_symmetric_bit_exact(matrix):
         B = matrix.permute.symmetric(A, p)
         assert np.array_equal(B, A[p[:, None], p[None, :]])                              # test_permute.py:60
         assert np.array_equal(matrix.permute.symmetric(B, matrix.permute.invert_permutation_vector(p)), A)
+    # above 8192 rows the permutation runs as a scatter with the inverse permutation (k_scatter_sym): sizes that do and
+    # do not fill the last chunk of 8192 source columns, a random permutation, the identity and a reversal
+    for n in (8193, 9000, 16384):
+        rng = np.random.default_rng(n)
+        A = rng.standard_normal((n, n))
+        for p in (rng.permutation(n), np.arange(n), np.arange(n)[::-1].copy()):
+            B = matrix.permute.symmetric(A, p)
+            assert np.array_equal(B, A[p[:, None], p[None, :]])
 
 
 # ---------------------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ def main():
     ctx = _native.context()
     lib = ctx.lib
     out = []
-    for n in (16384, 32768):
+    for n in (16384, 32768, 65536):
         dA, dB = ctx.malloc(n * n * 8), ctx.malloc(n * n * 8)
         ctx.check(lib.mdb_generate_f2(ctx.handle, n, 1, 10.0, ctypes.c_void_p(dA), n), 'gen')
         for name, p in (('random', np.random.default_rng(0).permutation(n).astype(np.int64)),
