@@ -71,24 +71,30 @@ __global__ void __launch_bounds__(256) k_dyn_select1(FactorDev F, int method, in
 __device__ __forceinline__ void dyn_commit(const FactorDev& F, int64_t i, const DynCand& c, double* __restrict__ minB,
                                            double* __restrict__ maxB, int64_t* __restrict__ p, DynSel* __restrict__ sel) {
   const int64_t js = c.j;
-  if (js != i) {  // Reimer.py:509-512 (p) -- and every per-row quantity kept in position order
-    double t;
-    t = F.gamma[i]; F.gamma[i] = F.gamma[js]; F.gamma[js] = t;
-    t = F.alpha[i]; F.alpha[i] = F.alpha[js]; F.alpha[js] = t;
-    t = F.beta[i]; F.beta[i] = F.beta[js]; F.beta[js] = t;
-    t = F.rowmax[i]; F.rowmax[i] = F.rowmax[js]; F.rowmax[js] = t;
-    t = minB[i]; minB[i] = minB[js]; minB[js] = t;
-    t = maxB[i]; maxB[i] = maxB[js]; maxB[js] = t;
-    const int64_t tp = p[i]; p[i] = p[js]; p[js] = tp;
+  // Reimer.py:509-512 (p) -- and every per-row quantity kept in position order.  All loads first (independent, one
+  // memory latency), then the stores: one thread swapping vector after vector paid ~14 dependent round trips per column.
+  // (alpha / beta / rowmax of row j* were written by another block of the same launch: loads that bypass L1)
+  const double g_i = __ldcg(F.gamma + i), g_s = __ldcg(F.gamma + js), a_i = __ldcg(F.alpha + i), a_s = __ldcg(F.alpha + js);
+  const double b_i = __ldcg(F.beta + i), b_s = __ldcg(F.beta + js), r_i = __ldcg(F.rowmax + i), r_s = __ldcg(F.rowmax + js);
+  const double m_i = __ldcg(minB + i), m_s = __ldcg(minB + js), M_i = __ldcg(maxB + i), M_s = __ldcg(maxB + js);
+  const int64_t p_i = (int64_t)__ldcg((const long long*)p + i), p_s = (int64_t)__ldcg((const long long*)p + js);
+  if (js != i) {
+    F.gamma[i] = g_s; F.gamma[js] = g_i;
+    F.alpha[i] = a_s; F.alpha[js] = a_i;
+    F.beta[i] = b_s; F.beta[js] = b_i;
+    F.rowmax[i] = r_s; F.rowmax[js] = r_i;
+    minB[i] = m_s; minB[js] = m_i;
+    maxB[i] = M_s; maxB[js] = M_i;
+    p[i] = p_s; p[js] = p_i;
   }
-  const double alpha_i = F.alpha[i], gamma_i = F.gamma[i];
+  const double alpha_i = a_s, gamma_i = g_s, rowmax_i = r_s;   // (js == i: the same values)
   F.d[i] = c.d;
   F.omega[i] = c.omega;
   F.delta[i] = (c.d - gamma_i) + (c.omega != 0 ? c.omega * c.omega * alpha_i : 0.0);  // Reimer.py:541-545
   F.clamped[i] = (uint8_t)c.clamped;
   sel->d = c.d;
   sel->omega = c.omega;
-  sel->drop = (c.omega == 0 || c.omega * F.rowmax[i] < F.prm.min_abs_value_L) ? 1.0 : 0.0;
+  sel->drop = (c.omega == 0 || c.omega * rowmax_i < F.prm.min_abs_value_L) ? 1.0 : 0.0;
   sel->jstar = js;
 }
 
@@ -133,41 +139,55 @@ __global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict_
 }
 
 // column i for every row below: current Schur complement entry (stored value + the pending updates of this panel),
-// mix, divide, alpha / beta / rowmax; x and y = -x d go into column kc of the operand buffers.  A thread per row with
-// the row of Y broadcast from shared memory.  With its alpha / beta current, every row then evaluates the rule for
-// step i + 1; the block minima are merged by the last block to finish, which commits the decision for step i + 1
-// into sel_next (the two DynSel slots alternate, so no block can still be reading the slot being written).
+// mix, divide, alpha / beta / rowmax; x and y = -x d go into column kc of the operand buffers.  A CTA owns
+// MDB_DYN_ROWS = 64 rows (4 CTAs per 256 rows: every SM gets work also at n = 16384):
+//   pass 1  a warp per row, lanes over the pending columns: sum_c X[j, c] Y[i, c] with coalesced loads of the row of X
+//           (a thread per row walked its row alone: 32 different cache lines per load instruction) and a fixed butterfly;
+//   pass 2  a thread per row: the mix, x, the row state and -- its alpha / beta being current -- the rule for step i + 1.
+// The block minima are merged by the last block to finish, which commits the decision for step i + 1 into sel_next
+// (the two DynSel slots alternate, so no block can still be reading the slot being written).
+#define MDB_DYN_ROWS 64
+
 __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, int64_t i, const DynSel* __restrict__ sel,
                                                     double* __restrict__ PX, double* __restrict__ PY, int64_t ldp,
                                                     int kc, DynCand* cand, unsigned* counter,
                                                     double* __restrict__ minB, double* __restrict__ maxB,
                                                     int64_t* __restrict__ p, DynSel* __restrict__ sel_next) {
   __shared__ double yi[MDB_NB];
+  __shared__ double s_sum[MDB_DYN_ROWS];
   __shared__ DynCand sh[256];
   __shared__ bool s_last;
-  for (int c = threadIdx.x; c < kc; c += 256) yi[c] = PY[i * ldp + c];   // Y[i, 0:kc]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = tid; c < kc; c += 256) yi[c] = PY[i * ldp + c];   // Y[i, 0:kc]
   __syncthreads();
-  const int64_t j = i + 1 + (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t j0 = i + 1 + (int64_t)blockIdx.x * MDB_DYN_ROWS;
+  const bool drop = sel->drop != 0.0;
+  if (!drop) {
+    for (int rr = warp; rr < MDB_DYN_ROWS; rr += 8) {   // pass 1
+      const int64_t j = j0 + rr;
+      double s = 0;
+      if (j < F.n) {
+        const double* xr = PX + j * ldp;
+#pragma unroll
+        for (int e = 0; e < MDB_NB / 32; ++e) {
+          const int c = lane + 32 * e;
+          if (c < kc) s = fma(xr[c], yi[c], s);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) s_sum[rr] = s;
+    }
+  }
+  __syncthreads();
   DynCand best;
   best.j = -1; best.d = 0; best.omega = 0; best.f = 0; best.clamped = 0;
-  if (j < F.n) {
+  const int64_t j = j0 + tid;
+  if (tid < MDB_DYN_ROWS && j < F.n) {   // pass 2
     const double d = sel->d, w = sel->omega;
-    const bool drop = sel->drop != 0.0;
     const double a = F.W[i * F.ldw + j];
     double r = a;
-    if (!drop) {
-      double s = F.W[j * F.ldw + i];
-      const double* xr = PX + j * ldp;
-      double s0 = 0, s1 = 0;
-      int c = 0;
-      for (; c + 1 < kc; c += 2) {
-        s0 = fma(xr[c], yi[c], s0);
-        s1 = fma(xr[c + 1], yi[c + 1], s1);
-      }
-      if (c < kc) s0 = fma(xr[c], yi[c], s0);
-      s += s0 + s1;
-      r = (1.0 - w) * a + w * s;
-    }
+    if (!drop) r = (1.0 - w) * a + w * (F.W[j * F.ldw + i] + s_sum[tid]);
     const double x = (d != 0) ? r / d : 0.0;
     F.W[j * F.ldw + i] = x;
     const double al = F.alpha[j] + x * x * d, be = F.beta[j] + 2.0 * a * a;
@@ -180,7 +200,7 @@ __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, int
     best.d = dec.d; best.omega = dec.omega; best.f = dec.f; best.clamped = dec.clamped; best.j = j;
   }
   best = dyn_block_reduce(method, best, sh);
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     cand[blockIdx.x] = best;
     __threadfence();
     s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
@@ -190,14 +210,14 @@ __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, int
   __threadfence();
   DynCand c;
   c.j = -1; c.d = 0; c.omega = 0; c.f = 0; c.clamped = 0;
-  for (int b = threadIdx.x; b < (int)gridDim.x; b += 256) {
+  for (int b = tid; b < (int)gridDim.x; b += 256) {
     const volatile DynCand* vc = cand + b;   // written by other blocks of this launch
     DynCand o;
     o.d = vc->d; o.omega = vc->omega; o.f = vc->f; o.j = vc->j; o.clamped = vc->clamped;
     if (dyn_better(method, o, c)) c = o;
   }
   c = dyn_block_reduce(method, c, sh);
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     *counter = 0;
     dyn_commit(F, i + 1, c, minB, maxB, p, sel_next);
   }

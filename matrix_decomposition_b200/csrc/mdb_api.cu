@@ -1129,7 +1129,7 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
       mb[(size_t)i] = bnd->min_diag_B ? bnd->min_diag_B[i * bnd->stride_B] : -INFINITY;
       Mb[(size_t)i] = bnd->max_diag_B ? bnd->max_diag_B[i * bnd->stride_B] : INFINITY;
     }
-    const int nb_max = (int)((n + 255) / 256);
+    const int nb_max = (int)((n + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS) + 1;   // candidates: one per block of k_dyn_select1 / k_dyn_column
     cudaError_t e = dev_malloc(ctx, (void**)&minB, (size_t)n * 8);
     if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&maxB, (size_t)n * 8);
     if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&cand, (size_t)nb_max * sizeof(DynCand));
@@ -1170,7 +1170,7 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
           k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, cur, f->PX, f->PY, LDP, kc);
           ctx->launches += 1;
           if (rem > 1) {
-            k_dyn_column<<<(unsigned)((rem - 1 + 255) / 256), 256, 0, ctx->stream>>>(
+            k_dyn_column<<<(unsigned)((rem - 1 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS), 256, 0, ctx->stream>>>(
                 F, method, i, cur, f->PX, f->PY, LDP, kc, cand, counter, minB, maxB, f->p_dev, sel + ((i + 1) & 1));
             ctx->launches += 1;
           }

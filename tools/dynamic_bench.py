@@ -17,9 +17,11 @@ for n in [int(a) for a in sys.argv[1:]] or [1000, 2000, 4000, 8000]:
     A, kw = workloads.shifted_goe(n, 5, 1.05)
     kw = dict(kw, permutation='maximal_stability')
     matrix.approximation.positive_semidefinite.decomposition(A[:256, :256].copy(), **dict(workloads.f2_bounds(256), permutation='maximal_stability'))
-    t = time.perf_counter()
-    dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
-    dt = time.perf_counter() - t
+    dt = 1e30
+    for _ in range(3):    # best of three: the first call at a size pays one-time allocations (pinned staging, buffers)
+        t = time.perf_counter()
+        dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
+        dt = min(dt, time.perf_counter() - t)
     d = np.asarray(dec.d, dtype=float)
     out.append(dict(n=n, seconds=dt, gflops=n ** 3 / 3 / dt / 1e9, n_clamped=int(dec.clamped.sum()), d_min=float(d.min())))
     print(json.dumps(out[-1]), flush=True)
