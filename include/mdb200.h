@@ -250,9 +250,9 @@ int mdb_dist_apply_update(mdb_dist *s, int64_t k_outer, int oslot, int64_t k_fir
  * diagonal, zeros above) and copies the replicated vectors to the host (position order; any may be NULL) */
 int mdb_dist_finalize(mdb_dist *s, double *d, double *omega, double *delta, uint8_t *clamped);
 /* device-side status word of the current factorization: 0 fine; > 0 first non-positive pivot + 1 (MDB_RULE_EXACT);
- * <= -1001 a bounded wait of the peer-store exchange ran out.  mdb_dist_finalize returns MDB_ERR_NOT_POSITIVE_DEFINITE
- * / MDB_ERR_STATE accordingly (results are still copied out, for diagnosis); callers exchange the word between the
- * ranks, because only the rank that timed out sees a protocol error (distributed.py all-reduces it). */
+ * negative values are reserved for device-side errors.  mdb_dist_finalize returns MDB_ERR_NOT_POSITIVE_DEFINITE /
+ * MDB_ERR_STATE accordingly (results are still copied out, for diagnosis); callers exchange the word between the
+ * ranks, because a failing pivot is only seen by the rank that owns its panel (distributed.py all-reduces it). */
 int mdb_dist_info(mdb_dist *s, int *info_out);
 
 /* ---- consumers of the distributed factor (config 4): the result must reach dec.solve (decompositions.py:983-991,
@@ -289,25 +289,6 @@ int mdb_dist_solve_scale(mdb_dist *s, double *r, int k);
 int mdb_dist_solve_bwd_colsum(mdb_dist *s, int64_t w, const double *r, double *xchg, double *partial, int k);
 int mdb_dist_solve_bwd_window(mdb_dist *s, int64_t w, const double *band, const double *tinv, double *r,
                               const double *xchg, int k);
-
-/* ---- optional (MDB200_P2P=1 in distributed.py; bit-identical to the NCCL path): panel exchange by unicast
- * peer-memory stores ----
- * Instead of the NCCL broadcast + mdb_dist_absorb_panel, the owner of a panel stores X, Y = -X D, the alpha / beta /
- * rowmax slices and d / omega / delta / clamped straight into every peer's buffers over NVLink and raises a flag
- * (csrc/mdb_peer.cuh).  Every rank provides one zero-filled "symmetric" buffer of mdb_dist_peer_buffer_elems(s)
- * doubles that is mapped into all ranks (torch.distributed._symmetric_memory); peer_base = host array of `world`
- * device pointers to those buffers as seen from this process.  Attach before mdb_dist_set_bounds; put a barrier
- * between mdb_dist_set_bounds and the first panel.
- *   mdb_dist_push_panel    owner, after mdb_dist_factor_panel on the same stream; outer_index = running index of the
- *                          panel's outer block (flow control against the double-buffered operand buffers)
- *   mdb_dist_wait_panel    every rank, on the stream that consumes panel k (replaces waiting for the broadcast)
- *   mdb_dist_release_outer every rank, on a stream ordered after all its kernels that read the operands of the first
- *                          `count` outer blocks */
-int64_t mdb_dist_peer_buffer_elems(const mdb_dist *s);
-int mdb_dist_attach_peers(mdb_dist *s, double *const *peer_base);
-int mdb_dist_push_panel(mdb_dist *s, int64_t k, int slot, int64_t k_outer, int oslot, int64_t outer_index);
-int mdb_dist_wait_panel(mdb_dist *s, int64_t k);
-int mdb_dist_release_outer(mdb_dist *s, int64_t count);
 
 #ifdef __cplusplus
 }

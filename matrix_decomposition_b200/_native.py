@@ -111,8 +111,6 @@ SIGNATURES = {
     'mdb_dist_absorb_panel': (_int, [_vp, _i64, _int, _i64, _int]),
     'mdb_dist_apply_update': (_int, [_vp, _i64, _int, _i64, _i64, _i64, _i64]),
     'mdb_dist_finalize': (_int, [_vp, _vp, _vp, _vp, _vp]),
-    'mdb_dist_peer_buffer_elems': (_i64, [_vp]),
-    'mdb_dist_attach_peers': (_int, [_vp, _vp]),
     'mdb_dist_info': (_int, [_vp, _vp]),
     'mdb_dist_place_columns': (_int, [_vp, _i64, _int, _int, _vp, _i64, _vp, _i64]),
     'mdb_factor_upload_device': (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _pp]),
@@ -126,9 +124,6 @@ SIGNATURES = {
     'mdb_dist_solve_scale': (_int, [_vp, _vp, _int]),
     'mdb_dist_solve_bwd_colsum': (_int, [_vp, _i64, _vp, _vp, _vp, _int]),
     'mdb_dist_solve_bwd_window': (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _int]),
-    'mdb_dist_push_panel': (_int, [_vp, _i64, _int, _i64, _int, _i64]),
-    'mdb_dist_wait_panel': (_int, [_vp, _i64]),
-    'mdb_dist_release_outer': (_int, [_vp, _i64]),
 }
 
 _lib = None

@@ -1878,5 +1878,4 @@ extern "C" int mdb_debug_gemm_tn(mdb_ctx* ctx, int64_t M, int64_t N, int64_t K, 
 }
 
 #include "mdb_dist.cuh"
-#include "mdb_peer.cuh"
 #include "mdb_dist_solve.cuh"

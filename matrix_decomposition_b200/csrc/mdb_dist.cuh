@@ -22,12 +22,6 @@ struct mdb_dist {
   int64_t* pcol_dev;   // scratch for the generator
   MdRuleParams prm;
   bool have_bounds;
-  // peer-store panel exchange (mdb_peer.cuh); p2p = the operand buffers and vectors live in a symmetric buffer owned by
-  // the caller and mapped into every rank
-  bool p2p;
-  double* peer_base[16];
-  unsigned int* push_counter;
-  uint32_t epoch;      // factorization counter, tags the arrival / release flags
 };
 
 static inline int64_t dist_local_blocks(int64_t n, int rank, int world) {
@@ -82,8 +76,6 @@ extern "C" int mdb_dist_create(mdb_ctx* ctx, int64_t n, int rank, int world, dou
   s->S = S_loc; s->A = A_loc; s->panel[0] = panel0; s->panel[1] = panel1;
   s->vec = nullptr; s->clamped = nullptr; s->minB = s->maxB = nullptr; s->info = nullptr; s->Ut = nullptr; s->Vinv = nullptr;
   s->pcol_dev = nullptr; s->have_bounds = false;
-  s->p2p = false; s->push_counter = nullptr; s->epoch = 0;
-  for (int q = 0; q < 16; ++q) s->peer_base[q] = nullptr;
   s->OPX[0] = s->OPX[1] = s->OPY[0] = s->OPY[1] = nullptr;
   s->ldp = dist_outer_width(ctx, n, 0) * NB;  // the first outer block is the widest
   cudaError_t e = dev_malloc(ctx, (void**)&s->vec, (size_t)7 * n * 8);
@@ -117,12 +109,10 @@ extern "C" int mdb_dist_destroy(mdb_dist* s) {
   if (!s) return MDB_OK;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
-  if (!s->p2p) {  // with peer stores these live in the caller's symmetric buffer
-    cudaFree(s->vec); cudaFree(s->clamped);
-    for (int i = 0; i < 2; ++i) { cudaFree(s->OPX[i]); cudaFree(s->OPY[i]); }
-  }
+  cudaFree(s->vec); cudaFree(s->clamped);
+  for (int i = 0; i < 2; ++i) { cudaFree(s->OPX[i]); cudaFree(s->OPY[i]); }
   cudaFree(s->minB); cudaFree(s->maxB); cudaFree(s->info); cudaFree(s->Ut); cudaFree(s->Vinv);
-  cudaFree(s->pcol_dev); cudaFree(s->push_counter);
+  cudaFree(s->pcol_dev);
   delete s;
   return MDB_OK;
 }
@@ -239,7 +229,6 @@ extern "C" int mdb_dist_set_bounds(mdb_dist* s, const mdb_bounds* bnd, const int
   s->prm.min_abs_value_L = (bnd->rule == MDB_RULE_EXACT) ? 0.0 : bnd->min_abs_value_L;
   s->prm.min_diag_B = sc_minB;
   s->prm.max_diag_B = sc_maxB;
-  s->epoch += 1;
   MDB_CUDA(ctx, cudaMemsetAsync(s->alpha, 0, (size_t)3 * n * 8, ctx->stream));
   MDB_CUDA(ctx, cudaMemsetAsync(s->info, 0, sizeof(int), ctx->stream));
   ctx->gemm_flop[0] = ctx->gemm_flop[1] = 0;  // mdb_ctx_get_update_stats counts this rank's share from here on
@@ -294,7 +283,7 @@ extern "C" int mdb_dist_factor_panel(mdb_dist* s, int64_t k, int slot, int64_t k
     k_panel_gemm<NB, true><<<grid, MDB_PANEL_THREADS, panel_smem, ctx->stream>>>(F, k0, k1, rows, s->A + lc0 - k0, s->ld, 1,
                                                                      s->S + lc0, s->ld, PX, PY, ob, s->ldp);
     MDB_LAUNCHED(ctx);
-    if (!s->p2p) {  // message = [hdr (already there) | alpha, beta, rowmax of the rows below | X], packed by one kernel
+    {  // message = [hdr (already there) | alpha, beta, rowmax of the rows below | X], packed by one kernel
       const unsigned grid = (unsigned)std::min<int64_t>((rows + 1) / 2, (int64_t)ctx->num_sms * 8);
       k_dist_pack<<<grid, 256, 0, ctx->stream>>>(rows, PX + (k1 - ob) * s->ldp, s->ldp, s->alpha + k1, s->beta + k1,
                                                  s->rowmax + k1, vecs, MX);
@@ -365,7 +354,6 @@ extern "C" int mdb_dist_absorb_panel(mdb_dist* s, int64_t k, int slot, int64_t k
   MDB_CHECK(ctx, k_outer >= 0 && k_outer <= k && (k - k_outer + 1) * NB <= s->ldp, "mdb_dist_absorb_panel: bad outer block");
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
   if ((k % s->world) == s->rank) return MDB_OK;  // the owner's arrays and operands are already in place
-  if (s->p2p) return MDB_OK;                     // the owner stored them straight into this rank's buffers
   const int64_t n = s->n, k0 = k * NB, k1 = std::min<int64_t>(k0 + NB, n), rows = n - k1, ob = k_outer * NB;
   double* buf = s->panel[slot];
   if (rows > 0) {
@@ -438,9 +426,7 @@ static int dist_info_status(mdb_dist* s, int info) {
     snprintf(ctx->err, sizeof(ctx->err), "distributed factorization: pivot %d is not positive", info - 1);
     return MDB_ERR_NOT_POSITIVE_DEFINITE;
   }
-  snprintf(ctx->err, sizeof(ctx->err),
-           "distributed factorization: panel exchange protocol error %d (a bounded wait on a peer ran out; the factor "
-           "is not valid)", info);
+  snprintf(ctx->err, sizeof(ctx->err), "distributed factorization: device-side status %d; the factor is not valid", info);
   return MDB_ERR_STATE;
 }
 
@@ -465,9 +451,9 @@ extern "C" int mdb_dist_finalize(mdb_dist* s, double* d, double* omega, double* 
 }
 
 // The device-side status word of the current factorization: 0 = fine, > 0 = first non-positive pivot + 1
-// (MDB_RULE_EXACT), <= -1001 = a bounded wait of the peer-store exchange ran out (mdb_peer.cuh).  The factor of a
-// run with info != 0 must not be used; mdb_dist_finalize returns the matching error status.  Every rank should
-// exchange the value (distributed.py all-reduces it) because only the rank that timed out sees a protocol error.
+// (MDB_RULE_EXACT); negative values are reserved for device-side errors.  The factor of a run with info != 0 must
+// not be used; mdb_dist_finalize returns the matching error status.  Every rank should exchange the value
+// (distributed.py all-reduces it): a failing pivot is only seen by the rank that owns its panel.
 extern "C" int mdb_dist_info(mdb_dist* s, int* info_out) {
   if (!s || !info_out) return MDB_ERR_INVALID;
   mdb_ctx* ctx = s->ctx;

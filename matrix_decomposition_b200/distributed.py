@@ -66,17 +66,11 @@ def factorize(n, rank, world, steps, comm, main=None, bulk=None, lookahead=True)
     works = {}
     bulk_done = {}
 
-    exchange = getattr(comm, 'exchange_panel', None)   # PeerComm: one-sided peer stores instead of a broadcast
-    release = getattr(steps, 'release_outer', None) if exchange is not None else None
-
     def issue_factor_and_broadcast(k, k_outer, oslot, outer_index):
         slot = k % 2
         if owner_of(k, world) == rank:
             steps.factor_panel(k, slot, k_outer, oslot, main)
-        if exchange is not None:
-            works[k] = exchange(steps, k, slot, k_outer, oslot, outer_index, owner_of(k, world), main)
-        else:
-            works[k] = comm.broadcast(steps.panel_tensor(slot, k), owner_of(k, world), main)
+        works[k] = comm.broadcast(steps.panel_tensor(slot, k), owner_of(k, world), main)
 
     issue_factor_and_broadcast(0, 0, 0, 0)
     kO, oidx = 0, 0
@@ -103,14 +97,9 @@ def factorize(n, rank, world, steps, comm, main=None, bulk=None, lookahead=True)
                 steps.apply_update(kO, oslot, kO, cnt, kE + 1, kE + cntn, main)   # rest of the next outer block
                 bulk.wait(ready)
                 steps.apply_update(kO, oslot, kO, cnt, kE + cntn, -1, bulk)       # everything beyond
-                if release is not None:     # nobody on this rank reads this outer block's operands any more
-                    bulk.wait(main.record())
-                    release(oidx + 1, bulk)
                 bulk_done[oidx] = bulk.record()
             else:
                 steps.apply_update(kO, oslot, kO, cnt, kE, -1, main)
-                if release is not None:
-                    release(oidx + 1, main)
                 bulk_done[oidx] = main.record()
                 issue_factor_and_broadcast(kE, kE, (oidx + 1) % 2, oidx + 1)
         kO, oidx = kE, oidx + 1
@@ -163,25 +152,6 @@ class NcclComm:
         return Handle()
 
 
-class PeerComm:
-    """MDB200_P2P=1: no collective at all -- the owner of a panel stores it into every peer's operand buffers over
-    NVLink (unicast stores, mdb_dist_push_panel, csrc/mdb_peer.cuh) and the consumers' streams wait for its arrival
-    flag.  Bit-identical to the NCCL path and to one GPU."""
-
-    def exchange_panel(self, steps, k, slot, k_outer, oslot, outer_index, owner, stream):
-        if owner == steps.rank:
-            steps.push_panel(k, slot, k_outer, oslot, outer_index, stream)
-
-        class Handle:
-            def wait(self, s):
-                steps.wait_panel(k, s)
-        return Handle()
-
-
-def peer_stores_requested():
-    return os.environ.get('MDB200_P2P', '0') == '1'
-
-
 class CudaSteps:
     """Per-rank device state: S_loc / A_loc / panel buffers are torch tensors, the steps are C-ABI calls."""
 
@@ -207,77 +177,17 @@ class CudaSteps:
         self.ctx.check(rc, 'mdb_dist_create')
         self.handle = h
         self.bulk_events = None
-        self._symm = None
 
     def close(self):
-        if self._symm is not None:
-            # peers may still have stores in flight into this rank's symmetric buffer (e.g. the release counter written
-            # from a peer's bulk stream): nobody unmaps before everybody has drained its streams
-            import torch
-            import torch.distributed as dist
-            torch.cuda.synchronize()
-            dist.barrier()
         if self.handle:
             self.ctx.lib.mdb_dist_destroy(self.handle)
             self.handle = None
-        self._symm = None
 
     def info(self):
         """The device-side status word of the current factorization (mdb_dist_info)."""
         v = ctypes.c_int(0)
         self.ctx.check(self.ctx.lib.mdb_dist_info(self.handle, ctypes.byref(v)), 'mdb_dist_info')
         return int(v.value)
-
-    # ---- experimental peer-store exchange (csrc/mdb_peer.cuh) ----
-    def enable_peer_stores(self):
-        """Allocates this rank's symmetric buffer, maps every rank's buffer into this process
-        (torch.distributed._symmetric_memory) and hands the pointers to the library.  Collective: every rank calls it.
-        Returns False (on every rank) when any rank could not set it up; the NCCL path then stays in place."""
-        import torch
-        import torch.distributed as dist
-        ok, ptrs, keep = 1, None, None
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-            elems = int(self.ctx.lib.mdb_dist_peer_buffer_elems(self.handle))
-            group = dist.group.WORLD
-            try:
-                symm_mem.enable_symm_mem_for_group(group.group_name)
-            except Exception:  # noqa: BLE001  (newer torch versions do not need it)
-                pass
-            t = symm_mem.empty(elems, dtype=torch.float64, device=torch.device('cuda', self.device))
-            t.zero_()
-            hdl = symm_mem.rendezvous(t, group)
-            ptrs = [int(x) for x in hdl.buffer_ptrs]
-            if len(ptrs) != self.world or ptrs[self.rank] != t.data_ptr():
-                raise RuntimeError('unexpected symmetric memory handle')
-            keep = (t, hdl)
-        except Exception as e:  # noqa: BLE001
-            ok = 0
-            if self.rank == 0:
-                import sys
-                print('[mdb200] peer stores unavailable ({}): staying with the NCCL broadcast'.format(e), file=sys.stderr)
-        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device('cuda', self.device))
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            return False
-        torch.cuda.synchronize()
-        arr = (ctypes.c_void_p * self.world)(*ptrs)
-        self.ctx.check(self.ctx.lib.mdb_dist_attach_peers(self.handle, arr), 'mdb_dist_attach_peers')
-        self._symm = keep
-        dist.barrier()
-        return True
-
-    def push_panel(self, k, slot, k_outer, oslot, outer_index, stream):
-        self._on(stream)
-        self.ctx.check(self.ctx.lib.mdb_dist_push_panel(self.handle, k, slot, k_outer, oslot, outer_index), 'mdb_dist_push_panel')
-
-    def wait_panel(self, k, stream):
-        self._on(stream)
-        self.ctx.check(self.ctx.lib.mdb_dist_wait_panel(self.handle, k), 'mdb_dist_wait_panel')
-
-    def release_outer(self, count, stream):
-        self._on(stream)
-        self.ctx.check(self.ctx.lib.mdb_dist_release_outer(self.handle, count), 'mdb_dist_release_outer')
 
     def _on(self, stream):
         self.ctx.set_stream(stream.stream.cuda_stream)
@@ -334,8 +244,8 @@ class CudaSteps:
 
     def finalize(self, stream, collective=True):
         """Finalises the local columns and returns the replicated vectors.  Raises on EVERY rank when any rank's
-        device-side status word is non-zero (a protocol time-out of the peer-store exchange is only seen by the
-        rank that waited): the word is all-reduced (min and max) before the local status is looked at."""
+        device-side status word is non-zero (a failing pivot is only seen by the rank that owns its panel): the word is
+        all-reduced (min and max) before the local status is looked at."""
         self._on(stream)
         n = self.n
         d, omega, delta = np.empty(n), np.empty(n), np.empty(n)
@@ -360,8 +270,8 @@ def check_status_all_ranks(info, device=None):
     if hi == 0 and lo == 0:
         return
     if lo < 0:
-        raise errors.NativeLibraryError('distributed factorization: panel exchange protocol error {} on some rank (a bounded '
-                                        'wait on a peer ran out); the factor is not valid'.format(lo))
+        raise errors.NativeLibraryError('distributed factorization: device-side status {} on some rank; the factor is not '
+                                        'valid'.format(lo))
     raise errors.NativeLibraryError('distributed factorization: pivot {} is not positive'.format(hi - 1))
 
 
@@ -395,15 +305,10 @@ def approximate_distributed(Ap_or_none, n, bounds_kwargs, p=None, generator=None
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, bounds_kwargs.get('min_diag_D'), bounds_kwargs.get('max_diag_D'),
                                        bounds_kwargs['min_abs_value_D'], bounds_kwargs['min_abs_value_L'],
                                        bounds_kwargs.get('min_diag_B'), bounds_kwargs.get('max_diag_B'))
-    peer = peer_stores_requested() and world > 1 and steps.enable_peer_stores()
     steps.set_bounds(bounds, p, main)
     torch.cuda.synchronize()
-    if peer:
-        dist.barrier()      # nobody stores into a peer that is still resetting its vectors
-    factorize(n, rank, world, steps, PeerComm() if peer else NcclComm(), main, bulk, lookahead=lookahead)
+    factorize(n, rank, world, steps, NcclComm(), main, bulk, lookahead=lookahead)
     torch.cuda.synchronize()
-    if peer:
-        dist.barrier()      # every rank's one-sided stores (release counters included) have landed before anyone goes on
     d, omega, delta, clamped = steps.finalize(main)
     return steps, d, omega, delta, clamped
 
@@ -703,8 +608,7 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None, peak_hbm_gbs
     st = CudaSteps(n, rank, world, device)
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, 0.015 * mu, 0.9 * mu, 0.015 * mu,
                                        float(np.finfo(np.float64).eps), None, 2 * mu)
-    peer = peer_stores_requested() and world > 1 and st.enable_peer_stores()
-    comm = PeerComm() if peer else NcclComm()
+    comm = NcclComm()
 
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
@@ -758,7 +662,7 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None, peak_hbm_gbs
         dsolve = dict(error='%s: %s' % (type(e).__name__, e))
     out = dict(ms_per_step=float(np.mean(times)), gpu_launches=int(launches), identity=ident,
                n_clamped=int(clamped.sum()), dist_solve=dsolve,
-               panel_exchange='peer-memory stores (MDB200_P2P=1, unicast)' if peer else 'NCCL broadcast')
+               panel_exchange='NCCL broadcast')
 
     # ---- roofline: one serialised pass (no lookahead, everything on the main stream), events per bulk update ----
     st.generate_f2(seed, mu, p, main)
@@ -807,9 +711,6 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None, peak_hbm_gbs
                 t0 = time.perf_counter()
                 st.set_local(host, main)                 # H2D of the slab (+ device copy into the working array)
                 st.set_bounds(bounds, p, main)
-                if peer:
-                    torch.cuda.synchronize()
-                    dist.barrier()
                 factorize(n, rank, world, st, comm, main, bulk, lookahead=True)
                 dv, ov, de, cl = st.finalize(main)       # D2H of d, omega, delta, clamped; L stays distributed on the GPUs
                 torch.cuda.synchronize()

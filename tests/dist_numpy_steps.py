@@ -162,30 +162,3 @@ class NumpySteps:
                 L[gc + 1:, lb * NB + c] = col
                 L[gc, lb * NB + c] = 1.0
         return L
-
-
-class OneSidedComm:
-    """Stand-in for distributed.PeerComm on CPU: same hooks (exchange_panel on the comm, release_outer on the steps),
-    the transfer itself is a gloo broadcast at the moment the owner would push.  Records the protocol."""
-
-    def __init__(self):
-        self.log = []
-
-    def exchange_panel(self, steps, k, slot, k_outer, oslot, outer_index, owner, stream):
-        import torch.distributed as dist
-        self.log.append(('exchange', k, outer_index, owner, max([0] + steps.released)))
-        dist.broadcast(steps.panel_tensor(slot, k), src=owner)
-
-        class Handle:
-            def wait(self_, s):
-                self.log.append(('wait', k))
-        return Handle()
-
-
-class OneSidedNumpySteps(NumpySteps):
-    def __init__(self, *a, **kw):
-        super().__init__(*a, **kw)
-        self.released = []
-
-    def release_outer(self, count, stream):
-        self.released.append(count)

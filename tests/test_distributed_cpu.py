@@ -81,52 +81,6 @@ def test_block_cyclic_loop_world2_gloo(tmp_path, lookahead, agg):
     assert np.all(np.abs(L - ref['L']) <= 1e-10 * np.maximum(1.0, np.abs(ref['L'])))
 
 
-def _worker_one_sided(rank, world, port, n, lookahead, agg, out_dir):
-    sys.path.insert(0, HERE)
-    sys.path.insert(0, os.path.dirname(HERE))
-    from dist_numpy_steps import OneSidedNumpySteps, OneSidedComm
-    os.environ['MASTER_ADDR'] = '127.0.0.1'
-    os.environ['MASTER_PORT'] = str(port)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
-    A, kw = workloads.shifted_goe(n, 31, 1.05)
-    p = orc.permutation_vector(A, kw['permutation'])
-    Ap = A[p[:, None], p[None, :]]
-    steps = OneSidedNumpySteps(n, rank, world, Ap, min_diag_D=kw['min_diag_D'], max_diag_D=kw['max_diag_D'],
-                               min_abs_value_D=kw['min_abs_value_D'], max_diag_B=kw['max_diag_B'], agg=agg)
-    comm = OneSidedComm()
-    md.factorize(n, rank, world, steps, comm, lookahead=lookahead)
-    np.savez(os.path.join(out_dir, f'r{rank}.npz'), d=steps.d, clamped=steps.clamped, log=np.array(repr(comm.log)),
-             released=np.array(steps.released, dtype=np.int64))
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-@pytest.mark.parametrize('lookahead', [True, False])
-def test_one_sided_exchange_hooks_world2_gloo(tmp_path, lookahead):
-    """The hooks of the experimental peer-store exchange (distributed.PeerComm / csrc/mdb_peer.cuh): every panel is
-    exchanged once with the running index of its outer block, operand buffers are released once per outer block that
-    has a bulk update, and when a panel of outer block O is pushed this rank has already released O - 1 outer blocks
-    (what the owner's flow control waits for on every peer) -- so the protocol cannot wait for itself."""
-    n, world, agg = 700, 2, 1      # 6 column blocks, outer blocks of one panel: the operand slots are reused 3 times
-    port = _free_port()
-    mp.spawn(_worker_one_sided, args=(world, port, n, lookahead, agg, str(tmp_path)), nprocs=world, join=True)
-    A, kw = workloads.shifted_goe(n, 31, 1.05)
-    ref = orc.approximate(A, **kw)
-    T = (n + md.NB - 1) // md.NB
-    for r in range(world):
-        z = np.load(os.path.join(str(tmp_path), f'r{r}.npz'))
-        np.testing.assert_array_equal(z['clamped'], ref['clamped'])
-        np.testing.assert_allclose(z['d'], ref['d'].astype(float), rtol=1e-10)
-        log = eval(str(z['log']))
-        ex = [e for e in log if e[0] == 'exchange']
-        assert [e[1] for e in ex] == list(range(T)) and [e[2] for e in ex] == list(range(T))   # agg = 1: outer index = k
-        assert all(e[3] == e[1] % world for e in ex)
-        assert sorted(e[1] for e in log if e[0] == 'wait') == list(range(T))
-        assert list(z['released']) == list(range(1, T))          # the last outer block has nothing beyond it
-        for e in ex:
-            assert e[4] >= e[2] - 1                              # flow control can be satisfied at push time
-
-
 def test_layout_helpers():
     assert md.local_blocks(400, 0, 2) == 2 and md.local_blocks(400, 1, 2) == 2
     assert md.local_blocks(300, 0, 2) == 2 and md.local_blocks(300, 1, 2) == 1

@@ -986,49 +986,18 @@ def test_distributed_factor_consumers_single_rank(matrix, n):
     fac.close()
 
 
-def test_peer_exchange_timeout_becomes_an_error_status(matrix):
-    """a bounded wait of the peer-store exchange that runs out must end in an error status, not in a
-    silently wrong factor.  One GPU plays rank 0 of 2 whose peer never pushes panel 1: mdb_dist_wait_panel times out
-    (~2 s), the status word becomes -1002, mdb_dist_finalize reports MDB_ERR_STATE."""
-    import torch
-    from matrix_decomposition_b200 import distributed as md, _native
-    n = 512
-    main, bulk = md._streams(torch.cuda.current_device())
-    steps = md.CudaSteps(n, 0, 2)
-    ctx, lib = steps.ctx, steps.ctx.lib
-    elems = int(lib.mdb_dist_peer_buffer_elems(steps.handle))
-    bufs = [torch.zeros(elems, dtype=torch.float64, device='cuda') for _ in range(2)]
-    arr = (ctypes.c_void_p * 2)(bufs[0].data_ptr(), bufs[1].data_ptr())
-    steps._on(main)
-    ctx.check(lib.mdb_dist_attach_peers(steps.handle, arr), 'mdb_dist_attach_peers')
-    steps._symm = None
-    A, kw = workloads.shifted_goe(n, 3, 1.05)
-    steps.set_matrix(A, main)
-    bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
-                                       float(np.finfo(float).eps), None, kw['max_diag_B'])
-    steps.set_bounds(bounds, None, main)
-    assert steps.info() == 0
-    steps.wait_panel(1, main)          # owner = rank 1, which does not exist here
-    torch.cuda.synchronize()
-    assert steps.info() == -1002
-    with pytest.raises(matrix.errors.NativeLibraryError, match='protocol error'):
-        steps.finalize(main, collective=False)
-    steps.close()
-
-
-@pytest.mark.parametrize('p2p', ['0', '1'])
-def test_two_gpu_block_cyclic_equals_single_gpu(p2p, tmp_path):
+def test_two_gpu_block_cyclic_equals_single_gpu(tmp_path):
     """Needs two GPUs (skipped on a single-GPU box; run with `gpurun --gpus 2`): tools/dist_check.py under torchrun --
-    the 1-D block-cyclic factorization with the NCCL panel broadcast (p2p = 0) and with the experimental peer-memory
-    stores (p2p = 1) must reproduce the single-GPU factor bit for bit (outer blocks of 1, 2 and 4 panels, with and
-    without lookahead) and satisfy the identity at a size with many outer blocks."""
+    the 1-D block-cyclic factorization with the NCCL panel broadcast must reproduce the single-GPU factor bit for bit
+    (outer blocks of 1, 2 and 4 panels, with and without lookahead) and satisfy the identity at a size with many outer
+    blocks."""
     import subprocess
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
-    env = dict(os.environ, MDB200_P2P=p2p, DIST_N='4096')
+    env = dict(os.environ, DIST_N='4096')
     env.pop('MDB200_DEVICE', None)
-    port = 29600 + int(p2p)
+    port = 29600
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
                         '--master-addr', '127.0.0.1', '--master-port', str(port),
                         os.path.join(REPO, 'tools', 'dist_check.py')], env=env, capture_output=True, text=True, timeout=300)
@@ -1042,4 +1011,4 @@ def test_two_gpu_block_cyclic_equals_single_gpu(p2p, tmp_path):
     big = out['bench_n4096_gpus2']
     assert big['identity'] <= 1e-12
     assert big['dist_solve']['residual_vs_original_matrix'] <= 1e-10
-    assert ('peer-memory' in big['panel_exchange']) == (p2p == '1')
+    assert big['panel_exchange'] == 'NCCL broadcast'
