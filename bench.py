@@ -43,12 +43,12 @@ UNIT = 'GFLOP/s'
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.jsonl);
                                # MEASURED_PEAKS.json holds only HBM and bf16 peaks
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the bulk kernel from one `ncu --set full` capture
-# (profiles/r01_ncu_summary.txt); None until captured for the current kernel
-NCU_TRAFFIC = 46.01e9   # bulk update part (b), grid 234240 tiles, 109.3 ms: read 30.94 GB + write 15.08 GB (profiles/r01b_ncu_summary.txt)
+# (round 2, the current kernel: profiles/r02_ncu_summary.txt)
+NCU_TRAFFIC = 46.04e9   # bulk update part (b), grid 234240 tiles, 109.3 ms: read 30.96 GB + write 15.08 GB
 NCU_TRAFFIC_NOTE = ('ncu --set full capture of the LARGEST bulk launch (part (b) of the first outer block, grid '
-                    '234240 tiles, 109.3 ms, DMMA pipe 95.4 % active): dram read 30.94 GB + write 15.08 GB vs '
+                    '234240 tiles, 109.3 ms, DMMA pipe 95.4 % active): dram read 30.96 GB + write 15.08 GB vs '
                     'algorithmic 31.7 GB (C triangle read + written 30.7 GB, operands 1.0 GB); the excess are '
-                    'operand re-reads that missed L2 (profiles/r01b_ncu_summary.txt)')
+                    'operand re-reads that missed L2 (hit rate 87 %; profiles/r02_ncu_summary.txt)')
 CPU_SAMPLE_N = 6144
 S_SHIFT = 1.05
 
@@ -321,11 +321,17 @@ def extra_permute(ctx, stream, n=65536):
                                                                         ctypes.c_void_p(dB), n, _native.DEVICE),
                                                  'mdb_permute_sym_f64'), reps=3)
         gbs = 16.0 * n * n / (ms * 1e-3) / 1e9
-        res[name] = dict(device_ms=ms, achieved=gbs, peak=hbm, unit='GB/s', frac=gbs / hbm)
+        moved = (32.0 if n > 8192 else 16.0) * n * n / (ms * 1e-3) / 1e9
+        res[name] = dict(device_ms=ms, achieved=gbs, peak=hbm, unit='GB/s', frac=gbs / hbm, moved_gbs=moved,
+                         moved_frac=moved / hbm)
     ctx.free(dA)
     ctx.free(dB)
-    return dict(n=n, algorithmic_bytes=16.0 * n * n, note='read + write of the full matrix; the event-timed region '
-                'includes the H2D copy of p (8 n bytes) and its validation on the host', **res)
+    return dict(n=n, algorithmic_bytes=16.0 * n * n,
+                note='achieved / frac: algorithmic bytes (read + write of the full matrix once) per second; above 8192 rows '
+                     'the permutation runs as two passes of "gather rows, transpose" (k_gather_rows_transpose) because a '
+                     'random p leaves a one-pass kernel with 8-byte gathers or scattered writes on one side (measured: '
+                     '61-169 ms at n = 65536, DESIGN.md 4), so 32 n^2 bytes cross HBM: moved_gbs / moved_frac.  The '
+                     'event-timed region includes the H2D copy of p (8 n bytes) and its validation on the host', **res)
 
 
 def extra_config5(ctx, stream, batch=512, n=512, seed=0):
