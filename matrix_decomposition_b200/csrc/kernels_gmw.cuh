@@ -16,9 +16,30 @@ struct GmwState {
   int phase;                    // 10 = phase 1, 15 = phase 1.5, 20 = phase 2   (GMW_SE.py:84, :100-110)
   int need_init;
   int use_abs, nondecreasing;
+  unsigned int init_done;       // blocks of k_gmw_init_decide that have contributed their maxima
 };
 
-// column k below the pivot -> cvec (contiguous), plus the reductions the decision needs.  One CTA.
+// phase 1 test (GMW_SE.py:100-104): keep d = a, or switch to phase 1.5 and ask for the trailing-matrix maxima
+// (one thread, at the end of k_gmw_reduce)
+__device__ __forceinline__ void gmw_phase(GmwState* st) {
+  if (st->phase == 10) {
+    const double a = st->a;
+    // np.all over an empty trailing matrix is True: m1 = m2 = +inf then
+    if (a >= st->min_diag_D && st->m1 >= st->min_d_next && st->m2 >= __dmul_rn(st->min_d_factor, a)) {
+      st->dk = a;
+    } else {
+      st->phase = 15;
+    }
+  }
+  if (st->phase == 15) {
+    st->need_init = 1;
+    st->max_diag_bits = 0ull;
+    st->max_off_bits = 0ull;
+  }
+  st->init_done = 0u;
+}
+
+// column k below the pivot -> cvec (contiguous), plus the reductions the decision needs and the phase test.  One CTA.
 __global__ void __launch_bounds__(1024) k_gmw_reduce(int64_t n, const double* __restrict__ W, int64_t ld, int64_t k,
                                                      double* __restrict__ cvec, GmwState* st) {
   __shared__ double s_cmax[32], s_m1[32], s_m2[32];
@@ -49,43 +70,15 @@ __global__ void __launch_bounds__(1024) k_gmw_reduce(int64_t n, const double* __
       m1 = fmin(m1, __shfl_xor_sync(0xffffffffu, m1, o));
       m2 = fmin(m2, __shfl_xor_sync(0xffffffffu, m2, o));
     }
-    if (l == 0) { st->a = a; st->cmax = cmax; st->m1 = m1; st->m2 = m2; }
-  }
-}
-
-// phase 1 test (GMW_SE.py:100-104): keep d = a, or switch to phase 1.5 and ask for the trailing-matrix maxima
-__global__ void k_gmw_phase(GmwState* st) {
-  if (st->phase == 10) {
-    const double a = st->a;
-    // np.all over an empty trailing matrix is True: m1 = m2 = +inf then
-    if (a >= st->min_diag_D && st->m1 >= st->min_d_next && st->m2 >= __dmul_rn(st->min_d_factor, a)) {
-      st->dk = a;
-    } else {
-      st->phase = 15;
+    if (l == 0) {
+      st->a = a; st->cmax = cmax; st->m1 = m1; st->m2 = m2;
+      gmw_phase(st);
     }
   }
-  if (st->phase == 15) {
-    st->need_init = 1;
-    st->max_diag_bits = 0ull;
-    st->max_off_bits = 0ull;
-  }
 }
 
-// max |diag| and max |strict lower| of the trailing matrix S[k+1:, k+1:] (GMW_SE.py:127-133); only when asked for
-__global__ void __launch_bounds__(256) k_gmw_init(int64_t n, const double* __restrict__ W, int64_t ld, int64_t k,
-                                                  GmwState* st) {
-  if (!st->need_init) return;
-  const int64_t i = k + 1 + blockIdx.x;
-  if (i >= n) return;
-  double moff = 0.0;
-  for (int64_t j = k + 1 + threadIdx.x; j < i; j += blockDim.x) moff = fmax(moff, fabs(W[i * ld + j]));
-  for (int o = 16; o > 0; o >>= 1) moff = fmax(moff, __shfl_xor_sync(0xffffffffu, moff, o));
-  if ((threadIdx.x & 31) == 0 && moff > 0.0) atomicMax(&st->max_off_bits, (unsigned long long)__double_as_longlong(moff));
-  if (threadIdx.x == 0) atomicMax(&st->max_diag_bits, (unsigned long long)__double_as_longlong(fabs(W[i * ld + i])));
-}
-
-// d_k (GMW_SE.py:106-117, :123-148), delta_k = d_k - a (:29)
-__global__ void k_gmw_decide(int64_t n, int64_t k, GmwState* st, double* __restrict__ d, double* __restrict__ delta) {
+// d_k (GMW_SE.py:106-117, :123-148), delta_k = d_k - a (:29).  One thread.
+__device__ __forceinline__ void gmw_decide(int64_t n, int64_t k, GmwState* st, double* __restrict__ d, double* __restrict__ delta) {
   const double eps = 2.220446049250313e-16;
   const int64_t m = n - k - 1;  // size of the trailing matrix
   if (st->need_init) {
@@ -117,6 +110,39 @@ __global__ void k_gmw_decide(int64_t n, int64_t k, GmwState* st, double* __restr
   }
   d[k] = dk;
   delta[k] = __dsub_rn(dk, a);
+}
+
+// One launch for the decision of column k: when phase 1.5 asked for them (once per factorization), max |diag| and
+// max |strict lower| of the trailing matrix S[k+1:, k+1:] (GMW_SE.py:127-133), one row per block, and the last block to
+// finish decides; otherwise block 0 decides at once and the others leave.  grid = max(n - k - 1, 1) blocks.
+__global__ void __launch_bounds__(256) k_gmw_init_decide(int64_t n, const double* __restrict__ W, int64_t ld, int64_t k,
+                                                         GmwState* st, double* __restrict__ d, double* __restrict__ delta) {
+  __shared__ bool s_last;
+  if (!st->need_init) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) gmw_decide(n, k, st, d, delta);
+    return;
+  }
+  const int64_t i = k + 1 + blockIdx.x;
+  if (i < n) {
+    double moff = 0.0;
+    for (int64_t j = k + 1 + threadIdx.x; j < i; j += blockDim.x) moff = fmax(moff, fabs(W[i * ld + j]));
+    for (int o = 16; o > 0; o >>= 1) moff = fmax(moff, __shfl_xor_sync(0xffffffffu, moff, o));
+    if ((threadIdx.x & 31) == 0 && moff > 0.0) atomicMax(&st->max_off_bits, (unsigned long long)__double_as_longlong(moff));
+    if (threadIdx.x == 0) atomicMax(&st->max_diag_bits, (unsigned long long)__double_as_longlong(fabs(W[i * ld + i])));
+  }
+  __syncthreads();   // this block's atomics have been issued
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&st->init_done, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    volatile GmwState* vs = st;   // the maxima were written by other blocks of this launch
+    st->max_off_bits = vs->max_off_bits;
+    st->max_diag_bits = vs->max_diag_bits;
+    gmw_decide(n, k, st, d, delta);
+  }
 }
 
 // S[i, j] -= c_i c_j / d_k  for i >= j > k  (A -= np.outer(c, c) / d[k], GMW_SE.py:31), 32 x 32 tiles of the lower triangle

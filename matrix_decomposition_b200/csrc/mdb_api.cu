@@ -1253,11 +1253,9 @@ extern "C" int mdb_gmw_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // `h` goes out of scope
     for (int64_t k = 0; k < n && e == cudaSuccess; ++k) {
       const int64_t m = n - k - 1;
-      k_gmw_reduce<<<1, 1024, 0, ctx->stream>>>(n, W, n, k, cvec, st);
-      k_gmw_phase<<<1, 1, 0, ctx->stream>>>(st);
-      if (m > 0) k_gmw_init<<<(unsigned)m, 256, 0, ctx->stream>>>(n, W, n, k, st);
-      k_gmw_decide<<<1, 1, 0, ctx->stream>>>(n, k, st, dd, dd + n);
-      ctx->launches += 4;
+      k_gmw_reduce<<<1, 1024, 0, ctx->stream>>>(n, W, n, k, cvec, st);   // + the phase test
+      k_gmw_init_decide<<<(unsigned)std::max<int64_t>(m, 1), 256, 0, ctx->stream>>>(n, W, n, k, st, dd, dd + n);
+      ctx->launches += 2;
       if (m > 0) {
         const unsigned t32 = (unsigned)((m + 31) / 32);
         k_gmw_rank1<<<dim3(t32, t32), 256, 0, ctx->stream>>>(n, W, n, k, cvec, st);
