@@ -117,7 +117,14 @@ __global__ void __launch_bounds__(256) k_dyn_select2(FactorDev F, int method, in
 // (Reimer.py:513-518 swaps the rows of L; the Schur complement and the original matrix must follow)
 __global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict__ W, int64_t ld, int64_t i,
                                                   const DynSel* __restrict__ sel, double* __restrict__ PX,
-                                                  double* __restrict__ PY, int64_t ldp, int kc) {
+                                                  double* __restrict__ PY, int64_t ldp, int kc,
+                                                  const long long* __restrict__ step) {
+  // step != null (replayed CUDA graph): the column index comes from device memory, sel points at the pair of slots
+  if (step) {
+    i = *step;
+    kc = (int)(i % MDB_NB);
+    sel += (i & 1);
+  }
   const int64_t js = sel->jstar;
   if (js == i) return;
   const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -152,7 +159,17 @@ __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, int
                                                     double* __restrict__ PX, double* __restrict__ PY, int64_t ldp,
                                                     int kc, DynCand* cand, unsigned* counter,
                                                     double* __restrict__ minB, double* __restrict__ maxB,
-                                                    int64_t* __restrict__ p, DynSel* __restrict__ sel_next) {
+                                                    int64_t* __restrict__ p, DynSel* __restrict__ sel_next,
+                                                    long long* __restrict__ step) {
+  // step != null (replayed CUDA graph): the column index comes from device memory and is advanced by the block that
+  // commits the next decision; sel / sel_next both point at the pair of slots; the grid is sized for the first column
+  // of the panel (blocks without rows only take part in the count)
+  if (step) {
+    i = *step;
+    kc = (int)(i % MDB_NB);
+    sel_next = const_cast<DynSel*>(sel) + ((i + 1) & 1);
+    sel += (i & 1);
+  }
   __shared__ double yi[MDB_NB];
   __shared__ double s_sum[MDB_DYN_ROWS];
   __shared__ DynCand sh[256];
@@ -220,6 +237,7 @@ __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, int
   if (tid == 0) {
     *counter = 0;
     dyn_commit(F, i + 1, c, minB, maxB, p, sel_next);
+    if (step) *step = i + 1;
   }
 }
 

@@ -1133,7 +1133,7 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
     cudaError_t e = dev_malloc(ctx, (void**)&minB, (size_t)n * 8);
     if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&maxB, (size_t)n * 8);
     if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&cand, (size_t)nb_max * sizeof(DynCand));
-    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&sel, 2 * sizeof(DynSel) + 16);
+    if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&sel, 2 * sizeof(DynSel) + 32);
     if (e == cudaSuccess && !f->p_dev) e = dev_malloc(ctx, (void**)&f->p_dev, (size_t)n * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(minB, mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(maxB, Mb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -1155,24 +1155,53 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
       // panels of NB columns: pending updates are applied on the fly inside a panel (k_dyn_column), the trailing
       // matrix gets one K = NB tensor-core update per panel
       const int64_t LDP = (int64_t)f->agg * NB;
+      // Every full panel but the last replays ONE captured CUDA graph of 128 x (swap, column) kernel nodes: the kernels
+      // read the column index from device memory (advanced by the column kernel), so the nodes are the same for every
+      // panel and the ~4 us gaps of 256 dependent stream launches per panel shrink to the graph's node-to-node latency.
+      long long* step = (long long*)((char*)(sel + 2) + 16);
+      cudaGraphExec_t gexec = nullptr;
+      const bool use_graph = n >= 3 * NB && !getenv("MDB200_DYN_NOGRAPH");
+      if (use_graph) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t ge = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+        if (ge == cudaSuccess) {
+          const unsigned gcol = (unsigned)((n - 2 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS);
+          for (int c = 0; c < NB; ++c) {
+            k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, -1, sel, f->PX, f->PY, LDP, 0, step);
+            k_dyn_column<<<gcol, 256, 0, ctx->stream>>>(F, method, -1, sel, f->PX, f->PY, LDP, 0, cand, counter, minB, maxB,
+                                                        f->p_dev, sel, step);
+          }
+          ge = cudaStreamEndCapture(ctx->stream, &graph);
+        }
+        if (ge == cudaSuccess) ge = cudaGraphInstantiate(&gexec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ge != cudaSuccess) { cudaGetLastError(); gexec = nullptr; }
+      }
       for (int64_t pb = 0; pb < n && !rc; pb += NB) {
         const int64_t pe = std::min<int64_t>(pb + NB, n);
-        for (int64_t i = pb; i < pe; ++i) {
-          const int64_t rem = n - i;
-          const int kc = (int)(i - pb);
-          DynSel* cur = sel + (i & 1);
-          if (i == 0) {  // later columns are selected by the column kernel of the step before
-            const int nblk = (int)((rem + 255) / 256);
-            k_dyn_select1<<<nblk, 256, 0, ctx->stream>>>(F, method, i, cand);
-            k_dyn_select2<<<1, 256, 0, ctx->stream>>>(F, method, i, nblk, cand, minB, maxB, f->p_dev, cur);
-            ctx->launches += 2;
-          }
-          k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, cur, f->PX, f->PY, LDP, kc);
-          ctx->launches += 1;
-          if (rem > 1) {
-            k_dyn_column<<<(unsigned)((rem - 1 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS), 256, 0, ctx->stream>>>(
-                F, method, i, cur, f->PX, f->PY, LDP, kc, cand, counter, minB, maxB, f->p_dev, sel + ((i + 1) & 1));
+        if (pb == 0) {  // the first column is selected here, later ones by the column kernel of the step before
+          const int nblk = (int)((n + 255) / 256);
+          k_dyn_select1<<<nblk, 256, 0, ctx->stream>>>(F, method, 0, cand);
+          k_dyn_select2<<<1, 256, 0, ctx->stream>>>(F, method, 0, nblk, cand, minB, maxB, f->p_dev, sel);
+          ctx->launches += 2;
+        }
+        if (gexec && pe < n && pe - pb == NB) {
+          const long long first = (long long)pb;
+          cudaMemcpyAsync(step, &first, sizeof(first), cudaMemcpyHostToDevice, ctx->stream);
+          cudaGraphLaunch(gexec, ctx->stream);
+          ctx->launches += 2 * NB;
+        } else {
+          for (int64_t i = pb; i < pe; ++i) {
+            const int64_t rem = n - i;
+            const int kc = (int)(i - pb);
+            DynSel* cur = sel + (i & 1);
+            k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, cur, f->PX, f->PY, LDP, kc, nullptr);
             ctx->launches += 1;
+            if (rem > 1) {
+              k_dyn_column<<<(unsigned)((rem - 1 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS), 256, 0, ctx->stream>>>(
+                  F, method, i, cur, f->PX, f->PY, LDP, kc, cand, counter, minB, maxB, f->p_dev, sel + ((i + 1) & 1), nullptr);
+              ctx->launches += 1;
+            }
           }
         }
         if (pe < n) {
@@ -1190,6 +1219,7 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
         }
       }
       cudaError_t e2 = cudaGetLastError();
+      if (gexec) { cudaStreamSynchronize(ctx->stream); cudaGraphExecDestroy(gexec); }
       if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(pfin.data(), f->p_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
       if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
       if (e2 != cudaSuccess) rc = mdb_fail(ctx, MDB_ERR_CUDA, "mdb_approximate_dynamic_f64: %s", cudaGetErrorString(e2));
