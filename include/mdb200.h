@@ -146,7 +146,9 @@ int mdb_approximate_batched_f64(mdb_ctx *ctx, int64_t batch, int64_t n, const do
 /* ---- device-resident factor objects (bench.py's HBM-resident leg, solve with a resident factor) ---- */
 int mdb_factor_create(mdb_ctx *ctx, int64_t n, int64_t batch, mdb_factor **out);
 int mdb_factor_destroy(mdb_factor *f);
-/* W = A[p][:, p], gamma = diag.  p may be NULL (identity).  a_loc: where A lives. */
+/* W = A[p][:, p], gamma = diag.  p may be NULL (identity).  a_loc: where A lives.  A is symmetric by contract
+ * (Reimer.py:476-686 reads A[j, i] and A[i, j] interchangeably): a HOST matrix is read through its upper triangle
+ * (row <= column) only, at every size; a DEVICE matrix must hold both triangles. */
 int mdb_factor_set_matrix(mdb_factor *f, const double *A, int64_t lda, const int64_t *p, int a_loc);
 /* Synthetic family F2 generated on the device: A = GOE(seed) + mu I, already permuted by p
  * (host, may be NULL).  mdb_generate_diag_f2 returns the diagonal so the host can argsort it. */

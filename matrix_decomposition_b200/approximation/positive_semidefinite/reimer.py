@@ -186,7 +186,9 @@ def decomposition(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, max_diag
     type `return_type` (default 'LDL') carrying the extra attributes `.omega` and `.delta`
     (R.py:810-812; indexed by ORIGINAL index, float128 like the reference's).  Additionally `.clamped`
     holds the boolean mask (by position) of the columns whose (d, omega) left the unclamped branch of
-    R.py:68.  `A` is never modified (`overwrite_A` only documents permission).
+    R.py:68.  `A` is never modified (`overwrite_A` only documents permission).  `A` is symmetric by contract (the
+    reference's loop reads A[j, i] and A[i, j] interchangeably): the static-permutation path reads it through its upper
+    triangle only, at every size, so a matrix that is not exactly symmetric gives size-independent results.
 
     The dynamic pivoting methods 'maximal_stability' (the default for permutation=None, R.py:415-416) and
     'minimal_difference' run as an unblocked right-looking factorization with a device-wide arg-min per

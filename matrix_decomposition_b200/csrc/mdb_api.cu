@@ -608,6 +608,7 @@ extern "C" int mdb_factor_set_matrix(mdb_factor* f, const double* A, int64_t lda
       }
     } else {
       rc = copy2d_async(ctx, staging, n, A, lda, f->batch * n, n, MDB_DEVICE, MDB_HOST);  // batch stride = n*lda
+      upper_only = 1;   // a host matrix is read through its upper triangle at EVERY size (the large ones upload nothing else)
     }
     if (rc) { cudaStreamSynchronize(ctx->stream); big_free(ctx, staging, staging_cap); return rc; }
     A_dev = staging;

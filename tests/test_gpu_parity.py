@@ -234,6 +234,23 @@ def test_randomized_configurations_against_oracle(matrix, orc):
     assert n_checked == 24
 
 
+def test_host_matrix_is_read_through_its_upper_triangle(matrix):
+    """symmetry is a contract, not something that is checked -- so that a matrix that is not exactly symmetric
+    gives the same result at every size, a host matrix is read through its upper triangle only (above 4096 rows nothing
+    else is uploaded).  Garbage below the diagonal must not change anything, for one matrix and for a batch."""
+    n = 300
+    A, kw = workloads.shifted_goe(n, 11, 1.05)
+    G = A.copy()
+    G[np.tril_indices(n, -1)] = np.random.default_rng(0).standard_normal(n * (n - 1) // 2)
+    psd = matrix.approximation.positive_semidefinite
+    a, g = psd.decomposition(A, **kw), psd.decomposition(G, **kw)
+    assert np.array_equal(a.p, g.p) and np.array_equal(a.clamped, g.clamped)
+    assert np.array_equal(np.asarray(a.d, dtype=float), np.asarray(g.d, dtype=float)) and np.array_equal(a.L, g.L)
+    b1 = psd.decomposition_batched(np.stack([A, A]), **kw)
+    b2 = psd.decomposition_batched(np.stack([A, G]), **kw)
+    assert np.array_equal(b1[1].L, b2[1].L) and np.array_equal(b1[0].L, a.L)
+
+
 def test_empty_matrix(matrix):
     dec = matrix.approximation.positive_semidefinite.decomposition(np.zeros((0, 0)), permutation='none')
     assert dec.n == 0 and dec.L.shape == (0, 0)
