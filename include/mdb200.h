@@ -194,6 +194,11 @@ int mdb_factor_psd_matrix(mdb_factor *f, const double *min_diag_B, const double 
  * numpy 2.x (GMW_SE.py:172), so there is nothing to pin them against. */
 int mdb_gmw_f64(mdb_ctx *ctx, int64_t n, const double *A, int64_t lda, int loc, int use_two_phases, int nondecreasing,
                 int use_abs, double mu, double min_diag_D, double *d_out, double *delta_out);
+/* The SE family of the same file (GMW_SE.py:155-194; SE_90 / SE_99 / SE_T1, SE_T2 = SE_99 at :374-558): same driver and
+ * arguments, d chosen from the 1-norm of the column, tau * max |diag| and a 2 x 2 eigenvalue step for the last two
+ * columns. */
+int mdb_se_f64(mdb_ctx *ctx, int64_t n, const double *A, int64_t lda, int loc, int use_two_phases, int nondecreasing,
+               int use_abs, double mu, double min_diag_D, double *d_out, double *delta_out);
 
 /* ---- introspection / unit-test hooks (used by tests/ and bench.py, not by the drop-in path) ----
  * mdb_factor_device_ptr: which = 0 W, 1 gamma, 2 alpha, 3 beta, 4 rowmax, 5 d, 6 omega, 7 delta (device addresses

@@ -88,6 +88,7 @@ SIGNATURES = {
     'mdb_generate_f2': (_int, [_vp, _i64, _u64, _dbl, _vp, _i64]),
     'mdb_factor_run': (_int, [_vp, ctypes.POINTER(Bounds)]),
     'mdb_gmw_f64': (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _dbl, _dbl, _vp, _vp]),
+    'mdb_se_f64': (_int, [_vp, _i64, _vp, _i64, _int, _int, _int, _int, _dbl, _dbl, _vp, _vp]),
     'mdb_factor_psd_matrix': (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _int]),
     'mdb_factor_get': (_int, [_vp, _int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     'mdb_factor_upload': (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _pp]),

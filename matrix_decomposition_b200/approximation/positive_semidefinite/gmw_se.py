@@ -1,14 +1,16 @@
-"""GMW family of modified Cholesky approximations: GMW_81, GMW_T1, GMW_T2.
+"""GMW and SE families of modified Cholesky approximations: GMW_81, GMW_T1, GMW_T2, SE_90, SE_99, SE_T1, SE_T2.
 
 Host-side mirror of matrix/approximation/positive_semidefinite/GMW_SE.py of the reference (same function names,
 arguments and return value: the positive definite approximation B of A).  The O(n^3) part -- the modified LDL^T
-without pivoting in which d_k is chosen from |c|_inf of the current column, GMW_SE.py:6-35, :95-148 -- runs on the
-device (mdb_gmw_f64); B = A + diag(delta) and the optional rescaling of the diagonal (GMW_SE.py:43-62) are O(n^2)
-numpy operations here.
+without pivoting in which d_k is chosen from |c|_inf (GMW, GMW_SE.py:121-152) or |c|_1 and a 2 x 2 eigenvalue step for
+the last two columns (SE, GMW_SE.py:155-194) of the current column, GMW_SE.py:6-35, :95-118 -- runs on the device
+(mdb_gmw_f64 / mdb_se_f64); B = A + diag(delta) and the optional rescaling of the diagonal (GMW_SE.py:43-62) are
+O(n^2) numpy operations here.
 
-The SE family of the same file (SE_90, SE_99, SE_T1, SE_T2) is not provided: the reference's own functions raise
-ValueError with numpy 2.x (GMW_SE.py:172 builds np.array([[a, c], [c, A]]) from array-valued c and A), so their
-results cannot be pinned; calling them here raises NotImplementedError.
+The reference's own SE_* functions raise ValueError with numpy >= 1.25 (GMW_SE.py:180 builds
+np.array([[a, c], [c, A]]) from a length-1 vector c and a 1 x 1 matrix A, which older numpy versions converted to
+scalars); the golden vectors these functions are tested against were generated from the reference with exactly that
+conversion restored (tests/golden/generate_se_goldens.py).
 """
 import math
 
@@ -20,7 +22,7 @@ __all__ = ['GMW_81', 'GMW_T1', 'GMW_T2', 'SE_90', 'SE_99', 'SE_T1', 'SE_T2']
 
 
 def _gmw(A, min_diag_B, max_diag_B, min_diag_D, overwrite_A, use_two_phases, nondecreasing_startegy, use_abs,
-         revisited_version_mu):
+         revisited_version_mu, family='gmw'):
     A = np.asarray(A)                                                   # GMW_SE.py:69-72
     if A.ndim != 2 or A.shape[0] != A.shape[1]:
         raise errors.MatrixNotSquareError(A)
@@ -36,9 +38,10 @@ def _gmw(A, min_diag_B, max_diag_B, min_diag_D, overwrite_A, use_two_phases, non
     delta = np.empty(n)
     ctx = _native.context()
     mu = math.nan if revisited_version_mu is None else float(revisited_version_mu)
-    rc = ctx.lib.mdb_gmw_f64(ctx.handle, n, _native.ptr(A64), n, _native.HOST, int(use_two_phases), int(nondecreasing_startegy),
-                             int(use_abs), mu, float(min_diag_D), _native.ptr(d), _native.ptr(delta))
-    ctx.check(rc, 'mdb_gmw_f64')
+    fn = ctx.lib.mdb_se_f64 if family == 'se' else ctx.lib.mdb_gmw_f64
+    rc = fn(ctx.handle, n, _native.ptr(A64), n, _native.HOST, int(use_two_phases), int(nondecreasing_startegy),
+            int(use_abs), mu, float(min_diag_D), _native.ptr(d), _native.ptr(delta))
+    ctx.check(rc, 'mdb_se_f64' if family == 'se' else 'mdb_gmw_f64')
     # _modified_A, GMW_SE.py:43-62
     B = A if overwrite_A and A.dtype == np.float64 else A64.copy()
     B[np.diag_indices(n)] += delta
@@ -72,16 +75,22 @@ def GMW_T2(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, overwrite_A=Fal
                 use_abs=False, revisited_version_mu=0.75)
 
 
-def _se_unavailable(name):
-    def fn(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, overwrite_A=False):
-        raise NotImplementedError(
-            name + ' (GMW_SE.py:155-194) is not provided: the reference implementation itself raises ValueError '
-            'with numpy 2.x (GMW_SE.py:172), so its results cannot be pinned.')
-    fn.__name__ = name
-    return fn
+def SE_90(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, overwrite_A=False):
+    """Positive definite approximation of `A` by the algorithm of Schnabel and Eskow 1990 (GMW_SE.py:374-430)."""
+    return _gmw(A, min_diag_B, max_diag_B, min_diag_D, overwrite_A, use_two_phases=True, nondecreasing_startegy=True,
+                use_abs=False, revisited_version_mu=None, family='se')
 
 
-SE_90 = _se_unavailable('SE_90')
-SE_99 = _se_unavailable('SE_99')
-SE_T1 = _se_unavailable('SE_T1')
-SE_T2 = _se_unavailable('SE_T2')
+def SE_99(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, overwrite_A=False):
+    """The revised algorithm of Schnabel and Eskow 1999 (GMW_SE.py:433-493)."""
+    return _gmw(A, min_diag_B, max_diag_B, min_diag_D, overwrite_A, use_two_phases=True, nondecreasing_startegy=True,
+                use_abs=False, revisited_version_mu=0.1, family='se')
+
+
+def SE_T1(A, min_diag_B=None, max_diag_B=None, min_diag_D=None, overwrite_A=False):
+    """SE-I of Fang and O'Leary 2008 (GMW_SE.py:496-555)."""
+    return _gmw(A, min_diag_B, max_diag_B, min_diag_D, overwrite_A, use_two_phases=True, nondecreasing_startegy=False,
+                use_abs=True, revisited_version_mu=0.1, family='se')
+
+
+SE_T2 = SE_99   # GMW_SE.py:558

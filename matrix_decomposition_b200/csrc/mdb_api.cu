@@ -1244,9 +1244,24 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
 
 // GMW family (GMW_SE.py:6-35, :67-152): d and delta of the modified LDL^T without pivoting; B = A + diag(delta) and
 // the optional diagonal rescaling (:43-62) are O(n^2) and stay with the caller.
+static int gmw_family_run(mdb_ctx* ctx, int family, int64_t n, const double* A, int64_t lda, int loc, int use_two_phases,
+                          int nondecreasing, int use_abs, double mu, double min_diag_D, double* d_out, double* delta_out);
+
 extern "C" int mdb_gmw_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda, int loc, int use_two_phases,
                            int nondecreasing, int use_abs, double mu, double min_diag_D, double* d_out,
                            double* delta_out) {
+  return gmw_family_run(ctx, 0, n, A, lda, loc, use_two_phases, nondecreasing, use_abs, mu, min_diag_D, d_out, delta_out);
+}
+
+// SE family (GMW_SE.py:155-194, :374-558): the same driver with the choose_d of _SE
+extern "C" int mdb_se_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda, int loc, int use_two_phases,
+                          int nondecreasing, int use_abs, double mu, double min_diag_D, double* d_out,
+                          double* delta_out) {
+  return gmw_family_run(ctx, 1, n, A, lda, loc, use_two_phases, nondecreasing, use_abs, mu, min_diag_D, d_out, delta_out);
+}
+
+static int gmw_family_run(mdb_ctx* ctx, int family, int64_t n, const double* A, int64_t lda, int loc, int use_two_phases,
+                          int nondecreasing, int use_abs, double mu, double min_diag_D, double* d_out, double* delta_out) {
   if (!ctx) return MDB_ERR_INVALID;
   MDB_CHECK(ctx, n >= 0 && (n == 0 || (A && lda >= n)), "mdb_gmw_f64: bad matrix");
   MDB_CHECK(ctx, d_out && delta_out, "mdb_gmw_f64: null output");
@@ -1268,6 +1283,12 @@ extern "C" int mdb_gmw_f64(mdb_ctx* ctx, int64_t n, const double* A, int64_t lda
     h.phase = use_two_phases ? 10 : 15;                       // :84
     h.min_diag_D = min_diag_D;
     h.use_abs = use_abs; h.nondecreasing = nondecreasing;
+    h.family = family;
+    {
+      const double eps = 2.220446049250313e-16;
+      h.tau = pow(eps, isnan(mu) ? 1.0 / 3.0 : 2.0 / 3.0);            // GMW_SE.py:158-161
+      h.eps13 = pow(eps, 1.0 / 3.0);
+    }
     if (!isnan(mu)) {                                         // :87-90: needs max |diag A|, a host-side pass over n values
       std::vector<double> diag((size_t)n);
       e = cudaMemcpy2DAsync(diag.data(), 8, W, (size_t)(n + 1) * 8, 8, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);

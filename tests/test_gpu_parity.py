@@ -509,8 +509,40 @@ def test_gmw_family_against_oracle_and_properties(matrix):
         np.testing.assert_allclose(getattr(aps, fn)(S), S, rtol=0, atol=1e-12)
     with pytest.raises(matrix.errors.MatrixNotSquareError):
         aps.GMW_81(np.ones((3, 4)))
-    with pytest.raises(NotImplementedError):
-        aps.SE_99(np.eye(3))
+
+
+def test_se_family_against_reference_goldens_and_oracle(matrix):
+    """SE_90 / SE_99 / SE_T1 (SE_T2 = SE_99) on the device against the 120 golden cases of the reference
+    (tests/golden/se.npz, see generate_se_goldens.py for how the reference was run) and, at sizes the goldens do not
+    reach, against the oracle.  Tolerance 1e-10 relative to max |B|: the column 1-norm is a tree sum here and numpy's
+    pairwise sum there, the 2 x 2 eigenvalues are a closed form here and LAPACK there."""
+    from oracle import gmw_oracle
+    z = load_golden('se.npz')
+    manifest = json.loads(str(z['manifest']))
+    aps = matrix.approximation.positive_semidefinite
+    for m in manifest:
+        A = z[m['matrix'] + '/A']
+        kw = {k: (np.asarray(v) if isinstance(v, list) else v) for k, v in m['kwargs'].items()}
+        A0 = A.copy()
+        B = getattr(aps, m['fn'])(A, **kw)
+        assert np.array_equal(A, A0)
+        ref = z[m['key'] + '/B']
+        np.testing.assert_allclose(B, ref, rtol=TOL, atol=TOL * np.abs(ref).max(), err_msg=m['key'])
+    rng = np.random.default_rng(12)
+    for n in (5, 257, 700):
+        g = rng.standard_normal((n, n))
+        A = (g + g.T) / 2
+        for fn in ('SE_90', 'SE_99', 'SE_T1', 'SE_T2'):
+            B = getattr(aps, fn)(A)
+            ref = gmw_oracle.approximate(A, fn)
+            np.testing.assert_allclose(B, ref, rtol=TOL, atol=TOL * max(1.0, np.abs(ref).max()))
+            off = ~np.eye(n, dtype=bool)
+            assert np.array_equal(B[off], A[off])                      # only the diagonal is modified
+            assert np.all(B.diagonal() >= A.diagonal())
+            assert np.linalg.eigvalsh(B).min() > 0                     # positive definite
+    S = workloads.lowrank_plus_diag(300, 2)                           # already positive definite: unchanged
+    for fn in ('SE_90', 'SE_99', 'SE_T1'):
+        np.testing.assert_allclose(getattr(aps, fn)(S), S, rtol=0, atol=1e-12)
 
 
 # ---------------------------------------------------------------------------------------------

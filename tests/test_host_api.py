@@ -192,8 +192,8 @@ def test_constants_and_facade_names():
 
 
 def test_gmw_family_host_side_contract():
-    """GMW_SE.py surface: argument errors are raised on the host before any device work; the SE half is declared
-    unavailable (the reference's own SE_* raise ValueError with numpy 2.x, GMW_SE.py:172)."""
+    """GMW_SE.py surface: argument errors are raised on the host before any device work; SE_T2 is SE_99
+    (GMW_SE.py:558)."""
     aps = matrix.approximation.positive_semidefinite
     for name in ('GMW_81', 'GMW_T1', 'GMW_T2', 'SE_90', 'SE_99', 'SE_T1', 'SE_T2'):
         assert callable(getattr(aps, name))
@@ -203,5 +203,8 @@ def test_gmw_family_host_side_contract():
         aps.GMW_81(np.eye(3), min_diag_D=0.0)
     with pytest.raises(ValueError):
         aps.GMW_T2(np.eye(3) * 1j)
-    with pytest.raises(NotImplementedError):
-        aps.SE_T2(np.eye(3))
+    assert aps.SE_T2 is aps.SE_99
+    with pytest.raises(matrix.errors.MatrixNotSquareError):
+        aps.SE_90(np.ones((2, 3)))
+    with pytest.raises(ValueError):
+        aps.SE_T1(np.eye(3), min_diag_D=-1.0)

@@ -239,3 +239,21 @@ def test_gmw_oracle_against_reference_goldens():
         kw = {k: (np.asarray(v) if isinstance(v, list) else v) for k, v in m['kwargs'].items()}
         B = gmw_oracle.approximate(A, m['fn'], **kw)
         np.testing.assert_array_equal(B, z[m['key'] + '/B'], err_msg=m['key'])
+
+
+def test_se_oracle_against_reference_goldens():
+    """The SE half of oracle/gmw_oracle.py on the 120 cases of tests/golden/se.npz (SE_90 / SE_99 / SE_T1 x bounds x
+    matrix families, n = 1 ... 96), produced by the reference with the size-1-array -> scalar conversion of older numpy
+    restored at GMW_SE.py:180 (tests/golden/generate_se_goldens.py): bit for bit.  SE_T2 is SE_99 (GMW_SE.py:558)."""
+    import json
+    from oracle import gmw_oracle
+    z = load_golden('se.npz')
+    manifest = json.loads(str(z['manifest']))
+    assert len(manifest) == 120 and all(m['ok'] for m in manifest)
+    for m in manifest:
+        A = z[m['matrix'] + '/A']
+        kw = {k: (np.asarray(v) if isinstance(v, list) else v) for k, v in m['kwargs'].items()}
+        B = gmw_oracle.approximate(A, m['fn'], **kw)
+        np.testing.assert_array_equal(B, z[m['key'] + '/B'], err_msg=m['key'])
+        if m['fn'] == 'SE_99':
+            np.testing.assert_array_equal(gmw_oracle.approximate(A, 'SE_T2', **kw), B)
