@@ -238,6 +238,10 @@ int mdb_dist_set_matrix(mdb_dist *s, const double *Ap, int64_t ld);
 /* this rank's slab from a buffer that already has the slab layout (n x ld_src, local column lc at [i * ld_src + lc];
  * loc = MDB_HOST / MDB_DEVICE): the end-to-end entry when every rank holds its own columns on the host */
 int mdb_dist_set_local(mdb_dist *s, const double *A_loc_src, int64_t ld_src, int loc);
+/* The same, transferring per column block only the rows from its diagonal block downwards -- everything the
+ * factorization, the solve and the gather read, half of the bytes.  A_loc is zero elsewhere afterwards, so checks that
+ * multiply by the whole original slab (the identity / residual helpers of distributed.py) are not available. */
+int mdb_dist_set_local_lower(mdb_dist *s, const double *A_loc_src, int64_t ld_src, int loc);
 /* bounds as in mdb_factor_run; p (host, may be NULL) maps position -> original index for vector B bounds.
  * Resets alpha / beta / rowmax. */
 int mdb_dist_set_bounds(mdb_dist *s, const mdb_bounds *bounds, const int64_t *p);

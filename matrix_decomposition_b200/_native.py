@@ -106,6 +106,7 @@ SIGNATURES = {
     'mdb_dist_generate_f2': (_int, [_vp, _u64, _dbl, _vp]),
     'mdb_dist_set_matrix': (_int, [_vp, _vp, _i64]),
     'mdb_dist_set_local': (_int, [_vp, _vp, _i64, _int]),
+    'mdb_dist_set_local_lower': (_int, [_vp, _vp, _i64, _int]),
     'mdb_dist_set_bounds': (_int, [_vp, ctypes.POINTER(Bounds), _vp]),
     'mdb_dist_outer_width': (_i64, [_vp, _i64]),
     'mdb_dist_factor_panel': (_int, [_vp, _i64, _int, _i64, _int]),

@@ -183,16 +183,37 @@ extern "C" int mdb_dist_set_matrix(mdb_dist* s, const double* Ap, int64_t ld) {
 
 // this rank's column slab from a host (or device) buffer that already has the slab layout: A_loc_src is n x ld_src
 // with local column lc at A_loc_src[i * ld_src + lc]  (the reverse of reading S_loc after mdb_dist_finalize)
-extern "C" int mdb_dist_set_local(mdb_dist* s, const double* A_loc_src, int64_t ld_src, int loc) {
+static int dist_set_local(mdb_dist* s, const double* A_loc_src, int64_t ld_src, int loc, bool lower_only) {
   if (!s || !A_loc_src) return MDB_ERR_INVALID;
   mdb_ctx* ctx = s->ctx;
   MDB_CHECK(ctx, ld_src >= s->ld, "mdb_dist_set_local: ld_src < local columns");
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
-  int rc = copy2d_async(ctx, s->A, s->ld, A_loc_src, ld_src, s->n, s->ld, MDB_DEVICE, loc);
+  int rc = MDB_OK;
+  if (!lower_only) {
+    rc = copy2d_async(ctx, s->A, s->ld, A_loc_src, ld_src, s->n, s->ld, MDB_DEVICE, loc);
+  } else {
+    // Per column block only the rows from its own diagonal block downwards are ever read by the factorization (the
+    // diagonal block with both its triangles, the rows below it; the part above belongs to finished rows of L): that
+    // is all that crosses PCIe -- half of the slab.  The rest of A_loc is zero afterwards.
+    MDB_CUDA(ctx, cudaMemsetAsync(s->A, 0, (size_t)s->n * s->ld * 8, ctx->stream));
+    for (int64_t lb = 0; lb < s->nblk_loc && !rc; ++lb) {
+      const int64_t gc0 = (lb * s->world + s->rank) * NB;
+      const int64_t w = std::min<int64_t>(NB, s->n - gc0);
+      rc = copy2d_async(ctx, s->A + gc0 * s->ld + lb * NB, s->ld, A_loc_src + gc0 * ld_src + lb * NB, ld_src, s->n - gc0, w,
+                        MDB_DEVICE, loc);
+    }
+  }
   if (!rc) rc = dist_after_matrix(s);
   if (rc) return rc;
   MDB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MDB_OK;
+}
+
+extern "C" int mdb_dist_set_local(mdb_dist* s, const double* A_loc_src, int64_t ld_src, int loc) {
+  return dist_set_local(s, A_loc_src, ld_src, loc, false);
+}
+extern "C" int mdb_dist_set_local_lower(mdb_dist* s, const double* A_loc_src, int64_t ld_src, int loc) {
+  return dist_set_local(s, A_loc_src, ld_src, loc, true);
 }
 
 extern "C" int mdb_dist_set_bounds(mdb_dist* s, const mdb_bounds* bnd, const int64_t* p) {

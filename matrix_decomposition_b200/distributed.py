@@ -235,12 +235,14 @@ class CudaSteps:
             e1.record(stream.stream)
             self.bulk_events.append((e0, e1))
 
-    def set_local(self, A_loc_host, stream):
-        """This rank's column slab from a host array in slab layout (n x ld_loc)."""
+    def set_local(self, A_loc_host, stream, lower_only=False):
+        """This rank's column slab from a host array in slab layout (n x ld_loc).  lower_only: transfer per column block
+        only the rows from its diagonal block downwards -- all the factorization, the solve and the gather read, half of
+        the bytes; the identity / residual helpers below, which multiply by the whole original slab, then do not apply."""
         self._on(stream)
         assert A_loc_host.shape == (self.n, self.ld) and A_loc_host.dtype == np.float64 and A_loc_host.flags.c_contiguous
-        self.ctx.check(self.ctx.lib.mdb_dist_set_local(self.handle, self._native.ptr(A_loc_host), self.ld, self._native.HOST),
-                       'mdb_dist_set_local')
+        fn = self.ctx.lib.mdb_dist_set_local_lower if lower_only else self.ctx.lib.mdb_dist_set_local
+        self.ctx.check(fn(self.handle, self._native.ptr(A_loc_host), self.ld, self._native.HOST), 'mdb_dist_set_local')
 
     def finalize(self, stream, collective=True):
         """Finalises the local columns and returns the replicated vectors.  Raises on EVERY rank when any rank's
@@ -709,7 +711,7 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None, peak_hbm_gbs
                 torch.cuda.synchronize()
                 dist.barrier()
                 t0 = time.perf_counter()
-                st.set_local(host, main)                 # H2D of the slab (+ device copy into the working array)
+                st.set_local(host, main, lower_only=True)   # H2D of the rows the factorization reads (+ device copy)
                 st.set_bounds(bounds, p, main)
                 factorize(n, rank, world, st, comm, main, bulk, lookahead=True)
                 dv, ov, de, cl = st.finalize(main)       # D2H of d, omega, delta, clamped; L stays distributed on the GPUs
@@ -720,7 +722,10 @@ def bench_f2(n, s, steps, warmup, seed, e2e=True, peak_tflops=None, peak_hbm_gbs
             _native.free_pinned(host)
             sec = float(np.mean(e2e_times))
             out['e2e'] = dict(value=n ** 3 / 3 / sec / 1e9, unit='GFLOP/s',
-                              h2d_bytes_per_step=int(sum(n * local_cols(n, r, world) * 8 for r in range(world))),
+                              h2d_bytes_per_step=int(sum((n - g * NB) * min(NB, n - g * NB) * 8 for g in range((n + NB - 1) // NB))),
+                              h2d_note='per column block only the rows from its diagonal block downwards cross PCIe (the host '
+                                       'slabs hold n x local columns = {} bytes in total)'.format(
+                                           int(sum(n * local_cols(n, r, world) * 8 for r in range(world)))),
                               d2h_bytes_per_step=int(world * (3 * n * 8 + n)), seconds_per_step=sec, steps=1,
                               call='distributed.CudaSteps.set_local (pinned host column slabs) + factorize + finalize; '
                                    'L stays distributed on the devices (SURVEY 8e), the vectors d/omega/delta/clamped '

@@ -1,14 +1,11 @@
 set -x
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "two_gpu" > gpurun_out/r2_pytest_2gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest_2gpu.log
+tail -3 gpurun_out/r2_pytest_2gpu.log
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err; echo "bench rc=$?"
-tail -2 gpurun_out/r2_bench_n8.err
-MDB200_P2P=1 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 2 --warmup 1 > gpurun_out/r2_bench_n8_p2p.json 2> gpurun_out/r2_bench_n8_p2p.err; echo "bench p2p rc=$?"
-tail -2 gpurun_out/r2_bench_n8_p2p.err
+tail -2 gpurun_out/r2_bench_n8.err | cut -c1-300
 python - <<'PY'
 import json
-for f in ('gpurun_out/r2_bench_n8.json','gpurun_out/r2_bench_n8_p2p.json'):
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f, d['value'], d['ms_per_step'], d['config'].get('frac_of_fp64_dmma_peak'), d['e2e'].get('value'), d['config']['workload'][-60:])
-    except Exception as e: print(f, 'ERR', e)
+d=json.loads(open('gpurun_out/r2_bench_n8.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['config'].get('frac_of_fp64_dmma_peak'), d['e2e'], d['parity']['ok'])
 PY
