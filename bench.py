@@ -543,7 +543,9 @@ def run_e2e(ctx, n, seed, mu, p, bounds, args):
     # ---- the public Python call on a PAGEABLE numpy array (what north_star's drop-in user does) ----
     e2e_numpy = None
     need = 1.15 * n * n * 8
-    if _mem_available_bytes() > need + (8 << 30):
+    if os.environ.get('BENCH_SKIP_NUMPY'):
+        e2e_numpy = dict(skipped='BENCH_SKIP_NUMPY set')
+    elif _mem_available_bytes() > need + (8 << 30):
         import matrix_decomposition_b200 as matrix
         An = np.empty((n, n))
         np.copyto(An, A)

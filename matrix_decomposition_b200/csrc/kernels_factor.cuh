@@ -1163,7 +1163,11 @@ __global__ void __launch_bounds__(MDB_PANEL_THREADS) k_panel_gemm(FactorDev F, i
 __global__ void __launch_bounds__(256) k_finalize(int64_t n, double* __restrict__ W, int64_t ldw, int64_t sW,
                                                   const double* __restrict__ d, const double* __restrict__ omega,
                                                   int64_t sVec, double mavL, int out_type, double* __restrict__ out,
-                                                  int64_t ldo, int64_t sOut, int64_t row0) {
+                                                  int64_t ldo, int64_t sOut, int64_t row0,
+                                                  uint8_t* __restrict__ changed = nullptr, int64_t changed_cols = 0) {
+  // changed (optional): changed[i] = 1 when an entry of row i left of column changed_cols differs from the unscaled
+  // value that was there (omega_i != 1 or an entry lost to the threshold) -- the one-shot call ships those columns of
+  // the late rows before the rows are final and must send such rows again (mdb_factor_run).
   const int64_t b = blockIdx.z;
   const int64_t i = row0 + blockIdx.x;   // rows [row0, row0 + gridDim.x)
   const double* Wrow = W + b * sW + i * ldw;
@@ -1177,8 +1181,10 @@ __global__ void __launch_bounds__(256) k_finalize(int64_t n, double* __restrict_
     if (j < n) {
       double v;
       if (j < i) {
-        v = w * Wrow[j];
+        const double lu = Wrow[j];
+        v = w * lu;
         if (w == 0 || fabs(v) < mavL) v = 0;
+        if (changed && j < changed_cols && !(v == lu)) changed[i] = 1;
         if (out_type == MDB_TYPE_LL) v *= sqrt(db[j]);
       } else if (j == i) {
         v = (out_type == MDB_TYPE_LDL) ? 1.0 : (out_type == MDB_TYPE_LL ? sqrt(db[i]) : db[i]);

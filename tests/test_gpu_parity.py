@@ -764,6 +764,38 @@ def test_permute_symmetric_bit_exact(matrix):
             assert np.array_equal(B, A[p[:, None], p[None, :]])
 
 
+@pytest.mark.parametrize('shift,rt', [(1.05, 'LDL'), (0.9, 'LDL'), (0.9, 'LDL_compressed')])
+def test_one_shot_early_shipment_of_late_rows(matrix, shift, rt, monkeypatch):
+    """Large one-shot calls ship the columns left of the last quarter of the rows before those rows are final (unscaled
+    values, equal to L unless omega != 1 or an entry is lost to the threshold) and send the rows whose early part turned
+    out different again (mdb_factor_run, k_finalize's `changed` flags).  Forced on at n = 4300 (MDB200_TAIL_MIN): with
+    s = 1.05 every omega is 1 (nothing is re-sent), with s = 0.9 rows are shrunk (omega < 1) and must be re-sent; the
+    streamed L must equal the factor that stayed on the device, bit for bit."""
+    from matrix_decomposition_b200 import _native
+    monkeypatch.setenv('MDB200_TAIL_MIN', '1024')
+    ctx = _native.context()
+    lib = ctx.lib
+    n = 4300
+    A, kw = workloads.shifted_goe(n, 78, shift)
+    p = np.argsort(-A.diagonal()).astype(np.int64)
+    bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
+                                       float(np.finfo(float).eps), None, kw['max_diag_B'])
+    L = ctx.pinned_array((n, n))
+    L[:] = np.nan
+    d, om, de = np.empty(n), np.empty(n), np.empty(n)
+    cl = np.zeros(n, dtype=np.uint8)
+    h = ctypes.c_void_p()
+    P = _native.ptr
+    ctx.check(lib.mdb_approximate_f64(ctx.handle, n, P(A), n, P(p), ctypes.byref(bounds), _native.TYPE_CODES[rt], P(L), n,
+                                      P(d), P(om), P(de), P(cl), _native.HOST, ctypes.byref(h)), 'one-shot')
+    resident = _native.Factor(ctx, h).download(n, _native.TYPE_CODES[rt])
+    same = np.array_equal(L, resident)
+    shrunk = int(np.count_nonzero(om[p][n - n // 4:] != 1.0))
+    _native.free_pinned(L)
+    assert same
+    assert (shrunk == 0) if shift > 1 else (shrunk > 10)      # the second case really exercises the re-send
+
+
 # ---------------------------------------------------------------------------------------------
 # the tile kernel, the device generator, and the full-size identity
 # ---------------------------------------------------------------------------------------------
