@@ -1,5 +1,8 @@
 // mdb_api.cu -- the C ABI of libmdb200.so (see include/mdb200.h).  Host orchestration of the blocked
 // right-looking modified LDL^T, the permutation gather, and solve / multiply with a resident factor.
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <math.h>
 #include <stdlib.h>
 #include <time.h>
@@ -66,7 +69,10 @@ static void ctx_reap(mdb_ctx* ctx) {
 // n = 65536) are kept in the context when they are released and handed out again to the next call that needs the
 // same amount: cudaMalloc + cudaFree of that size cost ~0.1 s per call.  mdb_ctx_trim() gives them back to the driver;
 // any allocation of the library that fails trims the cache and tries once more.  MDB200_CACHE=0 disables the cache.
+static void factor_release(mdb_factor* f);
 static void ctx_trim(mdb_ctx* ctx) {
+  if (ctx->parked) { factor_release(ctx->parked); ctx->parked = nullptr; }
+  if (ctx->tail_flags) { cudaFree(ctx->tail_flags); ctx->tail_flags = nullptr; ctx->tail_flags_cap = 0; }
   for (int i = 0; i < 3; ++i) {
     if (ctx->big_ptr[i]) cudaFree(ctx->big_ptr[i]);
     ctx->big_ptr[i] = nullptr;
@@ -300,15 +306,49 @@ static bool host_is_pageable(const void* p) {
   return attr.type == cudaMemoryTypeUnregistered;
 }
 
+// One row, source and destination anywhere: unless MDB200_COPY_NT=0 the destination is written with streaming stores
+// (no read-for-ownership of the destination lines; the staging buffers are read next by the DMA engine, not the CPU).
+static inline void row_copy(char* dst, const char* src, size_t bytes, bool nt) {
+#if defined(__x86_64__)
+  if (nt && bytes >= 256) {
+    size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    if (head) { memcpy(dst, src, head); dst += head; src += head; bytes -= head; }
+    const size_t body = bytes & ~(size_t)63;
+    for (size_t i = 0; i < body; i += 64) {
+      const __m128i a = _mm_loadu_si128((const __m128i*)(src + i)), b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+      const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32)), d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+      _mm_stream_si128((__m128i*)(dst + i), a); _mm_stream_si128((__m128i*)(dst + i + 16), b);
+      _mm_stream_si128((__m128i*)(dst + i + 32), c); _mm_stream_si128((__m128i*)(dst + i + 48), d);
+    }
+    if (bytes > body) memcpy(dst + body, src + body, bytes - body);
+    return;
+  }
+#endif
+  memcpy(dst, src, bytes);
+}
+
 static void parallel_rows_copy(char* dst, size_t dst_pitch, const char* src, size_t src_pitch, size_t row_bytes,
                                int64_t rows) {
-  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, std::thread::hardware_concurrency()), rows));
+  // measured on the 16-vCPU B200 host, 8.6 GB pageable -> device (tools/staging_bench.py, profiles/r02_staging_bench.json):
+  // 8 threads + memcpy 37 GB/s, 12 threads + streaming stores 50.5 GB/s (the pinned-memory rate is 52 - 55 GB/s)
+  const char* te = getenv("MDB200_COPY_THREADS");
+  const int64_t hw = std::max<int64_t>(1, (int64_t)std::thread::hardware_concurrency());
+  const int64_t cap = te ? std::max<int64_t>(1, atoll(te)) : std::min<int64_t>(12, std::max<int64_t>(1, hw * 3 / 4));
+  const char* ne = getenv("MDB200_COPY_NT");
+  const bool nt = !(ne && ne[0] == '0');
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(cap, hw), rows));
   std::vector<std::thread> th;
   for (int t = 1; t < T; ++t)
     th.emplace_back([=]() {
-      for (int64_t r = rows * t / T; r < rows * (t + 1) / T; ++r) memcpy(dst + r * dst_pitch, src + r * src_pitch, row_bytes);
+      for (int64_t r = rows * t / T; r < rows * (t + 1) / T; ++r) row_copy(dst + r * dst_pitch, src + r * src_pitch, row_bytes, nt);
+#if defined(__x86_64__)
+      if (nt) _mm_sfence();
+#endif
     });
-  for (int64_t r = 0; r < rows / T; ++r) memcpy(dst + r * dst_pitch, src + r * src_pitch, row_bytes);
+  for (int64_t r = 0; r < rows / T; ++r) row_copy(dst + r * dst_pitch, src + r * src_pitch, row_bytes, nt);
+#if defined(__x86_64__)
+  if (nt) _mm_sfence();
+#endif
   for (auto& x : th) x.join();
 }
 
@@ -338,18 +378,24 @@ static int staged_copy2d(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* sr
   const int64_t R = std::max<int64_t>(1, (int64_t)(chunk_bytes / row_bytes));   // rows per chunk
   const int64_t nchunks = (rows + R - 1) / R;
   if (h2d) {
+    // The buffers rotate across calls and nothing is drained at the end: once a chunk sits in a staging buffer the
+    // caller's memory is no longer needed, and the copy is ordered on ctx->stream like any other asynchronous copy
+    // (mdb_factor_set_matrix uploads 32 row blocks at n = 65536; a drain per block cost ~0.1 s of bubbles).
     for (int64_t c = 0; c < nchunks; ++c) {
-      const int b = (int)(c % 3);
+      const int b = ctx->stage_next;
+      ctx->stage_next = (b + 1) % 3;
       const int64_t r0 = c * R, nr = std::min<int64_t>(R, rows - r0);
-      if (c >= 3) MDB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b]));   // the DMA that read this buffer is done
+      if (ctx->stage_busy[b]) MDB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b]));   // the DMA that read this buffer is done
       parallel_rows_copy((char*)ctx->stage[b], row_bytes, (const char*)src + (size_t)r0 * ld_src * 8, (size_t)ld_src * 8,
                          row_bytes, nr);
       MDB_CUDA(ctx, cudaMemcpy2DAsync((char*)dst + (size_t)r0 * ld_dst * 8, (size_t)ld_dst * 8, ctx->stage[b], row_bytes,
                                       row_bytes, (size_t)nr, cudaMemcpyHostToDevice, ctx->stream));
       MDB_CUDA(ctx, cudaEventRecord(ctx->stage_ev[b], ctx->stream));
+      ctx->stage_busy[b] = true;
     }
-    for (int b = 0; b < 3 && b < nchunks; ++b) MDB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b]));
   } else {
+    for (int b = 0; b < 3; ++b)
+      if (ctx->stage_busy[b]) { MDB_CUDA(ctx, cudaEventSynchronize(ctx->stage_ev[b])); ctx->stage_busy[b] = false; }
     for (int64_t c = 0; c < nchunks + 2; ++c) {
       if (c < nchunks) {
         const int b = (int)(c % 3);
@@ -402,6 +448,25 @@ static void factor_detach_W(mdb_factor* f) {
   f->W_cap = 0;
 }
 
+// Keep the workspace of a finished one-shot factor (W already detached) for the next call of the same shape: what is
+// allocated on demand goes, the fixed-size buffers stay, the state is that of a fresh factor.
+static void factor_park(mdb_factor* f) {
+  mdb_ctx* ctx = f->ctx;
+  cudaSetDevice(ctx->device);
+  void* lazy[] = {f->minB, f->maxB, f->p_dev, f->Linv, f->LinvT, f->Ltri, f->Utri, f->trsv_tasks, f->trsv_sync,
+                  f->trsv_partial, f->ws[0], f->ws[1], f->ws[2]};
+  for (void* q : lazy) cudaFree(q);
+  f->minB = f->maxB = nullptr; f->p_dev = nullptr;
+  f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
+  f->trsv_tasks = nullptr; f->trsv_ntasks = 0; f->trsv_sync = nullptr; f->trsv_partial = nullptr; f->trsv_partial_rhs = 0;
+  for (int i = 0; i < 3; ++i) { f->ws[i] = nullptr; f->ws_cap[i] = 0; }
+  f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
+  f->out_host = nullptr; f->out_ld = 0; f->out_stream_type = MDB_TYPE_LDL;
+  f->p_host.clear();
+  if (ctx->parked) factor_release(ctx->parked);
+  ctx->parked = f;
+}
+
 static void factor_release(mdb_factor* f) {
   if (!f) return;
   cudaSetDevice(f->ctx->device);
@@ -419,6 +484,37 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   MDB_CHECK(ctx, n >= 0 && batch >= 1, "mdb_factor_create: n >= 0 and batch >= 1 required");
   ctx_reap(ctx);
   MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int agg_new = batch != 1 ? 1 : ctx->agg_fixed ? ctx->agg_fixed
+                      : std::max<int64_t>(n, 1) >= ctx->agg_thresh[2] ? 8 : std::max<int64_t>(n, 1) >= ctx->agg_thresh[1] ? 4
+                      : std::max<int64_t>(n, 1) >= ctx->agg_thresh[0] ? 2 : 1;
+  if (ctx->parked) {
+    // the previous one-shot call left its workspace behind: same shape -> take it over (saves ~10 cudaMalloc /
+    // cudaFree pairs, 2 GB at n = 65536, per call); another shape -> give it back first
+    mdb_factor* f = ctx->parked;
+    ctx->parked = nullptr;
+    if (f->n == n && f->batch == batch && f->agg == agg_new) {
+      const int64_t nn = std::max<int64_t>(n, 1), bn = batch * nn;
+      const size_t panel_bytes = (size_t)batch * f->panel_rows * f->agg * NB * 8;
+      cudaError_t e = big_malloc(ctx, (void**)&f->W, (size_t)batch * nn * f->ld * 8, &f->W_cap);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->W, 0, (size_t)batch * nn * f->ld * 8, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->vec, 0, (size_t)7 * bn * 8, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->clamped, 0, (size_t)bn, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->info, 0, (size_t)batch * sizeof(int), ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->Ut, 0, (size_t)batch * NB * NB * 8, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->PX, 0, panel_bytes, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->PY, 0, panel_bytes, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->PX2, 0, panel_bytes, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemsetAsync(f->PY2, 0, panel_bytes, ctx->stream);
+      if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "mdb_factor_create: %s", cudaGetErrorString(e));
+        factor_release(f);
+        return MDB_ERR_CUDA;
+      }
+      *out = f;
+      return MDB_OK;
+    }
+    factor_release(f);
+  }
   mdb_factor* f = new (std::nothrow) mdb_factor();
   if (!f) return mdb_fail(ctx, MDB_ERR_INVALID, "%s", "out of host memory");
   f->ctx = ctx; f->n = n; f->batch = batch;
@@ -484,7 +580,8 @@ extern "C" int mdb_factor_destroy(mdb_factor* f) {
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     factor_detach_W(f);
-    factor_release(f);
+    if (f->ctx->use_cache && f->n >= 4096) factor_park(f);   // the next factor of this shape takes the workspace over
+    else factor_release(f);
   }
   return MDB_OK;
 }
@@ -837,7 +934,15 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
         ob = std::min<int64_t>(ob + agg_for(n - ob) * NB, n);
       }
       if (r_tail < n) {
-        MDB_CUDA(ctx, cudaMallocAsync((void**)&tail_changed, (size_t)n, ctx->copy_stream));
+        // (context-owned, grow-only: a stream-ordered allocation here cost 0.1 - 0.5 s per call when its pool was
+        // trimmed at the next synchronisation, with ~100 GB of other allocations alive)
+        if (ctx->tail_flags_cap < (size_t)n) {
+          if (ctx->tail_flags) { MDB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); cudaFree(ctx->tail_flags); }
+          ctx->tail_flags = nullptr; ctx->tail_flags_cap = 0;
+          MDB_CUDA(ctx, dev_malloc(ctx, (void**)&ctx->tail_flags, (size_t)n));
+          ctx->tail_flags_cap = (size_t)n;
+        }
+        tail_changed = ctx->tail_flags;
         MDB_CUDA(ctx, cudaMemsetAsync(tail_changed, 0, (size_t)n, ctx->copy_stream));
       }
     }
@@ -970,7 +1075,6 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       j = j1;
     }
     if (run_timing) tw2 = wall();
-    cudaFreeAsync(tail_changed, ctx->copy_stream);
     MDB_CUDA(ctx, e);
   }
   if (f->out_host) {  // every row has been finalised and copied by the copy stream
@@ -1146,8 +1250,12 @@ static int one_shot(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int
     ctx_reap(ctx);
     factor_detach_W(f);
     mdb_factor* dead = f;
-    ctx->reaper = new (std::nothrow) std::thread([dead]() { factor_release(dead); });
-    if (!ctx->reaper) factor_release(dead);
+    if (!rc && ctx->use_cache) {
+      factor_park(dead);
+    } else {
+      ctx->reaper = new (std::nothrow) std::thread([dead]() { factor_release(dead); });
+      if (!ctx->reaper) factor_release(dead);
+    }
     f = nullptr;
   }
   if (timing)

@@ -41,6 +41,9 @@ struct mdb_ctx {
   void* big_ptr[3];           // released working matrix / staging / permutation buffers kept for the next call (mdb_ctx_trim)
   size_t big_bytes[3];
   int use_cache;
+  uint8_t* tail_flags; size_t tail_flags_cap;   // per-row 'sent too early' flags of the streamed download (mdb_factor_run)
+  int stage_next; bool stage_busy[3];   // rotation of the staging buffers across calls; buffer has a recorded, unwaited event
+  struct mdb_factor* parked;  // workspace (everything but W) of the last one-shot call, reused by a call of the same shape
   int last_input_nonfinite;   // set by mdb_factor_set_matrix: the matrix held an inf / NaN
   double gemm_flop[2];        // algorithmic flop of the bulk / inner trailing updates of the last mdb_factor_run
   int64_t gemm_launches[2];
