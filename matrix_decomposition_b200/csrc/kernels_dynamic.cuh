@@ -12,9 +12,10 @@
 #pragma once
 #include "mdb_common.cuh"
 
-struct DynSel {      // decision of the current step, written by k_dyn_select2
-  double d, omega, drop;
-  long long jstar;
+struct DynSel {      // decision of one step, written by dyn_commit: everything the swap and column kernels of that step
+  double d, omega, drop;   // need sits in one 40-byte record (one memory round trip; a separate step counter cost a
+  long long jstar;         // second, dependent one in both kernels of every column)
+  long long step;          // the column index this decision is for
 };
 
 struct DynCand {
@@ -38,23 +39,42 @@ __device__ __forceinline__ bool dyn_better(int method, const DynCand& a, const D
   return a.j < b.j;
 }
 
-__device__ __forceinline__ DynCand dyn_block_reduce(int method, DynCand c, DynCand* sh) {
-  const int tid = threadIdx.x;
-  sh[tid] = c;
-  __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (tid < s) {
-      DynCand o = sh[tid + s];
-      if (dyn_better(method, o, sh[tid])) sh[tid] = o;
+__device__ __forceinline__ DynCand dyn_shfl_xor(const DynCand& c, int o) {
+  DynCand r;
+  r.d = __shfl_xor_sync(0xffffffffu, c.d, o);
+  r.omega = __shfl_xor_sync(0xffffffffu, c.omega, o);
+  r.f = __shfl_xor_sync(0xffffffffu, c.f, o);
+  r.j = __shfl_xor_sync(0xffffffffu, c.j, o);
+  r.clamped = __shfl_xor_sync(0xffffffffu, c.clamped, o);
+  return r;
+}
+
+// Best candidate of the first `warps` warps of the block (the others only take part in the barrier): butterfly inside
+// each warp, one shared-memory slot per warp, the final few merged by every thread itself.  The key is a strict total
+// order (j is unique), so the result does not depend on the order of the comparisons.
+__device__ __forceinline__ DynCand dyn_block_reduce(int method, DynCand c, DynCand* sh, int warps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < warps) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const DynCand r = dyn_shfl_xor(c, o);
+      if (dyn_better(method, r, c)) c = r;
     }
-    __syncthreads();
+    if (lane == 0) sh[warp] = c;
   }
-  return sh[0];
+  __syncthreads();
+  DynCand best = sh[0];
+  for (int w = 1; w < warps; ++w) {
+    const DynCand o = sh[w];
+    if (dyn_better(method, o, best)) best = o;
+  }
+  __syncthreads();   // sh may be reused by the caller
+  return best;
 }
 
 // stage 1: one rule evaluation per remaining row, best per block
 __global__ void __launch_bounds__(256) k_dyn_select1(FactorDev F, int method, int64_t i, DynCand* __restrict__ cand) {
-  __shared__ DynCand sh[256];
+  __shared__ DynCand sh[8];
   const int64_t j = i + (int64_t)blockIdx.x * 256 + threadIdx.x;
   DynCand c;
   c.j = -1; c.d = 0; c.omega = 0; c.f = 0; c.clamped = 0;
@@ -62,7 +82,7 @@ __global__ void __launch_bounds__(256) k_dyn_select1(FactorDev F, int method, in
     const MdDecision dec = md_decide(F.prm, F.alpha[j], F.beta[j], F.gamma[j], F.minB[j], F.maxB[j]);
     c.d = dec.d; c.omega = dec.omega; c.f = dec.f; c.clamped = dec.clamped; c.j = j;
   }
-  c = dyn_block_reduce(method, c, sh);
+  c = dyn_block_reduce(method, c, sh, 8);
   if (threadIdx.x == 0) cand[blockIdx.x] = c;
 }
 
@@ -96,6 +116,7 @@ __device__ __forceinline__ void dyn_commit(const FactorDev& F, int64_t i, const 
   sel->omega = c.omega;
   sel->drop = (c.omega == 0 || c.omega * rowmax_i < F.prm.min_abs_value_L) ? 1.0 : 0.0;
   sel->jstar = js;
+  sel->step = i;
 }
 
 // stage 2: best over blocks, then dyn_commit.  Only the first column goes through select1 / select2: afterwards
@@ -104,27 +125,25 @@ __global__ void __launch_bounds__(256) k_dyn_select2(FactorDev F, int method, in
                                                      const DynCand* __restrict__ cand, double* __restrict__ minB,
                                                      double* __restrict__ maxB, int64_t* __restrict__ p,
                                                      DynSel* __restrict__ sel) {
-  __shared__ DynCand sh[256];
+  __shared__ DynCand sh[8];
   DynCand c;
   c.j = -1; c.d = 0; c.omega = 0; c.f = 0; c.clamped = 0;
   for (int b = threadIdx.x; b < nblocks; b += 256)
     if (dyn_better(method, cand[b], c)) c = cand[b];
-  c = dyn_block_reduce(method, c, sh);
-  if (threadIdx.x == 0) dyn_commit(F, i, c, minB, maxB, p, sel);
+  c = dyn_block_reduce(method, c, sh, 8);
+  if (threadIdx.x == 0) dyn_commit(F, i, c, minB, maxB, p, sel + (i & 1));
 }
 
 // symmetric swap of indices i and j* in both triangles of W: S(a, b) lives at W[max][min], A(a, b) at W[min][max]
 // (Reimer.py:513-518 swaps the rows of L; the Schur complement and the original matrix must follow)
-__global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict__ W, int64_t ld, int64_t i,
-                                                  const DynSel* __restrict__ sel, double* __restrict__ PX,
-                                                  double* __restrict__ PY, int64_t ldp, int kc,
-                                                  const long long* __restrict__ step) {
-  // step != null (replayed CUDA graph): the column index comes from device memory, sel points at the pair of slots
-  if (step) {
-    i = *step;
-    kc = (int)(i % MDB_NB);
-    sel += (i & 1);
-  }
+__global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict__ W, int64_t ld,
+                                                  const DynSel* __restrict__ sel, int slot, double* __restrict__ PX,
+                                                  double* __restrict__ PY, int64_t ldp) {
+  // the column index comes from the decision record (slot = parity of the column: the same kernel node serves every
+  // panel of a replayed CUDA graph)
+  sel += slot;
+  const int64_t i = sel->step;
+  const int kc = (int)(i % MDB_NB);
   const int64_t js = sel->jstar;
   if (js == i) return;
   const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -155,68 +174,83 @@ __global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict_
 // (the two DynSel slots alternate, so no block can still be reading the slot being written).
 #define MDB_DYN_ROWS 64
 
-__global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, int64_t i, const DynSel* __restrict__ sel,
+__global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, const DynSel* __restrict__ sel2, int slot,
                                                     double* __restrict__ PX, double* __restrict__ PY, int64_t ldp,
-                                                    int kc, DynCand* cand, unsigned* counter,
-                                                    double* __restrict__ minB, double* __restrict__ maxB,
-                                                    int64_t* __restrict__ p, DynSel* __restrict__ sel_next,
-                                                    long long* __restrict__ step) {
-  // step != null (replayed CUDA graph): the column index comes from device memory and is advanced by the block that
-  // commits the next decision; sel / sel_next both point at the pair of slots; the grid is sized for the first column
-  // of the panel (blocks without rows only take part in the count)
-  if (step) {
-    i = *step;
-    kc = (int)(i % MDB_NB);
-    sel_next = const_cast<DynSel*>(sel) + ((i + 1) & 1);
-    sel += (i & 1);
-  }
-  __shared__ double yi[MDB_NB];
+                                                    DynCand* cand, unsigned* counter, double* __restrict__ minB,
+                                                    double* __restrict__ maxB, int64_t* __restrict__ p) {
+  // sel2 = the pair of decision records; this step reads slot `slot` (the parity of its column) and the block that
+  // finishes last commits the next step into the other one (no block can still be reading the record being written).
+  // In a replayed CUDA graph the grid is sized for the first column of the panel: blocks without rows only take part
+  // in the count.
+  const DynSel* sel = sel2 + slot;
+  DynSel* sel_next = const_cast<DynSel*>(sel2) + (slot ^ 1);
+  const int64_t i = sel->step;
+  const int kc = (int)(i % MDB_NB);
+  const double d = sel->d, w = sel->omega;
+  const bool drop = sel->drop != 0.0;
   __shared__ double s_sum[MDB_DYN_ROWS];
-  __shared__ DynCand sh[256];
+  __shared__ DynCand sh[8];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int c = tid; c < kc; c += 256) yi[c] = PY[i * ldp + c];   // Y[i, 0:kc]
-  __syncthreads();
   const int64_t j0 = i + 1 + (int64_t)blockIdx.x * MDB_DYN_ROWS;
-  const bool drop = sel->drop != 0.0;
-  if (!drop) {
-    for (int rr = warp; rr < MDB_DYN_ROWS; rr += 8) {   // pass 1
-      const int64_t j = j0 + rr;
-      double s = 0;
-      if (j < F.n) {
-        const double* xr = PX + j * ldp;
+  // pass 2's operands are requested first: their latency (one strided element per row) overlaps pass 1
+  const int64_t j = j0 + tid;
+  const bool mine = tid < MDB_DYN_ROWS && j < F.n;
+  double a = 0, sji = 0, al0 = 0, be0 = 0, ga = 0, mb = 0, Mb = 0, rm = 0;
+  if (mine) {
+    a = F.W[i * F.ldw + j];
+    sji = F.W[j * F.ldw + i];
+    al0 = F.alpha[j]; be0 = F.beta[j]; ga = F.gamma[j]; rm = F.rowmax[j];
+    mb = minB[j]; Mb = maxB[j];
+  }
+  if (!drop) {   // pass 1: a warp per row, 8 consecutive rows per warp, every load issued before the first use
+    double y[MDB_NB / 32];
 #pragma unroll
-        for (int e = 0; e < MDB_NB / 32; ++e) {
-          const int c = lane + 32 * e;
-          if (c < kc) s = fma(xr[c], yi[c], s);
-        }
+    for (int e = 0; e < MDB_NB / 32; ++e) {
+      const int c = lane + 32 * e;
+      y[e] = (c < kc) ? PY[i * ldp + c] : 0.0;   // Y[i, 0:kc]
+    }
+    double xv[MDB_DYN_ROWS / 8][MDB_NB / 32];
+#pragma unroll
+    for (int q = 0; q < MDB_DYN_ROWS / 8; ++q) {
+      const int64_t jr = j0 + warp * (MDB_DYN_ROWS / 8) + q;
+#pragma unroll
+      for (int e = 0; e < MDB_NB / 32; ++e) {
+        const int c = lane + 32 * e;
+        xv[q][e] = (jr < F.n && c < kc) ? PX[jr * ldp + c] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < MDB_DYN_ROWS / 8; ++q) {
+      double s = 0;
+#pragma unroll
+      for (int e = 0; e < MDB_NB / 32; ++e) {
+        const int c = lane + 32 * e;
+        if (c < kc) s = fma(xv[q][e], y[e], s);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) s_sum[rr] = s;
+      if (lane == 0) s_sum[warp * (MDB_DYN_ROWS / 8) + q] = s;
     }
   }
   __syncthreads();
   DynCand best;
   best.j = -1; best.d = 0; best.omega = 0; best.f = 0; best.clamped = 0;
-  const int64_t j = j0 + tid;
-  if (tid < MDB_DYN_ROWS && j < F.n) {   // pass 2
-    const double d = sel->d, w = sel->omega;
-    const double a = F.W[i * F.ldw + j];
+  if (mine) {   // pass 2: a thread per row
     double r = a;
-    if (!drop) r = (1.0 - w) * a + w * (F.W[j * F.ldw + i] + s_sum[tid]);
+    if (!drop) r = (1.0 - w) * a + w * (sji + s_sum[tid]);
     const double x = (d != 0) ? r / d : 0.0;
     F.W[j * F.ldw + i] = x;
-    const double al = F.alpha[j] + x * x * d, be = F.beta[j] + 2.0 * a * a;
+    const double al = al0 + x * x * d, be = be0 + 2.0 * a * a;
     F.alpha[j] = al;
     F.beta[j] = be;
-    F.rowmax[j] = fmax(F.rowmax[j], fabs(x));
+    F.rowmax[j] = fmax(rm, fabs(x));
     PX[j * ldp + kc] = x;
     PY[j * ldp + kc] = -x * d;
-    const MdDecision dec = md_decide(F.prm, al, be, F.gamma[j], minB[j], maxB[j]);
+    const MdDecision dec = md_decide(F.prm, al, be, ga, mb, Mb);
     best.d = dec.d; best.omega = dec.omega; best.f = dec.f; best.clamped = dec.clamped; best.j = j;
   }
-  best = dyn_block_reduce(method, best, sh);
+  best = dyn_block_reduce(method, best, sh, MDB_DYN_ROWS / 32);
   if (tid == 0) {
     cand[blockIdx.x] = best;
     __threadfence();
@@ -233,11 +267,10 @@ __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, int
     o.d = vc->d; o.omega = vc->omega; o.f = vc->f; o.j = vc->j; o.clamped = vc->clamped;
     if (dyn_better(method, o, c)) c = o;
   }
-  c = dyn_block_reduce(method, c, sh);
+  c = dyn_block_reduce(method, c, sh, 8);
   if (tid == 0) {
     *counter = 0;
     dyn_commit(F, i + 1, c, minB, maxB, p, sel_next);
-    if (step) *step = i + 1;
   }
 }
 

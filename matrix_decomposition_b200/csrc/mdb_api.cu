@@ -1326,20 +1326,21 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
       // matrix gets one K = NB tensor-core update per panel
       const int64_t LDP = (int64_t)f->agg * NB;
       // Every full panel but the last replays ONE captured CUDA graph of 128 x (swap, column) kernel nodes: the kernels
-      // read the column index from device memory (advanced by the column kernel), so the nodes are the same for every
-      // panel and the ~4 us gaps of 256 dependent stream launches per panel shrink to the graph's node-to-node latency.
-      long long* step = (long long*)((char*)(sel + 2) + 16);
+      // read the column index from the decision record of their parity (written by the step before), so the nodes are
+      // the same for every panel and the ~4 us gaps of 256 dependent stream launches per panel shrink to the graph's
+      // node-to-node latency.
       cudaGraphExec_t gexec = nullptr;
       const bool use_graph = n >= 3 * NB && !getenv("MDB200_DYN_NOGRAPH");
+      const unsigned gswap = (unsigned)((n + 255) / 256);
       if (use_graph) {
         cudaGraph_t graph = nullptr;
         cudaError_t ge = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
         if (ge == cudaSuccess) {
           const unsigned gcol = (unsigned)((n - 2 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS);
           for (int c = 0; c < NB; ++c) {
-            k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, -1, sel, f->PX, f->PY, LDP, 0, step);
-            k_dyn_column<<<gcol, 256, 0, ctx->stream>>>(F, method, -1, sel, f->PX, f->PY, LDP, 0, cand, counter, minB, maxB,
-                                                        f->p_dev, sel, step);
+            k_dyn_swap<<<gswap, 256, 0, ctx->stream>>>(n, f->W, f->ld, sel, c & 1, f->PX, f->PY, LDP);
+            k_dyn_column<<<gcol, 256, 0, ctx->stream>>>(F, method, sel, c & 1, f->PX, f->PY, LDP, cand, counter, minB, maxB,
+                                                        f->p_dev);
           }
           ge = cudaStreamEndCapture(ctx->stream, &graph);
         }
@@ -1356,20 +1357,16 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
           ctx->launches += 2;
         }
         if (gexec && pe < n && pe - pb == NB) {
-          const long long first = (long long)pb;
-          cudaMemcpyAsync(step, &first, sizeof(first), cudaMemcpyHostToDevice, ctx->stream);
           cudaGraphLaunch(gexec, ctx->stream);
           ctx->launches += 2 * NB;
         } else {
           for (int64_t i = pb; i < pe; ++i) {
             const int64_t rem = n - i;
-            const int kc = (int)(i - pb);
-            DynSel* cur = sel + (i & 1);
-            k_dyn_swap<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->W, f->ld, i, cur, f->PX, f->PY, LDP, kc, nullptr);
+            k_dyn_swap<<<gswap, 256, 0, ctx->stream>>>(n, f->W, f->ld, sel, (int)(i & 1), f->PX, f->PY, LDP);
             ctx->launches += 1;
             if (rem > 1) {
               k_dyn_column<<<(unsigned)((rem - 1 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS), 256, 0, ctx->stream>>>(
-                  F, method, i, cur, f->PX, f->PY, LDP, kc, cand, counter, minB, maxB, f->p_dev, sel + ((i + 1) & 1), nullptr);
+                  F, method, sel, (int)(i & 1), f->PX, f->PY, LDP, cand, counter, minB, maxB, f->p_dev);
               ctx->launches += 1;
             }
           }
