@@ -7,8 +7,8 @@
 // panel column i is read as  S[j, i] + sum_c X[j, c] Y[i, c]  over the panel's earlier columns c (X = unscaled
 // rows, Y = -X D, kept for every row in the operand buffers; O(n * 64) per column instead of the O(n^2) rank-1
 // update), and after the panel the trailing matrix gets the same K = 128 tensor-core update as the static path.
-// Pivot swaps exchange the rows of X and Y together with the rows / columns of W.  Four small kernels per
-// column, no host round trip; n^2 / 2 rule evaluations in total.
+// Pivot swaps exchange the rows of X and Y together with the rows / columns of W.  One kernel per column
+// (k_dyn_column), no host round trip; n^2 / 2 rule evaluations in total.
 #pragma once
 #include "mdb_common.cuh"
 
@@ -134,123 +134,135 @@ __global__ void __launch_bounds__(256) k_dyn_select2(FactorDev F, int method, in
   if (threadIdx.x == 0) dyn_commit(F, i, c, minB, maxB, p, sel + (i & 1));
 }
 
-// symmetric swap of indices i and j* in both triangles of W: S(a, b) lives at W[max][min], A(a, b) at W[min][max]
-// (Reimer.py:513-518 swaps the rows of L; the Schur complement and the original matrix must follow)
-__global__ void __launch_bounds__(256) k_dyn_swap(int64_t n, double* __restrict__ W, int64_t ld,
-                                                  const DynSel* __restrict__ sel, int slot, double* __restrict__ PX,
-                                                  double* __restrict__ PY, int64_t ldp) {
-  // the column index comes from the decision record (slot = parity of the column: the same kernel node serves every
-  // panel of a replayed CUDA graph)
-  sel += slot;
-  const int64_t i = sel->step;
-  const int kc = (int)(i % MDB_NB);
-  const int64_t js = sel->jstar;
-  if (js == i) return;
-  const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (m < kc) {  // the pending (not yet applied) panel columns of the two rows follow them
-    double t = PX[i * ldp + m]; PX[i * ldp + m] = PX[js * ldp + m]; PX[js * ldp + m] = t;
-    t = PY[i * ldp + m]; PY[i * ldp + m] = PY[js * ldp + m]; PY[js * ldp + m] = t;
-  }
-  if (m >= n || m == i || m == js) return;
-  {  // lower triangle: S
-    double* a = &W[(i > m ? i : m) * ld + (i > m ? m : i)];
-    double* b = &W[(js > m ? js : m) * ld + (js > m ? m : js)];
-    const double t = *a; *a = *b; *b = t;
-  }
-  {  // upper triangle: A
-    double* a = &W[(i > m ? m : i) * ld + (i > m ? i : m)];
-    double* b = &W[(js > m ? m : js) * ld + (js > m ? js : m)];
-    const double t = *a; *a = *b; *b = t;
-  }
-}
-
-// column i for every row below: current Schur complement entry (stored value + the pending updates of this panel),
+// One kernel per column.  The pivot swap i <-> j* (Reimer.py:509-518: p, the rows of L; here also the Schur complement
+// in the lower triangle of W, S(a, b) at W[max][min], the original matrix in the upper one, A(a, b) at W[min][max], and
+// the pending rows of X / Y) is not a pass of its own: the column computation READS THROUGH the swap -- new row j is old
+// row (j == j* ? i : j), new column i is old column j* -- and each thread then puts the two pairs of elements of its own
+// row where the swap wants them (the value it consumed is replaced by what stood in column i; x goes to column i).  A
+// separate swap kernel in front of every column kernel cost a launch gap and ~3 us of dependent strided accesses per
+// column.  What no row thread owns is done by
+//   * the blocks behind the row blocks: positions m < i (the finished part of rows i and j* of L, coalesced, and of
+//     columns i and j* of A);
+//   * the block that finishes last: rows i and j* of X / Y (every block reads Y[j*] as the new Y[i], so they can only
+//     move when all are done), then the decision for step i + 1.
+//
+// Column i for every row below: current Schur complement entry (stored value + the pending updates of this panel),
 // mix, divide, alpha / beta / rowmax; x and y = -x d go into column kc of the operand buffers.  A CTA owns
 // MDB_DYN_ROWS = 64 rows (4 CTAs per 256 rows: every SM gets work also at n = 16384):
 //   pass 1  a warp per row, lanes over the pending columns: sum_c X[j, c] Y[i, c] with coalesced loads of the row of X
 //           (a thread per row walked its row alone: 32 different cache lines per load instruction) and a fixed butterfly;
 //   pass 2  a thread per row: the mix, x, the row state and -- its alpha / beta being current -- the rule for step i + 1.
-// The block minima are merged by the last block to finish, which commits the decision for step i + 1 into sel_next
-// (the two DynSel slots alternate, so no block can still be reading the slot being written).
+// The block minima are merged by the last block to finish, which commits the decision for step i + 1 into the other
+// decision record (the two alternate, so no block can still be reading the one being written).
 #define MDB_DYN_ROWS 64
 
 __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, const DynSel* __restrict__ sel2, int slot,
-                                                    double* __restrict__ PX, double* __restrict__ PY, int64_t ldp,
-                                                    DynCand* cand, unsigned* counter, double* __restrict__ minB,
-                                                    double* __restrict__ maxB, int64_t* __restrict__ p) {
-  // sel2 = the pair of decision records; this step reads slot `slot` (the parity of its column) and the block that
-  // finishes last commits the next step into the other one (no block can still be reading the record being written).
-  // In a replayed CUDA graph the grid is sized for the first column of the panel: blocks without rows only take part
-  // in the count.
+                                                    int row_blocks, double* __restrict__ PX, double* __restrict__ PY,
+                                                    int64_t ldp, DynCand* cand, unsigned* counter,
+                                                    double* __restrict__ minB, double* __restrict__ maxB,
+                                                    int64_t* __restrict__ p) {
+  // sel2 = the pair of decision records; this step reads record `slot` (the parity of its column).  In a replayed CUDA
+  // graph the grid is sized for the first column of the panel: blocks without rows only take part in the count.
   const DynSel* sel = sel2 + slot;
   DynSel* sel_next = const_cast<DynSel*>(sel2) + (slot ^ 1);
   const int64_t i = sel->step;
+  const int64_t js = sel->jstar;
   const int kc = (int)(i % MDB_NB);
   const double d = sel->d, w = sel->omega;
   const bool drop = sel->drop != 0.0;
+  const bool sw = js != i;
+  double* __restrict__ W = F.W;
+  const int64_t ld = F.ldw;
   __shared__ double s_sum[MDB_DYN_ROWS];
   __shared__ DynCand sh[8];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t j0 = i + 1 + (int64_t)blockIdx.x * MDB_DYN_ROWS;
-  // pass 2's operands are requested first: their latency (one strided element per row) overlaps pass 1
-  const int64_t j = j0 + tid;
-  const bool mine = tid < MDB_DYN_ROWS && j < F.n;
-  double a = 0, sji = 0, al0 = 0, be0 = 0, ga = 0, mb = 0, Mb = 0, rm = 0;
-  if (mine) {
-    a = F.W[i * F.ldw + j];
-    sji = F.W[j * F.ldw + i];
-    al0 = F.alpha[j]; be0 = F.beta[j]; ga = F.gamma[j]; rm = F.rowmax[j];
-    mb = minB[j]; Mb = maxB[j];
-  }
-  if (!drop) {   // pass 1: a warp per row, 8 consecutive rows per warp, every load issued before the first use
-    double y[MDB_NB / 32];
-#pragma unroll
-    for (int e = 0; e < MDB_NB / 32; ++e) {
-      const int c = lane + 32 * e;
-      y[e] = (c < kc) ? PY[i * ldp + c] : 0.0;   // Y[i, 0:kc]
-    }
-    double xv[MDB_DYN_ROWS / 8][MDB_NB / 32];
-#pragma unroll
-    for (int q = 0; q < MDB_DYN_ROWS / 8; ++q) {
-      const int64_t jr = j0 + warp * (MDB_DYN_ROWS / 8) + q;
-#pragma unroll
-      for (int e = 0; e < MDB_NB / 32; ++e) {
-        const int c = lane + 32 * e;
-        xv[q][e] = (jr < F.n && c < kc) ? PX[jr * ldp + c] : 0.0;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < MDB_DYN_ROWS / 8; ++q) {
-      double s = 0;
-#pragma unroll
-      for (int e = 0; e < MDB_NB / 32; ++e) {
-        const int c = lane + 32 * e;
-        if (c < kc) s = fma(xv[q][e], y[e], s);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) s_sum[warp * (MDB_DYN_ROWS / 8) + q] = s;
-    }
-  }
-  __syncthreads();
   DynCand best;
   best.j = -1; best.d = 0; best.omega = 0; best.f = 0; best.clamped = 0;
-  if (mine) {   // pass 2: a thread per row
-    double r = a;
-    if (!drop) r = (1.0 - w) * a + w * (sji + s_sum[tid]);
-    const double x = (d != 0) ? r / d : 0.0;
-    F.W[j * F.ldw + i] = x;
-    const double al = al0 + x * x * d, be = be0 + 2.0 * a * a;
-    F.alpha[j] = al;
-    F.beta[j] = be;
-    F.rowmax[j] = fmax(rm, fabs(x));
-    PX[j * ldp + kc] = x;
-    PY[j * ldp + kc] = -x * d;
-    const MdDecision dec = md_decide(F.prm, al, be, ga, mb, Mb);
-    best.d = dec.d; best.omega = dec.omega; best.f = dec.f; best.clamped = dec.clamped; best.j = j;
+  if ((int)blockIdx.x >= row_blocks) {
+    // positions m < i of the swap
+    const int64_t m = (int64_t)(blockIdx.x - row_blocks) * 256 + tid;
+    if (sw && m < i) {
+      const double l_i = W[i * ld + m], l_s = W[js * ld + m], a_i = W[m * ld + i], a_s = W[m * ld + js];
+      W[i * ld + m] = l_s; W[js * ld + m] = l_i;
+      W[m * ld + i] = a_s; W[m * ld + js] = a_i;
+    }
+  } else {
+    const int64_t j0 = i + 1 + (int64_t)blockIdx.x * MDB_DYN_ROWS;
+    // pass 2's operands are requested first: their latency (strided elements) overlaps pass 1
+    const int64_t j = j0 + tid;
+    const bool mine = tid < MDB_DYN_ROWS && j < F.n;
+    const bool moved = mine && sw && j != js;    // this row's elements of columns / rows i and j* change places
+    double a = 0, sji = 0, old_s = 0, old_a = 0, al0 = 0, be0 = 0, ga = 0, mb = 0, Mb = 0, rm = 0;
+    double *loc_s = nullptr, *loc_a = nullptr;
+    if (mine) {
+      loc_s = &W[j * ld + i];
+      loc_a = &W[i * ld + j];
+      if (moved) {
+        loc_s = &W[(js > j ? js : j) * ld + (js > j ? j : js)];   // old S(j, j*)
+        loc_a = &W[(js > j ? j : js) * ld + (js > j ? js : j)];   // old A(j*, j)
+        old_s = W[j * ld + i];
+        old_a = W[i * ld + j];
+      }
+      sji = *loc_s;
+      a = *loc_a;
+      al0 = F.alpha[j]; be0 = F.beta[j]; ga = F.gamma[j]; rm = F.rowmax[j];
+      mb = minB[j]; Mb = maxB[j];
+    }
+    if (!drop) {   // pass 1: a warp per row, 8 consecutive rows per warp, every load issued before the first use
+      double y[MDB_NB / 32];
+#pragma unroll
+      for (int e = 0; e < MDB_NB / 32; ++e) {
+        const int c = lane + 32 * e;
+        y[e] = (c < kc) ? PY[js * ldp + c] : 0.0;   // new Y[i, 0:kc] = old Y[j*, 0:kc]
+      }
+      double xv[MDB_DYN_ROWS / 8][MDB_NB / 32];
+#pragma unroll
+      for (int q = 0; q < MDB_DYN_ROWS / 8; ++q) {
+        const int64_t jr = j0 + warp * (MDB_DYN_ROWS / 8) + q;
+        const int64_t pr = (jr == js) ? i : jr;     // where the row still stands
+#pragma unroll
+        for (int e = 0; e < MDB_NB / 32; ++e) {
+          const int c = lane + 32 * e;
+          xv[q][e] = (jr < F.n && c < kc) ? PX[pr * ldp + c] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < MDB_DYN_ROWS / 8; ++q) {
+        double sacc = 0;
+#pragma unroll
+        for (int e = 0; e < MDB_NB / 32; ++e) {
+          const int c = lane + 32 * e;
+          if (c < kc) sacc = fma(xv[q][e], y[e], sacc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) s_sum[warp * (MDB_DYN_ROWS / 8) + q] = sacc;
+      }
+    }
+    __syncthreads();
+    if (mine) {   // pass 2: a thread per row
+      double r = a;
+      if (!drop) r = (1.0 - w) * a + w * (sji + s_sum[tid]);
+      const double x = (d != 0) ? r / d : 0.0;
+      W[j * ld + i] = x;
+      if (moved) {
+        *loc_s = old_s;          // new S(j, j*) = old S(j, i)
+        W[i * ld + j] = a;       // new A(i, j) = old A(j*, j)
+        *loc_a = old_a;          // new A(j*, j) = old A(i, j)
+      }
+      const double al = al0 + x * x * d, be = be0 + 2.0 * a * a;
+      F.alpha[j] = al;
+      F.beta[j] = be;
+      F.rowmax[j] = fmax(rm, fabs(x));
+      const int64_t pj = (sw && j == js) ? i : j;   // row j* of X / Y still stands at i (the last block moves it)
+      PX[pj * ldp + kc] = x;
+      PY[pj * ldp + kc] = -x * d;
+      const MdDecision dec = md_decide(F.prm, al, be, ga, mb, Mb);
+      best.d = dec.d; best.omega = dec.omega; best.f = dec.f; best.clamped = dec.clamped; best.j = j;
+    }
+    best = dyn_block_reduce(method, best, sh, MDB_DYN_ROWS / 32);
   }
-  best = dyn_block_reduce(method, best, sh, MDB_DYN_ROWS / 32);
   if (tid == 0) {
     cand[blockIdx.x] = best;
     __threadfence();
@@ -259,13 +271,24 @@ __global__ void __launch_bounds__(256) k_dyn_column(FactorDev F, int method, con
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // rows i and j* of X / Y, columns 0 .. kc (written by other blocks of this launch: loads that bypass L1)
+  double x_i = 0, x_s = 0, y_i = 0, y_s = 0;
+  const bool mv = sw && tid <= kc;
+  if (mv) {
+    x_i = __ldcg(PX + i * ldp + tid); x_s = __ldcg(PX + js * ldp + tid);
+    y_i = __ldcg(PY + i * ldp + tid); y_s = __ldcg(PY + js * ldp + tid);
+  }
   DynCand c;
   c.j = -1; c.d = 0; c.omega = 0; c.f = 0; c.clamped = 0;
-  for (int b = tid; b < (int)gridDim.x; b += 256) {
+  for (int b = tid; b < row_blocks; b += 256) {
     const volatile DynCand* vc = cand + b;   // written by other blocks of this launch
     DynCand o;
     o.d = vc->d; o.omega = vc->omega; o.f = vc->f; o.j = vc->j; o.clamped = vc->clamped;
     if (dyn_better(method, o, c)) c = o;
+  }
+  if (mv) {
+    PX[i * ldp + tid] = x_s; PX[js * ldp + tid] = x_i;
+    PY[i * ldp + tid] = y_s; PY[js * ldp + tid] = y_i;
   }
   c = dyn_block_reduce(method, c, sh, 8);
   if (tid == 0) {

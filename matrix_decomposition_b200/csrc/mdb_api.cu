@@ -1299,7 +1299,7 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
       mb[(size_t)i] = bnd->min_diag_B ? bnd->min_diag_B[i * bnd->stride_B] : -INFINITY;
       Mb[(size_t)i] = bnd->max_diag_B ? bnd->max_diag_B[i * bnd->stride_B] : INFINITY;
     }
-    const int nb_max = (int)((n + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS) + 1;   // candidates: one per block of k_dyn_select1 / k_dyn_column
+    const int nb_max = (int)((n + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS) + (int)((n + 255) / 256) + 2;   // candidates: one per block of k_dyn_select1 / k_dyn_column
     cudaError_t e = dev_malloc(ctx, (void**)&minB, (size_t)n * 8);
     if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&maxB, (size_t)n * 8);
     if (e == cudaSuccess) e = dev_malloc(ctx, (void**)&cand, (size_t)nb_max * sizeof(DynCand));
@@ -1325,23 +1325,20 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
       // panels of NB columns: pending updates are applied on the fly inside a panel (k_dyn_column), the trailing
       // matrix gets one K = NB tensor-core update per panel
       const int64_t LDP = (int64_t)f->agg * NB;
-      // Every full panel but the last replays ONE captured CUDA graph of 128 x (swap, column) kernel nodes: the kernels
-      // read the column index from the decision record of their parity (written by the step before), so the nodes are
-      // the same for every panel and the ~4 us gaps of 256 dependent stream launches per panel shrink to the graph's
-      // node-to-node latency.
+      // Every full panel but the last replays ONE captured CUDA graph of 128 column kernel nodes: the kernel reads the
+      // column index from the decision record of its parity (written by the step before), so the nodes are the same
+      // for every panel and the ~4 us gaps of dependent stream launches shrink to the graph's node-to-node latency.
       cudaGraphExec_t gexec = nullptr;
       const bool use_graph = n >= 3 * NB && !getenv("MDB200_DYN_NOGRAPH");
-      const unsigned gswap = (unsigned)((n + 255) / 256);
+      const unsigned gswap = (unsigned)((n + 255) / 256);   // blocks for the positions left of the pivot (k_dyn_column)
       if (use_graph) {
         cudaGraph_t graph = nullptr;
         cudaError_t ge = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
         if (ge == cudaSuccess) {
-          const unsigned gcol = (unsigned)((n - 2 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS);
-          for (int c = 0; c < NB; ++c) {
-            k_dyn_swap<<<gswap, 256, 0, ctx->stream>>>(n, f->W, f->ld, sel, c & 1, f->PX, f->PY, LDP);
-            k_dyn_column<<<gcol, 256, 0, ctx->stream>>>(F, method, sel, c & 1, f->PX, f->PY, LDP, cand, counter, minB, maxB,
-                                                        f->p_dev);
-          }
+          const unsigned gcol = (unsigned)((n - 1 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS);   // rows below the very first column
+          for (int c = 0; c < NB; ++c)
+            k_dyn_column<<<gcol + gswap, 256, 0, ctx->stream>>>(F, method, sel, c & 1, (int)gcol, f->PX, f->PY, LDP, cand,
+                                                                counter, minB, maxB, f->p_dev);
           ge = cudaStreamEndCapture(ctx->stream, &graph);
         }
         if (ge == cudaSuccess) ge = cudaGraphInstantiate(&gexec, graph, 0);
@@ -1358,15 +1355,14 @@ extern "C" int mdb_approximate_dynamic_f64(mdb_ctx* ctx, int64_t n, const double
         }
         if (gexec && pe < n && pe - pb == NB) {
           cudaGraphLaunch(gexec, ctx->stream);
-          ctx->launches += 2 * NB;
+          ctx->launches += NB;
         } else {
           for (int64_t i = pb; i < pe; ++i) {
             const int64_t rem = n - i;
-            k_dyn_swap<<<gswap, 256, 0, ctx->stream>>>(n, f->W, f->ld, sel, (int)(i & 1), f->PX, f->PY, LDP);
-            ctx->launches += 1;
-            if (rem > 1) {
-              k_dyn_column<<<(unsigned)((rem - 1 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS), 256, 0, ctx->stream>>>(
-                  F, method, sel, (int)(i & 1), f->PX, f->PY, LDP, cand, counter, minB, maxB, f->p_dev);
+            if (rem > 1) {   // (the last index is its own pivot: nothing to swap, nothing below)
+              const unsigned gcol = (unsigned)((rem - 1 + MDB_DYN_ROWS - 1) / MDB_DYN_ROWS);
+              k_dyn_column<<<gcol + (unsigned)((i + 255) / 256), 256, 0, ctx->stream>>>(
+                  F, method, sel, (int)(i & 1), (int)gcol, f->PX, f->PY, LDP, cand, counter, minB, maxB, f->p_dev);
               ctx->launches += 1;
             }
           }

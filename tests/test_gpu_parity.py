@@ -448,8 +448,9 @@ def test_dynamic_pivoting_reference_test_grid_n10(matrix):
         matrix.approximation.positive_semidefinite.decomposition(A, min_diag_D=0, permutation='minimal_difference')
 
 
-def test_dynamic_pivoting_against_oracle_moderate_n(matrix, orc):
-    A = workloads.goe(400, 21) + 2.0 * np.eye(400)
+@pytest.mark.parametrize('n', [400, 450])      # 450: n - 2 is a multiple of the 64 rows a block of k_dyn_column owns
+def test_dynamic_pivoting_against_oracle_moderate_n(matrix, orc, n):
+    A = workloads.goe(n, 21) + 2.0 * np.eye(n)
     for method in ('maximal_stability', 'minimal_difference'):
         kw = dict(min_diag_D=0.3, max_diag_D=30.0, permutation=method)
         dec = matrix.approximation.positive_semidefinite.decomposition(A, **kw)
