@@ -376,6 +376,28 @@ def extra_config5(ctx, stream, batch=512, n=512, seed=0):
                 n_clamped_mean=float(res.clamped.sum(axis=1).mean()))
 
 
+def extra_dynamic(n=16384):
+    """Dynamic pivoting (permutation='maximal_stability', what the reference does for permutation=None, Reimer.py:415-416
+    and :497-523) through the public Python call with a pageable numpy matrix: one k_dyn_column launch per column plus
+    one K = 128 tensor-core update per panel.  Wall time, best of two after a warm-up call."""
+    import workloads
+    import matrix_decomposition_b200 as matrix
+    A, kw = workloads.shifted_goe(n, 5, S_SHIFT)
+    kw = dict(kw, permutation='maximal_stability')
+    psd = matrix.approximation.positive_semidefinite
+    ts = []
+    for _ in range(3):
+        t = time.perf_counter()
+        dec = psd.decomposition(A, **kw)
+        ts.append(time.perf_counter() - t)
+        ncl = int(dec.clamped.sum())
+        del dec
+    sec = min(ts[1:])
+    return dict(n=n, method='maximal_stability', api_s=sec, us_per_column=sec / n * 1e6, tflops=n ** 3 / 3 / sec / 1e12,
+                n_clamped=ncl, call='approximation.positive_semidefinite.decomposition(A, permutation="maximal_stability", '
+                '**bounds), pageable numpy in, factor resident')
+
+
 def run_single(args):
     import torch
     import matrix_decomposition_b200 as matrix  # noqa: F401  (fails loudly without libmdb200.so)
@@ -474,7 +496,8 @@ def run_single(args):
     if not args.no_extra:
         for name, fn in (('config2_decompose_solve', lambda: extra_config2(ctx, stream)),
                          ('permute_symmetric', lambda: extra_permute(ctx, stream, min(n, 65536))),
-                         ('config5_batched_512x512', lambda: extra_config5(ctx, stream))):
+                         ('config5_batched_512x512', lambda: extra_config5(ctx, stream)),
+                         ('dynamic_pivoting', lambda: extra_dynamic())):
             try:
                 extra[name] = fn()
             except Exception as e:  # noqa: BLE001  (an extra must not take the headline line down)
