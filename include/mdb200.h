@@ -172,6 +172,10 @@ int mdb_factor_upload(mdb_ctx *ctx, int64_t n, int type, const double *L, int64_
 int mdb_factor_solve(mdb_factor *f, const double *B, int64_t ldb, int64_t nrhs, double *X, int64_t ldx, int loc);
 /* y = A x for the composed matrix (decompositions.py:961-968 LDL, :1324-1330 LL). */
 int mdb_factor_multiply(mdb_factor *f, const double *B, int64_t ldb, int64_t nrhs, double *X, int64_t ldx, int loc);
+/* The composed matrix itself, B = P^T L D L^T P (LL: P^T L L^T P), n x n row-major with ldb
+ * (DecompositionBase.composed_matrix, decompositions.py:826-830 LDL, :1202-1205 LL): n^3 / 3 multiply-adds on the
+ * tensor-core tile kernel from the resident factor.  loc: where B lives. */
+int mdb_factor_composed(mdb_factor *f, double *B, int64_t ldb, int loc);
 /* Oracle-free identity check usable at any n (Reimer.py:947-957, tests/test_approximate.py:503-506):
  * returns max over `nprobe` random vectors v of |P^T L D L^T P v - (A o Omega + diag(delta)) v|_inf /
  * |A v|_inf, all evaluated on the device from the resident W (which still holds A in its upper triangle). */

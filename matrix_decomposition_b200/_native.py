@@ -94,6 +94,7 @@ SIGNATURES = {
     'mdb_factor_upload': (_int, [_vp, _i64, _int, _vp, _i64, _vp, _vp, _pp]),
     'mdb_factor_solve': (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _int]),
     'mdb_factor_multiply': (_int, [_vp, _vp, _i64, _i64, _vp, _i64, _int]),
+    'mdb_factor_composed': (_int, [_vp, _vp, _i64, _int]),
     'mdb_factor_identity_residual': (_int, [_vp, _int, _u64, _vp]),
     'mdb_factor_device_ptr': (_vp, [_vp, _int]),
     'mdb_factor_ld': (_i64, [_vp]),
@@ -331,3 +332,9 @@ class Factor:
         rc = self.ctx.lib.mdb_factor_multiply(self.handle, ptr(b2), b2.shape[1], b2.shape[1], ptr(x), b2.shape[1], HOST)
         self.ctx.check(rc, 'mdb_factor_multiply')
         return x.reshape(b.shape)
+
+    def composed(self, n):
+        B = np.empty((n, n), dtype=np.float64)
+        rc = self.ctx.lib.mdb_factor_composed(self.handle, ptr(B), n, HOST)
+        self.ctx.check(rc, 'mdb_factor_composed')
+        return B

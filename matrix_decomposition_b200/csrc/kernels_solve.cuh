@@ -95,6 +95,25 @@ __global__ void __launch_bounds__(NB) k_prepare_blocks(int64_t n, const double* 
   }
 }
 
+// Operands of block column J of the composed matrix (mdb_factor_composed): rows [j0, j0 + NB) of L over the columns
+// [0, j0 + NB), clean (the diagonal block comes from Ltri[J]: zeros above the diagonal, identity padding past n; what
+// lies left of it in W is the strictly lower part anyway), once as they are (AJ) and once scaled by d (BJ = AJ D).
+// Row pitch ldt.  grid = (ceil(K / 256), NB).
+__global__ void __launch_bounds__(256) k_composed_operands(int64_t n, const double* __restrict__ W, int64_t ldw,
+                                                           const double* __restrict__ LtriJ, const double* __restrict__ d,
+                                                           int use_d, int64_t j0, int nb, double* __restrict__ AJ,
+                                                           double* __restrict__ BJ, int64_t ldt) {
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int c = blockIdx.y;
+  if (k >= j0 + nb) return;
+  double a;
+  if (k < j0) a = (j0 + c < n) ? W[(j0 + c) * ldw + k] : 0.0;
+  else a = LtriJ[c * nb + (k - j0)];
+  const double dk = use_d ? (k < n ? d[k] : 0.0) : 1.0;
+  AJ[c * ldt + k] = a;
+  BJ[c * ldt + k] = a * dk;
+}
+
 // Small-M "TN" product for up to 8 right-hand sides (bandwidth bound, one warp per B row):
 //   C[r, i] = beta C[r, i] + sign * sum_{k < K} A[r, k] B[i, k],  r < M <= 8, i < N, K multiple of 128.
 // A rows live in registers (each lane holds 4 consecutive doubles per 128-wide chunk), B rows are

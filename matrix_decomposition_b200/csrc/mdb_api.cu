@@ -1961,6 +1961,63 @@ extern "C" int mdb_factor_multiply(mdb_factor* f, const double* B, int64_t ldb, 
   return MDB_OK;
 }
 
+// B = P^T L D L^T P (LDL types) / P^T L L^T P (LL): the matrix the decomposition stands for (decompositions.py:826-830,
+// :1202-1205: `L @ diag(d) @ L.H` and the inverse permutation).  Block column J of the lower triangle is
+//   C[j0:n, J] = L[j0:n, 0:j1] (L[J, 0:j1] D)^T
+// two tile-kernel products per block column (the diagonal tile with the clean diagonal block, the rows below straight
+// from W): n^3 / 3 multiply-adds in total, a quarter of multiplying the factor with an identity matrix, and nothing
+// but the result crosses PCIe.  The upper triangle is the mirror image; the permutation is undone by the gather kernel.
+extern "C" int mdb_factor_composed(mdb_factor* f, double* B, int64_t ldb, int loc) {
+  if (!f) return MDB_ERR_INVALID;
+  mdb_ctx* ctx = f->ctx;
+  MDB_CHECK(ctx, B && ldb >= f->n, "mdb_factor_composed: bad output");
+  MDB_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = factor_prepare(f);
+  if (rc) return rc;
+  const int64_t n = f->n;
+  if (n == 0) return MDB_OK;
+  const int64_t T = (n + NB - 1) / NB, ldt = f->panel_rows;
+  double *C = nullptr, *O = nullptr;
+  int64_t* q = nullptr;
+  size_t capC = 0, capO = 0;
+  cudaError_t e = big_malloc(ctx, (void**)&C, (size_t)n * n * 8, &capC);
+  const bool permuted = f->p_dev != nullptr;
+  if (e == cudaSuccess && permuted) e = big_malloc(ctx, (void**)&O, (size_t)n * n * 8, &capO);
+  if (e == cudaSuccess && permuted) e = dev_malloc(ctx, (void**)&q, (size_t)n * 8);
+  if (e != cudaSuccess) {
+    big_free(ctx, C, capC); big_free(ctx, O, capO); cudaFree(q);
+    return mdb_fail(ctx, MDB_ERR_CUDA, "mdb_factor_composed: %s", cudaGetErrorString(e));
+  }
+  const int use_d = f->out_type != MDB_TYPE_LL ? 1 : 0;
+  for (int64_t J = 0; J < T && !rc; ++J) {
+    const int64_t j0 = J * NB, j1 = j0 + NB, nb = std::min<int64_t>(NB, n - j0);
+    k_composed_operands<<<dim3((unsigned)((j1 + 255) / 256), NB), 256, 0, ctx->stream>>>(
+        n, f->W, f->ld, f->Ltri + J * NB * NB, f->d, use_d, j0, NB, f->PX, f->PY, ldt);
+    MDB_LAUNCHED(ctx);
+    rc = product_tn(ctx, nb, nb, j1, f->PX, ldt, f->PY, ldt, C + j0 * n + j0, n, false, false);
+    if (!rc && j1 < n)
+      rc = product_tn(ctx, n - j1, nb, j1, f->W + j1 * f->ld, f->ld, f->PY, ldt, C + j1 * n + j0, n, false, false);
+  }
+  if (!rc) {
+    const int64_t t32 = (n + 31) / 32;
+    k_symmetrize<<<dim3((unsigned)t32, (unsigned)t32), 256, 0, ctx->stream>>>(n, C, n);
+    MDB_LAUNCHED(ctx);
+    const double* res = C;
+    if (permuted) {   // B[p[i], p[j]] = C[i, j]
+      k_invert_permutation<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, f->p_dev, q);
+      MDB_LAUNCHED(ctx);
+      rc = gather_sym(ctx, n, 1, C, n, 0, q, O, n, 0, nullptr);
+      res = O;
+    }
+    if (!rc) rc = copy2d_async(ctx, B, ldb, res, n, n, n, loc, MDB_DEVICE);
+  }
+  e = cudaStreamSynchronize(ctx->stream);
+  big_free(ctx, C, capC); big_free(ctx, O, capO); cudaFree(q);
+  if (rc) return rc;
+  MDB_CUDA(ctx, e);
+  return MDB_OK;
+}
+
 extern "C" int mdb_factor_identity_residual(mdb_factor* f, int nprobe, uint64_t seed, double* residual) {
   if (!f || !residual) return MDB_ERR_INVALID;
   mdb_ctx* ctx = f->ctx;

@@ -731,6 +731,29 @@ def test_solve_and_multiply_against_oracle(matrix, orc, n, nrhs):
         assert np.array_equal(fresh.solve(b), x)
 
 
+@pytest.mark.parametrize('n', [1, 100, 128, 700, 8300])
+def test_composed_matrix_on_device(matrix, n):
+    """DecompositionBase.composed_matrix (decompositions.py:826-830 LDL, :1202-1205 LL) is formed on the device from
+    the resident factor (mdb_factor_composed): against numpy's P^T (L D L^T) P for every decomposition type, with and
+    without a permutation; n = 8300 takes the two-pass permutation and several waves of the tile kernel.  Symmetric bit
+    for bit (the upper triangle is the mirror image of the lower one)."""
+    rng = np.random.default_rng(n)
+    L = np.tril(rng.standard_normal((n, n)) / np.sqrt(n), -1) + np.eye(n)
+    d = rng.uniform(0.5, 2.0, n)
+    for p in (None, rng.permutation(n)):
+        want = (L * d[None, :]) @ L.T
+        if p is not None:
+            full = np.empty_like(want)
+            full[np.ix_(p, p)] = want
+            want = full
+        ldl = matrix.decompositions.LDL_Decomposition(L, d, p=p)
+        decs = [ldl] if n > 1000 else [ldl, ldl.as_type('LDL_compressed'), ldl.as_type('LL')]
+        for dec in decs:
+            B = dec.composed_matrix
+            assert B.shape == (n, n) and np.array_equal(B, B.T)
+            assert np.max(np.abs(B - want)) <= 1e-12 * np.max(np.abs(want)), (n, dec.type_str)
+
+
 def test_solve_zero_and_integer_rhs_and_singular(matrix):
     A = workloads.reference_fixture_spd(10)
     dec = matrix.decompose(A, return_type='LDL')
@@ -765,18 +788,20 @@ def test_permute_symmetric_bit_exact(matrix):
             assert np.array_equal(B, A[p[:, None], p[None, :]])
 
 
-@pytest.mark.parametrize('shift,rt', [(1.05, 'LDL'), (0.9, 'LDL'), (0.9, 'LDL_compressed')])
-def test_one_shot_early_shipment_of_late_rows(matrix, shift, rt, monkeypatch):
+@pytest.mark.parametrize('shift,rt,n', [(1.05, 'LDL', 4300), (0.9, 'LDL', 4300), (0.9, 'LDL_compressed', 4300),
+                                        (0.9, 'LDL', 16500)])
+def test_one_shot_early_shipment_of_late_rows(matrix, shift, rt, n, monkeypatch):
     """Large one-shot calls ship the columns left of the last quarter of the rows before those rows are final (unscaled
     values, equal to L unless omega != 1 or an entry is lost to the threshold) and send the rows whose early part turned
-    out different again (mdb_factor_run, k_finalize's `changed` flags).  Forced on at n = 4300 (MDB200_TAIL_MIN): with
+    out different again (mdb_factor_run, k_finalize's `changed` flags).  Forced on at n = 4300 (MDB200_TAIL_MIN), as
+    shipped at n = 16500: with
     s = 1.05 every omega is 1 (nothing is re-sent), with s = 0.9 rows are shrunk (omega < 1) and must be re-sent; the
     streamed L must equal the factor that stayed on the device, bit for bit."""
     from matrix_decomposition_b200 import _native
-    monkeypatch.setenv('MDB200_TAIL_MIN', '1024')
+    if n < 16384:
+        monkeypatch.setenv('MDB200_TAIL_MIN', '1024')      # (n = 16500 runs it as shipped: on from n = 16384)
     ctx = _native.context()
     lib = ctx.lib
-    n = 4300
     A, kw = workloads.shifted_goe(n, 78, shift)
     p = np.argsort(-A.diagonal()).astype(np.int64)
     bounds, keep = _native.make_bounds(_native.RULE_REIMER, kw['min_diag_D'], kw['max_diag_D'], kw['min_abs_value_D'],
