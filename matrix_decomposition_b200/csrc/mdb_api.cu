@@ -67,7 +67,8 @@ static void ctx_reap(mdb_ctx* ctx) {
 // ---- device memory ----
 // The two largest buffers of a factorization (the working matrix and the upload staging area, 34 GB each at
 // n = 65536) are kept in the context when they are released and handed out again to the next call that needs the
-// same amount: cudaMalloc + cudaFree of that size cost ~0.1 s per call.  mdb_ctx_trim() gives them back to the driver;
+// same amount: cudaMalloc + cudaFree of that size cost ~0.1 s per call (and still 10-20 ms at 74 MB, so everything
+// from 1 MB on goes through the cache).  mdb_ctx_trim() gives them back to the driver;
 // any allocation of the library that fails trims the cache and tries once more.  MDB200_CACHE=0 disables the cache.
 static void factor_release(mdb_factor* f);
 static void ctx_trim(mdb_ctx* ctx) {
@@ -107,7 +108,7 @@ static cudaError_t big_malloc(mdb_ctx* ctx, void** p, size_t bytes, size_t* cap)
 // Caller's thread only (never the reaper), and only after the work that used the buffer has completed.
 static void big_free(mdb_ctx* ctx, void* p, size_t cap) {
   if (!p) return;
-  if (ctx->use_cache && cap >= ((size_t)256 << 20)) {
+  if (ctx->use_cache && cap >= ((size_t)1 << 20)) {   // (from n ~ 360: cudaMalloc + cudaFree cost 2 ms per call at 8 MB, 10-20 ms at 74 MB)
     int slot = 0;   // a free slot, else the smallest buffer
     for (int i = 0; i < 3; ++i) {
       if (!ctx->big_ptr[i]) { slot = i; break; }
@@ -359,7 +360,7 @@ static int staged_copy2d(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* sr
   const bool h2d = (src_loc == MDB_HOST && dst_loc == MDB_DEVICE), d2h = (src_loc == MDB_DEVICE && dst_loc == MDB_HOST);
   const size_t row_bytes = (size_t)cols * 8;
   const size_t total = (size_t)rows * row_bytes;
-  if (!(h2d || d2h) || total < ((size_t)64 << 20) || row_bytes > ((size_t)8 << 20)) return -1;
+  if (!(h2d || d2h) || total < ((size_t)4 << 20) || row_bytes > ((size_t)8 << 20)) return -1;
   if (!host_is_pageable(h2d ? src : dst)) return -1;
   const size_t SB = (size_t)64 << 20;
   if (!ctx->stage[0]) {
@@ -373,8 +374,8 @@ static int staged_copy2d(mdb_ctx* ctx, void* dst, int64_t ld_dst, const void* sr
     }
     ctx->stage_bytes = SB;
   }
-  // chunks of 8 ... 64 MB: at least ~8 of them, so that staging and DMA overlap also for a few hundred MB
-  const size_t chunk_bytes = std::min<size_t>(SB, std::max<size_t>((size_t)8 << 20, total / 8));
+  // chunks of 1 ... 64 MB: at least ~4-8 of them, so that staging and DMA overlap also for a few tens of MB
+  const size_t chunk_bytes = std::min<size_t>(SB, std::max<size_t>((size_t)1 << 20, total / 8));
   const int64_t R = std::max<int64_t>(1, (int64_t)(chunk_bytes / row_bytes));   // rows per chunk
   const int64_t nchunks = (rows + R - 1) / R;
   if (h2d) {
@@ -580,7 +581,7 @@ extern "C" int mdb_factor_destroy(mdb_factor* f) {
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     factor_detach_W(f);
-    if (f->ctx->use_cache && f->n >= 4096) factor_park(f);   // the next factor of this shape takes the workspace over
+    if (f->ctx->use_cache && f->n >= 256) factor_park(f);   // the next factor of this shape takes the workspace over
     else factor_release(f);
   }
   return MDB_OK;
