@@ -1087,9 +1087,13 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
   }
   if (run_timing) {
     cudaStreamSynchronize(main_s);
-    fprintf(stderr, "[mdb200] run n=%lld: factorization done %.3f s after the last launch was issued, copy stream idle "
-                    "%.3f s later, remaining copies %.3f s (r_tail %lld, rows sent again %lld)\n", (long long)n,
-            tw1 - tw0, tw2 - tw1, wall() - tw2, (long long)r_tail, (long long)resent);
+    if (tail_changed)
+      fprintf(stderr, "[mdb200] run n=%lld: factorization done %.3f s after the last launch was issued, copy stream idle "
+                      "%.3f s later, remaining copies %.3f s (r_tail %lld, rows sent again %lld)\n", (long long)n,
+              tw1 - tw0, tw2 - tw1, wall() - tw2, (long long)r_tail, (long long)resent);
+    else
+      fprintf(stderr, "[mdb200] run n=%lld: factorization done %.3f s after the last launch was issued, download %.3f s "
+                      "later\n", (long long)n, tw1 - tw0, wall() - tw1);
   }
   return MDB_OK;
 }
