@@ -467,6 +467,20 @@ def test_dynamic_pivoting_against_oracle_moderate_n(matrix, orc, n):
             assert abs(float(np.asarray(dec.d, dtype=float)[i]) - float(ref['d'][i])) <= 1e-8 * abs(float(ref['d'][i]))
 
 
+def test_dynamic_pivoting_identity_many_blocks(matrix):
+    """n = 3000: 47 row blocks plus the blocks for the positions left of the pivot in every k_dyn_column launch, 23
+    replayed panel graphs, pivot swaps across block boundaries -- checked through the oracle-free identity
+    P^T L D L^T P = A o Omega + diag(delta) and the bounds (test_approximate.py:187-250, :476-506), which only hold if
+    p, the rows of L, omega and delta went through the same swaps."""
+    n = 3000
+    A, kw = workloads.shifted_goe(n, 17, 0.97)
+    for method in ('maximal_stability', 'minimal_difference'):
+        kwm = dict(kw, permutation=method)
+        dec = matrix.approximation.positive_semidefinite.decomposition(A, **kwm)
+        assert not np.array_equal(np.asarray(dec.p), np.arange(n))
+        _check_identity_and_bounds(A, dec, kwm)
+
+
 # ---------------------------------------------------------------------------------------------
 # GMW family (GMW_SE.py): modified LDL^T without pivoting, d_k from |c|_inf of the current column
 # ---------------------------------------------------------------------------------------------
