@@ -65,9 +65,9 @@ int mdb_version(void);
  * fails after the context was allocated, *out still receives it so that mdb_last_error() can be read; destroy it. */
 int mdb_ctx_create(int device, mdb_ctx **out);
 int mdb_ctx_destroy(mdb_ctx *ctx);
-/* The working matrix and the upload staging buffer of a factorization (n x n doubles each) are kept by the context
- * when they are released and reused by the next call of the same size; every allocation of the library that fails
- * drops them and retries.  mdb_ctx_trim returns them to the driver at once (e.g. before another library needs the
+/* The working matrix, the upload staging buffer and the permutation temporary of a factorization (n x n doubles each,
+ * from 1 MB on) and the workspace of the last destroyed factor are kept by the context when they are released and
+ * reused by the next call of the same size; every allocation of the library that fails drops them and retries.  mdb_ctx_trim returns them to the driver at once (e.g. before another library needs the
  * memory).  MDB200_CACHE=0 in the environment disables the cache. */
 int mdb_ctx_trim(mdb_ctx *ctx);
 /* Use an existing stream (e.g. torch.cuda.current_stream().cuda_stream); NULL restores the own stream. */
