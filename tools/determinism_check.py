@@ -1,4 +1,5 @@
-"""Run-to-run and path-to-path determinism of the factorization (lookahead races would show up here)."""
+"""Run-to-run and path-to-path determinism of the factorization (lookahead races would show up here) and of dynamic
+pivoting (last-block merge of the arg-min)."""
 import ctypes
 import json
 import math
@@ -70,6 +71,20 @@ def main():
                                     n_diff=int(np.count_nonzero(d0 != d)))
         out[f'n{n}'] = res
         print(json.dumps({f'n{n}': res}), flush=True)
+    # dynamic pivoting: the arg-min is merged by whichever block finishes last -- p, d and L must not depend on that
+    import matrix_decomposition_b200 as matrix
+    nd = 6000
+    A, kw = workloads.shifted_goe(nd, 7, 0.97)
+    runs = []
+    for rep in range(3):
+        dec = matrix.approximation.positive_semidefinite.decomposition(A, **dict(kw, permutation='maximal_stability'))
+        runs.append((np.asarray(dec.p).copy(), np.asarray(dec.d, dtype=float).copy(), np.array(dec.L)))
+        del dec
+    res = dict(p_equal=all(np.array_equal(runs[0][0], r[0]) for r in runs[1:]),
+               d_equal=all(np.array_equal(runs[0][1], r[1]) for r in runs[1:]),
+               L_equal=all(np.array_equal(runs[0][2], r[2]) for r in runs[1:]))
+    out[f'dynamic_n{nd}'] = res
+    print(json.dumps({f'dynamic_n{nd}': res}), flush=True)
     with open(os.path.join(REPO, 'gpurun_out', 'determinism.json'), 'w') as fh:
         json.dump(out, fh, indent=1)
 
