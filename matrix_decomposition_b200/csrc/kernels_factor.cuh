@@ -1269,6 +1269,38 @@ __global__ void k_gather_by_p(int64_t n, const int64_t* __restrict__ p, const do
   if (i < n) out[i] = in[(p ? p[i] : i) * stride];
 }
 
+// Streamed download, late rows (mdb_factor_run): the left part [0, cols) of a row went home before the row was final;
+// where k_finalize found that the final values differ (changed[r]) it is written again, straight into the pinned host
+// matrix (zero-copy stores over PCIe) from the copy stream -- no host round trip, so it rides behind the factorization
+// like every other row block.  A SMALL grid (MDB_RESEND_CTAS) walks the (row, 1024-double segment) pairs: the kernel is
+// bound by PCIe, and one CTA per segment (tens of thousands, each waiting on its stores) took the registers of half of
+// the tile kernel's CTAs for 0.1 s (measured at n = 65536, F2 s = 0.9: factorization 0.11 s longer).
+#define MDB_RESEND_CTAS 32
+__global__ void __launch_bounds__(256) k_resend_rows(const uint8_t* __restrict__ changed, const double* __restrict__ W,
+                                                     int64_t ldw, double* __restrict__ out, int64_t ldo, int64_t row0,
+                                                     int64_t rows, int64_t cols) {
+  const int64_t segs = (cols + 1023) / 1024;
+  for (int64_t t = blockIdx.x; t < rows * segs; t += gridDim.x) {
+    const int64_t r = row0 + t / segs, c0 = (t % segs) * 1024;
+    if (!changed[r]) continue;
+    const double* __restrict__ src = W + r * ldw + c0;
+    double* __restrict__ dst = out + r * ldo + c0;
+    const int64_t m = cols - c0 < 1024 ? cols - c0 : 1024;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+      const int64_t ca = 2 * threadIdx.x, cb = ca + 512;
+      double2 va = make_double2(0, 0), vb = va;
+      if (ca + 1 < m) va = *reinterpret_cast<const double2*>(src + ca);
+      if (cb + 1 < m) vb = *reinterpret_cast<const double2*>(src + cb);
+      if (ca + 1 < m) *reinterpret_cast<double2*>(dst + ca) = va;
+      else if (ca < m) dst[ca] = src[ca];
+      if (cb + 1 < m) *reinterpret_cast<double2*>(dst + cb) = vb;
+      else if (cb < m) dst[cb] = src[cb];
+    } else {
+      for (int64_t c = threadIdx.x; c < m; c += 256) dst[c] = src[c];
+    }
+  }
+}
+
 // Distributed finalize: the local column slab S_loc (n x ld_loc) in place.  Local column lc belongs to global
 // column gc = ((lc / NB) * world + rank) * NB + lc % NB.
 __global__ void __launch_bounds__(256) k_finalize_cols(int64_t n, double* __restrict__ S, int64_t ld, int64_t ncols,

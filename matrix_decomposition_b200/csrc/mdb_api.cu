@@ -47,6 +47,7 @@ struct mdb_factor {
   double* ws[3]; size_t ws_cap[3];
   // streamed output (one-shot calls with a host L): rows of L are finalised and copied out per outer block
   double* out_host; int64_t out_ld; int out_stream_type;
+  double* out_host_dev;   // device-side address of out_host when the pinned memory is mapped (null: not addressable)
   // persistent triangular sweep (<= 8 right-hand sides): task list, flags, partial sums
   int2* trsv_tasks; int trsv_ntasks; unsigned int* trsv_sync; double* trsv_partial; int trsv_partial_rhs;
   std::vector<int64_t> p_host;
@@ -462,7 +463,7 @@ static void factor_park(mdb_factor* f) {
   f->trsv_tasks = nullptr; f->trsv_ntasks = 0; f->trsv_sync = nullptr; f->trsv_partial = nullptr; f->trsv_partial_rhs = 0;
   for (int i = 0; i < 3; ++i) { f->ws[i] = nullptr; f->ws_cap[i] = 0; }
   f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
-  f->out_host = nullptr; f->out_ld = 0; f->out_stream_type = MDB_TYPE_LDL;
+  f->out_host = nullptr; f->out_host_dev = nullptr; f->out_ld = 0; f->out_stream_type = MDB_TYPE_LDL;
   f->p_host.clear();
   if (ctx->parked) factor_release(ctx->parked);
   ctx->parked = f;
@@ -523,7 +524,7 @@ extern "C" int mdb_factor_create(mdb_ctx* ctx, int64_t n, int64_t batch, mdb_fac
   f->W = nullptr; f->vec = nullptr; f->clamped = nullptr; f->minB = f->maxB = nullptr; f->p_dev = nullptr;
   f->info = nullptr; f->Vinv = nullptr; f->Ut = f->hdr = f->PX = f->PY = f->PX2 = f->PY2 = nullptr; f->Linv = f->LinvT = f->Ltri = f->Utri = nullptr;
   f->state = ST_EMPTY; f->out_type = MDB_TYPE_LDL; f->rule = MDB_RULE_REIMER; f->mavL = 0; f->prepared = false;
-  f->out_host = nullptr; f->out_ld = 0; f->out_stream_type = MDB_TYPE_LDL;
+  f->out_host = nullptr; f->out_host_dev = nullptr; f->out_ld = 0; f->out_stream_type = MDB_TYPE_LDL;
   for (int i = 0; i < 3; ++i) { f->ws[i] = nullptr; f->ws_cap[i] = 0; }
   f->trsv_tasks = nullptr; f->trsv_ntasks = 0; f->trsv_sync = nullptr; f->trsv_partial = nullptr; f->trsv_partial_rhs = 0;
   const int64_t nn = std::max<int64_t>(n, 1);
@@ -1008,6 +1009,12 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       k_finalize<<<grid, 256, 0, ctx->copy_stream>>>(n, f->W, f->ld, F.sW, f->d, f->omega, n, f->mavL, f->out_stream_type,
                                                      f->W, f->ld, F.sW, ob, late ? tail_changed : nullptr, r_tail);
       MDB_LAUNCHED(ctx);
+      if (late && tail_changed && f->out_host_dev) {
+        // rows whose early-shipped left part is stale go again at once, written by the device into the pinned matrix
+        k_resend_rows<<<MDB_RESEND_CTAS, 256, 0, ctx->copy_stream>>>(tail_changed, f->W, f->ld, f->out_host_dev, f->out_ld, ob,
+                                                                     oe - ob, r_tail);
+        MDB_LAUNCHED(ctx);
+      }
       const int64_t c_first = late ? r_tail : 0;   // the late rows only send what has not been shipped yet
       MDB_CUDA(ctx, cudaMemcpy2DAsync(f->out_host + ob * f->out_ld + c_first, (size_t)f->out_ld * 8,
                                       f->W + ob * f->ld + c_first, (size_t)f->ld * 8, (size_t)(n - c_first) * 8,
@@ -1061,8 +1068,10 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
   double tw1 = tw0, tw2 = tw0;
   int64_t resent = 0;
   if (run_timing) { cudaStreamSynchronize(main_s); tw1 = wall(); }
-  if (f->out_host && tail_changed) {
-    // late rows whose early-shipped columns are not what L holds (omega != 1, thresholded entries): send them again
+  if (f->out_host && tail_changed && (!f->out_host_dev || run_timing)) {
+    // late rows whose early-shipped columns are not what L holds (omega != 1, thresholded entries): send them again --
+    // only when the device cannot address the host matrix itself (else k_resend_rows has done it on the way; with
+    // MDB200_TIMING the flags are still read for the count)
     std::vector<uint8_t> ch((size_t)(n - r_tail));
     cudaError_t e = cudaMemcpyAsync(ch.data(), tail_changed + r_tail, (size_t)(n - r_tail), cudaMemcpyDeviceToHost, ctx->copy_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
@@ -1070,8 +1079,9 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
       if (!ch[(size_t)(j - r_tail)]) { ++j; continue; }
       int64_t j1 = j;
       while (j1 < n && ch[(size_t)(j1 - r_tail)]) ++j1;
-      e = cudaMemcpy2DAsync(f->out_host + j * f->out_ld, (size_t)f->out_ld * 8, f->W + j * f->ld, (size_t)f->ld * 8,
-                            (size_t)r_tail * 8, (size_t)(j1 - j), cudaMemcpyDeviceToHost, ctx->copy_stream);
+      if (!f->out_host_dev)
+        e = cudaMemcpy2DAsync(f->out_host + j * f->out_ld, (size_t)f->out_ld * 8, f->W + j * f->ld, (size_t)f->ld * 8,
+                              (size_t)r_tail * 8, (size_t)(j1 - j), cudaMemcpyDeviceToHost, ctx->copy_stream);
       resent += j1 - j;
       j = j1;
     }
@@ -1084,6 +1094,7 @@ extern "C" int mdb_factor_run(mdb_factor* f, const mdb_bounds* bnd) {
     f->state = ST_FINAL;
     f->out_type = f->out_stream_type;
     f->out_host = nullptr;
+    f->out_host_dev = nullptr;
   }
   if (run_timing) {
     cudaStreamSynchronize(main_s);
@@ -1235,13 +1246,19 @@ static int one_shot(mdb_ctx* ctx, int64_t batch, int64_t n, const double* A, int
   // Streaming L out needs PINNED host memory: a device -> pageable copy blocks the calling thread until the data is
   // there, which would stall the launch loop of the factorization behind every row block.
   bool l_pinned = false;
+  double* l_dev = nullptr;
   if (!rc && loc == MDB_HOST && L) {
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, L) == cudaSuccess) l_pinned = (attr.type == cudaMemoryTypeHost);
-    else cudaGetLastError();
+    if (cudaPointerGetAttributes(&attr, L) == cudaSuccess) {
+      l_pinned = (attr.type == cudaMemoryTypeHost);
+      if (l_pinned && !getenv("MDB200_NO_ZEROCOPY")) l_dev = (double*)attr.devicePointer;   // (the switch is for the tests)
+    } else {
+      cudaGetLastError();
+    }
   }
   if (!rc && loc == MDB_HOST && L && l_pinned && batch == 1 && n >= 4096 && ldl >= n) {
     f->out_host = L; f->out_ld = ldl; f->out_stream_type = out_type;  // L leaves the device row block by row block
+    f->out_host_dev = l_dev;
     streamed = true;
   }
   if (!rc) rc = mdb_factor_run(f, bounds);

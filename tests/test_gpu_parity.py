@@ -802,18 +802,22 @@ def test_permute_symmetric_bit_exact(matrix):
             assert np.array_equal(B, A[p[:, None], p[None, :]])
 
 
-@pytest.mark.parametrize('shift,rt,n', [(1.05, 'LDL', 4300), (0.9, 'LDL', 4300), (0.9, 'LDL_compressed', 4300),
-                                        (0.9, 'LDL', 16500)])
-def test_one_shot_early_shipment_of_late_rows(matrix, shift, rt, n, monkeypatch):
+@pytest.mark.parametrize('shift,rt,n,zero_copy', [(1.05, 'LDL', 4300, True), (0.9, 'LDL', 4300, True),
+                                                  (0.9, 'LDL_compressed', 4300, True), (0.9, 'LDL', 4301, True),
+                                                  (0.9, 'LDL', 4300, False), (0.9, 'LDL', 16500, True)])
+def test_one_shot_early_shipment_of_late_rows(matrix, shift, rt, n, zero_copy, monkeypatch):
     """Large one-shot calls ship the columns left of the last quarter of the rows before those rows are final (unscaled
     values, equal to L unless omega != 1 or an entry is lost to the threshold) and send the rows whose early part turned
-    out different again (mdb_factor_run, k_finalize's `changed` flags).  Forced on at n = 4300 (MDB200_TAIL_MIN), as
-    shipped at n = 16500: with
+    out different again (mdb_factor_run, k_finalize's `changed` flags; k_resend_rows writes them into the pinned matrix
+    from the device, n = 4301: rows of the host matrix not 16-byte aligned).  Forced on at n = 4300 (MDB200_TAIL_MIN),
+    as shipped at n = 16500: with
     s = 1.05 every omega is 1 (nothing is re-sent), with s = 0.9 rows are shrunk (omega < 1) and must be re-sent; the
     streamed L must equal the factor that stayed on the device, bit for bit."""
     from matrix_decomposition_b200 import _native
     if n < 16384:
         monkeypatch.setenv('MDB200_TAIL_MIN', '1024')      # (n = 16500 runs it as shipped: on from n = 16384)
+    if not zero_copy:    # the re-send through copies issued by the host at the end (host matrix not device-addressable)
+        monkeypatch.setenv('MDB200_NO_ZEROCOPY', '1')
     ctx = _native.context()
     lib = ctx.lib
     A, kw = workloads.shifted_goe(n, 78, shift)

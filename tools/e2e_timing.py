@@ -15,7 +15,10 @@ from matrix_decomposition_b200 import _native  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--size', type=int, default=65536)
 ap.add_argument('--steps', type=int, default=2)
+ap.add_argument('--shift', type=float, default=None, help='s of the F2 family (default: the bench value 1.05; 0.9 = indefinite, many rows with omega < 1)')
 a = ap.parse_args()
+if a.shift is not None:
+    bench.S_SHIFT = a.shift
 n = a.size
 ctx = _native.context(0)
 mu = bench.S_SHIFT * math.sqrt(2 * n)
